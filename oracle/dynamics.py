@@ -1,0 +1,248 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+Committed NumPy version of the analytic relative-dynamics stand-in (SURVEY.md
+A.3).  There is NO reference function for this row (R4): the reference gets
+its observations from Gazebo + RotorS + PID/attitude nodes.  The parameters
+are traced to the reference:
+
+  * pitch first-order lag  tau = k_omega/k_R = 0.1/0.7   (PKG/attitude_controller.py:86-87)
+  * g = 9.81                                             (PKG/attitude_controller.py:59)
+  * rotor-drag c_d ~= 0.2 1/s        (rotors_gazebo_plugins/src/gazebo_motor_model.cpp:464-466,
+                                      rotors_description/urdf/hummingbird.xacro:29-42)
+  * platform x = r sin(w t), u = r w cos(w t), w = v/r    (PKG/moving_platform.py:116-125)
+  * rel = platform - drone                                (PKG/observation_utils.py:225,249)
+  * contact height 0.515 m, platform 1x1 m                (urdf/moving_platform.urdf:16,38,51,58)
+
+Two versions of the SAME equations:
+
+``StandInDet``  fp32, every operation a separately rounded IEEE add/mul/div/sqrt
+                (no FMA, own polynomial sin/cos/tan/log), so the CUDA kernel, the
+                C oracle and NumPy agree BIT FOR BIT.  Used for replay parity.
+``standin_f64`` float64 with np.sin/np.tan -- the "textbook" form; the fp32
+                path must stay within 1e-5 of it (north_star tolerance).
+
+The platform phase is a uint32 in "turns" (2**32 == one period): phase
+advance is exact integer arithmetic, range reduction is exact, and a random
+start phase is just a Philox word.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+f32 = np.float32
+TWO_PI = 2.0 * math.pi
+
+
+@dataclass(frozen=True)
+class StandInParams:
+    f_ag: float = 22.92          # PKG/trainer.py:42
+    tau_theta: float = 1.0 / 7.0
+    c_d: float = 0.2
+    g: float = 9.81
+    r_mp: float = 2.0            # PKG/moving_platform.py r_x default
+    v_mp: float = 1.6            # launch/environment.launch:62-64 (intended)
+    z_init: float = 4.0          # PKG/trainer.py:41
+    v_z: float = -0.1            # PKG/mdp.py:212 (training); -0.4 PKG/mdp.py:580 (simulation)
+    z_touch: float = 0.515
+    half_platform: float = 0.5
+    p_max: float = 4.5
+    n_sub: int = 1
+
+
+@dataclass(frozen=True)
+class DerivedF32:
+    """fp32 constants derived on the host in float64, then rounded once."""
+    h: np.float32
+    half_h2: np.float32
+    k_theta: np.float32
+    g: np.float32
+    c_d: np.float32
+    r: np.float32
+    rw: np.float32
+    rw2: np.float32
+    dz: np.float32
+    z_init: np.float32
+    z_touch: np.float32
+    half_platform: np.float32
+    p_max: np.float32
+    two_p_max: np.float32
+    sigma_x: np.float32
+    dphase: int                  # uint32 turns per sub-step
+    n_sub: int
+
+
+def derive(p: StandInParams) -> DerivedF32:
+    h = (1.0 / p.f_ag) / p.n_sub
+    w = p.v_mp / p.r_mp
+    return DerivedF32(
+        h=f32(h), half_h2=f32(0.5 * h * h), k_theta=f32(-math.expm1(-h / p.tau_theta)),
+        g=f32(p.g), c_d=f32(p.c_d), r=f32(p.r_mp), rw=f32(p.r_mp * w), rw2=f32(p.r_mp * w * w),
+        dz=f32(p.v_z * (1.0 / p.f_ag)), z_init=f32(p.z_init), z_touch=f32(p.z_touch),
+        half_platform=f32(p.half_platform), p_max=f32(p.p_max), two_p_max=f32(2.0 * p.p_max),
+        sigma_x=f32(p.p_max / 3.0),
+        dphase=int(round(w * h / TWO_PI * 2.0 ** 32)) & 0xFFFFFFFF, n_sub=p.n_sub,
+    )
+
+
+# ----------------------------------------------------------------------------------------
+# deterministic fp32 math: every op is one correctly rounded IEEE operation on np.float32
+# ----------------------------------------------------------------------------------------
+_TURN_TO_RAD = f32(TWO_PI / 2.0 ** 32)
+_S = [f32(-1.0 / 6.0), f32(1.0 / 120.0), f32(-1.0 / 5040.0), f32(1.0 / 362880.0)]
+_C = [f32(-0.5), f32(1.0 / 24.0), f32(-1.0 / 720.0), f32(1.0 / 40320.0), f32(-1.0 / 3628800.0)]
+_T = [f32(1.0 / 3.0), f32(2.0 / 15.0), f32(17.0 / 315.0), f32(62.0 / 2835.0),
+      f32(1382.0 / 155925.0), f32(21844.0 / 6081075.0)]
+_L = [f32(1.0 / 3.0), f32(1.0 / 5.0), f32(1.0 / 7.0), f32(1.0 / 9.0)]
+_LN2 = f32(math.log(2.0))
+_SQRT2 = f32(math.sqrt(2.0))
+ONE = f32(1.0)
+
+
+def det_sincos_turns(phase):
+    """sin, cos of 2*pi*phase/2**32 for uint32 phase (array)."""
+    phase = np.atleast_1d(np.asarray(phase, dtype=np.uint32))
+    q = ((phase + np.uint32(0x20000000)) >> np.uint32(30)).astype(np.uint32)
+    rem = (phase - (q << np.uint32(30))).astype(np.uint32).view(np.int32)
+    x = rem.astype(np.float32) * _TURN_TO_RAD
+    z = x * x
+    ps = _S[3]
+    for c in (_S[2], _S[1], _S[0]):
+        ps = ps * z + c
+    s = x + x * (z * ps)
+    pc = _C[4]
+    for c in (_C[3], _C[2], _C[1], _C[0]):
+        pc = pc * z + c
+    c_ = ONE + z * pc
+    qq = q & np.uint32(3)
+    sin = np.where(qq == 0, s, np.where(qq == 1, c_, np.where(qq == 2, -s, -c_)))
+    cos = np.where(qq == 0, c_, np.where(qq == 1, -s, np.where(qq == 2, -c_, s)))
+    return sin.astype(np.float32), cos.astype(np.float32)
+
+
+def det_tan(x):
+    """tan(x) for |x| <= ~0.45 rad (odd Taylor polynomial to x**13, Horner, no FMA)."""
+    x = np.atleast_1d(np.asarray(x, dtype=np.float32))
+    z = x * x
+    p = _T[5]
+    for c in (_T[4], _T[3], _T[2], _T[1], _T[0]):
+        p = p * z + c
+    return (x + x * (z * p)).astype(np.float32)
+
+
+def det_log(u):
+    """ln(u) for normal positive fp32 u (atanh series after exact exponent split)."""
+    u = np.ascontiguousarray(np.atleast_1d(np.asarray(u, dtype=np.float32)))
+    bits = u.reshape(-1).view(np.uint32).reshape(u.shape)
+    e = ((bits >> np.uint32(23)) & np.uint32(0xFF)).astype(np.int32) - 127
+    m = ((bits & np.uint32(0x007FFFFF)) | np.uint32(0x3F800000)).reshape(-1).view(np.float32).reshape(u.shape)
+    big = m > _SQRT2
+    m = np.where(big, m * f32(0.5), m).astype(np.float32)
+    e = np.where(big, e + 1, e)
+    s = (m - ONE) / (m + ONE)
+    z = s * s
+    p = _L[3]
+    for c in (_L[2], _L[1], _L[0]):
+        p = p * z + c
+    lm = (s + s) * (ONE + z * p)
+    return (e.astype(np.float32) * _LN2 + lm).astype(np.float32)
+
+
+def det_normal(x0, x1):
+    """Standard normal from two Philox words (Box-Muller, deterministic)."""
+    u1 = ((np.atleast_1d(np.asarray(x0, dtype=np.uint32)) >> np.uint32(8)).astype(np.float32) + ONE) * f32(2.0 ** -24)
+    rad = np.sqrt(f32(-2.0) * det_log(u1)).astype(np.float32)
+    _, c = det_sincos_turns(x1)
+    return (rad * c).astype(np.float32)
+
+
+class StandInDet:
+    """Vectorised (over envs) deterministic fp32 stand-in.  State arrays are np.float32/uint32."""
+
+    def __init__(self, params: StandInParams, n: int):
+        self.p = params
+        self.d = derive(params)
+        self.n = n
+        self.x_d = np.zeros(n, f32)
+        self.v_d = np.zeros(n, f32)
+        self.theta = np.zeros(n, f32)
+        self.phase = np.zeros(n, np.uint32)
+        self.a_d = np.zeros(n, f32)
+
+    # R1 (PKG/landing_simulation_env.py:181-216) / R15 (:327-340)
+    def reset(self, idx, w0, w1, w2, *, normal_init: bool, simulation: bool = False):
+        d = self.d
+        idx = np.asarray(idx)
+        w0 = np.asarray(w0, dtype=np.uint32)
+        if normal_init:
+            x_init = d.sigma_x * det_normal(w0, w1)
+        else:
+            u = (w0 >> np.uint32(8)).astype(np.float32) * f32(2.0 ** -24)
+            x_init = -d.p_max + d.two_p_max * u
+        phase = np.asarray(w2, dtype=np.uint32)
+        s, _ = det_sincos_turns(phase)
+        x_mp = d.r * s
+        if simulation:
+            # absolute clip, platform minus offset (PKG/landing_simulation_env.py:331-335)
+            x_d = np.clip(x_mp - x_init, -d.p_max, d.p_max)
+        else:
+            # clip(x_init + x_mp, x_mp +- p_max) == x_mp + clip(x_init, +-p_max) up to rounding;
+            # the stand-in defines it as the latter (PKG/landing_simulation_env.py:197-201)
+            x_d = x_mp + np.clip(x_init, -d.p_max, d.p_max)
+        self.x_d[idx] = x_d.astype(np.float32)
+        self.v_d[idx] = 0
+        self.theta[idx] = 0
+        self.phase[idx] = phase
+
+    def advance(self, theta_sp, idx=None):
+        """One agent period (n_sub sub-steps) toward set-point theta_sp (fp32 array)."""
+        d = self.d
+        sl = slice(None) if idx is None else idx
+        x, v, th, ph = self.x_d[sl], self.v_d[sl], self.theta[sl], self.phase[sl]
+        sp = np.asarray(theta_sp, dtype=np.float32)
+        a = self.a_d[sl]
+        for _ in range(d.n_sub):
+            th = th + (sp - th) * d.k_theta
+            a = d.g * det_tan(th) - d.c_d * v
+            x = (x + v * d.h) + a * d.half_h2
+            v = v + a * d.h
+            ph = ph + np.uint32(d.dphase)
+        self.x_d[sl], self.v_d[sl], self.theta[sl], self.phase[sl], self.a_d[sl] = x, v, th, ph, a
+
+    def observe(self, step_count, idx=None):
+        """(rel_p, rel_v, rel_a, pitch, z, contact) after `step_count` agent steps of the episode."""
+        d = self.d
+        sl = slice(None) if idx is None else idx
+        s, c = det_sincos_turns(self.phase[sl])
+        rel_p = d.r * s - self.x_d[sl]
+        rel_v = d.rw * c - self.v_d[sl]
+        rel_a = -(d.rw2 * s) - self.a_d[sl]
+        z = d.z_init + np.asarray(step_count).astype(np.float32) * d.dz
+        contact = (z <= d.z_touch) & (np.abs(rel_p) <= d.half_platform)
+        return (rel_p.astype(np.float32), rel_v.astype(np.float32), rel_a.astype(np.float32),
+                self.theta[sl].copy(), z.astype(np.float32), contact)
+
+
+def standin_f64(params: StandInParams, x_d0, phase0, theta_sp_seq):
+    """Float64 'textbook' trajectory for one env: returns arrays (rel_p, rel_v, rel_a, pitch, z)
+    after each agent step, given the set-point applied at each step.  Same equations, np.sin/np.tan."""
+    h = (1.0 / params.f_ag) / params.n_sub
+    w = params.v_mp / params.r_mp
+    k = -math.expm1(-h / params.tau_theta)
+    dph = float(int(round(w * h / TWO_PI * 2.0 ** 32)) & 0xFFFFFFFF)
+    x, v, th, ph = float(x_d0), 0.0, 0.0, float(phase0)
+    out = []
+    for i, sp in enumerate(theta_sp_seq):
+        for _ in range(params.n_sub):
+            th = th + (float(sp) - th) * k
+            a = params.g * math.tan(th) - params.c_d * v
+            x = x + v * h + 0.5 * a * h * h
+            v = v + a * h
+            ph = (ph + dph) % 2.0 ** 32
+        ang = TWO_PI * ph / 2.0 ** 32
+        xm, vm, am = params.r_mp * math.sin(ang), params.r_mp * w * math.cos(ang), -params.r_mp * w * w * math.sin(ang)
+        z = params.z_init + (i + 1) * params.v_z * (1.0 / params.f_ag)
+        out.append((xm - x, vm - v, am - a, th, z))
+    return np.asarray(out, dtype=np.float64)

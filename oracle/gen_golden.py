@@ -1,0 +1,333 @@
+"""TEST INFRASTRUCTURE ONLY.  Generates the committed fixtures under tests/golden/ by running the
+UNMODIFIED reference modules (imported from /root/reference through oracle/ref_stubs.py).
+
+Run in the build container only (the reference tree does not exist on the GPU box):
+
+    python -m oracle.gen_golden
+
+Fixtures:
+  discretise.npz   random + near-threshold fp32 observations -> TrainingMdp/SimulationMdp state tuples, w = 0..4
+  mdp_trace_w*.npz forced-action episodes: reference TrainingMdp check codes, rewards (float64), states
+  replay_*.npz     the reference trainer loop (guess/update/alpha/exploration_rate + TrainingMdp), single env,
+                   Philox draws injected through np.random, float32 tables (NEP 50) and float64 tables
+  schedules.npz    Trainer.alpha / exploration_rate / transfer_learning_ratio tables
+  sim_trace.npz    SimulationMdp greedy episodes with the committed assets policy
+"""
+from __future__ import annotations
+
+import os
+import pathlib
+import tempfile
+
+import numpy as np
+
+from . import philox, ref_stubs
+from .agent_oracle import state_id
+from .dynamics import StandInDet, StandInParams
+from .mdp_oracle import TERMINATION_STRINGS, NON_TERMINAL, NON_TERMINAL_SUCCESS
+
+GOLDEN = pathlib.Path(__file__).resolve().parent.parent / "tests" / "golden"
+F_AG, T_MAX, P_MAX = 22.92, 20, 4.5
+_STR2CODE = {v: k for k, v in TERMINATION_STRINGS.items()}
+
+
+def _ref_code(mdp, ns) -> int:
+    cr = mdp._check_result
+    if cr == ns.mdp.CheckResult.NON_TERMINAL:
+        return NON_TERMINAL
+    if cr == ns.mdp.CheckResult.NON_TERMINAL_SUCCESS:
+        return NON_TERMINAL_SUCCESS
+    return _STR2CODE[cr.value]
+
+
+def _obs(ns, rel_p, rel_v, rel_a, pitch, z, contact):
+    o = ns.Observation(rel_p_x=float(rel_p), rel_v_x=float(rel_v), rel_a_x=float(rel_a), contact=bool(contact))
+    return ns.mdp.ContinuousObservation(o, float(pitch), 0.0, float(z))
+
+
+def probe_values(rng, n_random=4000):
+    """fp32 probes: broad random values plus +-2 ulp neighbourhoods of every threshold candidate."""
+    from .mdp_oracle import LIMITS_P, LIMITS_V, MdpParams, linspace7
+    prm = MdpParams()
+    cands_p, cands_v, cands_a, cands_t = [], [], [], []
+    for w in range(5):
+        for l in range(w + 1):
+            for sign in (-1, 1):
+                cands_p += [sign * LIMITS_P[l] * P_MAX, sign * LIMITS_P[l] * prm.beta * P_MAX]
+                cands_v += [sign * LIMITS_V[l] * prm.v_max, sign * LIMITS_V[l] * prm.beta * prm.v_max]
+                if l < w:
+                    cands_p.append(sign * LIMITS_P[l] * (LIMITS_P[l + 1] / LIMITS_P[l]) * P_MAX)
+                    cands_v.append(sign * LIMITS_V[l] * (LIMITS_V[l + 1] / LIMITS_V[l]) * prm.v_max)
+    for sign in (-1, 1):
+        cands_a += [sign * prm.a_max, sign * prm.sigma_a * prm.a_max, sign * prm.sigma_a * prm.beta * prm.a_max]
+    ang = linspace7(prm.theta_max, prm.n_theta)
+    cands_t += ang + [(ang[i] + ang[i + 1]) / 2 for i in range(6)]
+
+    def around(c):
+        x = np.float32(c)
+        out = [x]
+        lo = hi = x
+        for _ in range(3):
+            lo = np.nextafter(lo, np.float32(-np.inf)); hi = np.nextafter(hi, np.float32(np.inf))
+            out += [lo, hi]
+        return out
+
+    def expand(cands, scale):
+        vals = [v for c in cands for v in around(c)]
+        vals += list((rng.standard_normal(n_random) * scale).astype(np.float32))
+        vals += [np.float32(0.0), np.float32(-0.0)]
+        return np.asarray(vals, np.float32)
+
+    return expand(cands_p, 2.5), expand(cands_v, 2.0), expand(cands_a, 1.0), expand(cands_t, 0.25)
+
+
+def gen_discretise(ns):
+    rng = np.random.default_rng(1234)
+    P, V, A, T = probe_values(rng)
+    n = 6000
+    # every probe value appears at least once; the other coordinates are random picks
+    rows = []
+    for arr, col in ((P, 0), (V, 1), (A, 2), (T, 3)):
+        for x in arr:
+            r = [rng.choice(P), rng.choice(V), rng.choice(A), rng.choice(T)]
+            r[col] = x
+            rows.append(r)
+    obs = np.asarray(rows, np.float32)
+    out_train = np.zeros((5, len(obs), 5), np.int8)
+    out_sim = np.zeros((5, len(obs), 5), np.int8)
+    for w in range(5):
+        tm = ns.mdp.TrainingMdp(w, F_AG, T_MAX, P_MAX)
+        sm = ns.mdp.SimulationMdp(w, F_AG, T_MAX)
+        tm.reset(); sm.reset()
+        for k, (p, v, a, t) in enumerate(obs):
+            out_train[w, k] = tm.discrete_state(_obs(ns, p, v, a, t, 3.0, False))
+            out_sim[w, k] = sm.discrete_state(_obs(ns, p, v, a, t, 3.0, False))[0]
+    np.savez_compressed(GOLDEN / "discretise.npz", obs=obs, train=out_train, sim=out_sim)
+    print("discretise:", obs.shape)
+
+
+def gen_mdp_trace(ns, w, n_episodes=12, seed=7, sp=None, tag=None):
+    """Forced random actions through the stand-in; the reference MDP consumes the fp32 observations."""
+    rng = np.random.default_rng(seed + w)
+    sp = sp or StandInParams()
+    dyn = StandInDet(sp, 1)
+    mdp = ns.mdp.TrainingMdp(w, F_AG, T_MAX, P_MAX)
+    rec = {k: [] for k in ("obs", "contact", "action", "state", "code", "done", "reward", "theta_sp", "episode", "cum")}
+    idx = np.asarray([0])
+    for ep in range(n_episodes):
+        words = philox.draws(99, w, idx, ep, philox.PURPOSE_RESET)
+        dyn.reset(idx, words[0], words[1], words[2], normal_init=(w == 0))
+        mdp.reset()
+        dyn.advance(np.zeros(1, np.float32))
+        rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.zeros(1)))
+        s = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+        rec["obs"].append((rp, rv, ra, pit, z)); rec["contact"].append(c); rec["action"].append(255)
+        rec["state"].append(state_id(s)); rec["code"].append(0); rec["done"].append(0); rec["reward"].append(0.0)
+        rec["theta_sp"].append(0.0); rec["episode"].append(ep); rec["cum"].append(0.0)
+        # a policy mix so that goal states, fly-zone exits and timeouts all occur
+        mode = ep % 4
+        done, k = False, 0
+        while not done:
+            if mode == 0:
+                a = int(rng.integers(3))
+            elif mode == 1:
+                a = 2
+            elif mode == 2:   # crude stabiliser -> reaches the goal bins
+                a = 0 if (rp + 0.8 * rv) > 0.05 else (1 if (rp + 0.8 * rv) < -0.05 else 2)
+                if abs(pit) > 0.2:
+                    a = 1 if pit > 0 else 0
+            else:
+                a = int(rng.integers(2))
+            act = mdp.continuous_action(a, 2)
+            dyn.advance(np.asarray([act.pitch], np.float32))
+            k += 1
+            rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.asarray([k])))
+            s = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+            info = mdp.check()
+            r = mdp.reward()
+            done = "Termination condition" in info
+            rec["obs"].append((rp, rv, ra, pit, z)); rec["contact"].append(c); rec["action"].append(a)
+            rec["state"].append(state_id(s)); rec["code"].append(_ref_code(mdp, ns)); rec["done"].append(int(done))
+            rec["reward"].append(r); rec["theta_sp"].append(act.pitch); rec["episode"].append(ep)
+            rec["cum"].append(mdp._cumulative_reward)
+    out = dict(
+        obs=np.asarray(rec["obs"], np.float32), contact=np.asarray(rec["contact"], np.uint8),
+        action=np.asarray(rec["action"], np.uint8), state=np.asarray(rec["state"], np.uint16),
+        code=np.asarray(rec["code"], np.uint8), done=np.asarray(rec["done"], np.uint8),
+        reward=np.asarray(rec["reward"], np.float64), theta_sp=np.asarray(rec["theta_sp"], np.float64),
+        episode=np.asarray(rec["episode"], np.int32), cum=np.asarray(rec["cum"], np.float64), w=np.int32(w),
+        z_init=np.float64(sp.z_init), v_z=np.float64(sp.v_z), v_mp=np.float64(sp.v_mp),
+    )
+    np.savez_compressed(GOLDEN / f"mdp_trace_{tag or ('w%d' % w)}.npz", **out)
+    codes, cnt = np.unique(out["code"][out["done"] == 1], return_counts=True)
+    print(f"mdp_trace w={w}: {len(out['action'])} rows, terminal codes {dict(zip(codes.tolist(), cnt.tolist()))}")
+
+
+class _DrawFeeder:
+    """Feeds Philox words to the reference through np.random (order per SURVEY.md A.1 Q4)."""
+
+    def __init__(self):
+        self.queue = []
+
+    def uniform(self, lo=0.0, hi=1.0, size=None):
+        return float(philox.uniform01(self.queue.pop(0))) * (hi - lo) + lo
+
+    def randint(self, n):
+        return int(philox.random_action(self.queue.pop(0)))
+
+
+def gen_replay(ns, w, n_steps, dtype, seed=42, tag="", q_init=None, ep0=0):
+    """The reference trainer loop body (PKG/trainer.py:187-236) on one env."""
+    feeder = _DrawFeeder()
+    saved = (np.random.uniform, np.random.randint)
+    np.random.uniform, np.random.randint = feeder.uniform, feeder.randint
+    try:
+        trainer = ns.trainer.Trainer(save_path=pathlib.Path(tempfile.mkdtemp()), seed=seed)
+        agent = trainer._double_q_learning_agent
+        if q_init is not None:
+            agent.Q_table_a = q_init[0].astype(dtype).copy()
+            agent.Q_table_b = q_init[1].astype(dtype).copy()
+        else:
+            agent.Q_table_a = agent.Q_table_a.astype(dtype)
+            agent.Q_table_b = agent.Q_table_b.astype(dtype)
+        qa0, qb0 = agent.Q_table_a.copy(), agent.Q_table_b.copy()
+        sp = StandInParams()
+        dyn = StandInDet(sp, 1)
+        mdp = ns.mdp.TrainingMdp(w, F_AG, T_MAX, P_MAX)
+        idx = np.asarray([0])
+        rec = {k: [] for k in ("obs", "action", "state", "next_state", "code", "done", "reward", "episode", "alpha")}
+        t, ep = 0, ep0
+
+        def reset(birth):
+            words = philox.draws(seed, 0, idx, birth, philox.PURPOSE_RESET)
+            dyn.reset(idx, words[0], words[1], words[2], normal_init=(w == 0))
+            mdp.reset()
+            dyn.advance(np.zeros(1, np.float32))
+            rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.zeros(1)))
+            return mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+
+        s = reset(0)
+        k = 0
+        while t < n_steps:
+            words = philox.draws(seed, 0, idx, t, philox.PURPOSE_STEP)
+            feeder.queue = [words[0][0], words[1][0], words[2][0]]
+            a = agent.guess(s, trainer.exploration_rate(ep, w))
+            act = mdp.continuous_action(a, 2)
+            dyn.advance(np.asarray([act.pitch], np.float32))
+            k += 1
+            rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.asarray([k])))
+            s2 = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+            info = mdp.check()
+            r = mdp.reward()
+            done = "Termination condition" in info
+            sa = s + (a,)
+            alpha = trainer.alpha(sa)
+            agent.update(sa, s2, alpha, trainer._gamma, r)
+            assert not feeder.queue
+            rec["obs"].append((rp, rv, ra, pit, z)); rec["action"].append(a); rec["state"].append(state_id(s))
+            rec["next_state"].append(state_id(s2)); rec["code"].append(_ref_code(mdp, ns)); rec["done"].append(int(done))
+            rec["reward"].append(r); rec["episode"].append(ep); rec["alpha"].append(alpha)
+            t += 1
+            if done:
+                ep += 1
+                k = 0
+                s = reset(t)
+            else:
+                s = s2
+    finally:
+        np.random.uniform, np.random.randint = saved
+    out = dict(
+        obs=np.asarray(rec["obs"], np.float32), action=np.asarray(rec["action"], np.uint8),
+        state=np.asarray(rec["state"], np.uint16), next_state=np.asarray(rec["next_state"], np.uint16),
+        code=np.asarray(rec["code"], np.uint8), done=np.asarray(rec["done"], np.uint8),
+        reward=np.asarray(rec["reward"], np.float64), episode=np.asarray(rec["episode"], np.int32),
+        alpha=np.asarray(rec["alpha"], np.float64), qa=agent.Q_table_a, qb=agent.Q_table_b,
+        count=agent.state_action_counter, qa0=qa0, qb0=qb0, w=np.int32(w), seed=np.int64(seed), ep0=np.int32(ep0),
+    )
+    name = f"replay_w{w}_{np.dtype(dtype).name}{tag}.npz"
+    np.savez_compressed(GOLDEN / name, **out)
+    print(f"{name}: {n_steps} steps, {ep} episodes, visited cells {int((agent.state_action_counter > 0).sum())},"
+          f" explore-free steps {int((np.asarray(rec['episode']) > 800).sum())}")
+
+
+def gen_schedules(ns):
+    trainer = ns.trainer.Trainer(save_path=pathlib.Path(tempfile.mkdtemp()))
+    agent = trainer._double_q_learning_agent
+    sa = (0, 1, 1, 1, 3, 2)
+    alphas = []
+    for c in range(0, 1200):
+        agent.state_action_counter[sa] = c
+        alphas.append(trainer.alpha(sa))
+    eps = [trainer.exploration_rate(e, 0) for e in range(0, 2300)]
+    eps1 = [trainer.exploration_rate(e, 1) for e in range(0, 10)]
+    ratios = [trainer.transfer_learning_ratio(k) for k in range(5)]
+    np.savez_compressed(GOLDEN / "schedules.npz", alpha=np.asarray(alphas), eps=np.asarray(eps), eps1=np.asarray(eps1),
+                        ratios=np.asarray(ratios))
+    print("schedules ok")
+
+
+def gen_sim_trace(ns, n_episodes=6, seed=5):
+    """Greedy SimulationMdp episodes with the committed policy (scripts/simulation.py:48-63)."""
+    agent = ns.dql.DoubleQLearningAgent.load()
+    sp = StandInParams(v_z=-0.4)
+    dyn = StandInDet(sp, 1)
+    mdp = ns.mdp.SimulationMdp(4, F_AG, T_MAX)
+    idx = np.asarray([0])
+    rec = {k: [] for k in ("obs", "contact", "action", "state", "code", "done", "episode")}
+    for ep in range(n_episodes):
+        words = philox.draws(seed, 0, idx + ep, 0, philox.PURPOSE_RESET)
+        dyn.reset(idx, words[0], words[1], words[2], normal_init=False, simulation=True)
+        mdp.reset()
+        dyn.advance(np.zeros(1, np.float32))
+        rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.zeros(1)))
+        sx, _sy = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+        rec["obs"].append((rp, rv, ra, pit, z)); rec["contact"].append(c); rec["action"].append(255)
+        rec["state"].append(state_id(sx)); rec["code"].append(0); rec["done"].append(0); rec["episode"].append(ep)
+        done, k = False, 0
+        while not done:
+            a = agent.predict(sx)
+            act = mdp.continuous_action(a, 2)
+            dyn.advance(np.asarray([act.pitch], np.float32))
+            k += 1
+            rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.asarray([k])))
+            sx, _sy = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+            info = mdp.check()
+            done = "Termination condition" in info
+            rec["obs"].append((rp, rv, ra, pit, z)); rec["contact"].append(c); rec["action"].append(a)
+            rec["state"].append(state_id(sx)); rec["code"].append(_ref_code(mdp, ns)); rec["done"].append(int(done))
+            rec["episode"].append(ep)
+    out = dict(obs=np.asarray(rec["obs"], np.float32), contact=np.asarray(rec["contact"], np.uint8),
+               action=np.asarray(rec["action"], np.uint8), state=np.asarray(rec["state"], np.uint16),
+               code=np.asarray(rec["code"], np.uint8), done=np.asarray(rec["done"], np.uint8),
+               episode=np.asarray(rec["episode"], np.int32), seed=np.int64(seed))
+    np.savez_compressed(GOLDEN / "sim_trace.npz", **out)
+    codes, cnt = np.unique(out["code"][out["done"] == 1], return_counts=True)
+    print(f"sim_trace: {len(out['action'])} rows, terminal codes {dict(zip(codes.tolist(), cnt.tolist()))}")
+
+
+def main():
+    ns = ref_stubs.install()
+    GOLDEN.mkdir(parents=True, exist_ok=True)
+    gen_schedules(ns)
+    gen_discretise(ns)
+    for w in range(5):
+        gen_mdp_trace(ns, w)
+    # altitude terminals are unreachable with the training defaults (z: 4.0 -> 2.0 m): vary the stand-in
+    gen_mdp_trace(ns, 0, 16, sp=StandInParams(z_init=0.9, v_z=-0.4, v_mp=0.4), tag="lowz")
+    gen_mdp_trace(ns, 1, 4, sp=StandInParams(z_init=4.6), tag="highz")
+    gen_replay(ns, 0, 6000, np.float32)
+    gen_replay(ns, 0, 3000, np.float64)
+    gen_replay(ns, 0, 8000, np.float32, tag="_ep1950", ep0=1950)
+    gen_replay(ns, 0, 4000, np.float64, tag="_ep1950", ep0=1950)
+    # later curriculum steps are greedy (eps = 0): start from the committed tables so the policy is non-trivial
+    agent = ns.dql.DoubleQLearningAgent.load()
+    q0 = (agent.Q_table_a, agent.Q_table_b)
+    gen_replay(ns, 2, 3000, np.float32, q_init=q0)
+    gen_replay(ns, 4, 3000, np.float32, q_init=q0)
+    gen_sim_trace(ns)
+    total = sum(f.stat().st_size for f in GOLDEN.glob("*.npz"))
+    print("golden bytes:", total)
+
+
+if __name__ == "__main__":
+    main()

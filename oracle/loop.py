@@ -1,0 +1,197 @@
+"""TEST INFRASTRUCTURE ONLY -- never imported by the product package.
+
+The trainer hot loop (PKG/trainer.py:169-245 with PKG/landing_simulation_env.py
+:167-282 ordering) re-hosted on the analytic stand-in, for ONE population of
+``n_envs`` environments sharing one Q-table pair.  With n_envs == 1 it is the
+reference loop step for step; for n_envs > 1 it DEFINES the
+batched semantics the CUDA kernel must reproduce ("S1"):
+
+  * every env selects its action and reads its bootstrap value from the tables
+    as they were at the START of the global step (snapshot);
+  * the Q/count updates are applied one after the other in env-index order on
+    the live table, each with the learning rate of the live (pre-increment)
+    count -- exactly as if the envs took turns in the reference loop;
+  * finished episodes are appended to the success window in env order, the
+    promotion test runs after every append (PKG/trainer.py:219-236) and takes
+    effect at the end of the global step (all envs restart with a fresh MDP).
+
+Pure Python: use small n_envs * steps (the C restatement oracle/c covers
+large cases and is pinned against this file).
+"""
+from __future__ import annotations
+
+from collections import deque
+from dataclasses import dataclass, field
+from typing import Optional
+
+import numpy as np
+
+from . import philox
+from .agent_oracle import AgentOracle, exploration_rate, explore_threshold, state_id, transfer_ratio
+from .dynamics import StandInDet, StandInParams
+from .mdp_oracle import (MdpParams, TERMINAL_SUCCESS, TrainingMdpOracle)
+
+
+@dataclass
+class TrainerParams:
+    """Defaults of Trainer.__init__ (PKG/trainer.py:20-44)."""
+    curriculum_steps: int = 5
+    successive_successful_episodes: int = 100
+    success_rate: float = 0.96
+    max_num_episodes: int = 50000
+    alpha_min: float = 0.02949
+    omega: float = 0.51
+    gamma: float = 0.99
+    t_max: float = 20
+    f_ag: float = 22.92
+    p_max: float = 4.5
+    transfer_mode: str = "reference"      # "reference" (quirk Q7) | "paper"
+
+
+class PopulationOracle:
+    def __init__(self, n_envs: int, seed: int = 42, population: int = 0, w0: int = 0,
+                 tp: Optional[TrainerParams] = None, mp: Optional[MdpParams] = None,
+                 sp: Optional[StandInParams] = None, dtype=np.float32, agent: Optional[AgentOracle] = None):
+        self.n, self.seed, self.pop = n_envs, seed, population
+        self.tp = tp or TrainerParams()
+        self.mp = mp or MdpParams()
+        self.sp = sp or StandInParams(f_ag=self.tp.f_ag, p_max=self.tp.p_max)
+        self.agent = agent or AgentOracle(self.tp.curriculum_steps, dtype, self.tp.alpha_min, self.tp.omega, self.tp.gamma)
+        self.dyn = StandInDet(self.sp, n_envs)
+        self.w = w0
+        self.t = 0                      # global step index (Philox counter word 1)
+        self.finished = False
+        self.window = deque([], maxlen=self.tp.successive_successful_episodes)
+        self.episodes_done = 0          # completed episodes in this curriculum step
+        self.total_steps = 0
+        self.total_episodes = 0
+        self.total_successes = 0
+        self.term_hist = np.zeros(9, np.int64)
+        self.promotions = []            # (t, w) log
+        self._fresh_mdps()
+        self._reset_envs(range(self.n), birth=self.t)
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _fresh_mdps(self):
+        tp = self.tp
+        self.mdps = [TrainingMdpOracle(self.w, tp.f_ag, tp.t_max, tp.p_max, self.mp, self.sp.v_z) for _ in range(self.n)]
+        self.ep = np.zeros(self.n, np.int64)
+        self.state = [None] * self.n
+
+    def _reset_envs(self, idx, birth: int):
+        """R1 + one hover period + first discrete_state (PKG/landing_simulation_env.py:167-243)."""
+        idx = np.asarray(list(idx), dtype=np.int64)
+        if idx.size == 0:
+            return
+        w0, w1, w2, _ = philox.draws(self.seed, self.pop, idx, birth, philox.PURPOSE_RESET)
+        self.dyn.reset(idx, w0, w1, w2, normal_init=(self.w == 0))
+        self.dyn.advance(np.zeros(idx.size, np.float32), idx)
+        rel_p, rel_v, rel_a, pitch, z, contact = self.dyn.observe(np.zeros(idx.size), idx)
+        for k, i in enumerate(idx):
+            m = self.mdps[i]
+            m.reset()
+            self.state[i] = m.observe(rel_p[k], rel_v[k], rel_a[k], pitch[k], z[k], contact[k])
+
+    # -- one global step -----------------------------------------------------------------------
+    def step(self, actions_override=None):
+        """Advance every env by one agent step.  Returns a trace dict of per-env arrays."""
+        n, tp, ag = self.n, self.tp, self.agent
+        tr = dict(
+            obs=np.zeros((n, 5), np.float32), contact=np.zeros(n, np.uint8), action=np.zeros(n, np.uint8),
+            state=np.zeros(n, np.uint16), next_state=np.zeros(n, np.uint16), code=np.zeros(n, np.uint8),
+            done=np.zeros(n, np.uint8), reward=np.zeros(n, np.float64), episode=np.zeros(n, np.int64),
+        )
+        if self.finished:
+            return tr
+        env = np.arange(n)
+        d0, d1, _d2, _ = philox.draws(self.seed, self.pop, env, self.t, philox.PURPOSE_STEP)
+        snap_a, snap_b = ag.qa.copy(), ag.qb.copy()
+        promote = advance = False
+        finished_envs = []
+        for i in range(n):
+            m, s = self.mdps[i], self.state[i]
+            eps = exploration_rate(int(self.ep[i]), self.w)
+            explore = (int(d0[i]) >> 8) < explore_threshold(eps)
+            greedy = int(np.argmax(np.add(snap_a[s], snap_b[s]) / 2))
+            a = int((int(d1[i]) * 3) >> 32) if explore else greedy
+            if actions_override is not None:
+                a = int(actions_override[i])
+            th_sp = m.act(a)
+            self.dyn.advance(np.asarray([th_sp], np.float32), np.asarray([i]))
+            rel_p, rel_v, rel_a, pitch, z, contact = (x[0] for x in self.dyn.observe(np.asarray([m.step_count + 1]), np.asarray([i])))
+            s2 = m.observe(rel_p, rel_v, rel_a, pitch, z, contact)
+            code, done = m.check()
+            r = m.reward()
+            sa = s + (a,)
+            ag.update(sa, s2, ag.alpha(sa), r, q_snapshot=snap_a)
+            tr["obs"][i] = (rel_p, rel_v, rel_a, pitch, z)
+            tr["contact"][i], tr["action"][i], tr["code"][i], tr["done"][i] = contact, a, code, done
+            tr["state"][i], tr["next_state"][i], tr["reward"][i], tr["episode"][i] = state_id(s), state_id(s2), r, self.ep[i]
+            self.total_steps += 1
+            if done:
+                ok = int(code == TERMINAL_SUCCESS)          # PKG/trainer.py:219-221
+                self.window.append(ok)
+                self.total_episodes += 1
+                self.total_successes += ok
+                self.term_hist[code] += 1
+                self.episodes_done += 1
+                if sum(self.window) / tp.successive_successful_episodes > tp.success_rate:
+                    promote = True
+                if self.episodes_done >= tp.max_num_episodes:
+                    advance = True
+                self.ep[i] += 1
+                finished_envs.append(i)
+            else:
+                self.state[i] = s2
+        self._reset_envs(finished_envs, birth=self.t + 1)
+        if promote or advance:
+            self._advance_curriculum(promote)
+        self.t += 1
+        return tr
+
+    def _advance_curriculum(self, promoted: bool):
+        """PKG/trainer.py:232-245: clear the window on promotion, transfer, next working step."""
+        tp, ag = self.tp, self.agent
+        if promoted:
+            self.window.clear()
+        self.promotions.append((self.t, self.w, promoted))
+        if tp.transfer_mode == "reference":
+            ag.transfer(self.w, transfer_ratio(self.w))
+        elif self.w + 1 < tp.curriculum_steps:
+            ag.transfer(self.w + 1, transfer_ratio(self.w + 1))
+        self.w += 1
+        self.episodes_done = 0
+        if self.w >= tp.curriculum_steps:
+            self.finished = True
+            self.w = tp.curriculum_steps - 1
+            return
+        self._fresh_mdps()
+        self._reset_envs(range(self.n), birth=self.t + 1)
+
+
+def eval_episode(policy, seed: int, population: int, episode_id: int, sp: StandInParams,
+                 tp: Optional[TrainerParams] = None, mp: Optional[MdpParams] = None, w: int = 4):
+    """One greedy SimulationMdp episode (scripts/simulation.py:48-63 + PKG/landing_simulation_env.py:327-340).
+    ``policy`` maps a 5-tuple state to an action.  Returns a list of per-step dict rows (row 0 = reset)."""
+    from .mdp_oracle import SimulationMdpOracle
+    tp = tp or TrainerParams()
+    mdp = SimulationMdpOracle(w, tp.f_ag, tp.t_max, tp.p_max, mp)
+    dyn = StandInDet(sp, 1)
+    idx = np.asarray([0])
+    w0, w1, w2, _ = philox.draws(seed, population, np.asarray([episode_id]), 0, philox.PURPOSE_RESET)
+    dyn.reset(idx, w0, w1, w2, normal_init=False, simulation=True)
+    dyn.advance(np.zeros(1, np.float32))
+    rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.zeros(1)))
+    sx, _ = mdp.observe(rp, rv, ra, pit, z, c)
+    rows = [dict(obs=(rp, rv, ra, pit, z), contact=c, action=255, state=state_id(sx), code=0, done=0)]
+    done, k = False, 0
+    while not done:
+        a = policy(sx)
+        th = mdp.act(a)
+        dyn.advance(np.asarray([th], np.float32))
+        k += 1
+        rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.asarray([k])))
+        sx, _ = mdp.observe(rp, rv, ra, pit, z, c)
+        code, done = mdp.check()
+        rows.append(dict(obs=(rp, rv, ra, pit, z), contact=c, action=a, state=state_id(sx), code=code, done=int(done)))
+    return rows

@@ -1,0 +1,122 @@
+"""The CPU restatement (oracle/) against the fixtures generated from the UNMODIFIED reference
+(tests/golden/, made by oracle/gen_golden.py).  Integer outputs bit-exact, float64 rewards and
+tables compared with == (same IEEE operations in the same order)."""
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.agent_oracle import (AgentOracle, alpha_of, exploration_rate, state_from_id, state_id, transfer_ratio)
+from oracle.dynamics import StandInParams
+from oracle.loop import PopulationOracle, TrainerParams, eval_episode
+from oracle.mdp_oracle import MdpParams, TrainingMdpOracle, discretise, linspace7
+
+F_AG, T_MAX, P_MAX = 22.92, 20, 4.5
+
+
+def test_philox_known_answers():
+    kat = [
+        ((0, 0, 0, 0), (0, 0), (0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8)),
+        ((0xFFFFFFFF,) * 4, (0xFFFFFFFF,) * 2, (0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD)),
+        ((0x243F6A88, 0x85A308D3, 0x13198A2E, 0x03707344), (0xA4093822, 0x299F31D0),
+         (0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1)),
+    ]
+    for ctr, key, out in kat:
+        got = philox.philox4x32_10(*[[c] for c in ctr], *key)
+        assert tuple(int(g[0]) for g in got) == out
+
+
+def test_linspace_matches_numpy():
+    prm = MdpParams()
+    assert linspace7(prm.theta_max, 3) == list(np.linspace(-prm.theta_max, prm.theta_max, 7))
+    assert prm.theta_max == np.deg2rad(21.37723) and prm.delta_theta == np.deg2rad(7.12574)
+
+
+def test_schedules(golden_dir):
+    g = np.load(golden_dir / "schedules.npz")
+    assert [alpha_of(c) for c in range(len(g["alpha"]))] == list(g["alpha"])
+    assert [exploration_rate(e, 0) for e in range(len(g["eps"]))] == list(g["eps"])
+    assert [exploration_rate(e, 1) for e in range(len(g["eps1"]))] == list(g["eps1"])
+    assert [transfer_ratio(k) for k in range(5)] == list(g["ratios"])
+    assert alpha_of(1001) > 0.02949 and alpha_of(1002) == 0.02949
+
+
+def test_discretise(golden_dir):
+    g = np.load(golden_dir / "discretise.npz")
+    prm = MdpParams()
+    ang = linspace7(prm.theta_max, prm.n_theta)
+    obs = g["obs"].astype(np.float64)
+    for w in range(5):
+        got = np.asarray([discretise(w, prm, P_MAX, ang, *row) for row in obs], np.int8)
+        assert np.array_equal(got, g["train"][w])
+        assert np.array_equal(got, g["sim"][w])
+
+
+@pytest.mark.parametrize("name", ["w0", "w1", "w2", "w3", "w4", "lowz", "highz"])
+def test_mdp_trace(golden_dir, name):
+    g = np.load(golden_dir / f"mdp_trace_{name}.npz")
+    w = int(g["w"])
+    m = TrainingMdpOracle(w, F_AG, T_MAX, P_MAX)
+    for i in range(len(g["action"])):
+        o = g["obs"][i].astype(np.float64)
+        if g["action"][i] == 255:
+            m.reset()
+            s = m.observe(o[0], o[1], o[2], o[3], o[4], bool(g["contact"][i]))
+            assert state_id(s) == g["state"][i]
+            continue
+        th = m.act(int(g["action"][i]))
+        assert th == g["theta_sp"][i]
+        s = m.observe(o[0], o[1], o[2], o[3], o[4], bool(g["contact"][i]))
+        code, done = m.check()
+        r = m.reward()
+        assert (state_id(s), code, int(done)) == (g["state"][i], g["code"][i], g["done"][i]), i
+        assert r == g["reward"][i], i
+        assert m.cumulative_reward == g["cum"][i]
+
+
+@pytest.mark.parametrize("name,dtype", [
+    ("replay_w0_float32", np.float32), ("replay_w0_float64", np.float64),
+    ("replay_w0_float32_ep1950", np.float32), ("replay_w0_float64_ep1950", np.float64),
+    ("replay_w2_float32", np.float32), ("replay_w4_float32", np.float32),
+])
+def test_replay_single_env(golden_dir, name, dtype):
+    """PopulationOracle(n_envs=1) == the reference trainer loop, fully independent run
+    (own dynamics, own Philox draws): observations, actions, states, flags, rewards and tables identical."""
+    g = np.load(golden_dir / f"{name}.npz")
+    w = int(g["w"])
+    ag = AgentOracle(5, dtype)
+    ag.qa[...] = g["qa0"]
+    ag.qb[...] = g["qb0"]
+    pop = PopulationOracle(1, seed=int(g["seed"]), population=0, w0=w, dtype=dtype, agent=ag,
+                           tp=TrainerParams(max_num_episodes=10 ** 9, success_rate=2.0))
+    pop.ep[0] = int(g["ep0"])
+    n = len(g["action"])
+    for t in range(n):
+        tr = pop.step()
+        assert np.array_equal(tr["obs"][0].view(np.uint32), g["obs"][t].view(np.uint32)), t
+        assert (tr["action"][0], tr["state"][0], tr["next_state"][0], tr["code"][0], tr["done"][0]) == \
+               (g["action"][t], g["state"][t], g["next_state"][t], g["code"][t], g["done"][t]), t
+        assert tr["reward"][0] == g["reward"][t], t
+        assert tr["episode"][0] == g["episode"][t]
+    assert ag.qa.dtype == g["qa"].dtype
+    assert np.array_equal(ag.qa, g["qa"]) and np.array_equal(ag.qb, g["qb"])
+    assert np.array_equal(ag.count, g["count"])
+
+
+def test_sim_trace(golden_dir):
+    g = np.load(golden_dir / "sim_trace.npz")
+    qa, qb = np.load(golden_dir.parent.parent / "assets" / "Q_table_a.npy"), np.load(golden_dir.parent.parent / "assets" / "Q_table_b.npy")
+    policy = lambda s: int(np.argmax(np.add(qa[s], qb[s]) / 2))
+    rows = []
+    n_ep = int(g["episode"].max()) + 1
+    for ep in range(n_ep):
+        rows += eval_episode(policy, int(g["seed"]), 0, ep, StandInParams(v_z=-0.4))
+    assert len(rows) == len(g["action"])
+    for i, r in enumerate(rows):
+        assert np.array_equal(np.asarray(r["obs"], np.float32).view(np.uint32), g["obs"][i].view(np.uint32)), i
+        assert (r["action"], r["state"], r["code"], r["done"], int(r["contact"])) == \
+               (g["action"][i], g["state"][i], g["code"][i], g["done"][i], g["contact"][i]), i
+
+
+def test_state_id_roundtrip():
+    for i in range(945):
+        assert state_id(state_from_id(i)) == i
