@@ -1,0 +1,73 @@
+"""ctypes binding of libdqlb200.so (include/dqlb200.h).  There is no CPU fallback: if the CUDA library is
+missing or does not export every symbol the header declares, importing the product path raises."""
+from __future__ import annotations
+
+import ctypes as C
+import pathlib
+
+from . import constants as K
+
+PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = PKG / "libdqlb200.so"
+
+SYMBOLS = [
+    "dqlb200_abi_version", "dqlb200_config_bytes", "dqlb200_population_state_bytes", "dqlb200_last_error",
+    "dqlb200_termination_string", "dqlb200_create", "dqlb200_destroy", "dqlb200_bind", "dqlb200_reset",
+    "dqlb200_train", "dqlb200_train_host", "dqlb200_eval_greedy", "dqlb200_transfer", "dqlb200_check_errors",
+    "dqlb200_shared_pack", "dqlb200_shared_apply", "dqlb200_mdp_facade_step",
+]
+
+OP_ACTION, OP_OBSERVE, OP_CHECK, OP_REWARD, OP_RESET, OP_SIMULATION = 1, 2, 4, 8, 16, 256
+
+_lib = None
+
+
+class Dqlb200Error(RuntimeError):
+    pass
+
+
+def load() -> C.CDLL:
+    """Load the library (building it is the job of build.py / __graft_entry__.build())."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise Dqlb200Error(f"{LIB_PATH} not found: run `python -m dql_multirotor_landing_b200.build` "
+                           "(nvcc, sm_100a). There is no CPU fallback.")
+    lib = C.CDLL(str(LIB_PATH))
+    missing = [s for s in SYMBOLS if not hasattr(lib, s)]
+    if missing:
+        raise Dqlb200Error(f"libdqlb200.so does not export {missing}")
+    vp, i32, i64 = C.c_void_p, C.c_int, C.c_int64
+    lib.dqlb200_abi_version.restype = C.c_int
+    lib.dqlb200_config_bytes.restype = C.c_size_t
+    lib.dqlb200_population_state_bytes.restype = C.c_size_t
+    lib.dqlb200_last_error.restype = C.c_char_p
+    lib.dqlb200_termination_string.restype = C.c_char_p
+    lib.dqlb200_termination_string.argtypes = [i32]
+    lib.dqlb200_create.argtypes = [C.POINTER(K.Config), C.POINTER(C.c_float), C.POINTER(K.PopulationParams), i32, C.POINTER(vp)]
+    lib.dqlb200_destroy.argtypes = [vp]
+    lib.dqlb200_bind.argtypes = [vp, vp, vp, vp]
+    lib.dqlb200_reset.argtypes = [vp, i32, vp]
+    lib.dqlb200_train.argtypes = [vp, i32, C.POINTER(K.Trace), vp]
+    lib.dqlb200_train_host.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.dqlb200_eval_greedy.argtypes = [vp, i32, vp, i64, i64, i32, vp, C.POINTER(K.Trace), i32, vp]
+    lib.dqlb200_transfer.argtypes = [vp, i32, C.c_float, vp]
+    lib.dqlb200_check_errors.argtypes = [vp, vp]
+    lib.dqlb200_shared_pack.argtypes = [vp, vp, vp, vp]
+    lib.dqlb200_shared_apply.argtypes = [vp, vp, vp, vp]
+    lib.dqlb200_mdp_facade_step.argtypes = [vp, i32, i32, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    if lib.dqlb200_abi_version() != K.ABI_VERSION:
+        raise Dqlb200Error("libdqlb200.so ABI version mismatch; rebuild")
+    if lib.dqlb200_config_bytes() != C.sizeof(K.Config) or lib.dqlb200_population_state_bytes() != C.sizeof(K.PopulationState):
+        raise Dqlb200Error("struct layout mismatch between constants.py and include/dqlb200.h; rebuild")
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        msg = load().dqlb200_last_error().decode("utf-8", "replace")
+        if rc == -4:
+            raise ValueError(msg)          # the reference raises ValueError for these (PKG/mdp.py:170,353,442-452)
+        raise Dqlb200Error(f"libdqlb200 error {rc}: {msg}")

@@ -1,0 +1,948 @@
+// libdqlb200: kernels + C-ABI (include/dqlb200.h).  Compile for sm_100a only:
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -Xcompiler -fPIC -shared
+//
+// Kernel inventory
+//   train_kernel<WARPS>   one CTA per population (agent); K fused global steps per launch.  Per step and
+//                         env: epsilon-greedy select (R9/R10), set-point (R3), stand-in dynamics (R4),
+//                         discretise (R5), check (R6), reward (R7), learning rate (R11), table update
+//                         (R12), auto-reset (R1/R8), success window / promotion / transfer (R13/R14).
+//                         Q_a/Q_b/count live in shared memory for the whole launch.
+//   reset_kernel          R1 + R8 for every env of every population.
+//   eval_kernel           R15: greedy SimulationMdp episodes, one thread per episode.
+//   facade_kernel         float64 single-object TrainingMdp/SimulationMdp calls for the Python facade.
+//   transfer/shared_*     R13 on bound tables; shared-table mode pack/apply.
+//
+// Same-cell update semantics ("S1"): all envs of a population select and bootstrap from the
+// tables as of the START of the global step; the updates are then applied one by one in env-index order
+// to the live table, each with the learning rate of the live pre-increment count.  Implementation: env
+// index = slot * blockDim + thread; the commit of (slot, warp) chunks is serialised by a baton passed
+// between warps with named barriers; inside a chunk, lanes hitting the same cell are found with
+// __match_any_sync and applied sequentially in lane order by shuffles.  Bit-exact vs the sequential
+// oracle for any number of envs.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "dqlb200_device.cuh"
+
+namespace dql {
+
+constexpr int CELLS = DQLB200_MAX_CELLS;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// env-state word C.x layout
+constexpr uint32_t SID_BITS = 10, STEP_SHIFT = 10, STEP_BITS = 9, CC_SHIFT = 19, CC_BITS = 5;
+constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25;
+
+struct Env {
+  Body b;
+  double theta_sp;     // NOT cleared by an episode reset while `fresh` (keeps the shaping potential, quirk Q11)
+  float prev_rel_p, prev_rel_v;
+  uint32_t sid, step_count, curriculum_check;
+  bool sticky_success, fresh;
+  uint32_t episode;
+  double cum_reward;
+};
+
+struct EnvPtrs {
+  float4* a;
+  uint4* b;
+  uint4* c;
+};
+
+__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) {
+  const float4 A = p.a[i];
+  const uint4 B = p.b[i];
+  const uint4 Cw = p.c[i];
+  e.b.x_d = A.x; e.b.v_d = A.y; e.b.theta = A.z; e.b.phase = __float_as_uint(A.w); e.b.a_d = 0.0f;
+  e.theta_sp = __hiloint2double((int)B.y, (int)B.x);
+  e.prev_rel_p = __uint_as_float(B.z);
+  e.prev_rel_v = __uint_as_float(B.w);
+  e.sid = Cw.x & ((1u << SID_BITS) - 1u);
+  e.step_count = (Cw.x >> STEP_SHIFT) & ((1u << STEP_BITS) - 1u);
+  e.curriculum_check = (Cw.x >> CC_SHIFT) & ((1u << CC_BITS) - 1u);
+  e.sticky_success = (Cw.x & STICKY_BIT) != 0u;
+  e.fresh = (Cw.x & FRESH_BIT) != 0u;
+  e.episode = Cw.y;
+  e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
+}
+
+__device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) {
+  p.a[i] = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
+  p.b[i] = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
+                      __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
+                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u);
+  p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
+                      (uint32_t)__double2hiint(e.cum_reward));
+}
+
+// R1 + R8: new episode.  `fresh_mdp` additionally clears what only a NEW TrainingMdp clears
+// (shaping potentials, PKG/trainer.py:176 + quirk Q11) and the per-step episode index.
+__device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population_params& pp,
+                                          const dqlb200_cuts& cuts, const float* angle_cut, Env& e,
+                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
+  const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
+  const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
+  e.sid = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+  e.step_count = 0;
+  e.curriculum_check = 0;
+  e.sticky_success = false;
+  e.fresh = true;
+  e.cum_reward = 0.0;
+  if (fresh_mdp) {
+    e.theta_sp = 0.0;
+    e.prev_rel_p = 0.0f;
+    e.prev_rel_v = 0.0f;
+    e.episode = 0;
+  }
+}
+
+__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+struct TrainArgs {
+  EnvPtrs env;
+  uint32_t* tables;                        // [P][3][CELLS]
+  dqlb200_population_state* pop_state;     // [P]
+  const dqlb200_population_params* pop_params;
+  const float* alpha_luts;                 // [n_luts][ALPHA_LUT]
+  const uint32_t* eps_threshold;           // [EPS_LUT]
+  dqlb200_trace trace;
+  int k_steps;
+  long long n_total;
+};
+
+struct Shared {
+  float qa[CELLS];        // live table A
+  float qs[CELLS];        // snapshot of table A at the start of the global step
+  float qb[CELLS];        // table B (never written by training, quirk Q1)
+  uint32_t cnt[CELLS];    // state_action_counter
+  float alpha[DQLB200_ALPHA_LUT];
+  dqlb200_cuts cuts;
+  dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
+  float angle_cut[8];
+  dqlb200_population_params pp;
+  dqlb200_population_state ps;
+  unsigned long long n_episodes, n_success, ep_steps, hist[9];
+  int promote, advance, do_advance;
+};
+
+template <int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NT = WARPS * 32;
+  const int pop = blockIdx.x;
+  const int n_p = kc.envs_per_population;
+  const int n_slots = (n_p + NT - 1) / NT;
+  const size_t env_base = (size_t)pop * n_p;
+  uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
+
+  // ---- stage tables, LUTs and population state in shared memory -------------------------------
+  for (int i = tid; i < CELLS; i += NT) {
+    sh.qa[i] = __uint_as_float(gt[i]);
+    sh.qb[i] = __uint_as_float(gt[CELLS + i]);
+    sh.cnt[i] = gt[2 * CELLS + i];
+  }
+  if (tid == 0) {
+    sh.pp = args.pop_params[pop];
+    sh.ps = args.pop_state[pop];
+    sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
+    for (int i = 0; i < 9; ++i) sh.hist[i] = 0ull;
+    sh.promote = sh.advance = sh.do_advance = 0;
+  }
+  if (tid < 5) sh.reward[tid] = kc.reward[tid];
+  if (tid < 6) sh.angle_cut[tid] = kc.angle_cut[tid];
+  __syncthreads();
+  for (int i = tid; i < DQLB200_ALPHA_LUT; i += NT) sh.alpha[i] = args.alpha_luts[(size_t)sh.pp.alpha_lut * DQLB200_ALPHA_LUT + i];
+  if (tid == 0) sh.cuts = kc.cuts[sh.ps.working_step];
+  __syncthreads();
+
+  const dqlb200_population_params pp = sh.pp;
+  uint64_t steps_done = 0;
+
+  for (int k = 0; k < args.k_steps; ++k) {
+    if (sh.ps.finished) break;     // uniform: written only between barriers
+    const int w = sh.ps.working_step;
+    const uint32_t t = sh.ps.t;
+    for (int i = tid; i < CELLS; i += NT) sh.qs[i] = sh.qa[i];
+    __syncthreads();
+
+    for (int slot = 0; slot < n_slots; ++slot) {
+      const int env_i = slot * NT + tid;
+      const bool valid = env_i < n_p;
+      const size_t gi = env_base + (size_t)(valid ? env_i : 0);
+      // ---------------- phase A: everything that only reads the snapshot ----------------------
+      uint32_t cell = 0;
+      float target = 0.0f;
+      bool done = false, success = false;
+      int code = 0;
+      uint32_t ep_steps = 0;
+      double ep_return = 0.0;
+      if (valid) {
+        Env e;
+        env_load(args.env, gi, e);
+        const uint32_t sid = e.sid;
+        // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4)
+        const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+        const uint32_t thr = (w == 0) ? __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1))) : 0u;
+        const float p0 = fmul(fadd(sh.qs[sid * 3 + 0], sh.qb[sid * 3 + 0]), 0.5f);
+        const float p1 = fmul(fadd(sh.qs[sid * 3 + 1], sh.qb[sid * 3 + 1]), 0.5f);
+        const float p2 = fmul(fadd(sh.qs[sid * 3 + 2], sh.qb[sid * 3 + 2]), 0.5f);
+        int a = 0;
+        float best = p0;
+        if (p1 > best) { best = p1; a = 1; }
+        if (p2 > best) { a = 2; }
+        if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+        const size_t trace_i = (size_t)k * (size_t)args.n_total + gi;
+        if (args.trace.action_override) {
+          const int o = args.trace.action_override[trace_i];
+          if (o >= 0) a = o;
+        }
+        // R3: set-point (float64).  A fresh episode starts from 0 but keeps the old value for shaping.
+        const double prev_sp = e.theta_sp;
+        const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
+        // R4
+        dyn_advance(kc, pp, e.b, (float)sp);
+        const uint32_t step_count = e.step_count + 1u;
+        const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
+        // R5
+        const DState ds = discretise_cuts(sh.cuts, sh.angle_cut, o);
+        const uint32_t sid2 = (uint32_t)ds.id();
+        // R6 (sticky result: only ever set, quirk Q9)
+        code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
+        uint32_t cc = e.curriculum_check;
+        if (o.contact) code = DQLB200_TERMINAL_CONTACT;
+        else if (!(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
+        else if (!(o.z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+        else if (o.z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
+        else if ((int)step_count >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
+        else if (ds.bp == 1 && ds.bv == 1) {
+          if ((int)(sid / DQLB200_STATES_PER_LEVEL) == w && ds.level == w) {
+            cc += 1u;
+            code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+          } else {
+            cc = 0u;
+          }
+        }
+        done = code >= DQLB200_TERMINAL_SUCCESS;
+        success = code == DQLB200_TERMINAL_SUCCESS;
+        if (o.rel_p != o.rel_p || o.rel_v != o.rel_v || o.rel_a != o.rel_a) atomicOr(&sh.ps.error_flags, 1u);
+        // R7 (float64, reference operation order; level-dependent constants from the host)
+        const double phi_p = shaping(kc.w_p, (double)o.rel_p, kc.p_max);
+        const double phi_v = shaping(kc.w_v, (double)o.rel_v, kc.v_max);
+        const double phi_t = __dmul_rn(kc.w_theta, fabs(__ddiv_rn(sp, kc.theta_max)));
+        const double prev_p = shaping(kc.w_p, (double)e.prev_rel_p, kc.p_max);
+        const double prev_v = shaping(kc.w_v, (double)e.prev_rel_v, kc.v_max);
+        const double prev_t = __dmul_rn(kc.w_theta, fabs(__ddiv_rn(prev_sp, kc.theta_max)));
+        const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
+        const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
+        // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
+        const float qn = fmaxf(fmaxf(sh.qs[sid2 * 3 + 0], sh.qs[sid2 * 3 + 1]), sh.qs[sid2 * 3 + 2]);
+        const float changed = (((sid / 63u) % 3u) != (uint32_t)ds.bp) ? 1.0f : 0.0f;
+        target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
+        cell = sid * 3u + (uint32_t)a;
+        if (args.trace.obs) {
+          float* po = args.trace.obs + trace_i * 5;
+          po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z;
+        }
+        if (args.trace.reward) args.trace.reward[trace_i] = r;
+        if (args.trace.action) args.trace.action[trace_i] = (uint8_t)a;
+        if (args.trace.code) args.trace.code[trace_i] = (uint8_t)code;
+        if (args.trace.done) args.trace.done[trace_i] = (uint8_t)done;
+        if (args.trace.contact) args.trace.contact[trace_i] = (uint8_t)o.contact;
+        if (args.trace.state) args.trace.state[trace_i] = (uint16_t)sid;
+        if (args.trace.next_state) args.trace.next_state[trace_i] = (uint16_t)sid2;
+        if (args.trace.episode) args.trace.episode[trace_i] = (int32_t)e.episode;
+        // carry
+        e.theta_sp = sp;
+        e.prev_rel_p = o.rel_p;
+        e.prev_rel_v = o.rel_v;
+        if (done) {
+          ep_steps = step_count;
+          ep_return = e.cum_reward;               // quirk Q12: the last reward is not in the logged sum
+          e.episode += 1u;
+          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w, /*fresh_mdp=*/false);
+        } else {
+          e.sid = sid2;
+          e.step_count = step_count;
+          e.curriculum_check = cc;
+          e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
+          e.fresh = false;
+          e.cum_reward = __dadd_rn(e.cum_reward, r);
+        }
+        env_store(args.env, gi, e);
+      }
+      // ---------------- phase B: ordered commit (baton between warps) --------------------------
+      if (WARPS > 1 && !(slot == 0 && warp == 0)) bar_sync(1 + warp, 64);
+      {
+        const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
+        const uint32_t peers = __match_any_sync(FULL, key);
+        const int rank = __popc(peers & ((1u << lane) - 1u));
+        float q = valid ? sh.qa[cell] : 0.0f;
+        const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
+        const float alpha = sh.alpha[min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1))];   // R11 (pre-increment count)
+        uint32_t rem = valid ? peers : 0u;
+        while (__any_sync(FULL, rem != 0u)) {
+          const int src = rem ? (__ffs(rem) - 1) : lane;
+          const float a_j = __shfl_sync(FULL, alpha, src);
+          const float t_j = __shfl_sync(FULL, target, src);
+          if (rem) q = fadd(q, fmul(a_j, fsub(t_j, q)));      // q += alpha * (target - q)
+          rem &= rem - 1u;
+        }
+        if (valid && rank == 0) {
+          sh.qa[cell] = q;
+          sh.cnt[cell] = c0 + (uint32_t)__popc(peers);
+        }
+        // finished episodes, in env order: success window + promotion test after every append (R14)
+        const uint32_t dmask = __ballot_sync(FULL, valid && done);
+        if (dmask) {
+          const uint32_t smask = __ballot_sync(FULL, valid && success);
+          if (valid && done) {
+            atomicAdd(&sh.hist[code], 1ull);
+            atomicAdd(&sh.ep_steps, (unsigned long long)ep_steps);
+          }
+          // deterministic (fixed-tree) sum of the finished episodes' returns
+          double ret = (valid && done) ? ep_return : 0.0;
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) ret = __dadd_rn(ret, __shfl_xor_sync(FULL, ret, off));
+          const int last = 31 - __clz(dmask);
+          const int last_steps = __shfl_sync(FULL, (int)ep_steps, last);
+          const int last_code = __shfl_sync(FULL, code, last);
+          const double last_cum = __shfl_sync(FULL, ep_return, last);
+          if (lane == 0) {
+            dqlb200_population_state& ps = sh.ps;
+            uint32_t m = dmask;
+            while (m) {
+              const int b = __ffs(m) - 1;
+              m &= m - 1u;
+              const int ok = (smask >> b) & 1u;
+              if (ps.window_count == kc.window_len) ps.window_sum -= ps.window[ps.window_head];
+              else ps.window_count += 1;
+              ps.window[ps.window_head] = (uint8_t)ok;
+              ps.window_sum += ok;
+              ps.window_head = (ps.window_head + 1 == kc.window_len) ? 0 : ps.window_head + 1;
+              ps.episodes_in_step += 1;
+              if (ps.window_sum >= kc.promote_successes) sh.promote = 1;
+              if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
+            }
+            sh.n_episodes += (unsigned long long)__popc(dmask);
+            sh.n_success += (unsigned long long)__popc(smask);
+            ps.return_sum = __dadd_rn(ps.return_sum, ret);
+            ps.last_code = last_code;
+            ps.last_steps = last_steps;
+            ps.last_cumulative = last_cum;
+          }
+        }
+      }
+      if (WARPS > 1 && !(slot == n_slots - 1 && warp == WARPS - 1)) {
+        __threadfence_block();
+        bar_arrive(1 + (warp + 1) % WARPS, 64);
+      }
+    }
+    __syncthreads();
+    // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
+    steps_done += (uint64_t)n_p;
+    if (tid == 0) {
+      sh.ps.t = t + 1u;
+      sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
+    }
+    __syncthreads();
+    if (sh.do_advance) {
+      const int cs = kc.curriculum_steps;
+      // DoubleQLearningAgent.transfer_learning (PKG/double_q_learning.py:77-89)
+      int dst = -1, src = 0;
+      float ratio = 1.0f;
+      if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
+      else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
+      if (dst >= 0 && dst != src) {
+        for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+          sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+          sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        }
+      } else if (dst >= 0) {
+        for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+          sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i], ratio);
+          sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        }
+      }
+      __syncthreads();
+      if (tid == 0) {
+        dqlb200_population_state& ps = sh.ps;
+        if (sh.promote) { ps.window_head = ps.window_count = ps.window_sum = 0; }
+        ps.promoted_at[w] = ps.t;
+        ps.episodes_in_step = 0;
+        sh.promote = sh.advance = sh.do_advance = 0;
+        if (w + 1 >= cs) ps.finished = 1;
+        else {
+          ps.working_step = w + 1;
+          sh.cuts = kc.cuts[w + 1];
+        }
+      }
+      __syncthreads();
+      if (!sh.ps.finished) {
+        // a fresh env + TrainingMdp per curriculum step (PKG/trainer.py:176-189)
+        for (int slot = 0; slot < n_slots; ++slot) {
+          const int env_i = slot * NT + tid;
+          if (env_i < n_p) {
+            Env e;
+            env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w + 1, /*fresh_mdp=*/true);
+            env_store(args.env, env_base + env_i, e);
+          }
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- write back -----------------------------------------------------------------------------
+  __syncthreads();
+  for (int i = tid; i < CELLS; i += NT) {
+    gt[i] = __float_as_uint(sh.qa[i]);
+    gt[CELLS + i] = __float_as_uint(sh.qb[i]);
+    gt[2 * CELLS + i] = sh.cnt[i];
+  }
+  if (tid == 0) {
+    dqlb200_population_state& ps = sh.ps;
+    ps.total_steps += steps_done;
+    ps.total_episodes += sh.n_episodes;
+    ps.total_successes += sh.n_success;
+    ps.episode_steps_sum += sh.ep_steps;
+    for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
+    args.pop_state[pop] = ps;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, dqlb200_population_state* pop_state,
+                             const dqlb200_population_params* pop_params, int initial_step) {
+  const int pop = blockIdx.y;
+  const int env_i = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ dqlb200_cuts cuts;
+  __shared__ float angle_cut[8];
+  if (threadIdx.x == 0) cuts = kc.cuts[initial_step];
+  if (threadIdx.x < 6) angle_cut[threadIdx.x] = kc.angle_cut[threadIdx.x];
+  __syncthreads();
+  if (env_i < kc.envs_per_population) {
+    const dqlb200_population_params pp = pop_params[pop];
+    Env e;
+    env_reset(kc, pp, cuts, angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true);
+    env_store(env, (size_t)pop * kc.envs_per_population + env_i, e);
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    dqlb200_population_state ps;
+    memset(&ps, 0, sizeof(ps));
+    ps.working_step = initial_step;
+    pop_state[pop] = ps;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// R15: greedy evaluation, SimulationMdp semantics (PKG/mdp.py:784-886, scripts/simulation.py:48-63)
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc, const dqlb200_population_params* pop_params,
+                                                   int population, const uint8_t* __restrict__ policy,
+                                                   long long first_episode, long long n_episodes, int w,
+                                                   dqlb200_eval_stats* stats, dqlb200_trace trace, int trace_steps) {
+  __shared__ uint8_t s_policy[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
+  __shared__ dqlb200_cuts cuts;
+  __shared__ float angle_cut[8];
+  __shared__ unsigned long long s_hist[9], s_steps, s_eps;
+  for (int i = threadIdx.x; i < DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL; i += blockDim.x) s_policy[i] = policy[i];
+  if (threadIdx.x == 0) { cuts = kc.cuts[w]; s_steps = s_eps = 0ull; }
+  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0ull;
+  if (threadIdx.x < 6) angle_cut[threadIdx.x] = kc.angle_cut[threadIdx.x];
+  __syncthreads();
+  const dqlb200_population_params pp = pop_params[population];
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_episodes) {
+    const unsigned long long ep = (unsigned long long)(first_episode + i);
+    const uint4 d = philox4x32_10(make_uint4((uint32_t)ep, 0u, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
+    Body b;
+    Obs o = dyn_reset(kc, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim);
+    uint32_t sid = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+    double sp = 0.0;
+    int code = DQLB200_NON_TERMINAL;
+    int step = 0;
+    while (code < DQLB200_TERMINAL_SUCCESS) {
+      const int a = s_policy[sid];
+      sp = apply_action(kc, sp, a);
+      dyn_advance(kc, pp, b, (float)sp);
+      step += 1;
+      o = dyn_observe(kc, pp, b, step, kc.dz_sim);
+      const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+      if (o.contact) code = DQLB200_TERMINAL_CONTACT;
+      else if (!(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
+      else if (!(o.z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+      else if (o.z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
+      else if (step >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
+      if (step <= trace_steps) {
+        const size_t ti = (size_t)(step - 1) * (size_t)n_episodes + (size_t)i;
+        if (trace.obs) {
+          float* po = trace.obs + ti * 5;
+          po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z;
+        }
+        if (trace.action) trace.action[ti] = (uint8_t)a;
+        if (trace.code) trace.code[ti] = (uint8_t)code;
+        if (trace.done) trace.done[ti] = (uint8_t)(code >= DQLB200_TERMINAL_SUCCESS);
+        if (trace.contact) trace.contact[ti] = (uint8_t)o.contact;
+        if (trace.state) trace.state[ti] = (uint16_t)sid;
+        if (trace.next_state) trace.next_state[ti] = (uint16_t)sid2;
+      }
+      sid = sid2;
+    }
+    atomicAdd(&s_hist[code], 1ull);
+    atomicAdd(&s_steps, (unsigned long long)step);
+    atomicAdd(&s_eps, 1ull);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    atomicAdd((unsigned long long*)&stats->steps, s_steps);
+    atomicAdd((unsigned long long*)&stats->episodes, s_eps);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Facade kernel: float64 observations, the reference's comparisons in float64 (PKG/mdp.py:149-170,
+// 257-333, 335-439, 441-541, 784-845).  One thread per MDP object.
+// -------------------------------------------------------------------------------------------------
+__device__ int level_f64(const double* lim, int w, double v) {
+  for (int idx = 1; idx <= w; ++idx)
+    if (v < -lim[idx] || v > lim[idx]) return idx - 1;
+  return w;
+}
+__device__ int bin_f64(double v, double goal, double limit) {
+  if (-limit <= v && v < -goal) return 0;
+  if (-goal <= v && v <= goal) return 1;
+  if (v <= limit) return 2;
+  return -1;   // NaN: the reference raises ValueError (PKG/mdp.py:170)
+}
+__device__ int discretise_f64(const dqlb200_config* cfg, int w, double rel_p, double rel_v, double rel_a, double pitch) {
+  const double p = clipd(__ddiv_rn(rel_p, cfg->p_max), -1.0, 1.0);
+  const double v = clipd(__ddiv_rn(rel_v, cfg->v_max), -1.0, 1.0);
+  const double a = clipd(__ddiv_rn(rel_a, cfg->a_max), -1.0, 1.0);
+  const int lvl = min(min(level_f64(cfg->limits[0], w, p), level_f64(cfg->limits[1], w, v)), level_f64(cfg->limits[2], w, a));
+  const int bp = bin_f64(p, cfg->goal_width[w][0][lvl], cfg->limits[0][lvl]);
+  const int bv = bin_f64(v, cfg->goal_width[w][1][lvl], cfg->limits[1][lvl]);
+  const int ba = bin_f64(a, cfg->goal_width[w][2][lvl], cfg->limits[2][lvl]);
+  if (bp < 0 || bv < 0 || ba < 0 || pitch != pitch) return -1;
+  const double cl = clipd(pitch, -cfg->theta_max, cfg->theta_max);
+  int bi = 0;
+  double best = fabs(__dsub_rn(cfg->angles[0], cl));
+  for (int i = 1; i < 7; ++i) {
+    const double d = fabs(__dsub_rn(cfg->angles[i], cl));
+    if (d < best) { best = d; bi = i; }
+  }
+  return (((lvl * 3 + bp) * 3 + bv) * 3 + ba) * 7 + bi;
+}
+
+__global__ void facade_kernel(const dqlb200_config* __restrict__ cfg, int w, int ops, long long n,
+                              const double* __restrict__ obs, const uint8_t* __restrict__ contact,
+                              const int8_t* __restrict__ action, double* __restrict__ st,
+                              uint16_t* out_state, uint8_t* out_code, double* out_reward, uint32_t* error_flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double* s = st + i * 12;
+  const bool sim = (ops & DQLB200_OP_SIMULATION) != 0;
+  if (ops & DQLB200_OP_RESET) {        // phi (s[1..3]) survives: quirk Q11
+    s[0] = 0.0; s[4] = 0.0; s[5] = 0.0; s[6] = 0.0; s[7] = 0.0; s[8] = -1.0; s[9] = -1.0;
+  }
+  if (ops & DQLB200_OP_ACTION) {
+    const int a = action[i];
+    if (a == 0) s[0] = fmin(__dadd_rn(s[0], cfg->delta_theta), cfg->theta_max);
+    else if (a == 1) s[0] = fmax(__dsub_rn(s[0], cfg->delta_theta), -cfg->theta_max);
+  }
+  if (ops & DQLB200_OP_OBSERVE) {
+    const double* o = obs + i * 6;
+    const int sid = discretise_f64(cfg, w, o[0], o[1], o[2], o[3]);
+    if (sid < 0) { atomicOr(error_flag, 1u); return; }
+    s[9] = s[8];
+    s[8] = (double)sid;
+    s[10] = o[0];
+    s[11] = o[1];
+    if (out_state) out_state[i] = (uint16_t)sid;
+  }
+  if (ops & DQLB200_OP_CHECK) {
+    const double* o = obs + i * 6;
+    if (s[8] < 0.0) { atomicOr(error_flag, 2u); return; }
+    const int cur = (int)s[8];
+    const int lvl = cur / DQLB200_STATES_PER_LEVEL, bp = (cur / 63) % 3, bv = (cur / 21) % 3;
+    int code = (int)s[7];
+    s[5] += 1.0;
+    if (contact[i]) code = DQLB200_TERMINAL_CONTACT;
+    else if (o[0] < -cfg->p_max || o[0] > cfg->p_max) code = DQLB200_TERMINAL_FLYZONE_X;
+    else if (o[5] < -cfg->p_max || o[5] > cfg->p_max) code = DQLB200_TERMINAL_FLYZONE_Y;
+    else if (o[4] < cfg->minimum_altitude) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+    else if (o[4] > cfg->p_max) code = DQLB200_TERMINAL_FLYZONE_Z;
+    else if (s[5] >= cfg->timeout_threshold) code = DQLB200_TERMINAL_TIMEOUT;
+    else if (!sim && s[9] >= 0.0 && bp == 1 && bv == 1) {
+      const int prev_lvl = (int)s[9] / DQLB200_STATES_PER_LEVEL;
+      if (prev_lvl == w && lvl == w) {
+        s[6] += 1.0;
+        code = (s[6] >= cfg->f_ag) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+      } else {
+        s[6] = 0.0;
+      }
+    }
+    s[7] = (double)code;
+    if (out_code) out_code[i] = (uint8_t)code;
+  }
+  if (ops & DQLB200_OP_REWARD) {
+    if (s[8] < 0.0 || s[9] < 0.0) { atomicOr(error_flag, 4u); return; }
+    const int lvl = (int)s[8] / DQLB200_STATES_PER_LEVEL;
+    const dqlb200_reward_level rl = cfg->reward[lvl];
+    const double phi_p = __dmul_rn(cfg->w_p, fabs(clipd(__ddiv_rn(s[10], cfg->p_max), -1.0, 1.0)));
+    const double phi_v = __dmul_rn(cfg->w_v, fabs(clipd(__ddiv_rn(s[11], cfg->v_max), -1.0, 1.0)));
+    const double phi_t = __dmul_rn(cfg->w_theta, fabs(__ddiv_rn(s[0], cfg->theta_max)));
+    const int code = (int)s[7];
+    const double r_p = clipd(__dsub_rn(phi_p, s[1]), -rl.r_p_max, rl.r_p_max);
+    const double r_v = clipd(__dsub_rn(phi_v, s[2]), -rl.r_v_max, rl.r_v_max);
+    const double r_t = __dmul_rn(__ddiv_rn(__dmul_rn(cfg->w_theta, __dsub_rn(fabs(phi_t), fabs(s[3]))), cfg->theta_max), rl.lim_v);
+    const double r_term = (code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS) ? rl.r_term_succ : rl.r_term_fail;
+    const double r = __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
+    s[1] = phi_p; s[2] = phi_v; s[3] = phi_t;
+    s[4] = __dadd_rn(s[4], r);
+    if (out_reward) out_reward[i] = r;
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
+__global__ void transfer_kernel(uint32_t* tables, int n_pop, int cs, int step, float ratio) {
+  const int pop = blockIdx.x;
+  float* qa = reinterpret_cast<float*>(tables + (size_t)pop * 3 * CELLS);
+  float* qb = qa + CELLS;
+  const int src = (step - 1 + cs) % cs;
+  for (int i = threadIdx.x; i < DQLB200_CELLS_PER_LEVEL; i += blockDim.x) {
+    qa[step * DQLB200_CELLS_PER_LEVEL + i] = fmul(qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+    qb[step * DQLB200_CELLS_PER_LEVEL + i] = fmul(qb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+  }
+}
+
+// Shared-table mode (one agent replicated on G devices).  Each replica trains on its own envs for a few
+// steps; the replicas are then merged with a visit-weighted mean of their Q deltas and the sum of
+// their visit counts:  Q <- Q_snap + sum_g(dcount_g * dQ_g) / sum_g(dcount_g),  count <- count_snap + sum_g dcount_g.
+__global__ void shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, int n_pop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pop * CELLS) return;
+  const long long pop = i / CELLS, c = i % CELLS;
+  const size_t base = (size_t)pop * 3 * CELLS;
+  const float dc = (float)(tables[base + 2 * CELLS + c] - snap[base + 2 * CELLS + c]);
+  const float dq = fsub(__uint_as_float(tables[base + c]), __uint_as_float(snap[base + c]));
+  delta[base + c] = fmul(dq, dc);
+  delta[base + CELLS + c] = dc;
+  delta[base + 2 * CELLS + c] = 0.0f;
+}
+__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, const float* delta, int n_pop) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_pop * CELLS) return;
+  const long long pop = i / CELLS, c = i % CELLS;
+  const size_t base = (size_t)pop * 3 * CELLS;
+  const float own_dc = (float)(tables[base + 2 * CELLS + c] - snap[base + 2 * CELLS + c]);
+  const float dc = delta[base + CELLS + c];
+  if (dc != own_dc) {      // some other replica visited the cell too (dc == own_dc: keep the local value exactly)
+    const float q = fadd(__uint_as_float(snap[base + c]), __fdiv_rn(delta[base + c], dc));
+    tables[base + c] = __float_as_uint(q);
+    tables[base + 2 * CELLS + c] = snap[base + 2 * CELLS + c] + (uint32_t)__float2uint_rn(dc);
+  }
+  snap[base + c] = tables[base + c];
+  snap[base + CELLS + c] = tables[base + CELLS + c];
+  snap[base + 2 * CELLS + c] = tables[base + 2 * CELLS + c];
+}
+
+}  // namespace dql
+
+// =================================================================================================
+// C-ABI
+// =================================================================================================
+struct dqlb200_handle {
+  dqlb200_config cfg;
+  dql::KC kc;
+  int device;
+  dqlb200_config* d_cfg;
+  float* d_alpha;
+  dqlb200_population_params* d_pop_params;
+  uint32_t* d_error;
+  void* env_state;
+  void* tables;
+  void* pop_state;
+  size_t smem_bytes;
+};
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string& msg) {
+  g_last_error = msg;
+  return code;
+}
+#define CUDA_TRY(expr)                                                                                      \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess) return fail(DQLB200_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+  } while (0)
+
+extern "C" {
+
+int dqlb200_abi_version(void) { return DQLB200_ABI_VERSION; }
+size_t dqlb200_config_bytes(void) { return sizeof(dqlb200_config); }
+size_t dqlb200_population_state_bytes(void) { return sizeof(dqlb200_population_state); }
+const char* dqlb200_last_error(void) { return g_last_error.c_str(); }
+
+const char* dqlb200_termination_string(int code) {
+  switch (code) {
+    case DQLB200_TERMINAL_SUCCESS: return "SUCCESS: Goal state reached";
+    case DQLB200_TERMINAL_CONTACT: return "SUCCESS: Touched platform";
+    case DQLB200_TERMINAL_FLYZONE_X: return "FAILURE: Drone moved too far from platform in x direction";
+    case DQLB200_TERMINAL_FLYZONE_Y: return "FAILURE: Drone moved too far from platform in y direction";
+    case DQLB200_TERMINAL_FLYZONE_Z: return "FAILURE: Drone moved too far from platform in z direction";
+    case DQLB200_TERMINAL_MINIMUM_ALTITUDE: return "FAILURE: Reached minimum altitude";
+    case DQLB200_TERMINAL_TIMEOUT: return "FAILURE: Maximum episode duration";
+    default: return nullptr;
+  }
+}
+
+static void fill_kc(const dqlb200_config& c, dql::KC& k) {
+  memcpy(k.cuts, c.cuts, sizeof(k.cuts));
+  memcpy(k.reward, c.reward, sizeof(k.reward));
+  k.p_max = c.p_max; k.v_max = c.v_max; k.theta_max = c.theta_max; k.delta_theta = c.delta_theta;
+  k.w_p = c.w_p; k.w_v = c.w_v; k.w_theta = c.w_theta;
+  memcpy(k.angle_cut, c.angle_cut, sizeof(k.angle_cut));
+  k.fz_lo = c.fz_lo; k.fz_hi = c.fz_hi; k.z_min_cut = c.z_min_cut; k.z_max_cut = c.z_max_cut;
+  k.h = c.h; k.half_h2 = c.half_h2; k.k_theta = c.k_theta; k.g = c.g; k.c_d = c.c_d;
+  k.dz_train = c.dz_train; k.dz_sim = c.dz_sim; k.z_init = c.z_init; k.z_touch = c.z_touch;
+  k.half_platform = c.half_platform; k.p_max_f = c.p_max_f; k.two_p_max_f = c.two_p_max_f; k.sigma_x = c.sigma_x;
+  k.gamma = c.gamma;
+  memcpy(k.transfer_ratio, c.transfer_ratio, sizeof(k.transfer_ratio));
+  k.timeout_steps = c.timeout_steps; k.success_steps = c.success_steps; k.n_sub = c.n_sub;
+  k.transfer_mode = c.transfer_mode; k.window_len = c.window_len; k.promote_successes = c.promote_successes;
+  k.curriculum_steps = c.curriculum_steps; k.envs_per_population = c.envs_per_population;
+  k.n_populations = c.n_populations; k.max_num_episodes = c.max_num_episodes;
+}
+
+int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dqlb200_population_params* pop_params,
+                   int device, dqlb200_handle** out) {
+  if (!cfg || !alpha_luts || !pop_params || !out) return fail(DQLB200_ERR_ARG, "null argument");
+  if (cfg->struct_bytes != sizeof(dqlb200_config) || cfg->abi_version != DQLB200_ABI_VERSION)
+    return fail(DQLB200_ERR_ARG, "dqlb200_config size/ABI mismatch: host " + std::to_string(cfg->struct_bytes) +
+                                     " vs library " + std::to_string(sizeof(dqlb200_config)));
+  if (cfg->n_populations < 1 || cfg->envs_per_population < 1) return fail(DQLB200_ERR_ARG, "empty layout");
+  if (cfg->curriculum_steps < 1 || cfg->curriculum_steps > DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "curriculum_steps out of range");
+  const int tpb = cfg->threads_per_block;
+  if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) return fail(DQLB200_ERR_ARG, "threads_per_block must be 32, 64, 128 or 256");
+  if (cfg->window_len < 1 || cfg->window_len > DQLB200_MAX_WINDOW) return fail(DQLB200_ERR_ARG, "window_len out of range");
+  if (cfg->n_alpha_luts < 1 || cfg->n_sub < 1) return fail(DQLB200_ERR_ARG, "n_alpha_luts / n_sub must be >= 1");
+  for (int p = 0; p < cfg->n_populations; ++p)
+    if (pop_params[p].alpha_lut < 0 || pop_params[p].alpha_lut >= cfg->n_alpha_luts) return fail(DQLB200_ERR_ARG, "population alpha_lut index out of range");
+  int count = 0;
+  CUDA_TRY(cudaGetDeviceCount(&count));
+  if (device < 0 || device >= count) return fail(DQLB200_ERR_ARG, "no such CUDA device");
+  CUDA_TRY(cudaSetDevice(device));
+  dqlb200_handle* h = new (std::nothrow) dqlb200_handle();
+  if (!h) return fail(DQLB200_ERR_STATE, "out of host memory");
+  h->cfg = *cfg;
+  fill_kc(*cfg, h->kc);
+  h->device = device;
+  h->env_state = h->tables = h->pop_state = nullptr;
+  h->smem_bytes = sizeof(dql::Shared);
+  CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
+  CUDA_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(dqlb200_config), cudaMemcpyHostToDevice));
+  const size_t lut_bytes = (size_t)cfg->n_alpha_luts * DQLB200_ALPHA_LUT * sizeof(float);
+  CUDA_TRY(cudaMalloc(&h->d_alpha, lut_bytes));
+  CUDA_TRY(cudaMemcpy(h->d_alpha, alpha_luts, lut_bytes, cudaMemcpyHostToDevice));
+  const size_t pp_bytes = (size_t)cfg->n_populations * sizeof(dqlb200_population_params);
+  CUDA_TRY(cudaMalloc(&h->d_pop_params, pp_bytes));
+  CUDA_TRY(cudaMemcpy(h->d_pop_params, pop_params, pp_bytes, cudaMemcpyHostToDevice));
+  CUDA_TRY(cudaMalloc(&h->d_error, sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->d_error, 0, sizeof(uint32_t)));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  *out = h;
+  return DQLB200_OK;
+}
+
+int dqlb200_destroy(dqlb200_handle* h) {
+  if (!h) return DQLB200_OK;
+  cudaSetDevice(h->device);
+  cudaFree(h->d_cfg);
+  cudaFree(h->d_alpha);
+  cudaFree(h->d_pop_params);
+  cudaFree(h->d_error);
+  delete h;
+  return DQLB200_OK;
+}
+
+int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_state) {
+  if (!h || !env_state || !tables || !pop_state) return fail(DQLB200_ERR_ARG, "null argument");
+  if (((uintptr_t)env_state & 15u) || ((uintptr_t)tables & 3u) || ((uintptr_t)pop_state & 7u))
+    return fail(DQLB200_ERR_ARG, "misaligned buffer (env_state needs 16 B, pop_state 8 B)");
+  h->env_state = env_state;
+  h->tables = tables;
+  h->pop_state = pop_state;
+  return DQLB200_OK;
+}
+
+static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
+  const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
+  dql::EnvPtrs p;
+  p.a = reinterpret_cast<float4*>(base);
+  p.b = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 16 * n);
+  p.c = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 32 * n);
+  return p;
+}
+
+int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream) {
+  if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (initial_step < 0 || initial_step >= h->cfg.curriculum_steps) return fail(DQLB200_ERR_ARG, "initial_step out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const dim3 grid((h->cfg.envs_per_population + 255) / 256, h->cfg.n_populations);
+  dql::reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state),
+                                                           (dqlb200_population_state*)h->pop_state, h->d_pop_params, initial_step);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* env_state, void* tables,
+                        void* pop_state, cudaStream_t stream) {
+  dql::TrainArgs a;
+  a.env = env_ptrs(h, env_state);
+  a.tables = (uint32_t*)tables;
+  a.pop_state = (dqlb200_population_state*)pop_state;
+  a.pop_params = h->d_pop_params;
+  a.alpha_luts = h->d_alpha;
+  a.eps_threshold = h->d_cfg->eps_threshold;
+  if (trace) a.trace = *trace; else memset(&a.trace, 0, sizeof(a.trace));
+  a.k_steps = k_steps;
+  a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
+  const int grid = h->cfg.n_populations;
+  const size_t smem = h->smem_bytes;
+  switch (h->cfg.threads_per_block) {
+    case 32: dql::train_kernel<1><<<grid, 32, smem, stream>>>(h->kc, a); break;
+    case 64: dql::train_kernel<2><<<grid, 64, smem, stream>>>(h->kc, a); break;
+    case 128: dql::train_kernel<4><<<grid, 128, smem, stream>>>(h->kc, a); break;
+    default: dql::train_kernel<8><<<grid, 256, smem, stream>>>(h->kc, a); break;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* stream) {
+  if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
+  if (k_steps == 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return launch_train(h, k_steps, trace, h->env_state, h->tables, h->pop_state, (cudaStream_t)stream);
+}
+
+int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host, void* pop_state_host,
+                       void* stream) {
+  if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
+  if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
+  const size_t env_bytes = n * DQLB200_ENV_STATE_BYTES;
+  const size_t tab_bytes = (size_t)h->cfg.n_populations * 3 * DQLB200_MAX_CELLS * 4;
+  const size_t ps_bytes = (size_t)h->cfg.n_populations * sizeof(dqlb200_population_state);
+  CUDA_TRY(cudaMemcpyAsync(h->env_state, env_state_host, env_bytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->tables, tables_host, tab_bytes, cudaMemcpyHostToDevice, s));
+  CUDA_TRY(cudaMemcpyAsync(h->pop_state, pop_state_host, ps_bytes, cudaMemcpyHostToDevice, s));
+  if (k_steps > 0) {
+    const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, s);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaMemcpyAsync(env_state_host, h->env_state, env_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(tables_host, h->tables, tab_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(pop_state_host, h->pop_state, ps_bytes, cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  return DQLB200_OK;
+}
+
+int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy, int64_t first_episode, int64_t n_episodes,
+                        int working_step, void* stats_out, const dqlb200_trace* trace, int trace_steps, void* stream) {
+  if (!h || !policy || !stats_out) return fail(DQLB200_ERR_ARG, "null argument");
+  if (population < 0 || population >= h->cfg.n_populations) return fail(DQLB200_ERR_ARG, "population out of range");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  if (n_episodes <= 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  dqlb200_trace tr;
+  if (trace) tr = *trace; else memset(&tr, 0, sizeof(tr));
+  const long long blocks = (n_episodes + 255) / 256;
+  dql::eval_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode,
+                                                                     n_episodes, working_step, (dqlb200_eval_stats*)stats_out,
+                                                                     tr, trace ? trace_steps : 0);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream) {
+  if (!h || !h->tables) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (step < 0 || step >= h->cfg.curriculum_steps) return fail(DQLB200_ERR_ARG, "step out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  dql::transfer_kernel<<<h->cfg.n_populations, 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, h->cfg.n_populations,
+                                                                             h->cfg.curriculum_steps, step, ratio);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_check_errors(dqlb200_handle* h, void* stream) {
+  if (!h || !h->pop_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  uint32_t facade = 0;
+  CUDA_TRY(cudaMemcpy(&facade, h->d_error, sizeof(facade), cudaMemcpyDeviceToHost));
+  if (facade) {
+    CUDA_TRY(cudaMemset(h->d_error, 0, sizeof(uint32_t)));
+    return fail(DQLB200_ERR_DEVICE_FLAG, facade & 1u ? "Unexpected discretization case: NaN observation"
+                                                     : (facade & 2u ? "Cannot check an empty state" : "Previous state missing"));
+  }
+  for (int p = 0; p < h->cfg.n_populations; ++p) {
+    dqlb200_population_state ps;
+    CUDA_TRY(cudaMemcpy(&ps, (dqlb200_population_state*)h->pop_state + p, sizeof(ps), cudaMemcpyDeviceToHost));
+    if (ps.error_flags) return fail(DQLB200_ERR_DEVICE_FLAG, "population " + std::to_string(p) + ": NaN observation (error_flags=" + std::to_string(ps.error_flags) + ")");
+  }
+  return DQLB200_OK;
+}
+
+int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream) {
+  if (!h || !h->tables || !snapshot || !delta) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)h->cfg.n_populations * DQLB200_MAX_CELLS;
+  dql::shared_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)h->tables, (const uint32_t*)snapshot,
+                                                                                       (float*)delta, h->cfg.n_populations);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, void* stream) {
+  if (!h || !h->tables || !snapshot || !delta_reduced) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)h->cfg.n_populations * DQLB200_MAX_CELLS;
+  dql::shared_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
+                                                                                        (const float*)delta_reduced, h->cfg.n_populations);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_t n, const double* obs, const uint8_t* contact,
+                            const int8_t* action, double* mdp_state, uint16_t* out_state, uint8_t* out_code, double* out_reward,
+                            void* stream) {
+  if (!h || !mdp_state) return fail(DQLB200_ERR_ARG, "null argument");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  if ((ops & (DQLB200_OP_OBSERVE | DQLB200_OP_CHECK)) && !obs) return fail(DQLB200_ERR_ARG, "obs required");
+  if ((ops & DQLB200_OP_CHECK) && !contact) return fail(DQLB200_ERR_ARG, "contact required");
+  if ((ops & DQLB200_OP_ACTION) && !action) return fail(DQLB200_ERR_ARG, "action required");
+  if (n <= 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  dql::facade_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d_cfg, working_step, ops, n, obs, contact, action,
+                                                                                   mdp_state, out_state, out_code, out_reward, h->d_error);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+}  // extern "C"

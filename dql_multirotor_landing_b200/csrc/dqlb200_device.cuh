@@ -1,0 +1,235 @@
+// Device-side building blocks of libdqlb200: Philox4x32-10, the deterministic fp32 math used by the
+// stand-in dynamics, the cut-table discretisation, terminal checks and the float64 reward.
+//
+// Reference rows: R3 continuous_action PKG/mdp.py:543-560, R4 analytic stand-in
+// (no reference function), R5 discrete_state PKG/mdp.py:257-333, R6 check PKG/mdp.py:335-439,
+// R7 reward PKG/mdp.py:441-541, R9 guess/predict PKG/double_q_learning.py:110-124.
+//
+// Bit-exactness rules used throughout:
+//   * fp32 dynamics: every operation is an explicit __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn (never
+//     contracted to FMA), polynomials in Horner form -> identical to NumPy float32 and to C with
+//     -ffp-contract=off;
+//   * float64 reward: explicit __dmul_rn/__dadd_rn/__ddiv_rn in the reference's operation order;
+//   * comparisons on fp32 observations use host-computed cut points (constants.py).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/dqlb200.h"
+
+namespace dql {
+
+// Compact copy of dqlb200_config passed to kernels by value (constant bank).
+struct KC {
+  dqlb200_cuts cuts[DQLB200_MAX_CURRICULUM];
+  dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
+  double p_max, v_max, theta_max, delta_theta, w_p, w_v, w_theta;
+  float angle_cut[6];
+  float fz_lo, fz_hi, z_min_cut, z_max_cut;
+  float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
+  float p_max_f, two_p_max_f, sigma_x;
+  float gamma;
+  float transfer_ratio[DQLB200_MAX_CURRICULUM];
+  int32_t timeout_steps, success_steps, n_sub;
+  int32_t transfer_mode, window_len, promote_successes;
+  int32_t curriculum_steps, envs_per_population, n_populations;
+  long long max_num_episodes;
+};
+
+__device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al. 2011).  Counter = (env, step, purpose, population), key = seed.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return c;
+}
+constexpr uint32_t PURPOSE_STEP = 0u, PURPOSE_RESET = 1u;
+
+// ---------------------------------------------------------------------------------------------
+// deterministic fp32 math
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void det_sincos_turns(uint32_t phase, float& s_out, float& c_out) {
+  const uint32_t q = (phase + 0x20000000u) >> 30;
+  const int32_t rem = (int32_t)(phase - (q << 30));
+  const float x = fmul(__int2float_rn(rem), (float)(6.283185307179586 / 4294967296.0));
+  const float z = fmul(x, x);
+  float ps = (float)(1.0 / 362880.0);
+  ps = fadd(fmul(ps, z), (float)(-1.0 / 5040.0));
+  ps = fadd(fmul(ps, z), (float)(1.0 / 120.0));
+  ps = fadd(fmul(ps, z), (float)(-1.0 / 6.0));
+  const float s = fadd(x, fmul(x, fmul(z, ps)));
+  float pc = (float)(-1.0 / 3628800.0);
+  pc = fadd(fmul(pc, z), (float)(1.0 / 40320.0));
+  pc = fadd(fmul(pc, z), (float)(-1.0 / 720.0));
+  pc = fadd(fmul(pc, z), (float)(1.0 / 24.0));
+  pc = fadd(fmul(pc, z), -0.5f);
+  const float c = fadd(1.0f, fmul(z, pc));
+  const uint32_t qq = q & 3u;
+  s_out = (qq == 0u) ? s : (qq == 1u) ? c : (qq == 2u) ? -s : -c;
+  c_out = (qq == 0u) ? c : (qq == 1u) ? -s : (qq == 2u) ? -c : s;
+}
+
+__device__ __forceinline__ float det_tan(float x) {
+  const float z = fmul(x, x);
+  float p = (float)(21844.0 / 6081075.0);
+  p = fadd(fmul(p, z), (float)(1382.0 / 155925.0));
+  p = fadd(fmul(p, z), (float)(62.0 / 2835.0));
+  p = fadd(fmul(p, z), (float)(17.0 / 315.0));
+  p = fadd(fmul(p, z), (float)(2.0 / 15.0));
+  p = fadd(fmul(p, z), (float)(1.0 / 3.0));
+  return fadd(x, fmul(x, fmul(z, p)));
+}
+
+__device__ __forceinline__ float det_log(float u) {
+  const uint32_t bits = __float_as_uint(u);
+  int e = (int)((bits >> 23) & 0xFFu) - 127;
+  float m = __uint_as_float((bits & 0x007FFFFFu) | 0x3F800000u);
+  if (m > (float)1.4142135623730951) {
+    m = fmul(m, 0.5f);
+    e += 1;
+  }
+  const float s = __fdiv_rn(fsub(m, 1.0f), fadd(m, 1.0f));
+  const float z = fmul(s, s);
+  float p = (float)(1.0 / 9.0);
+  p = fadd(fmul(p, z), (float)(1.0 / 7.0));
+  p = fadd(fmul(p, z), (float)(1.0 / 5.0));
+  p = fadd(fmul(p, z), (float)(1.0 / 3.0));
+  const float lm = fmul(fadd(s, s), fadd(1.0f, fmul(z, p)));
+  return fadd(fmul(__int2float_rn(e), (float)0.6931471805599453), lm);
+}
+
+__device__ __forceinline__ float det_normal(uint32_t x0, uint32_t x1) {
+  const float u1 = fmul(fadd(__uint2float_rn(x0 >> 8), 1.0f), (float)(1.0 / 16777216.0));
+  const float rad = __fsqrt_rn(fmul(-2.0f, det_log(u1)));
+  float s, c;
+  det_sincos_turns(x1, s, c);
+  return fmul(rad, c);
+}
+
+__device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
+__device__ __forceinline__ double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+
+// ---------------------------------------------------------------------------------------------
+// stand-in dynamics (R4).  Body state: drone position/velocity, pitch, platform phase.
+// ---------------------------------------------------------------------------------------------
+struct Body {
+  float x_d, v_d, theta, a_d;
+  uint32_t phase;
+};
+
+struct Obs {
+  float rel_p, rel_v, rel_a, pitch, z;
+  bool contact;
+};
+
+__device__ __forceinline__ void dyn_advance(const KC& kc, const dqlb200_population_params& pp, Body& b, float sp) {
+  for (int i = 0; i < kc.n_sub; ++i) {
+    b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
+    b.a_d = fsub(fmul(kc.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
+    b.x_d = fadd(fadd(b.x_d, fmul(b.v_d, kc.h)), fmul(b.a_d, kc.half_h2));
+    b.v_d = fadd(b.v_d, fmul(b.a_d, kc.h));
+    b.phase += pp.dphase;
+  }
+}
+
+__device__ __forceinline__ Obs dyn_observe(const KC& kc, const dqlb200_population_params& pp, const Body& b,
+                                           int step_count, float dz) {
+  float s, c;
+  det_sincos_turns(b.phase, s, c);
+  Obs o;
+  o.rel_p = fsub(fmul(pp.r, s), b.x_d);
+  o.rel_v = fsub(fmul(pp.rw, c), b.v_d);
+  o.rel_a = fsub(-fmul(pp.rw2, s), b.a_d);
+  o.pitch = b.theta;
+  o.z = fadd(kc.z_init, fmul(__int2float_rn(step_count), dz));
+  o.contact = (o.z <= kc.z_touch) && (fabsf(o.rel_p) <= kc.half_platform);
+  return o;
+}
+
+// R1 (PKG/landing_simulation_env.py:181-216) and R15 (:327-340), then one hover period (:222-224).
+__device__ __forceinline__ Obs dyn_reset(const KC& kc, const dqlb200_population_params& pp, Body& b, uint4 w,
+                                         bool normal_init, bool simulation, float dz) {
+  float x_init;
+  if (normal_init) {
+    x_init = fmul(kc.sigma_x, det_normal(w.x, w.y));
+  } else {
+    const float u = fmul(__uint2float_rn(w.x >> 8), (float)(1.0 / 16777216.0));
+    x_init = fadd(-kc.p_max_f, fmul(kc.two_p_max_f, u));
+  }
+  b.phase = w.z;
+  float s, c;
+  det_sincos_turns(b.phase, s, c);
+  const float x_mp = fmul(pp.r, s);
+  b.x_d = simulation ? clipf(fsub(x_mp, x_init), -kc.p_max_f, kc.p_max_f)
+                     : fadd(x_mp, clipf(x_init, -kc.p_max_f, kc.p_max_f));
+  b.v_d = 0.0f;
+  b.theta = 0.0f;
+  b.a_d = 0.0f;
+  dyn_advance(kc, pp, b, 0.0f);
+  return dyn_observe(kc, pp, b, 0, dz);
+}
+
+// ---------------------------------------------------------------------------------------------
+// R5: discretisation through the fp32 cut tables of the current working step
+// ---------------------------------------------------------------------------------------------
+struct DState {
+  int level, bp, bv, ba, bt;
+  __device__ __forceinline__ int id() const { return (((level * 3 + bp) * 3 + bv) * 3 + ba) * 7 + bt; }
+};
+
+__device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const float* __restrict__ angle_cut,
+                                                  const Obs& o) {
+  int lp = 0, lv = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    lp += (o.rel_p >= c.lvl_lo[0][i]) && !(o.rel_p >= c.lvl_hi[0][i]);
+    lv += (o.rel_v >= c.lvl_lo[1][i]) && !(o.rel_v >= c.lvl_hi[1][i]);
+  }
+  DState d;
+  d.level = min(lp, lv);   // the acceleration limit is 1.0 at every level and never restricts
+  d.bp = (o.rel_p >= c.bin1[0][d.level]) + (o.rel_p >= c.bin2[0][d.level]);
+  d.bv = (o.rel_v >= c.bin1[1][d.level]) + (o.rel_v >= c.bin2[1][d.level]);
+  d.ba = (o.rel_a >= c.bin1[2][d.level]) + (o.rel_a >= c.bin2[2][d.level]);
+  int t = 0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) t += (o.pitch >= angle_cut[i]);
+  d.bt = t;
+  return d;
+}
+
+// R3: pitch set-point integrator, float64 like the reference
+__device__ __forceinline__ double apply_action(const KC& kc, double theta_sp, int a) {
+  if (a == 0) return fmin(__dadd_rn(theta_sp, kc.delta_theta), kc.theta_max);
+  if (a == 1) return fmax(__dsub_rn(theta_sp, kc.delta_theta), -kc.theta_max);
+  return theta_sp;
+}
+
+// Shaping potential of one observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
+__device__ __forceinline__ double shaping(double w, double x, double x_max) {
+  return __dmul_rn(w, fabs(clipd(__ddiv_rn(x, x_max), -1.0, 1.0)));
+}
+
+// R7 with the level-dependent constants pre-evaluated on the host.
+__device__ __forceinline__ double reward_f64(const KC& kc, const dqlb200_reward_level& rl, double phi_p,
+                                             double phi_v, double phi_t, double prev_p, double prev_v,
+                                             double prev_t, bool success) {
+  const double r_p = clipd(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
+  const double r_v = clipd(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
+  const double r_t =
+      __dmul_rn(__ddiv_rn(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max), rl.lim_v);
+  const double r_term = success ? rl.r_term_succ : rl.r_term_fail;
+  return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
+}
+
+}  // namespace dql

@@ -1,0 +1,177 @@
+"""Batched device driver: owns the torch tensors (device memory handles) and calls the C-ABI.
+
+One ``Engine`` = one CUDA device = ``n_populations`` independent agents (Q-table pairs), each with
+``envs_per_population`` environments; one CTA per population (csrc/dqlb200.cu: train_kernel).
+This replaces the `while not done` loop of Trainer.curriculum_training (PKG/trainer.py:187-245)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _ffi
+from . import constants as K
+
+
+class Engine:
+    def __init__(self, n_populations: int, envs_per_population: int, *, device: int = 0, threads_per_block: int = 256,
+                 seeds: Optional[Sequence[int]] = None, population_ids: Optional[Sequence[int]] = None,
+                 v_mp: Optional[Sequence[float]] = None, alpha_variants: Optional[Sequence[tuple]] = None,
+                 alpha_index: Optional[Sequence[int]] = None,
+                 mp: Optional[K.MdpParameters] = None, dp: Optional[K.DynamicsParameters] = None,
+                 tp: Optional[K.TrainerParameters] = None):
+        if not torch.cuda.is_available():
+            raise _ffi.Dqlb200Error("no CUDA device: dql_multirotor_landing_b200 has no CPU fallback")
+        self.lib = _ffi.load()
+        self.mp, self.dp, self.tp = mp or K.MdpParameters(), dp or K.DynamicsParameters(), tp or K.TrainerParameters()
+        self.P, self.n_p, self.device_index = n_populations, envs_per_population, device
+        self.device = torch.device("cuda", device)
+        alpha_variants = list(alpha_variants or [(self.tp.alpha_min, self.tp.omega)])
+        self.cfg = K.build_config(n_populations, envs_per_population, threads_per_block, self.mp, self.dp, self.tp,
+                                  n_alpha_luts=len(alpha_variants))
+        luts = np.concatenate([K.alpha_lut(a, o) for a, o in alpha_variants]).astype(np.float32)
+        seeds = list(seeds) if seeds is not None else [42] * n_populations
+        population_ids = list(population_ids) if population_ids is not None else list(range(n_populations))
+        v_mp = list(v_mp) if v_mp is not None else [self.dp.v_mp] * n_populations
+        alpha_index = list(alpha_index) if alpha_index is not None else [0] * n_populations
+        pps = (K.PopulationParams * n_populations)()
+        for p in range(n_populations):
+            dphase, r, rw, rw2 = K.platform_constants(self.dp.r_mp, v_mp[p], self.mp.f_ag, self.dp.n_sub)
+            pps[p] = K.PopulationParams(seeds[p] & 0xFFFFFFFF, (seeds[p] >> 32) & 0xFFFFFFFF, population_ids[p], dphase,
+                                        r, rw, rw2, alpha_index[p])
+        self.handle = C.c_void_p()
+        _ffi.check(self.lib.dqlb200_create(C.byref(self.cfg), luts.ctypes.data_as(C.POINTER(C.c_float)), pps, device,
+                                           C.byref(self.handle)))
+        n = n_populations * envs_per_population
+        self.n_total = n
+        with torch.cuda.device(self.device):
+            self.env_state = torch.zeros(3 * n * 4, dtype=torch.int32, device=self.device)        # [3][n][16 B]
+            self.tables = torch.zeros((n_populations, 3, K.MAX_CELLS), dtype=torch.int32, device=self.device)
+            self.pop_state = torch.zeros(n_populations * C.sizeof(K.PopulationState), dtype=torch.uint8, device=self.device)
+        _ffi.check(self.lib.dqlb200_bind(self.handle, self.env_state.data_ptr(), self.tables.data_ptr(), self.pop_state.data_ptr()))
+        self._trace_keep = None
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.dqlb200_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def reset(self, initial_step: int = 0):
+        _ffi.check(self.lib.dqlb200_reset(self.handle, initial_step, self._stream()))
+
+    def train(self, k_steps: int, trace: bool = False, action_override: Optional[np.ndarray] = None):
+        """k_steps fused global steps for every population.  With trace=True returns per-step arrays [k][n_total]."""
+        tr = None
+        out = None
+        if trace or action_override is not None:
+            n, dev = self.n_total, self.device
+            out = dict(
+                obs=torch.zeros((k_steps, n, 5), dtype=torch.float32, device=dev),
+                reward=torch.zeros((k_steps, n), dtype=torch.float64, device=dev),
+                action=torch.zeros((k_steps, n), dtype=torch.uint8, device=dev),
+                code=torch.zeros((k_steps, n), dtype=torch.uint8, device=dev),
+                done=torch.zeros((k_steps, n), dtype=torch.uint8, device=dev),
+                contact=torch.zeros((k_steps, n), dtype=torch.uint8, device=dev),
+                state=torch.zeros((k_steps, n), dtype=torch.int16, device=dev),
+                next_state=torch.zeros((k_steps, n), dtype=torch.int16, device=dev),
+                episode=torch.zeros((k_steps, n), dtype=torch.int32, device=dev),
+            )
+            ov = None
+            if action_override is not None:
+                ov = torch.as_tensor(np.ascontiguousarray(action_override, dtype=np.int8).reshape(k_steps, n), device=dev)
+            tr = K.Trace(*[out[k].data_ptr() for k in ("obs", "reward", "action", "code", "done", "contact", "state",
+                                                       "next_state", "episode")], ov.data_ptr() if ov is not None else None)
+            self._trace_keep = (out, ov)
+        _ffi.check(self.lib.dqlb200_train(self.handle, k_steps, C.byref(tr) if tr is not None else None, self._stream()))
+        if out is not None:
+            torch.cuda.synchronize(self.device)
+            return {k: v.cpu().numpy() for k, v in out.items()}
+        return None
+
+    def train_host(self, k_steps: int, env_state_host: torch.Tensor, tables_host: torch.Tensor, pop_state_host: torch.Tensor):
+        """End-to-end call with pinned HOST buffers (copies in, k_steps, copies out, synchronises)."""
+        _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
+                                               pop_state_host.data_ptr(), self._stream()))
+
+    def check_errors(self):
+        _ffi.check(self.lib.dqlb200_check_errors(self.handle, self._stream()))
+
+    # ------------------------------------------------------------------------------------------
+    # tables <-> DoubleQLearningAgent arrays (float64, shape (cs,3,3,3,7,3); PKG/double_q_learning.py:38-40)
+    def set_tables(self, population: int, qa: np.ndarray, qb: np.ndarray, count: np.ndarray):
+        cs = self.tp.curriculum_steps
+        host = np.zeros((3, K.MAX_CELLS), np.uint32)
+        host[0, : cs * K.CELLS_PER_LEVEL] = np.asarray(qa, np.float64).astype(np.float32).reshape(-1).view(np.uint32)
+        host[1, : cs * K.CELLS_PER_LEVEL] = np.asarray(qb, np.float64).astype(np.float32).reshape(-1).view(np.uint32)
+        host[2, : cs * K.CELLS_PER_LEVEL] = np.asarray(count, np.float64).reshape(-1).astype(np.uint32)
+        self.tables[population].copy_(torch.from_numpy(host.view(np.int32)))
+
+    def get_tables(self, population: int, dtype=np.float64):
+        cs = self.tp.curriculum_steps
+        host = self.tables[population].cpu().numpy().view(np.uint32)
+        shape = (cs, 3, 3, 3, 7, 3)
+        n = cs * K.CELLS_PER_LEVEL
+        qa = host[0, :n].view(np.float32).astype(dtype).reshape(shape)
+        qb = host[1, :n].view(np.float32).astype(dtype).reshape(shape)
+        count = host[2, :n].astype(np.float64).reshape(shape)
+        return qa, qb, count
+
+    def population_state(self) -> np.ndarray:
+        raw = self.pop_state.cpu().numpy()
+        return raw.view(K.POPULATION_STATE_DTYPE).copy()
+
+    def set_episode_index(self, episode: int):
+        """Test hook: set every env's per-curriculum-step episode index (word C.y of the state)."""
+        n = self.n_total
+        v = self.env_state.view(3, n, 4)
+        v[2, :, 1] = int(episode)
+
+    # ------------------------------------------------------------------------------------------
+    def eval_greedy(self, policy: np.ndarray, n_episodes: int, *, population: int = 0, first_episode: int = 0,
+                    working_step: int = 4, trace_steps: int = 0):
+        """Greedy SimulationMdp episodes (scripts/simulation.py:48-63).  policy: uint8 action per state id (945)."""
+        dev = self.device
+        pol = np.zeros(K.MAX_CURRICULUM * K.STATES_PER_LEVEL, np.uint8)
+        pol[: len(policy)] = policy
+        d_pol = torch.as_tensor(pol, device=dev)
+        stats = torch.zeros(C.sizeof(K.EvalStats), dtype=torch.uint8, device=dev)
+        tr, out = None, None
+        if trace_steps > 0:
+            out = dict(
+                obs=torch.zeros((trace_steps, n_episodes, 5), dtype=torch.float32, device=dev),
+                action=torch.zeros((trace_steps, n_episodes), dtype=torch.uint8, device=dev),
+                code=torch.zeros((trace_steps, n_episodes), dtype=torch.uint8, device=dev),
+                done=torch.zeros((trace_steps, n_episodes), dtype=torch.uint8, device=dev),
+                contact=torch.zeros((trace_steps, n_episodes), dtype=torch.uint8, device=dev),
+                state=torch.zeros((trace_steps, n_episodes), dtype=torch.int16, device=dev),
+                next_state=torch.zeros((trace_steps, n_episodes), dtype=torch.int16, device=dev),
+            )
+            tr = K.Trace(out["obs"].data_ptr(), None, out["action"].data_ptr(), out["code"].data_ptr(), out["done"].data_ptr(),
+                         out["contact"].data_ptr(), out["state"].data_ptr(), out["next_state"].data_ptr(), None, None)
+        _ffi.check(self.lib.dqlb200_eval_greedy(self.handle, population, d_pol.data_ptr(), first_episode, n_episodes, working_step,
+                                                stats.data_ptr(), C.byref(tr) if tr is not None else None, trace_steps, self._stream()))
+        torch.cuda.synchronize(dev)
+        st = K.EvalStats.from_buffer_copy(stats.cpu().numpy().tobytes())
+        res = dict(episodes=int(st.episodes), steps=int(st.steps), termination_hist=[int(x) for x in st.termination_hist])
+        if out is not None:
+            res["trace"] = {k: v.cpu().numpy() for k, v in out.items()}
+        return res
+
+
+def greedy_policy(qa: np.ndarray, qb: np.ndarray) -> np.ndarray:
+    """DoubleQLearningAgent.predict for every state (PKG/double_q_learning.py:119-124), evaluated in the
+    tables' own precision (float64 for the committed .npy files) -> uint8 action LUT indexed by state id."""
+    avg = np.add(qa, qb) / 2
+    return np.argmax(avg.reshape(-1, 3), axis=1).astype(np.uint8)

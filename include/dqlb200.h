@@ -1,0 +1,242 @@
+/*
+ * dqlb200.h -- C-ABI of libdqlb200.so: the B200 (sm_100a) implementation of the batched
+ * landing-MDP step + tabular Double-Q update.
+ *
+ * The reference (valerio98-lab/DQL_multirotor_landing) has NO FFI for this path: its boundary is the
+ * Python class API in src/dql_multirotor_landing/src/dql_multirotor_landing/{mdp,double_q_learning,
+ * trainer}.py ("PKG/" below).  Each entry point names the reference code it replaces.  The Python
+ * side of this repo (dql_multirotor_landing_b200/) binds these symbols with ctypes and mirrors the
+ * reference classes on top; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative dqlb200_status otherwise; the message of the
+ *     last error of the calling thread is dqlb200_last_error();
+ *   - device buffers are BORROWED (caller-owned, e.g. torch tensors; they must outlive the calls);
+ *   - all work is enqueued on the caller's cudaStream_t (passed as void*); nothing synchronises
+ *     unless the name says so (`_host` entry points copy and synchronise);
+ *   - one host thread per handle; no global mutable state besides the thread-local error string.
+ */
+#ifndef DQLB200_H
+#define DQLB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DQLB200_ABI_VERSION 1
+#define DQLB200_MAX_CURRICULUM 5
+#define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
+#define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
+#define DQLB200_MAX_CELLS (DQLB200_MAX_CURRICULUM * DQLB200_CELLS_PER_LEVEL)   /* 2835 */
+#define DQLB200_ALPHA_LUT 1003                /* count 0..1002; alpha(count >= 1002) == alpha_min */
+#define DQLB200_EPS_LUT 2002                  /* episode 0..2000, [2001] = every later episode */
+#define DQLB200_MAX_WINDOW 128                /* success window (Trainer successive_successful_episodes) */
+#define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, SoA: [3][n_envs_total][16 B] */
+
+typedef enum dqlb200_status {
+  DQLB200_OK = 0,
+  DQLB200_ERR_ARG = -1,
+  DQLB200_ERR_CUDA = -2,
+  DQLB200_ERR_STATE = -3,
+  DQLB200_ERR_DEVICE_FLAG = -4                /* a kernel raised an error flag (e.g. NaN observation) */
+} dqlb200_status;
+
+/* CheckResult codes (PKG/mdp.py:68-77); the strings are returned by dqlb200_termination_string(). */
+enum {
+  DQLB200_NON_TERMINAL = 0, DQLB200_NON_TERMINAL_SUCCESS = 1, DQLB200_TERMINAL_SUCCESS = 2,
+  DQLB200_TERMINAL_CONTACT = 3, DQLB200_TERMINAL_FLYZONE_X = 4, DQLB200_TERMINAL_FLYZONE_Y = 5,
+  DQLB200_TERMINAL_FLYZONE_Z = 6, DQLB200_TERMINAL_MINIMUM_ALTITUDE = 7, DQLB200_TERMINAL_TIMEOUT = 8
+};
+
+/* fp32 cut points of the discretisation for ONE working curriculum step w.  Every comparison the
+ * reference makes in float64 on clip(x / x_max, -1, 1) (PKG/mdp.py:149-170, 263-317) is monotone in
+ * the fp32 observation x, so it equals "x >= cut" for a cut found on the host by bisection over the
+ * fp32 number line with the reference's own float64 expression (constants.py).  q: 0 = position,
+ * 1 = velocity, 2 = acceleration. */
+typedef struct dqlb200_cuts {
+  float lvl_lo[2][4];   /* [q][idx-1]: first x with NOT (v < -limit[idx])      idx = 1..4 */
+  float lvl_hi[2][4];   /* [q][idx-1]: first x with      v >  limit[idx]                  */
+  float bin1[3][5];     /* [q][level]: first x whose bin is >= 1  (v >= -goal)            */
+  float bin2[3][5];     /* [q][level]: first x whose bin is == 2  (v >   goal)            */
+} dqlb200_cuts;
+
+/* float64 reward constants for one discretisation level (PKG/mdp.py:476-536). */
+typedef struct dqlb200_reward_level {
+  double lim_v;         /* Limits.velocity[level]                                          */
+  double r_p_max;       /* |w_p| * lim_v * dt                                              */
+  double r_v_max;       /* |w_v| * lim_a * dt                                              */
+  double r_dur;         /* w_dur * lim_v * dt                                              */
+  double r_term_succ;   /* w_succ * r_max                                                  */
+  double r_term_fail;   /* w_fail * r_max   (also for plain NON_TERMINAL, quirk Q8)         */
+} dqlb200_reward_level;
+
+/* Everything the kernels need that does not change during a run.  Built by constants.py with the
+ * reference's own expressions; POD, copied to the device by dqlb200_create(). */
+typedef struct dqlb200_config {
+  uint32_t struct_bytes;            /* = sizeof(dqlb200_config), checked */
+  uint32_t abi_version;
+  /* ---- layout ---- */
+  int32_t n_populations;            /* independent agents (Q-table pairs) on this device */
+  int32_t envs_per_population;
+  int32_t curriculum_steps;         /* 1..5 (DoubleQLearningAgent(curriculum_steps)) */
+  int32_t threads_per_block;        /* 32, 64, 128 or 256: one block per population */
+  /* ---- MDP (PKG/mdp.py) ---- */
+  dqlb200_cuts cuts[DQLB200_MAX_CURRICULUM];         /* indexed by working step w */
+  float angle_cut[6];               /* first pitch whose argmin index is >= i+1 (PKG/mdp.py:318-323) */
+  float fz_lo, fz_hi;               /* fly zone x: out  <=>  !(x >= fz_lo) || (x >= fz_hi)  (PKG/mdp.py:365-368) */
+  float z_min_cut, z_max_cut;       /* z < minimum_altitude <=> !(z >= z_min_cut); z > p_max <=> z >= z_max_cut */
+  int32_t timeout_steps;            /* first integer n with n >= t_max * f_ag   (459) */
+  int32_t success_steps;            /* first integer n with n >= f_ag           (23)  */
+  dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
+  double p_max, v_max, theta_max, delta_theta, w_p, w_v, w_theta;
+  /* float64 tables for the facade kernel, which discretises arbitrary float64 observations with the
+   * reference's own comparisons (PKG/mdp.py:149-170, 285-323, 383-395) */
+  double a_max, minimum_altitude, timeout_threshold /* t_max * f_ag */, f_ag;
+  double limits[3][DQLB200_MAX_CURRICULUM];          /* Limits.position / velocity / acceleration */
+  double goal_width[DQLB200_MAX_CURRICULUM][3][DQLB200_MAX_CURRICULUM];   /* [w][q][level] */
+  double angles[7];                                   /* np.linspace(-theta_max, theta_max, 7) */
+  /* ---- stand-in dynamics, fp32, one rounding each (DESIGN.md "dynamics") ---- */
+  float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
+  float p_max_f, two_p_max_f, sigma_x;
+  int32_t n_sub;
+  /* ---- agent / trainer schedules (PKG/trainer.py:88-138, PKG/double_q_learning.py) ---- */
+  float gamma;
+  float transfer_ratio[DQLB200_MAX_CURRICULUM];      /* float32(transfer_learning_ratio(k)) */
+  int32_t transfer_mode;            /* 0 = reference (quirk Q7), 1 = paper */
+  int32_t window_len;               /* successive_successful_episodes (<= DQLB200_MAX_WINDOW) */
+  int32_t promote_successes;        /* first integer s with s / window_len > success_rate */
+  int64_t max_num_episodes;
+  int32_t n_alpha_luts;             /* learning-rate variants for sweeps (>= 1) */
+  int32_t reserved0;
+  uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
+} dqlb200_config;
+
+/* Per-population constants (sweep axes: seed x platform speed x learning-rate schedule). */
+typedef struct dqlb200_population_params {
+  uint32_t seed_lo, seed_hi;        /* Philox key */
+  uint32_t population_id;           /* Philox counter word 3 */
+  uint32_t dphase;                  /* platform phase advance per sub-step, uint32 turns */
+  float r, rw, rw2;                 /* platform amplitude, r*w, r*w^2 */
+  int32_t alpha_lut;                /* index into the alpha LUT array */
+} dqlb200_population_params;
+
+/* Per-population mutable trainer state (device resident, 320 B).  Mirrors the Trainer fields the
+ * reference pickles (PKG/trainer.py:83-86) plus counters replacing its per-episode log. */
+typedef struct dqlb200_population_state {
+  int32_t working_step;             /* Trainer._working_curriculum_step */
+  int32_t finished;                 /* 1 after the last curriculum step ended */
+  uint32_t t;                       /* global step index (Philox counter word 1) */
+  uint32_t error_flags;             /* bit 0: NaN observation */
+  int64_t episodes_in_step;         /* completed episodes in this curriculum step */
+  int32_t window_head, window_count, window_sum, reserved;
+  uint8_t window[DQLB200_MAX_WINDOW];
+  uint64_t total_steps, total_episodes, total_successes;
+  uint64_t termination_hist[9];
+  double return_sum;                /* sum of "Cumulative reward" of finished episodes (quirk Q12) */
+  uint64_t episode_steps_sum;
+  uint32_t promoted_at[DQLB200_MAX_CURRICULUM];      /* t at which step k ended (0 = not yet) */
+  int32_t last_code, last_steps;    /* last finished episode, in env order */
+  double last_cumulative;
+} dqlb200_population_state;
+
+/* Optional per-step trace for parity tests: arrays of [n_steps][n_envs_total], any may be NULL. */
+typedef struct dqlb200_trace {
+  float* obs;                       /* [..][5] rel_p, rel_v, rel_a, pitch, z */
+  double* reward;
+  uint8_t* action; uint8_t* code; uint8_t* done; uint8_t* contact;
+  uint16_t* state; uint16_t* next_state;
+  int32_t* episode;
+  const int8_t* action_override;    /* [n_steps][n_envs_total], < 0 = use the agent */
+} dqlb200_trace;
+
+/* Result of dqlb200_eval_greedy (scripts/simulation.py loop, N episodes at once). */
+typedef struct dqlb200_eval_stats {
+  uint64_t episodes, steps;
+  uint64_t termination_hist[9];
+} dqlb200_eval_stats;
+
+typedef struct dqlb200_handle dqlb200_handle;
+
+int dqlb200_abi_version(void);
+size_t dqlb200_config_bytes(void);
+size_t dqlb200_population_state_bytes(void);
+const char* dqlb200_last_error(void);
+/* CheckResult.value strings (PKG/mdp.py:69-75); NULL for non-terminal codes. */
+const char* dqlb200_termination_string(int code);
+
+/* Replaces: Trainer.__init__ / gym.make("Landing-Training-v0") (PKG/trainer.py:20-86,176-183).
+ * alpha_luts: n_alpha_luts x DQLB200_ALPHA_LUT floats (host); pop_params: n_populations entries (host). */
+int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts,
+                   const dqlb200_population_params* pop_params, int device, dqlb200_handle** out);
+int dqlb200_destroy(dqlb200_handle* h);
+
+/* Borrow device buffers.
+ *   env_state : DQLB200_ENV_STATE_BYTES * n_populations * envs_per_population bytes, 16-B aligned
+ *   tables    : [n_populations][3][DQLB200_MAX_CELLS] 32-bit words: Q_a (f32), Q_b (f32), count (u32)
+ *               == DoubleQLearningAgent.Q_table_a / Q_table_b / state_action_counter, row-major
+ *               (curriculum, p, v, a, theta, action) like the .npy files (PKG/double_q_learning.py:38-53)
+ *   pop_state : n_populations x dqlb200_population_state */
+int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_state);
+
+/* Replaces: env.reset() for every env + a fresh TrainingMdp (PKG/landing_simulation_env.py:167-243,
+ * PKG/trainer.py:176-189).  Sets every population to working step `initial_step`, t = 0. */
+int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream);
+
+/* Replaces: the `while not done` body of Trainer.curriculum_training for every env, k_steps times
+ * (PKG/trainer.py:191-245): guess -> continuous_action -> [stand-in physics] -> discrete_state ->
+ * check -> reward -> alpha -> update -> auto-reset -> success window / promotion / transfer.
+ * trace may be NULL. */
+int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* stream);
+
+/* Same with HOST buffers: copies env_state/tables/pop_state in, runs k_steps, copies them back and
+ * synchronises.  This is the end-to-end call bench.py times as `e2e`. */
+int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host,
+                       void* pop_state_host, void* stream);
+
+/* Replaces: scripts/simulation.py:48-63 (+ SimulationLandingEnv.reset/step, SimulationMdp):
+ * n_episodes greedy episodes of population `population`'s policy, episode i uses reset draws
+ * (env = first_episode + i).  policy: 945-byte action LUT (device) = argmax((Q_a+Q_b)/2) per state.
+ * stats_out: device pointer to dqlb200_eval_stats (accumulated, caller zeroes).  trace may be NULL
+ * (arrays [max_steps][n_episodes]). */
+int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy, int64_t first_episode,
+                        int64_t n_episodes, int working_step, void* stats_out, const dqlb200_trace* trace,
+                        int trace_steps, void* stream);
+
+/* Replaces: DoubleQLearningAgent.transfer_learning (PKG/double_q_learning.py:77-89) on the bound
+ * tables of every population. */
+int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream);
+
+/* Checks the populations' error flags (synchronises the stream). */
+int dqlb200_check_errors(dqlb200_handle* h, void* stream);
+
+/* Shared-table mode helpers (one population replicated on G devices; NCCL all-reduce between them):
+ * delta  = [3][DQLB200_MAX_CELLS] floats per population: sum_w(dQ_a * dcount), dcount, unused.
+ * pack:   delta <- (tables - snapshot) weighted;   apply: tables <- snapshot + reduced delta. */
+int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream);
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, void* stream);
+
+/* Facade kernels behind TrainingMdp / SimulationMdp / DoubleQLearningAgent single-object calls
+ * (float64 observations from the host, reference comparisons in float64; PKG/mdp.py:257-541).
+ * obs: [n][6] doubles rel_p, rel_v, rel_a, pitch, z, rel_p_y; contact [n]; action [n];
+ * mdp_state: [n] records of 12 doubles {theta_sp, phi_p, phi_v, phi_theta, cumulative_reward,
+ * step_count, curriculum_check, result_code, cur_state(-1 none), prev_state(-1 none), rel_p, rel_v};
+ * out_state [n] uint16; out_code [n] uint8; out_reward [n] double.  `ops` is an OR of DQLB200_OP_*,
+ * applied in the order RESET, ACTION, OBSERVE, CHECK, REWARD.  All pointers are device pointers. */
+#define DQLB200_OP_ACTION 1    /* continuous_action   (PKG/mdp.py:543-560) */
+#define DQLB200_OP_OBSERVE 2   /* discrete_state      (PKG/mdp.py:257-333) */
+#define DQLB200_OP_CHECK 4     /* check               (PKG/mdp.py:335-439 / 784-845) */
+#define DQLB200_OP_REWARD 8    /* reward              (PKG/mdp.py:441-541) */
+#define DQLB200_OP_RESET 16    /* reset               (PKG/mdp.py:562-569 / 879-886) */
+#define DQLB200_OP_SIMULATION 256   /* SimulationMdp semantics instead of TrainingMdp */
+int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_t n,
+                            const double* obs, const uint8_t* contact, const int8_t* action,
+                            double* mdp_state, uint16_t* out_state, uint8_t* out_code, double* out_reward,
+                            void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DQLB200_H */

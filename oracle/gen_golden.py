@@ -114,8 +114,9 @@ def gen_mdp_trace(ns, w, n_episodes=12, seed=7, sp=None, tag=None):
     mdp = ns.mdp.TrainingMdp(w, F_AG, T_MAX, P_MAX)
     rec = {k: [] for k in ("obs", "contact", "action", "state", "code", "done", "reward", "theta_sp", "episode", "cum")}
     idx = np.asarray([0])
+    t = 0                      # global step index: reset draws use birth = t (the RNG contract)
     for ep in range(n_episodes):
-        words = philox.draws(99, w, idx, ep, philox.PURPOSE_RESET)
+        words = philox.draws(99, 0, idx, t, philox.PURPOSE_RESET)
         dyn.reset(idx, words[0], words[1], words[2], normal_init=(w == 0))
         mdp.reset()
         dyn.advance(np.zeros(1, np.float32))
@@ -141,6 +142,7 @@ def gen_mdp_trace(ns, w, n_episodes=12, seed=7, sp=None, tag=None):
             act = mdp.continuous_action(a, 2)
             dyn.advance(np.asarray([act.pitch], np.float32))
             k += 1
+            t += 1
             rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.asarray([k])))
             s = mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
             info = mdp.check()
@@ -156,7 +158,7 @@ def gen_mdp_trace(ns, w, n_episodes=12, seed=7, sp=None, tag=None):
         code=np.asarray(rec["code"], np.uint8), done=np.asarray(rec["done"], np.uint8),
         reward=np.asarray(rec["reward"], np.float64), theta_sp=np.asarray(rec["theta_sp"], np.float64),
         episode=np.asarray(rec["episode"], np.int32), cum=np.asarray(rec["cum"], np.float64), w=np.int32(w),
-        z_init=np.float64(sp.z_init), v_z=np.float64(sp.v_z), v_mp=np.float64(sp.v_mp),
+        z_init=np.float64(sp.z_init), v_z=np.float64(sp.v_z), v_mp=np.float64(sp.v_mp), seed=np.int64(99),
     )
     np.savez_compressed(GOLDEN / f"mdp_trace_{tag or ('w%d' % w)}.npz", **out)
     codes, cnt = np.unique(out["code"][out["done"] == 1], return_counts=True)

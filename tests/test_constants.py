@@ -1,0 +1,114 @@
+"""Host logic: the fp32 cut tables / LUTs of constants.py against the reference-generated fixtures
+(no GPU; a NumPy emulation of the kernel's compare chain is used to evaluate the cut tables)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from dql_multirotor_landing_b200 import constants as K
+
+
+def cut_discretise(cfg, w, obs):
+    """What the kernel does with the cut tables (csrc/dqlb200.cu: discretise_cuts)."""
+    c = cfg.cuts[w]
+    x = [obs[:, 0], obs[:, 1], obs[:, 2]]
+    with np.errstate(invalid="ignore"):
+        lvl = []
+        for q in range(2):
+            n = np.zeros(len(obs), np.int32)
+            for i in range(4):
+                n += (x[q] >= np.float32(c.lvl_lo[q][i])) & ~(x[q] >= np.float32(c.lvl_hi[q][i]))
+            lvl.append(n)
+        level = np.minimum(lvl[0], lvl[1])
+        bins = []
+        for q in range(3):
+            b1 = np.asarray([c.bin1[q][l] for l in range(5)], np.float32)[level]
+            b2 = np.asarray([c.bin2[q][l] for l in range(5)], np.float32)[level]
+            bins.append((x[q] >= b1).astype(np.int32) + (x[q] >= b2))
+        ang = np.zeros(len(obs), np.int32)
+        for i in range(6):
+            ang += obs[:, 3] >= np.float32(cfg.angle_cut[i])
+    return np.stack([level, bins[0], bins[1], bins[2], ang], axis=1).astype(np.int8)
+
+
+@pytest.fixture(scope="module")
+def cfg():
+    return K.build_config(1, 1)
+
+
+def test_struct_sizes(cfg):
+    assert cfg.struct_bytes == C.sizeof(K.Config)
+    assert C.sizeof(K.PopulationState) == K.POPULATION_STATE_DTYPE.itemsize == 320
+    assert C.sizeof(K.PopulationParams) == 32
+
+
+def test_cut_tables_vs_reference_fixture(cfg, golden_dir):
+    g = np.load(golden_dir / "discretise.npz")
+    for w in range(5):
+        got = cut_discretise(cfg, w, g["obs"])
+        bad = np.nonzero((got != g["train"][w]).any(axis=1))[0]
+        assert bad.size == 0, (w, g["obs"][bad[:5]], got[bad[:5]], g["train"][w][bad[:5]])
+
+
+def test_cut_tables_vs_reference_live(cfg, reference_ns):
+    """Dense probe around every cut (+-4 ulp) against the imported reference."""
+    ns = reference_ns
+    for w in (0, 2, 4):
+        mdp = ns.mdp.TrainingMdp(w, 22.92, 20, 4.5)
+        mdp.reset()
+        c = cfg.cuts[w]
+        probes = []
+        for q in range(3):
+            vals = [c.bin1[q][l] for l in range(w + 1)] + [c.bin2[q][l] for l in range(w + 1)]
+            if q < 2:
+                vals += [c.lvl_lo[q][i] for i in range(w)] + [c.lvl_hi[q][i] for i in range(w)]
+            for v in vals:
+                x = np.float32(v)
+                for _ in range(4):
+                    x = np.nextafter(x, np.float32(-np.inf))
+                for _ in range(9):
+                    row = [np.float32(0.01), np.float32(0.01), np.float32(0.01), np.float32(0.0)]
+                    row[q] = x
+                    probes.append(row)
+                    x = np.nextafter(x, np.float32(np.inf))
+        for v in cfg.angle_cut:
+            x = np.float32(v)
+            for _ in range(4):
+                x = np.nextafter(x, np.float32(-np.inf))
+            for _ in range(9):
+                probes.append([np.float32(0.3), np.float32(-0.2), np.float32(0.1), x])
+                x = np.nextafter(x, np.float32(np.inf))
+        obs = np.asarray(probes, np.float32)
+        got = cut_discretise(cfg, w, obs)
+        for k, row in enumerate(obs):
+            o = ns.Observation(rel_p_x=float(row[0]), rel_v_x=float(row[1]), rel_a_x=float(row[2]))
+            ref = mdp.discrete_state(ns.mdp.ContinuousObservation(o, float(row[3]), 0.0, 3.0))
+            assert tuple(got[k]) == ref, (w, row, got[k], ref)
+
+
+def test_schedule_luts(cfg, golden_dir):
+    g = np.load(golden_dir / "schedules.npz")
+    lut = K.alpha_lut()
+    assert np.array_equal(lut, g["alpha"][: K.ALPHA_LUT].astype(np.float32))
+    assert lut[-1] == np.float32(0.02949) and np.all(g["alpha"][K.ALPHA_LUT - 1:] == 0.02949)
+    thr = np.asarray(list(cfg.eps_threshold), np.uint64)
+    eps = g["eps"]
+    # exhaustive equivalence on a sample of 24-bit draws: (u24 * 2^-24 < eps)  <=>  (u24 < thr)
+    rng = np.random.default_rng(0)
+    u = np.concatenate([rng.integers(0, 2 ** 24, 4096), [0, 1, 2 ** 24 - 1, 167772, 167773]]).astype(np.uint64)
+    for e in list(range(0, 2001, 37)) + [800, 801, 1999, 2000, 2001]:
+        ref = (u.astype(np.float64) * 2.0 ** -24) < eps[e]
+        assert np.array_equal(ref, u < thr[min(e, K.EPS_LUT - 1)]), e
+    assert np.all(eps[2001:] == eps[2001]) and thr[2001] == K.explore_threshold(0.01)
+    assert [cfg.transfer_ratio[k] for k in range(5)] == [np.float32(r) for r in g["ratios"]]
+
+
+def test_scalar_thresholds(cfg):
+    assert cfg.timeout_steps == 459 and cfg.success_steps == 23
+    assert cfg.promote_successes == 97                                 # > 0.96 of 100
+    assert cfg.fz_hi == np.nextafter(np.float32(4.5), np.float32(np.inf)) and cfg.fz_lo == np.float32(-4.5)
+    assert np.float64(cfg.z_min_cut) >= 0.2 > np.float64(np.nextafter(np.float32(cfg.z_min_cut), np.float32(-1)))
+    r0 = cfg.reward[0]
+    assert abs(r0.r_term_fail / -2.6 - 5.054188) < 1e-6                # r_max level 0, SURVEY.md A.5
+    with pytest.raises(ValueError):
+        K.alpha_lut(alpha_min=0.001)                                   # does not saturate within the LUT

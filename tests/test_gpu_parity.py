@@ -1,0 +1,236 @@
+"""GPU parity (-m gpu): the CUDA path, called through the C-ABI, against
+  (a) the committed fixtures generated from the UNMODIFIED reference (tests/golden/), and
+  (b) the CPU oracle (oracle/) on the same seeded inputs.
+Bit-exact for observations (same fp32 operations), state indices, actions, terminal flags, rewards
+(float64 ==) and -- with float32 tables -- the Q tables and counts.  Float64-table fixtures: Q within
+1e-6 relative (north_star tolerance).  Nothing here reads /root/reference."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from oracle import philox
+from oracle.agent_oracle import AgentOracle
+from oracle.dynamics import StandInParams, det_normal, det_sincos_turns, standin_f64
+from oracle.loop import PopulationOracle, TrainerParams, eval_episode
+from oracle.mdp_oracle import MdpParams
+
+NO_PROMOTION = dict(success_rate=2.0, max_num_episodes=10 ** 12)
+
+
+def _engine(P, n_p, **kw):
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.engine import Engine
+    tp = K.TrainerParameters(**kw.pop("tp", {}))
+    dp = K.DynamicsParameters(**kw.pop("dp", {}))
+    return Engine(P, n_p, tp=tp, dp=dp, **kw)
+
+
+@pytest.mark.parametrize("name", ["w0", "w1", "w2", "w3", "w4", "lowz", "highz"])
+def test_mdp_trace_forced_actions(golden_dir, name):
+    """R3-R8: forced action sequences; every integer output and the float64 reward equal the reference's."""
+    g = np.load(golden_dir / f"mdp_trace_{name}.npz")
+    w = int(g["w"])
+    rows = np.nonzero(g["action"] != 255)[0]
+    acts = g["action"][rows].astype(np.int8)
+    eng = _engine(1, 1, threads_per_block=32, seeds=[int(g["seed"])], tp=NO_PROMOTION,
+                  dp=dict(z_init=float(g["z_init"]), v_z_train=float(g["v_z"]), v_mp=float(g["v_mp"])))
+    eng.reset(w)
+    tr = eng.train(len(acts), trace=True, action_override=acts.reshape(-1, 1))
+    eng.check_errors()
+    assert np.array_equal(tr["obs"][:, 0].view(np.uint32), g["obs"][rows].view(np.uint32))
+    assert np.array_equal(tr["action"][:, 0], g["action"][rows])
+    assert np.array_equal(tr["next_state"][:, 0].astype(np.uint16), g["state"][rows])
+    assert np.array_equal(tr["code"][:, 0], g["code"][rows])
+    assert np.array_equal(tr["done"][:, 0], g["done"][rows])
+    assert np.array_equal(tr["contact"][:, 0], g["contact"][rows])
+    assert np.array_equal(tr["reward"][:, 0], g["reward"][rows])          # float64, bit for bit
+    assert np.array_equal(tr["episode"][:, 0], g["episode"][rows])
+
+
+@pytest.mark.parametrize("name", ["replay_w0_float32", "replay_w0_float32_ep1950", "replay_w2_float32", "replay_w4_float32"])
+def test_replay_single_env_bit_exact(golden_dir, name):
+    """Config 1: the reference trainer loop (guess/update/alpha/eps + TrainingMdp) on one env, float32 tables
+    (NumPy >= 2 / NEP 50 arithmetic): identical actions, indices, flags, rewards, tables and counts."""
+    g = np.load(golden_dir / f"{name}.npz")
+    w, n = int(g["w"]), len(g["action"])
+    eng = _engine(1, 1, threads_per_block=32, seeds=[int(g["seed"])], tp=NO_PROMOTION)
+    eng.reset(w)
+    eng.set_tables(0, g["qa0"], g["qb0"], np.zeros_like(g["count"]))
+    eng.set_episode_index(int(g["ep0"]))
+    tr = eng.train(n, trace=True)
+    eng.check_errors()
+    for key, col in (("action", "action"), ("state", "state"), ("next_state", "next_state"), ("code", "code"), ("done", "done")):
+        assert np.array_equal(tr[key][:, 0].astype(np.int64), g[col].astype(np.int64)), key
+    assert np.array_equal(tr["obs"][:, 0].view(np.uint32), g["obs"].view(np.uint32))
+    assert np.array_equal(tr["reward"][:, 0], g["reward"])
+    assert np.array_equal(tr["episode"][:, 0], g["episode"])
+    qa, qb, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(qa.view(np.uint32), g["qa"].view(np.uint32))
+    assert np.array_equal(qb.view(np.uint32), g["qb"].view(np.uint32))
+    assert np.array_equal(cnt, g["count"])
+    ps = eng.population_state()[0]
+    assert ps["total_steps"] == n and ps["total_episodes"] == int(g["done"].sum())
+    assert ps["total_successes"] == int((g["code"][g["done"] == 1] == 2).sum())
+
+
+def test_replay_float64_reference_tolerance(golden_dir):
+    """Same loop with the reference's default float64 tables: pure exploration (eps = 1) so the trajectory
+    cannot depend on Q; device fp32 tables within 1e-6 relative of the float64 ones, counts identical."""
+    g = np.load(golden_dir / "replay_w0_float64.npz")
+    n = len(g["action"])
+    eng = _engine(1, 1, threads_per_block=32, seeds=[int(g["seed"])], tp=NO_PROMOTION)
+    eng.reset(0)
+    tr = eng.train(n, trace=True)
+    assert np.array_equal(tr["action"][:, 0], g["action"]) and np.array_equal(tr["done"][:, 0], g["done"])
+    assert np.array_equal(tr["next_state"][:, 0].astype(np.uint16), g["next_state"])
+    qa, _, cnt = eng.get_tables(0)
+    assert np.array_equal(cnt, g["count"])
+    np.testing.assert_allclose(qa, g["qa"], rtol=1e-6, atol=1e-6 * np.abs(g["qa"]).max())
+
+
+@pytest.mark.parametrize("tpb,n_envs", [(64, 70), (256, 300)])
+def test_multi_env_population_vs_oracle(tpb, n_envs):
+    """Batched semantics S1 (oracle/loop.py): several envs share a table pair; ragged env count; two
+    populations with different seeds and platform speeds.  Traces, tables, counts, counters identical."""
+    steps = 120
+    seeds, v_mp = [42, 7], [1.6, 0.8]
+    eng = _engine(2, n_envs, threads_per_block=tpb, seeds=seeds, v_mp=v_mp, tp=NO_PROMOTION)
+    eng.reset(0)
+    tr = eng.train(steps, trace=True)
+    eng.check_errors()
+    ps = eng.population_state()
+    for p in range(2):
+        pop = PopulationOracle(n_envs, seed=seeds[p], population=p, w0=0, dtype=np.float32,
+                               tp=TrainerParams(**NO_PROMOTION), sp=StandInParams(v_mp=v_mp[p]))
+        sl = slice(p * n_envs, (p + 1) * n_envs)
+        for t in range(steps):
+            o = pop.step()
+            assert np.array_equal(tr["obs"][t, sl].view(np.uint32), o["obs"].view(np.uint32)), (p, t)
+            for key in ("action", "code", "done"):
+                assert np.array_equal(tr[key][t, sl], o[key]), (p, t, key)
+            assert np.array_equal(tr["next_state"][t, sl].astype(np.uint16), o["next_state"]), (p, t)
+            assert np.array_equal(tr["reward"][t, sl], o["reward"]), (p, t)
+        qa, qb, cnt = eng.get_tables(p, np.float32)
+        assert np.array_equal(cnt, pop.agent.count)
+        assert np.array_equal(qa.view(np.uint32), pop.agent.qa.view(np.uint32))
+        assert ps[p]["total_episodes"] == pop.total_episodes and ps[p]["total_successes"] == pop.total_successes
+        assert list(ps[p]["termination_hist"]) == list(pop.term_hist)
+        assert ps[p]["window_sum"] == sum(pop.window) and ps[p]["window_count"] == len(pop.window)
+
+
+@pytest.mark.parametrize("mode", ["reference", "paper"])
+def test_curriculum_promotion_and_transfer(mode):
+    """R13/R14: success window, promotion latch, max_num_episodes advance, transfer (quirk Q7 and the
+    'paper' variant), fresh-MDP restart -- run until the last curriculum step ends."""
+    kw = dict(success_rate=0.2, successive_successful_episodes=5, max_num_episodes=40, transfer_mode=mode)
+    n_envs, steps = 48, 700
+    eng = _engine(1, n_envs, threads_per_block=32, seeds=[3], tp=kw)
+    eng.reset(0)
+    pop = PopulationOracle(n_envs, seed=3, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw))
+    done_steps = 0
+    for chunk in (1, 7, 64, 128, 500):
+        tr = eng.train(chunk, trace=True)
+        for t in range(chunk):
+            if pop.finished:
+                break
+            o = pop.step()
+            assert np.array_equal(tr["action"][t], o["action"]), (done_steps, t)
+            assert np.array_equal(tr["next_state"][t].astype(np.uint16), o["next_state"]), (done_steps, t)
+            assert np.array_equal(tr["reward"][t], o["reward"]), (done_steps, t)
+        done_steps += chunk
+    ps = eng.population_state()[0]
+    assert pop.finished and ps["finished"] == 1
+    assert ps["t"] == pop.t and ps["working_step"] == pop.w
+    assert [int(x) for x in ps["promoted_at"]] == [t + 1 for (t, _w, _p) in pop.promotions]
+    qa, qb, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(qa.view(np.uint32), pop.agent.qa.view(np.uint32))
+    assert np.array_equal(qb.view(np.uint32), pop.agent.qb.view(np.uint32))
+    assert np.array_equal(cnt, pop.agent.count)
+    assert ps["total_steps"] == pop.total_steps and ps["total_episodes"] == pop.total_episodes
+
+
+def test_chunking_and_block_size_invariance():
+    """K fused steps == K single-step launches, and the result does not depend on threads_per_block."""
+    results = []
+    for tpb, chunks in ((256, [96]), (256, [1] * 96), (32, [32, 64]), (128, [96])):
+        eng = _engine(3, 200, threads_per_block=tpb, seeds=[1, 2, 3], tp=NO_PROMOTION)
+        eng.reset(0)
+        for c in chunks:
+            eng.train(c)
+        torch.cuda.synchronize()
+        results.append((eng.env_state.cpu().numpy().copy(), eng.tables.cpu().numpy().copy(), eng.pop_state.cpu().numpy().copy()))
+    for r in results[1:]:
+        assert np.array_equal(r[0], results[0][0]) and np.array_equal(r[1], results[0][1]) and np.array_equal(r[2], results[0][2])
+
+
+def test_dynamics_vs_float64_equations():
+    """R4: the fp32 stand-in vs the float64 'textbook' form of the same equations, full episodes, <= 1e-5."""
+    n_envs, steps, seed = 64, 200, 11
+    eng = _engine(1, n_envs, threads_per_block=64, seeds=[seed], tp=NO_PROMOTION)
+    eng.reset(0)
+    rng = np.random.default_rng(0)
+    acts = rng.integers(0, 3, size=(steps, n_envs)).astype(np.int8)
+    tr = eng.train(steps, trace=True, action_override=acts)
+    mp, sp = MdpParams(), StandInParams()
+    w0, w1, w2, _ = philox.draws(seed, 0, np.arange(n_envs), 0, philox.PURPOSE_RESET)
+    x_init = np.float32(1.5) * det_normal(w0, w1)
+    s0, _ = det_sincos_turns(w2)
+    x_d0 = np.float32(2.0) * s0 + np.clip(x_init, -4.5, 4.5)
+    worst = 0.0
+    for i in range(n_envs):
+        first_done = np.nonzero(tr["done"][:, i])[0]
+        T = int(first_done[0]) + 1 if first_done.size else steps
+        th, sps = 0.0, []
+        for a in acts[:T, i]:
+            th = min(th + mp.delta_theta, mp.theta_max) if a == 0 else (max(th - mp.delta_theta, -mp.theta_max) if a == 1 else th)
+            sps.append(float(np.float32(th)))
+        # one hover period precedes the first observation: advance the platform phase by one step first
+        ref = standin_f64(sp, float(x_d0[i]), int(w2[i]) + int(eng.cfg.n_sub) * K_DPHASE(eng), sps)
+        worst = max(worst, float(np.abs(tr["obs"][:T, i, :5] - ref[:, :5]).max()))
+    assert worst <= 1e-5, worst
+
+
+def K_DPHASE(eng):
+    from dql_multirotor_landing_b200 import constants as K
+    return K.platform_constants(eng.dp.r_mp, eng.dp.v_mp, eng.mp.f_ag, eng.dp.n_sub)[0]
+
+
+def test_eval_greedy_fixture_and_oracle(golden_dir):
+    """R15 / config 2: greedy SimulationMdp episodes of the committed policy; first episodes against the
+    reference-generated fixture, a larger batch against the oracle, landing rate as in SURVEY.md A.4."""
+    from dql_multirotor_landing_b200.engine import greedy_policy
+    assets = golden_dir.parent.parent / "assets"
+    qa, qb = np.load(assets / "Q_table_a.npy"), np.load(assets / "Q_table_b.npy")
+    policy = greedy_policy(qa, qb)
+    g = np.load(golden_dir / "sim_trace.npz")
+    eng = _engine(1, 1, threads_per_block=32, seeds=[int(g["seed"])])
+    n_ep = int(g["episode"].max()) + 1
+    res = eng.eval_greedy(policy, n_ep, trace_steps=460)
+    tr = res["trace"]
+    for ep in range(n_ep):
+        rows = np.nonzero((g["episode"] == ep) & (g["action"] != 255))[0]
+        T = len(rows)
+        assert np.array_equal(tr["obs"][:T, ep].view(np.uint32), g["obs"][rows].view(np.uint32)), ep
+        assert np.array_equal(tr["action"][:T, ep], g["action"][rows])
+        assert np.array_equal(tr["next_state"][:T, ep].astype(np.uint16), g["state"][rows])
+        assert np.array_equal(tr["code"][:T, ep], g["code"][rows]) and tr["done"][T - 1, ep] == 1
+    # oracle on more episodes
+    pol = lambda s: int(np.argmax(np.add(qa[s], qb[s]) / 2))
+    n2 = 24
+    res2 = eng.eval_greedy(policy, n2, first_episode=100, trace_steps=460)
+    hist = np.zeros(9, np.int64)
+    steps = 0
+    for ep in range(n2):
+        rows = eval_episode(pol, int(g["seed"]), 0, 100 + ep, StandInParams(v_z=-0.4))[1:]
+        hist[rows[-1]["code"]] += 1
+        steps += len(rows)
+        assert [r["action"] for r in rows] == list(res2["trace"]["action"][: len(rows), ep])
+    assert list(hist) == res2["termination_hist"] and steps == res2["steps"] and res2["episodes"] == n2
+    # size-independent property at scale: every episode terminates, landing rate in the survey's band
+    big = eng.eval_greedy(policy, 1 << 16)
+    assert big["episodes"] == 1 << 16 and sum(big["termination_hist"]) == 1 << 16
+    assert big["termination_hist"][0] == 0 and big["termination_hist"][1] == 0
+    assert big["termination_hist"][3] / big["episodes"] > 0.85
