@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/s INCLUDING Q-updates (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    (N > 1: launched by the driver as  python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+
+Workload (BASELINE.json configs[4], one GPU's shard; named in config.workload): independent agent
+populations (seed x platform-speed x learning-rate sweep), x axis, curriculum step 0, ~1M envs per GPU,
+every population with its own Q-table pair; weak scaling over GPUs with NO data-path collective.
+
+A bench "step" = ONE global step of every env on the GPU = one launch of train_kernel (select -> dynamics ->
+discretise -> check -> reward -> alpha -> Q update -> auto-reset).  `value` = env-steps/s summed over all
+ranks, timed with CUDA events on the launching stream, L2 flushed (untimed) between timed launches, max over
+ranks.  `e2e` = the same metric through the C-ABI host-buffer entry point dqlb200_train_host (pinned host
+env-state + tables + trainer state copied in, E2E_CHUNK global steps, everything copied back, every call).
+`cpu_baseline` = the reference's single-env Python loop (oracle port) on one host core, bounded sample.
+`--impl reference` = that loop on every host core.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env_steps_per_sec_incl_q_updates"
+UNIT = "env-steps/s"
+POPULATIONS_PER_GPU = 592          # 4 CTAs per SM x 148 SMs
+ENVS_PER_POPULATION = 1792         # 592 * 1792 = 1,060,864 envs per GPU  (BASELINE config 5: "1M envs per GPU")
+THREADS_PER_BLOCK = 128
+E2E_CHUNK = 64                     # global steps per host-buffer call (about one episode, the reference's save interval)
+ALGORITHMIC_BYTES_PER_ENV_STEP = 96   # 48 B env state read + 48 B written, one step per launch
+
+
+def workload_config(n_gpus: int) -> dict:
+    return {
+        "workload": "BASELINE configs[4] per-GPU shard: independent populations (seed x platform-speed x learning-rate "
+                    "sweep), x axis, curriculum step 0, training incl. Q-updates",
+        "populations_per_gpu": POPULATIONS_PER_GPU, "envs_per_population": ENVS_PER_POPULATION,
+        "envs_per_gpu": POPULATIONS_PER_GPU * ENVS_PER_POPULATION, "n_gpus": n_gpus,
+        "global_steps_per_launch": 1, "e2e_global_steps_per_call": E2E_CHUNK,
+        "threads_per_block": THREADS_PER_BLOCK, "parallelism": f"population-partitioned x{n_gpus}, no collective",
+        "l2": "flushed (256 MiB write) between timed launches; env state 51 MB < L2",
+        "rng": "Philox4x32-10, seeds 0..P-1 per rank", "platform_speeds": [0.4, 0.8, 1.2, 1.6],
+        "alpha_variants": [[0.02949, 0.51], [0.05, 0.6]],
+    }
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.idx = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_hbm():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def cpu_baseline(seconds: float = 12.0) -> dict:
+    from oracle.cpu_loop import run_single_env
+    steps, t = 0, 0.0
+    while t < seconds:                       # bounded sample of the same workload: curriculum step 0, one env
+        n, _, s = run_single_env(50000, seed=42 + steps)
+        steps += n
+        t += s
+    return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": f"{steps} env-steps of the single-env reference loop (oracle port, float64 tables, analytic stand-in), "
+                      f"{t:.1f} s on 1 of {os.cpu_count()} host cores"}
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_reference(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path (oracle port: /root/reference is Python and cannot
+    travel to the GPU box) on every host core; rank 0 only."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle.cpu_loop import run_all_cores
+    cores = os.cpu_count() or 1
+    steps_per_proc = 4000                     # one bench step = cores x 4000 env-steps (bounded sample)
+    pool = mp.get_context("fork").Pool(cores)
+    try:
+        for w in range(args.warmup):
+            run_all_cores(steps_per_proc, cores, seed0=1000 * w, pool=pool)
+        total, wall = 0, 0.0
+        for k in range(args.steps):
+            n, s = run_all_cores(steps_per_proc, cores, seed0=7919 * (k + 1), pool=pool)
+            total += n
+            wall += s
+    finally:
+        pool.close()
+        pool.join()
+    v = total / wall
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{args.steps} steps x {cores} processes x {steps_per_proc} env-steps of the single-env reference loop"},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.engine import Engine, greedy_policy
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    P, n_p = POPULATIONS_PER_GPU, ENVS_PER_POPULATION
+    speeds = [0.4, 0.8, 1.2, 1.6]
+    variants = [(0.02949, 0.51), (0.05, 0.6)]
+    eng = Engine(P, n_p, device=local_rank, threads_per_block=THREADS_PER_BLOCK,
+                 seeds=[rank * P + p for p in range(P)], population_ids=[rank * P + p for p in range(P)],
+                 v_mp=[speeds[p % 4] for p in range(P)], alpha_variants=variants, alpha_index=[(p // 4) % 2 for p in range(P)],
+                 tp=K.TrainerParameters(max_num_episodes=10 ** 12, success_rate=2.0))   # stay in curriculum step 0 while timing
+    eng.reset(0)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream(dev)
+
+    # clock ramp (untimed, not counted as warm-up steps): ~0.3 s of the same kernel
+    t_end = time.perf_counter() + 0.3
+    while time.perf_counter() < t_end:
+        eng.train(32)
+        torch.cuda.synchronize(dev)
+    for _ in range(args.warmup):
+        flush.zero_()
+        eng.train(1)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches = 0
+    for k in range(args.steps):
+        flush.zero_()                          # untimed L2 flush
+        ev[k][0].record(stream)
+        eng.train(1)
+        ev[k][1].record(stream)
+        launches += 1
+    barrier()
+    ms = sum(a.elapsed_time(b) for a, b in ev)
+    eng.check_errors()
+
+    # ---- e2e: host buffers through dqlb200_train_host ----------------------------------------------
+    env_h = torch.empty_like(eng.env_state, device="cpu").pin_memory()
+    tab_h = torch.empty_like(eng.tables, device="cpu").pin_memory()
+    ps_h = torch.empty_like(eng.pop_state, device="cpu").pin_memory()
+    env_h.copy_(eng.env_state); tab_h.copy_(eng.tables); ps_h.copy_(eng.pop_state)
+    torch.cuda.synchronize(dev)
+    e2e_calls = max(3, min(args.steps, 20))
+    for _ in range(2):
+        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_calls):
+        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h)          # synchronises inside
+        launches += 1
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+    h2d = env_h.numel() * 4 + tab_h.numel() * 4 + ps_h.numel()
+    steps_done = int(np.frombuffer(ps_h.numpy().tobytes(), dtype=K.POPULATION_STATE_DTYPE)["total_steps"].sum())
+
+    t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    ms_max, e2e_ms_max = float(t_ms[0]), float(t_ms[1])
+    envs_gpu = P * n_p
+    value = world * envs_gpu * args.steps / (ms_max * 1e-3)
+    e2e_value = world * envs_gpu * E2E_CHUNK * e2e_calls / (e2e_ms_max * 1e-3)
+
+    line = None
+    if rank == 0:
+        peak, peak_src = measured_peak_hbm()
+        launch_s = ms_max * 1e-3 / args.steps
+        achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu / launch_s / 1e9
+        traffic = None
+        prof = ROOT / "profiles" / "train_kernel_traffic.json"
+        if prof.exists():
+            try:
+                traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        extra = {}
+        if not args.no_extra:
+            extra = extra_measurements(eng, dev, np, torch, greedy_policy)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src, "kernel": "dql::train_kernel<4>",
+                         "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu,
+                         "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 6 and profiles/"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+                    "global_steps_per_call": E2E_CHUNK, "calls": e2e_calls, "api": "dqlb200_train_host (pinned host buffers)"},
+            "gpu_launches": launches, "clocks": clocks, "total_env_steps_counted_on_device": steps_done,
+            "cpu_baseline": cpu_baseline() if not args.no_cpu else None,
+            "extra": extra,
+        }
+    eng.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
+    """Other BASELINE configs, device-timed, for context (not the headline)."""
+    out = {}
+
+    def timed(fn, reps=3):
+        best = 1e30
+        for _ in range(reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); fn(); b.record(); torch.cuda.synchronize(dev)
+            best = min(best, a.elapsed_time(b))
+        return best * 1e-3
+
+    eng.train(64); torch.cuda.synchronize(dev)
+    s = timed(lambda: eng.train(64))
+    out["fused_64_steps_per_launch_env_steps_per_s"] = eng.n_total * 64 / s
+    # config 2: greedy evaluation of the committed policy, 1,048,576 episodes
+    qa, qb = np.load(ROOT / "assets" / "Q_table_a.npy"), np.load(ROOT / "assets" / "Q_table_b.npy")
+    pol = greedy_policy(qa, qb)
+    n_ep = 1 << 20
+    eng.eval_greedy(pol, 4096)
+    t0 = time.perf_counter()
+    res = eng.eval_greedy(pol, n_ep)
+    s = time.perf_counter() - t0
+    out["config2_greedy_eval"] = {"episodes": res["episodes"], "env_steps": res["steps"], "env_steps_per_s": res["steps"] / s,
+                                  "landing_rate": res["termination_hist"][3] / max(res["episodes"], 1),
+                                  "termination_hist": res["termination_hist"], "timing": "host wall clock incl. launch+sync"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the other-config measurements")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # not under torchrun: relaunch as one process per GPU
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 2000), __file__,
+               "--gpus", str(args.gpus), "--steps", str(args.steps), "--warmup", str(args.warmup)]
+        cmd += ["--no-cpu"] if args.no_cpu else []
+        cmd += ["--no-extra"] if args.no_extra else []
+        sys.exit(subprocess.call(cmd))
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -101,8 +101,28 @@ __device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population
   }
 }
 
-__device__ __forceinline__ void bar_sync(int id, int n) { asm volatile("barrier.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
-__device__ __forceinline__ void bar_arrive(int id, int n) { asm volatile("barrier.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// Baton between the warps of a CTA: warp w waits on named barrier 1+w (its 32 threads + the 32 arriving
+// threads of the previous warp).  The ids are IMMEDIATES so that ptxas allocates WARPS+1 barriers per CTA;
+// with a register id it reserves all 16 and the 64-barriers-per-SM limit caps occupancy at 4 CTAs
+// (ncu launch__occupancy_limit_barriers).
+#define DQL_BAR_CASE(OP, ID) case (ID - 1): if (WARPS >= ID) asm volatile("barrier." OP " " #ID ", 64;" ::: "memory"); break;
+template <int WARPS>
+__device__ __forceinline__ void baton_wait(int warp) {
+  switch (warp) {
+    DQL_BAR_CASE("sync", 1) DQL_BAR_CASE("sync", 2) DQL_BAR_CASE("sync", 3) DQL_BAR_CASE("sync", 4)
+    DQL_BAR_CASE("sync", 5) DQL_BAR_CASE("sync", 6) DQL_BAR_CASE("sync", 7) DQL_BAR_CASE("sync", 8)
+    default: break;
+  }
+}
+template <int WARPS>
+__device__ __forceinline__ void baton_pass(int next_warp) {
+  switch (next_warp) {
+    DQL_BAR_CASE("arrive", 1) DQL_BAR_CASE("arrive", 2) DQL_BAR_CASE("arrive", 3) DQL_BAR_CASE("arrive", 4)
+    DQL_BAR_CASE("arrive", 5) DQL_BAR_CASE("arrive", 6) DQL_BAR_CASE("arrive", 7) DQL_BAR_CASE("arrive", 8)
+    default: break;
+  }
+}
+#undef DQL_BAR_CASE
 
 struct TrainArgs {
   EnvPtrs env;
@@ -116,12 +136,12 @@ struct TrainArgs {
   long long n_total;
 };
 
+// Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
+// loop, L1-resident): that keeps the footprint at ~38 KB so that five CTAs fit on one SM.
 struct Shared {
   float qa[CELLS];        // live table A
   float qs[CELLS];        // snapshot of table A at the start of the global step
-  float qb[CELLS];        // table B (never written by training, quirk Q1)
   uint32_t cnt[CELLS];    // state_action_counter
-  float alpha[DQLB200_ALPHA_LUT];
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   float angle_cut[8];
@@ -129,9 +149,10 @@ struct Shared {
   dqlb200_population_state ps;
   unsigned long long n_episodes, n_success, ep_steps, hist[9];
   int promote, advance, do_advance;
+  // followed by: uint16_t reset_queue[WARPS][n_slots * 32]   (dynamic)
 };
 
-template <int WARPS>
+template <int WARPS, bool TRACE>
 __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -140,13 +161,14 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
   const int pop = blockIdx.x;
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
+  uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * n_slots * 32;
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
+  float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
 
-  // ---- stage tables, LUTs and population state in shared memory -------------------------------
+  // ---- stage tables and population state in shared memory -------------------------------------
   for (int i = tid; i < CELLS; i += NT) {
     sh.qa[i] = __uint_as_float(gt[i]);
-    sh.qb[i] = __uint_as_float(gt[CELLS + i]);
     sh.cnt[i] = gt[2 * CELLS + i];
   }
   if (tid == 0) {
@@ -159,11 +181,11 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
   if (tid < 5) sh.reward[tid] = kc.reward[tid];
   if (tid < 6) sh.angle_cut[tid] = kc.angle_cut[tid];
   __syncthreads();
-  for (int i = tid; i < DQLB200_ALPHA_LUT; i += NT) sh.alpha[i] = args.alpha_luts[(size_t)sh.pp.alpha_lut * DQLB200_ALPHA_LUT + i];
   if (tid == 0) sh.cuts = kc.cuts[sh.ps.working_step];
   __syncthreads();
 
   const dqlb200_population_params pp = sh.pp;
+  const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
   uint64_t steps_done = 0;
 
   for (int k = 0; k < args.k_steps; ++k) {
@@ -172,6 +194,7 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
     const uint32_t t = sh.ps.t;
     for (int i = tid; i < CELLS; i += NT) sh.qs[i] = sh.qa[i];
     __syncthreads();
+    int n_queued = 0;              // warp-uniform: envs of this warp that finished an episode in this step
 
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
@@ -188,21 +211,27 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         Env e;
         env_load(args.env, gi, e);
         const uint32_t sid = e.sid;
-        // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4)
-        const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
-        const uint32_t thr = (w == 0) ? __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1))) : 0u;
-        const float p0 = fmul(fadd(sh.qs[sid * 3 + 0], sh.qb[sid * 3 + 0]), 0.5f);
-        const float p1 = fmul(fadd(sh.qs[sid * 3 + 1], sh.qb[sid * 3 + 1]), 0.5f);
-        const float p2 = fmul(fadd(sh.qs[sid * 3 + 2], sh.qb[sid * 3 + 2]), 0.5f);
+        // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
+        // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
+        const float p0 = fmul(fadd(sh.qs[sid * 3 + 0], gqb[sid * 3 + 0]), 0.5f);
+        const float p1 = fmul(fadd(sh.qs[sid * 3 + 1], gqb[sid * 3 + 1]), 0.5f);
+        const float p2 = fmul(fadd(sh.qs[sid * 3 + 2], gqb[sid * 3 + 2]), 0.5f);
         int a = 0;
         float best = p0;
         if (p1 > best) { best = p1; a = 1; }
         if (p2 > best) { a = 2; }
-        if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
-        const size_t trace_i = (size_t)k * (size_t)args.n_total + gi;
-        if (args.trace.action_override) {
-          const int o = args.trace.action_override[trace_i];
-          if (o >= 0) a = o;
+        if (w == 0) {
+          const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
+          const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+          if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+        }
+        size_t trace_i = 0;
+        if (TRACE) {
+          trace_i = (size_t)k * (size_t)args.n_total + gi;
+          if (args.trace.action_override) {
+            const int o = args.trace.action_override[trace_i];
+            if (o >= 0) a = o;
+          }
         }
         // R3: set-point (float64).  A fresh episode starts from 0 but keeps the old value for shaping.
         const double prev_sp = e.theta_sp;
@@ -232,14 +261,15 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         }
         done = code >= DQLB200_TERMINAL_SUCCESS;
         success = code == DQLB200_TERMINAL_SUCCESS;
-        if (o.rel_p != o.rel_p || o.rel_v != o.rel_v || o.rel_a != o.rel_a) atomicOr(&sh.ps.error_flags, 1u);
+        if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
+          atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
         // R7 (float64, reference operation order; level-dependent constants from the host)
-        const double phi_p = shaping(kc.w_p, (double)o.rel_p, kc.p_max);
-        const double phi_v = shaping(kc.w_v, (double)o.rel_v, kc.v_max);
-        const double phi_t = __dmul_rn(kc.w_theta, fabs(__ddiv_rn(sp, kc.theta_max)));
-        const double prev_p = shaping(kc.w_p, (double)e.prev_rel_p, kc.p_max);
-        const double prev_v = shaping(kc.w_v, (double)e.prev_rel_v, kc.v_max);
-        const double prev_t = __dmul_rn(kc.w_theta, fabs(__ddiv_rn(prev_sp, kc.theta_max)));
+        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
+        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
+        const double phi_t = __dmul_rn(kc.w_theta, fabs(div_guard0(sp, kc.theta_max)));
+        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
+        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
+        const double prev_t = __dmul_rn(kc.w_theta, fabs(div_guard0(prev_sp, kc.theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
         const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
         // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
@@ -247,19 +277,22 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         const float changed = (((sid / 63u) % 3u) != (uint32_t)ds.bp) ? 1.0f : 0.0f;
         target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
         cell = sid * 3u + (uint32_t)a;
-        if (args.trace.obs) {
-          float* po = args.trace.obs + trace_i * 5;
-          po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z;
+        if (TRACE) {
+          if (args.trace.obs) {
+            float* po = args.trace.obs + trace_i * 5;
+            po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z;
+          }
+          if (args.trace.reward) args.trace.reward[trace_i] = r;
+          if (args.trace.action) args.trace.action[trace_i] = (uint8_t)a;
+          if (args.trace.code) args.trace.code[trace_i] = (uint8_t)code;
+          if (args.trace.done) args.trace.done[trace_i] = (uint8_t)done;
+          if (args.trace.contact) args.trace.contact[trace_i] = (uint8_t)o.contact;
+          if (args.trace.state) args.trace.state[trace_i] = (uint16_t)sid;
+          if (args.trace.next_state) args.trace.next_state[trace_i] = (uint16_t)sid2;
+          if (args.trace.episode) args.trace.episode[trace_i] = (int32_t)e.episode;
         }
-        if (args.trace.reward) args.trace.reward[trace_i] = r;
-        if (args.trace.action) args.trace.action[trace_i] = (uint8_t)a;
-        if (args.trace.code) args.trace.code[trace_i] = (uint8_t)code;
-        if (args.trace.done) args.trace.done[trace_i] = (uint8_t)done;
-        if (args.trace.contact) args.trace.contact[trace_i] = (uint8_t)o.contact;
-        if (args.trace.state) args.trace.state[trace_i] = (uint16_t)sid;
-        if (args.trace.next_state) args.trace.next_state[trace_i] = (uint16_t)sid2;
-        if (args.trace.episode) args.trace.episode[trace_i] = (int32_t)e.episode;
-        // carry
+        // carry.  A finished env only gets its shaping memory and episode index written here; its new
+        // episode (R1) is set up by the batched reset pass after the slot loop.
         e.theta_sp = sp;
         e.prev_rel_p = o.rel_p;
         e.prev_rel_v = o.rel_v;
@@ -267,7 +300,6 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
           ep_steps = step_count;
           ep_return = e.cum_reward;               // quirk Q12: the last reward is not in the logged sum
           e.episode += 1u;
-          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w, /*fresh_mdp=*/false);
         } else {
           e.sid = sid2;
           e.step_count = step_count;
@@ -279,14 +311,15 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         env_store(args.env, gi, e);
       }
       // ---------------- phase B: ordered commit (baton between warps) --------------------------
-      if (WARPS > 1 && !(slot == 0 && warp == 0)) bar_sync(1 + warp, 64);
+      if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
+      const uint32_t dmask = __ballot_sync(FULL, valid && done);
       {
         const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
         const uint32_t peers = __match_any_sync(FULL, key);
         const int rank = __popc(peers & ((1u << lane) - 1u));
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
-        const float alpha = sh.alpha[min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1))];   // R11 (pre-increment count)
+        const float alpha = alpha_lut[min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1))];   // R11 (pre-increment count)
         uint32_t rem = valid ? peers : 0u;
         while (__any_sync(FULL, rem != 0u)) {
           const int src = rem ? (__ffs(rem) - 1) : lane;
@@ -300,7 +333,6 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
           sh.cnt[cell] = c0 + (uint32_t)__popc(peers);
         }
         // finished episodes, in env order: success window + promotion test after every append (R14)
-        const uint32_t dmask = __ballot_sync(FULL, valid && done);
         if (dmask) {
           const uint32_t smask = __ballot_sync(FULL, valid && success);
           if (valid && done) {
@@ -342,7 +374,25 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
       }
       if (WARPS > 1 && !(slot == n_slots - 1 && warp == WARPS - 1)) {
         __threadfence_block();
-        bar_arrive(1 + (warp + 1) % WARPS, 64);
+        baton_pass<WARPS>((warp + 1) % WARPS);
+      }
+      // queue the finished envs of this warp for the batched reset (outside the baton)
+      if (dmask) {
+        if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);
+        n_queued += __popc(dmask);
+      }
+    }
+    // ---------------- batched R1/R8: new episodes for the envs that finished, full lanes ---------
+    __syncwarp();
+    for (int base = 0; base < n_queued; base += 32) {
+      if (base + lane < n_queued) {
+        const int qv = reset_queue[base + lane];
+        const int env_i = (qv >> 5) * NT + warp * 32 + (qv & 31);
+        const size_t gi = env_base + (size_t)env_i;
+        Env e;
+        env_load(args.env, gi, e);
+        env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w, /*fresh_mdp=*/false);
+        env_store(args.env, gi, e);
       }
     }
     __syncthreads();
@@ -360,15 +410,10 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
       float ratio = 1.0f;
       if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
       else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
-      if (dst >= 0 && dst != src) {
+      if (dst >= 0) {
         for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
           sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
-          sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
-        }
-      } else if (dst >= 0) {
-        for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
-          sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i], ratio);
-          sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qb[dst * DQLB200_CELLS_PER_LEVEL + i], ratio);
+          gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
         }
       }
       __syncthreads();
@@ -404,7 +449,6 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
   __syncthreads();
   for (int i = tid; i < CELLS; i += NT) {
     gt[i] = __float_as_uint(sh.qa[i]);
-    gt[CELLS + i] = __float_as_uint(sh.qb[i]);
     gt[2 * CELLS + i] = sh.cnt[i];
   }
   if (tid == 0) {
@@ -416,6 +460,30 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
     for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
     args.pop_state[pop] = ps;
   }
+}
+
+// Exhaustive self-test of div_f32_by_const against __ddiv_rn: every FINITE fp32 bit pattern (non-finite
+// observations raise the population's error flag instead).  out[0]: mismatches of the production routine,
+// out[1]: of the variant with a single correction step (diagnostic).
+__global__ void selftest_division_kernel(const __grid_constant__ KC kc, unsigned long long* mismatches) {
+  unsigned long long bad = 0, bad1 = 0;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32);
+       b += (unsigned long long)gridDim.x * blockDim.x) {
+    const float x = __uint_as_float((uint32_t)b);
+    if (!(fabsf(x) <= 3.4028234664e38f)) continue;
+#pragma unroll
+    for (int v = 0; v < 2; ++v) {
+      const double d = v ? kc.v_max : kc.p_max, rcp = v ? kc.rcp_v_max : kc.rcp_p_max;
+      const double exact = __ddiv_rn((double)x, d);
+      // compare magnitudes bit for bit (the sign of a zero quotient is irrelevant to the callers)
+      bad += __double_as_longlong(fabs(div_f32_by_const(x, d, rcp, kc.div_two_steps != 0))) != __double_as_longlong(fabs(exact));
+      const double q0 = __dmul_rn((double)x, rcp);
+      const double q1 = __fma_rn(__fma_rn(-q0, d, (double)x), rcp, q0);
+      bad1 += __double_as_longlong(fabs(q1)) != __double_as_longlong(fabs(exact));
+    }
+  }
+  if (bad) atomicAdd(mismatches, bad);
+  if (bad1) atomicAdd(mismatches + 1, bad1);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -524,6 +592,7 @@ __device__ int bin_f64(double v, double goal, double limit) {
   return -1;   // NaN: the reference raises ValueError (PKG/mdp.py:170)
 }
 __device__ int discretise_f64(const dqlb200_config* cfg, int w, double rel_p, double rel_v, double rel_a, double pitch) {
+  if (rel_p != rel_p || rel_v != rel_v || rel_a != rel_a) return -1;   // fmin/fmax would swallow the NaN np.clip keeps
   const double p = clipd(__ddiv_rn(rel_p, cfg->p_max), -1.0, 1.0);
   const double v = clipd(__ddiv_rn(rel_v, cfg->v_max), -1.0, 1.0);
   const double a = clipd(__ddiv_rn(rel_a, cfg->a_max), -1.0, 1.0);
@@ -609,6 +678,49 @@ __global__ void facade_kernel(const dqlb200_config* __restrict__ cfg, int w, int
     s[1] = phi_p; s[2] = phi_v; s[3] = phi_t;
     s[4] = __dadd_rn(s[4], r);
     if (out_reward) out_reward[i] = r;
+  }
+}
+
+// Single-object DoubleQLearningAgent calls in float64 (the reference's table dtype).  One thread: the
+// facade is an API mirror, not a throughput path.
+__global__ void agent_facade_kernel(int op, long long n, double* t, int cs, const int32_t* state, const int32_t* action,
+                                    const int32_t* next_state, const double* alpha, const double* reward, double gamma,
+                                    int32_t* out_action) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  double* qa = t;
+  double* qb = t + CELLS;
+  double* cnt = t + 2 * CELLS;
+  if (op == DQLB200_AGENT_PREDICT) {
+    for (long long i = 0; i < n; ++i) {
+      const int s = state[i] * 3;
+      int a = 0;
+      double best = __ddiv_rn(__dadd_rn(qa[s], qb[s]), 2.0);
+      for (int k = 1; k < 3; ++k) {
+        const double v = __ddiv_rn(__dadd_rn(qa[s + k], qb[s + k]), 2.0);
+        if (v > best) { best = v; a = k; }
+      }
+      out_action[i] = a;
+    }
+  } else if (op == DQLB200_AGENT_UPDATE) {
+    for (long long i = 0; i < n; ++i) {
+      const int sa = state[i] * 3 + action[i];
+      const int s2 = next_state[i] * 3;
+      cnt[sa] = __dadd_rn(cnt[sa], 1.0);
+      int b = 0;
+      for (int k = 1; k < 3; ++k)
+        if (qa[s2 + k] > qa[s2 + b]) b = k;
+      const double changed = (((state[i] / 63) % 3) != ((next_state[i] / 63) % 3)) ? 1.0 : 0.0;
+      const double tgt = __dadd_rn(reward[i], __dmul_rn(__dmul_rn(gamma, qa[s2 + b]), changed));
+      qa[sa] = __dadd_rn(qa[sa], __dmul_rn(alpha[i], __dsub_rn(tgt, qa[sa])));
+    }
+  } else if (op == DQLB200_AGENT_TRANSFER) {
+    const int step = state[0];
+    const int src = (step - 1 + cs) % cs;
+    const double ratio = alpha[0];
+    for (int i = 0; i < DQLB200_CELLS_PER_LEVEL; ++i) {
+      qa[step * DQLB200_CELLS_PER_LEVEL + i] = __dmul_rn(qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+      qb[step * DQLB200_CELLS_PER_LEVEL + i] = __dmul_rn(qb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+    }
   }
 }
 
@@ -710,6 +822,8 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   memcpy(k.reward, c.reward, sizeof(k.reward));
   k.p_max = c.p_max; k.v_max = c.v_max; k.theta_max = c.theta_max; k.delta_theta = c.delta_theta;
   k.w_p = c.w_p; k.w_v = c.w_v; k.w_theta = c.w_theta;
+  k.rcp_p_max = 1.0 / c.p_max; k.rcp_v_max = 1.0 / c.v_max;
+  k.div_two_steps = (c.p_max == 4.5 && c.v_max == 3.39411) ? 0 : 1;
   memcpy(k.angle_cut, c.angle_cut, sizeof(k.angle_cut));
   k.fz_lo = c.fz_lo; k.fz_hi = c.fz_hi; k.z_min_cut = c.z_min_cut; k.z_max_cut = c.z_max_cut;
   k.h = c.h; k.half_h2 = c.half_h2; k.k_theta = c.k_theta; k.g = c.g; k.c_d = c.c_d;
@@ -747,7 +861,6 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   fill_kc(*cfg, h->kc);
   h->device = device;
   h->env_state = h->tables = h->pop_state = nullptr;
-  h->smem_bytes = sizeof(dql::Shared);
   CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
   CUDA_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(dqlb200_config), cudaMemcpyHostToDevice));
   const size_t lut_bytes = (size_t)cfg->n_alpha_luts * DQLB200_ALPHA_LUT * sizeof(float);
@@ -758,10 +871,19 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   CUDA_TRY(cudaMemcpy(h->d_pop_params, pop_params, pp_bytes, cudaMemcpyHostToDevice));
   CUDA_TRY(cudaMalloc(&h->d_error, sizeof(uint32_t)));
   CUDA_TRY(cudaMemset(h->d_error, 0, sizeof(uint32_t)));
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  {
+    const int tpb_ = cfg->threads_per_block;
+    const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
+    if (n_slots * 32 > 65535) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots)");
+    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * n_slots * 32 * sizeof(uint16_t);
+    if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
+  }
+#define DQL_SET_SMEM(W)                                                                                                   \
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
+#undef DQL_SET_SMEM
   *out = h;
   return DQLB200_OK;
 }
@@ -821,12 +943,17 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
   const int grid = h->cfg.n_populations;
   const size_t smem = h->smem_bytes;
+  const bool tracing = trace != nullptr;
+#define DQL_LAUNCH(W)                                                                        \
+  if (tracing) dql::train_kernel<W, true><<<grid, W * 32, smem, stream>>>(h->kc, a);         \
+  else dql::train_kernel<W, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
-    case 32: dql::train_kernel<1><<<grid, 32, smem, stream>>>(h->kc, a); break;
-    case 64: dql::train_kernel<2><<<grid, 64, smem, stream>>>(h->kc, a); break;
-    case 128: dql::train_kernel<4><<<grid, 128, smem, stream>>>(h->kc, a); break;
-    default: dql::train_kernel<8><<<grid, 256, smem, stream>>>(h->kc, a); break;
+    case 32: DQL_LAUNCH(1) break;
+    case 64: DQL_LAUNCH(2) break;
+    case 128: DQL_LAUNCH(4) break;
+    default: DQL_LAUNCH(8) break;
   }
+#undef DQL_LAUNCH
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
@@ -891,7 +1018,7 @@ int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream) {
 }
 
 int dqlb200_check_errors(dqlb200_handle* h, void* stream) {
-  if (!h || !h->pop_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (!h) return fail(DQLB200_ERR_ARG, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   uint32_t facade = 0;
@@ -901,7 +1028,7 @@ int dqlb200_check_errors(dqlb200_handle* h, void* stream) {
     return fail(DQLB200_ERR_DEVICE_FLAG, facade & 1u ? "Unexpected discretization case: NaN observation"
                                                      : (facade & 2u ? "Cannot check an empty state" : "Previous state missing"));
   }
-  for (int p = 0; p < h->cfg.n_populations; ++p) {
+  for (int p = 0; h->pop_state && p < h->cfg.n_populations; ++p) {
     dqlb200_population_state ps;
     CUDA_TRY(cudaMemcpy(&ps, (dqlb200_population_state*)h->pop_state + p, sizeof(ps), cudaMemcpyDeviceToHost));
     if (ps.error_flags) return fail(DQLB200_ERR_DEVICE_FLAG, "population " + std::to_string(p) + ": NaN observation (error_flags=" + std::to_string(ps.error_flags) + ")");
@@ -941,6 +1068,39 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
   CUDA_TRY(cudaSetDevice(h->device));
   dql::facade_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d_cfg, working_step, ops, n, obs, contact, action,
                                                                                    mdp_state, out_state, out_code, out_reward, h->d_error);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void* stream) {
+  if (!h || !mismatches_out) return fail(DQLB200_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  unsigned long long* d = nullptr;
+  CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+  dql::selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(h->kc, d);
+  CUDA_TRY(cudaGetLastError());
+  unsigned long long v[2] = {0, 0};
+  CUDA_TRY(cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_TRY(cudaFree(d));
+  mismatches_out[0] = v[0];
+  mismatches_out[1] = v[1];
+  return DQLB200_OK;
+}
+
+int dqlb200_agent_facade(dqlb200_handle* h, int op, int64_t n, double* tables_f64, const int32_t* state, const int32_t* action,
+                         const int32_t* next_state, const double* alpha, const double* reward, double gamma, int32_t* out_action,
+                         void* stream) {
+  if (!h || !tables_f64 || !state) return fail(DQLB200_ERR_ARG, "null argument");
+  if (op == DQLB200_AGENT_PREDICT && !out_action) return fail(DQLB200_ERR_ARG, "out_action required");
+  if (op == DQLB200_AGENT_UPDATE && (!action || !next_state || !alpha || !reward)) return fail(DQLB200_ERR_ARG, "update operands required");
+  if (op == DQLB200_AGENT_TRANSFER && !alpha) return fail(DQLB200_ERR_ARG, "ratio required");
+  if (op != DQLB200_AGENT_PREDICT && op != DQLB200_AGENT_UPDATE && op != DQLB200_AGENT_TRANSFER) return fail(DQLB200_ERR_ARG, "unknown op");
+  if (n <= 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  dql::agent_facade_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(op, n, tables_f64, h->cfg.curriculum_steps, state, action, next_state,
+                                                            alpha, reward, gamma, out_action);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

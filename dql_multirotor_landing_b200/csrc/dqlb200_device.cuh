@@ -24,6 +24,7 @@ struct KC {
   dqlb200_cuts cuts[DQLB200_MAX_CURRICULUM];
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   double p_max, v_max, theta_max, delta_theta, w_p, w_v, w_theta;
+  double rcp_p_max, rcp_v_max;   // RN(1/p_max), RN(1/v_max) for div_f32_by_const
   float angle_cut[6];
   float fz_lo, fz_hi, z_min_cut, z_max_cut;
   float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
@@ -33,6 +34,7 @@ struct KC {
   int32_t timeout_steps, success_steps, n_sub;
   int32_t transfer_mode, window_len, promote_successes;
   int32_t curriculum_steps, envs_per_population, n_populations;
+  int32_t div_two_steps;        // 0 only for the exhaustively verified default divisors
   long long max_num_episodes;
 };
 
@@ -46,9 +48,9 @@ __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b)
 __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
 #pragma unroll
   for (int i = 0; i < 10; ++i) {
-    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
-    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
-    c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+    const unsigned long long p0 = (unsigned long long)0xD2511F53u * c.x;   // one IMAD.WIDE each
+    const unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c.z;
+    c = make_uint4((uint32_t)(p1 >> 32) ^ c.y ^ k0, (uint32_t)p1, (uint32_t)(p0 >> 32) ^ c.w ^ k1, (uint32_t)p0);
     k0 += 0x9E3779B9u;
     k1 += 0xBB67AE85u;
   }
@@ -215,9 +217,29 @@ __device__ __forceinline__ double apply_action(const KC& kc, double theta_sp, in
   return theta_sp;
 }
 
-// Shaping potential of one observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
-__device__ __forceinline__ double shaping(double w, double x, double x_max) {
-  return __dmul_rn(w, fabs(clipd(__ddiv_rn(x, x_max), -1.0, 1.0)));
+// Correctly rounded (double)x / d for a finite fp32 numerator x and a constant divisor d, rcp = RN(1/d):
+// q0 = RN(x*rcp);  r = x - q0*d (exact in one FMA);  q = RN(q0 + r*rcp)   (Markstein's correction step).
+// Three instructions instead of the ~25 + slow path of the generic __ddiv_rn (which is taken for zero
+// numerators).  For the reference's divisors (p_max = 4.5, v_max = 3.39411) one correction step is verified
+// EXHAUSTIVELY on the device against __ddiv_rn for all finite fp32 numerators (dqlb200_selftest_division,
+// tests/test_gpu_parity.py); for any other divisor a second step is added (`two_steps`), which is exact
+// whenever the first step is faithful.  |q| is only ever used through fabs/clip, so the sign of a zero
+// quotient is irrelevant.
+__device__ __forceinline__ double div_f32_by_const(float x, double d, double rcp, bool two_steps) {
+  const double xd = (double)x;
+  double q = __dmul_rn(xd, rcp);
+  q = __fma_rn(__fma_rn(-q, d, xd), rcp, q);
+  if (two_steps) q = __fma_rn(__fma_rn(-q, d, xd), rcp, q);
+  return q;
+}
+
+// generic float64 division that skips the (slow) zero-numerator path; callers only use |result| or add it
+// to a non-zero sum, so the sign of zero does not matter
+__device__ __forceinline__ double div_guard0(double x, double d) { return (x == 0.0) ? 0.0 : __ddiv_rn(x, d); }
+
+// Shaping potential of one fp32 observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
+__device__ __forceinline__ double shaping(double w, float x, double x_max, double rcp, bool two_steps) {
+  return __dmul_rn(w, fabs(clipd(div_f32_by_const(x, x_max, rcp, two_steps), -1.0, 1.0)));
 }
 
 // R7 with the level-dependent constants pre-evaluated on the host.
@@ -227,7 +249,7 @@ __device__ __forceinline__ double reward_f64(const KC& kc, const dqlb200_reward_
   const double r_p = clipd(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
   const double r_v = clipd(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
   const double r_t =
-      __dmul_rn(__ddiv_rn(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max), rl.lim_v);
+      __dmul_rn(div_guard0(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max), rl.lim_v);
   const double r_term = success ? rl.r_term_succ : rl.r_term_fail;
   return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
 }

@@ -105,6 +105,13 @@ class Engine:
         _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
                                                pop_state_host.data_ptr(), self._stream()))
 
+    def selftest_division(self) -> int:
+        """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""
+        out = (C.c_uint64 * 2)()
+        _ffi.check(self.lib.dqlb200_selftest_division(self.handle, out, self._stream()))
+        self.selftest_one_step_mismatches = int(out[1])
+        return int(out[0])
+
     def check_errors(self):
         _ffi.check(self.lib.dqlb200_check_errors(self.handle, self._stream()))
 

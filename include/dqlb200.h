@@ -236,6 +236,25 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
                             double* mdp_state, uint16_t* out_state, uint8_t* out_code, double* out_reward,
                             void* stream);
 
+/* Device self-test: the 3-instruction float64 division used for fp32 numerators (x / p_max, x / v_max) against
+ * the IEEE division for every finite fp32 bit pattern; mismatches_out[0] = wrong quotients of the production
+ * routine (must be 0), mismatches_out[1] = of the one-correction-step variant (diagnostic).  Synchronises. */
+int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void* stream);
+
+/* Facade kernel behind single-object DoubleQLearningAgent calls, float64 like the reference's tables
+ * (PKG/double_q_learning.py:38-40).  tables_f64: device [3][DQLB200_MAX_CELLS] doubles (Q_a, Q_b, count).
+ *   DQLB200_AGENT_PREDICT : out_action[i] = argmax((Q_a[s_i] + Q_b[s_i]) / 2)          (PKG/double_q_learning.py:119-124)
+ *   DQLB200_AGENT_UPDATE  : for i in order: count[sa_i] += 1; Q_a[sa_i] += alpha_i * (reward_i + (gamma * max Q_a[s'_i])
+ *                           * [p-bin changed] - Q_a[sa_i])                               (PKG/double_q_learning.py:91-108,126-146)
+ *   DQLB200_AGENT_TRANSFER: Q_{a,b}[step] = Q_{a,b}[step-1] * ratio  (step = state[0], ratio = alpha[0]; :77-89)
+ * state / next_state are state ids (< 945), action in 0..2; all pointers are device pointers. */
+#define DQLB200_AGENT_PREDICT 1
+#define DQLB200_AGENT_UPDATE 2
+#define DQLB200_AGENT_TRANSFER 4
+int dqlb200_agent_facade(dqlb200_handle* h, int op, int64_t n, double* tables_f64, const int32_t* state,
+                         const int32_t* action, const int32_t* next_state, const double* alpha,
+                         const double* reward, double gamma, int32_t* out_action, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,178 @@
+"""GPU tests of the drop-in Python classes (TrainingMdp / SimulationMdp / DoubleQLearningAgent / Trainer): written the
+way tests of the reference classes would read, checked against fixtures generated from the unmodified reference."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+F_AG, T_MAX, P_MAX = 22.92, 20, 4.5
+
+
+def _obs(rel_p=0.0, rel_v=0.0, rel_a=0.0, pitch=0.0, z=3.0, contact=False, rel_p_y=0.0):
+    from dql_multirotor_landing_b200.mdp import ContinuousObservation
+    from dql_multirotor_landing_b200.msg import Observation
+    return ContinuousObservation(Observation(rel_p_x=float(rel_p), rel_v_x=float(rel_v), rel_a_x=float(rel_a), rel_p_y=float(rel_p_y),
+                                             contact=bool(contact)), float(pitch), 0.0, float(z))
+
+
+def test_known_answers_goal_state():
+    """MDP held at the origin reaches TERMINAL_SUCCESS at step 23 with r = 12.879109319249501."""
+    from dql_multirotor_landing_b200.mdp import TrainingMdp
+    m = TrainingMdp(0, F_AG, T_MAX, P_MAX)
+    m.reset()
+    assert m.discrete_state(_obs()) == (0, 1, 1, 1, 3)
+    for k in range(1, 24):
+        m.continuous_action(2)
+        assert m.discrete_state(_obs()) == (0, 1, 1, 1, 3)
+        info = m.check()
+        assert m.reward() == 12.879109319249501
+        assert ("Termination condition" in info) == (k == 23)
+    assert info["Termination condition"] == "SUCCESS: Goal state reached" and info["Number of steps"] == 23
+    assert info["Cumulative reward"] == 283.3404050234889
+
+
+def test_known_answers_timeout_and_discretisation():
+    from dql_multirotor_landing_b200.mdp import TrainingMdp
+    m = TrainingMdp(0, F_AG, T_MAX, P_MAX)
+    m.reset()
+    m.discrete_state(_obs(rel_p=3.0))
+    rewards, info = [], {}
+    for k in range(1, 460):
+        m.continuous_action(2)
+        assert m.discrete_state(_obs(rel_p=3.0)) == (0, 2, 1, 1, 3)
+        info = m.check()
+        rewards.append(m.reward())
+        assert ("Termination condition" in info) == (k == 459)
+    assert rewards[0] == -17.765671273874283 and rewards[1] == -13.402669528673584
+    assert info["Termination condition"] == "FAILURE: Maximum episode duration"
+    for w, want in ((0, (0, 1, 1, 1, 4)), (1, (1, 0, 1, 1, 4)), (3, (3, 0, 1, 1, 4)), (4, (3, 0, 1, 1, 4))):
+        mm = TrainingMdp(w, F_AG, T_MAX, P_MAX)
+        mm.reset()
+        assert mm.discrete_state(_obs(-1.0, 0.5, 0.1, 0.1)) == want
+    mm = TrainingMdp(2, F_AG, T_MAX, P_MAX)
+    mm.reset()
+    assert mm.discrete_state(_obs(-4.6, 5, 2, 1)) == (0, 0, 2, 2, 6)
+
+
+def test_value_errors_like_the_reference():
+    from dql_multirotor_landing_b200.mdp import TrainingMdp
+    m = TrainingMdp(0, F_AG, T_MAX, P_MAX)
+    m.reset()
+    with pytest.raises(ValueError):
+        m.check()                                  # PKG/mdp.py:352-356
+    m.discrete_state(_obs())
+    with pytest.raises(ValueError):
+        m.reward()                                 # PKG/mdp.py:442-447
+    with pytest.raises(ValueError):
+        m.continuous_action(0, 1)                  # PKG/mdp.py:544-545
+    with pytest.raises(ValueError):
+        m.discrete_state(_obs(rel_p=float("nan")))  # PKG/mdp.py:170
+
+
+@pytest.mark.parametrize("name", ["w0", "w3", "lowz", "highz"])
+def test_training_mdp_against_reference_fixture(golden_dir, name):
+    from dql_multirotor_landing_b200.mdp import TrainingMdp, state_id
+    g = np.load(golden_dir / f"mdp_trace_{name}.npz")
+    m = TrainingMdp(int(g["w"]), F_AG, T_MAX, P_MAX)
+    for i in range(min(len(g["action"]), 700)):
+        o = g["obs"][i].astype(np.float64)
+        if g["action"][i] == 255:
+            m.reset()
+            assert state_id(m.discrete_state(_obs(o[0], o[1], o[2], o[3], o[4], g["contact"][i]))) == g["state"][i]
+            continue
+        assert m.continuous_action(int(g["action"][i])).pitch == g["theta_sp"][i]
+        s = m.discrete_state(_obs(o[0], o[1], o[2], o[3], o[4], g["contact"][i]))
+        info = m.check()
+        r = m.reward()
+        assert state_id(s) == g["state"][i] and ("Termination condition" in info) == bool(g["done"][i]), i
+        assert r == g["reward"][i], i
+        if g["done"][i]:
+            from dql_multirotor_landing_b200 import constants as K
+            assert info["Termination condition"] == K.TERMINATION_STRINGS[int(g["code"][i])]
+
+
+def test_simulation_mdp_against_reference_fixture(golden_dir):
+    from dql_multirotor_landing_b200.mdp import SimulationMdp, state_id
+    g = np.load(golden_dir / "sim_trace.npz")
+    m = SimulationMdp(4, F_AG, T_MAX)
+    for i in range(len(g["action"])):
+        o = g["obs"][i].astype(np.float64)
+        if g["action"][i] == 255:
+            m.reset()
+            sx, sy = m.discrete_state(_obs(o[0], o[1], o[2], o[3], o[4], g["contact"][i]))
+            assert state_id(sx) == g["state"][i] and sy == (4, 1, 1, 1, 3)
+            continue
+        m.continuous_action(int(g["action"][i]), 2)
+        sx, _ = m.discrete_state(_obs(o[0], o[1], o[2], o[3], o[4], g["contact"][i]))
+        info = m.check()
+        assert state_id(sx) == g["state"][i] and ("Termination condition" in info) == bool(g["done"][i]), i
+
+
+def test_agent_float64_replay_exact(golden_dir, monkeypatch):
+    """DoubleQLearningAgent.guess/update with the reference's float64 tables: fed the fixture's transitions and the same
+    draws, actions and final tables are identical to the reference's (float64 ==)."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.double_q_learning import DoubleQLearningAgent
+    from dql_multirotor_landing_b200.mdp import state_tuple
+    from oracle import philox
+    g = np.load(golden_dir / "replay_w0_float64_ep1950.npz")
+    agent = DoubleQLearningAgent(5)
+    queue = []
+    monkeypatch.setattr(np.random, "uniform", lambda lo=0.0, hi=1.0, size=None: float(philox.uniform01(queue.pop(0))))
+    monkeypatch.setattr(np.random, "randint", lambda n: int(philox.random_action(queue.pop(0))))
+    idx = np.asarray([0])
+    n = 1500
+    for t in range(n):
+        w = philox.draws(int(g["seed"]), 0, idx, t, philox.PURPOSE_STEP)
+        queue[:] = [w[0][0], w[1][0], w[2][0]]
+        s, s2 = state_tuple(int(g["state"][t])), state_tuple(int(g["next_state"][t]))
+        a = agent.guess(s, K.exploration_rate(int(g["episode"][t]), 0))
+        assert a == g["action"][t], t
+        agent.update(s + (a,), s2, float(g["alpha"][t]), 0.99, float(g["reward"][t]))
+        assert not queue
+    # replay the same prefix on the oracle side to get the reference tables after n steps
+    from oracle.agent_oracle import AgentOracle
+    ref = AgentOracle(5, np.float64)
+    for t in range(n):
+        s, s2 = state_tuple(int(g["state"][t])), state_tuple(int(g["next_state"][t]))
+        ref.update(s + (int(g["action"][t]),), s2, float(g["alpha"][t]), float(g["reward"][t]))
+    assert np.array_equal(agent.Q_table_a, ref.qa) and np.array_equal(agent.state_action_counter, ref.count)
+
+
+def test_agent_save_load_transfer(tmp_path, golden_dir):
+    from dql_multirotor_landing_b200.double_q_learning import DoubleQLearningAgent
+    agent = DoubleQLearningAgent.load()                       # committed assets
+    assert agent.Q_table_a.shape == (5, 3, 3, 3, 7, 3) and agent.Q_table_a.dtype == np.float64
+    ref_a = np.load(golden_dir.parent.parent / "assets" / "Q_table_a.npy")
+    assert agent.predict((4, 1, 1, 1, 3)) == int(np.argmax((ref_a[4, 1, 1, 1, 3] + agent.Q_table_b[4, 1, 1, 1, 3]) / 2))
+    agent.transfer_learning(2, 0.8211253690681617)
+    assert np.array_equal(agent.Q_table_a[2], ref_a[1] * 0.8211253690681617)
+    agent.transfer_learning(0, 1.0)                           # quirk Q7: slot 0 <- slot -1
+    assert np.array_equal(agent.Q_table_a[0], ref_a[4])
+    agent.save(tmp_path)
+    again = DoubleQLearningAgent.load(tmp_path)
+    assert np.array_equal(again.Q_table_a, agent.Q_table_a) and np.array_equal(again.state_action_counter, agent.state_action_counter)
+    raw = (tmp_path / "Q_table_a.npy").read_bytes()
+    assert raw[:6] == b"\x93NUMPY" and raw[6:8] == b"\x01\x00" and b"'<f8'" in raw[:128] and b"(5, 3, 3, 3, 7, 3)" in raw[:128]
+
+
+def test_trainer_schedules_and_short_curriculum(tmp_path):
+    from dql_multirotor_landing_b200.trainer import Trainer
+    tr = Trainer(save_path=tmp_path / "run", successive_successful_episodes=5, success_rate=0.2, max_num_episodes=60,
+                 num_envs=64, chunk_steps=32, threads_per_block=64, verbose=False, max_global_steps=4000)
+    assert tr.alpha((0, 1, 1, 1, 3, 2)) == 0.02949 and tr.exploration_rate(900, 0) == 0.9175
+    assert tr.transfer_learning_ratio(0) == 1.0 and tr.transfer_learning_ratio(1) == 0.8172650252856599
+    with pytest.raises(ValueError):
+        tr.transfer_learning_ratio(5)
+    info = tr.curriculum_training()
+    assert "Termination condition" in info and (tmp_path / "run" / "trainer.pickle").exists()
+    for name in ("Q_table_a.npy", "Q_table_b.npy", "state_action_count.npy"):
+        assert (tmp_path / "run" / name).exists() and (tmp_path / name).exists()      # dual save, PKG/trainer.py:148-152
+    agent = tr._double_q_learning_agent
+    assert agent.state_action_counter.sum() > 0 and agent.state_action_counter.dtype == np.float64
+    ps = tr._engine.population_state()[0]
+    assert ps["finished"] == 1 and agent.state_action_counter.sum() == ps["total_steps"]
+    import pickle
+    again = pickle.load(open(tmp_path / "run" / "trainer.pickle", "rb"))
+    assert np.array_equal(again._double_q_learning_agent.Q_table_a, agent.Q_table_a)

@@ -28,6 +28,13 @@ def _engine(P, n_p, **kw):
     return Engine(P, n_p, tp=tp, dp=dp, **kw)
 
 
+def test_fast_division_is_exact_for_every_fp32_numerator():
+    """div_f32_by_const (3 instructions) == IEEE float64 division for all 2^32 fp32 numerators, both divisors."""
+    eng = _engine(1, 1, threads_per_block=32)
+    assert eng.selftest_division() == 0
+    print("one-correction-step variant mismatches:", eng.selftest_one_step_mismatches)
+
+
 @pytest.mark.parametrize("name", ["w0", "w1", "w2", "w3", "w4", "lowz", "highz"])
 def test_mdp_trace_forced_actions(golden_dir, name):
     """R3-R8: forced action sequences; every integer output and the float64 reward equal the reference's."""

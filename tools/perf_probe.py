@@ -19,7 +19,6 @@ def run(P, n_p, tpb, k, reps=3):
     eng.close()
 
 if __name__ == "__main__":
-    for (P, n_p, tpb, k) in [(148, 7168, 256, 32), (296, 3584, 256, 32), (592, 1792, 128, 32), (592, 1792, 256, 32),
-                             (1184, 896, 128, 32), (1184, 896, 64, 32), (2368, 448, 64, 32), (4736, 224, 32, 32),
-                             (296, 3584, 256, 1), (1, 65536, 256, 8)]:
+    for (P, n_p, tpb, k) in [(592, 1792, 128, 32), (740, 1434, 128, 32), (740, 1408, 128, 32), (888, 1195, 128, 32), (1480, 717, 64, 32), (370, 2868, 256, 32), (444, 2390, 256, 32),
+                             (592, 1792, 128, 1), (740, 1434, 128, 1), (1, 65536, 256, 8)]:
         run(P, n_p, tpb, k)
