@@ -266,10 +266,10 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         // R7 (float64, reference operation order; level-dependent constants from the host)
         const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
         const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
-        const double phi_t = __dmul_rn(kc.w_theta, fabs(div_guard0(sp, kc.theta_max)));
+        const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
         const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
         const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
-        const double prev_t = __dmul_rn(kc.w_theta, fabs(div_guard0(prev_sp, kc.theta_max)));
+        const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
         const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
         // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
@@ -482,8 +482,23 @@ __global__ void selftest_division_kernel(const __grid_constant__ KC kc, unsigned
       bad1 += __double_as_longlong(fabs(q1)) != __double_as_longlong(fabs(exact));
     }
   }
+  // float64 numerators (set-points, set-point differences): 2^32 pseudo-random values in [-1, 1] with all
+  // 52 mantissa bits random, exponents spread over 2^-40 .. 2^0, plus the multiples of delta_theta
+  unsigned long long bad2 = 0;
+  for (unsigned long long b = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; b < (1ull << 32);
+       b += (unsigned long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(make_uint4((uint32_t)b, 0u, 7u, 0u), 0x5EEDu, 0u);
+    const unsigned long long mant = (((unsigned long long)r.x << 32) | r.y) & 0x000FFFFFFFFFFFFFull;
+    const unsigned long long expo = 1023ull - (unsigned long long)(r.z % 41u);
+    const unsigned long long sign = (unsigned long long)(r.w & 1u) << 63;
+    double x = __longlong_as_double((long long)(sign | (expo << 52) | mant));
+    if (b < 16) x = (double)((long long)b - 8) * kc.delta_theta;
+    const double q = div_f64_by_const(x, kc.theta_max, kc.rcp_theta_max);
+    bad2 += __double_as_longlong(fabs(q)) != __double_as_longlong(fabs(__ddiv_rn(x, kc.theta_max)));
+  }
   if (bad) atomicAdd(mismatches, bad);
   if (bad1) atomicAdd(mismatches + 1, bad1);
+  if (bad2) atomicAdd(mismatches + 2, bad2);
 }
 
 // -------------------------------------------------------------------------------------------------
@@ -822,7 +837,7 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   memcpy(k.reward, c.reward, sizeof(k.reward));
   k.p_max = c.p_max; k.v_max = c.v_max; k.theta_max = c.theta_max; k.delta_theta = c.delta_theta;
   k.w_p = c.w_p; k.w_v = c.w_v; k.w_theta = c.w_theta;
-  k.rcp_p_max = 1.0 / c.p_max; k.rcp_v_max = 1.0 / c.v_max;
+  k.rcp_p_max = 1.0 / c.p_max; k.rcp_v_max = 1.0 / c.v_max; k.rcp_theta_max = 1.0 / c.theta_max;
   k.div_two_steps = (c.p_max == 4.5 && c.v_max == 3.39411) ? 0 : 1;
   memcpy(k.angle_cut, c.angle_cut, sizeof(k.angle_cut));
   k.fz_lo = c.fz_lo; k.fz_hi = c.fz_hi; k.z_min_cut = c.z_min_cut; k.z_max_cut = c.z_max_cut;
@@ -1076,16 +1091,17 @@ int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void*
   if (!h || !mismatches_out) return fail(DQLB200_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));
   unsigned long long* d = nullptr;
-  CUDA_TRY(cudaMalloc(&d, 2 * sizeof(unsigned long long)));
-  CUDA_TRY(cudaMemsetAsync(d, 0, 2 * sizeof(unsigned long long), (cudaStream_t)stream));
+  CUDA_TRY(cudaMalloc(&d, 3 * sizeof(unsigned long long)));
+  CUDA_TRY(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), (cudaStream_t)stream));
   dql::selftest_division_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(h->kc, d);
   CUDA_TRY(cudaGetLastError());
-  unsigned long long v[2] = {0, 0};
+  unsigned long long v[3] = {0, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(v, d, sizeof(v), cudaMemcpyDeviceToHost, (cudaStream_t)stream));
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
   CUDA_TRY(cudaFree(d));
   mismatches_out[0] = v[0];
   mismatches_out[1] = v[1];
+  mismatches_out[2] = v[2];
   return DQLB200_OK;
 }
 

@@ -24,7 +24,7 @@ struct KC {
   dqlb200_cuts cuts[DQLB200_MAX_CURRICULUM];
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   double p_max, v_max, theta_max, delta_theta, w_p, w_v, w_theta;
-  double rcp_p_max, rcp_v_max;   // RN(1/p_max), RN(1/v_max) for div_f32_by_const
+  double rcp_p_max, rcp_v_max, rcp_theta_max;   // RN(1/x) for div_f32_by_const / div_f64_by_const
   float angle_cut[6];
   float fz_lo, fz_hi, z_min_cut, z_max_cut;
   float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
@@ -233,9 +233,19 @@ __device__ __forceinline__ double div_f32_by_const(float x, double d, double rcp
   return q;
 }
 
-// generic float64 division that skips the (slow) zero-numerator path; callers only use |result| or add it
-// to a non-zero sum, so the sign of zero does not matter
-__device__ __forceinline__ double div_guard0(double x, double d) { return (x == 0.0) ? 0.0 : __ddiv_rn(x, d); }
+// Correctly rounded x / d for a float64 numerator of ordinary magnitude (|x| in [2^-900, 2^900] or zero) and a
+// constant divisor d with rcp = RN(1/d): q0 = RN(x*rcp) has relative error < 2^-52; the first correction step
+// (exact residual in one FMA) makes it faithful, the second one correctly rounded (Markstein 1990, Cornea et al.
+// 1999: q' = RN(q + r*y) = RN(a/b) when y = RN(1/b) and q is faithful).  Five instructions, no slow path for
+// zero numerators (the generic __ddiv_rn takes a ~90-instruction subroutine for them, and set-points and
+// set-point differences are zero most of the time).  Cross-checked against __ddiv_rn on 2^32 random numerators by
+// dqlb200_selftest_division.  Callers use |q| or add q to a non-zero sum: the sign of a zero quotient is irrelevant.
+__device__ __forceinline__ double div_f64_by_const(double x, double d, double rcp) {
+  double q = __dmul_rn(x, rcp);
+  q = __fma_rn(__fma_rn(-q, d, x), rcp, q);
+  q = __fma_rn(__fma_rn(-q, d, x), rcp, q);
+  return q;
+}
 
 // Shaping potential of one fp32 observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
 __device__ __forceinline__ double shaping(double w, float x, double x_max, double rcp, bool two_steps) {
@@ -249,7 +259,7 @@ __device__ __forceinline__ double reward_f64(const KC& kc, const dqlb200_reward_
   const double r_p = clipd(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
   const double r_v = clipd(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
   const double r_t =
-      __dmul_rn(div_guard0(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max), rl.lim_v);
+      __dmul_rn(div_f64_by_const(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max, kc.rcp_theta_max), rl.lim_v);
   const double r_term = success ? rl.r_term_succ : rl.r_term_fail;
   return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
 }

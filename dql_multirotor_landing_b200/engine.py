@@ -107,10 +107,10 @@ class Engine:
 
     def selftest_division(self) -> int:
         """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""
-        out = (C.c_uint64 * 2)()
+        out = (C.c_uint64 * 3)()
         _ffi.check(self.lib.dqlb200_selftest_division(self.handle, out, self._stream()))
         self.selftest_one_step_mismatches = int(out[1])
-        return int(out[0])
+        return int(out[0]) + int(out[2])
 
     def check_errors(self):
         _ffi.check(self.lib.dqlb200_check_errors(self.handle, self._stream()))

@@ -238,7 +238,8 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
 
 /* Device self-test: the 3-instruction float64 division used for fp32 numerators (x / p_max, x / v_max) against
  * the IEEE division for every finite fp32 bit pattern; mismatches_out[0] = wrong quotients of the production
- * routine (must be 0), mismatches_out[1] = of the one-correction-step variant (diagnostic).  Synchronises. */
+ * routine (must be 0), [1] = of the one-correction-step variant (diagnostic), [2] = of the float64-numerator
+ * routine used for x / theta_max on 2^32 pseudo-random numerators (must be 0).  Synchronises. */
 int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void* stream);
 
 /* Facade kernel behind single-object DoubleQLearningAgent calls, float64 like the reference's tables
