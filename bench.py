@@ -49,7 +49,7 @@ def workload_config(n_gpus: int) -> dict:
         "global_steps_per_launch": 1, "e2e_global_steps_per_call": E2E_CHUNK,
         "threads_per_block": THREADS_PER_BLOCK, "parallelism": f"population-partitioned x{n_gpus}, no collective",
         "l2": "flushed (256 MiB write) between timed launches; env state 51 MB < L2",
-        "rng": "Philox4x32-10, seeds 0..P-1 per rank", "platform_speeds": [0.4, 0.8, 1.2, 1.6],
+        "rng": "Philox4x32-10, key = seed (5 seeds per sweep point), counter word 3 = global population id", "platform_speeds": [0.4, 0.8, 1.2, 1.6],
         "alpha_variants": [[0.02949, 0.51], [0.05, 0.6]],
     }
 
@@ -169,12 +169,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             dist.barrier()
         torch.cuda.synchronize(dev)
 
+    from dql_multirotor_landing_b200 import parallel
     P, n_p = POPULATIONS_PER_GPU, ENVS_PER_POPULATION
     speeds = [0.4, 0.8, 1.2, 1.6]
     variants = [(0.02949, 0.51), (0.05, 0.6)]
-    eng = Engine(P, n_p, device=local_rank, threads_per_block=THREADS_PER_BLOCK,
-                 seeds=[rank * P + p for p in range(P)], population_ids=[rank * P + p for p in range(P)],
-                 v_mp=[speeds[p % 4] for p in range(P)], alpha_variants=variants, alpha_index=[(p // 4) % 2 for p in range(P)],
+    mine = parallel.partition_populations(P * world, world, rank)          # global population ids of this rank
+    seeds, v_mp, alpha_index = parallel.sweep_axes(mine, 5, speeds, len(variants))
+    eng = Engine(P, n_p, device=local_rank, threads_per_block=THREADS_PER_BLOCK, seeds=seeds, population_ids=list(mine),
+                 v_mp=v_mp, alpha_variants=variants, alpha_index=alpha_index,
                  tp=K.TrainerParameters(max_num_episodes=10 ** 12, success_rate=2.0))   # stay in curriculum step 0 while timing
     eng.reset(0)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)

@@ -1,0 +1,69 @@
+"""Multi-GPU plumbing (one process per GPU, torch.distributed).
+
+The path shards by POPULATION: every rank owns a disjoint set of agents (Q-table pairs) with their envs, so the
+data path needs no collective (bench.py, `"scaling": "weak"`).  The only exchange step is the optional
+shared-table mode: one agent replicated on G ranks, merged every `sync_every` global steps by ONE all-reduce
+(SUM) of a fused [sum(dQ_a * dcount) | dcount] buffer (2 x 2835 floats per population, NCCL over NVLink on
+GPUs, gloo in the CPU tests) -- see csrc/dqlb200.cu: shared_pack_kernel / shared_apply_kernel.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition_populations(total: int, world_size: int, rank: int) -> range:
+    """Contiguous block partition of population ids 0..total-1; sizes differ by at most one."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    base, extra = divmod(total, world_size)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def sweep_axes(population_ids: Sequence[int], seeds_per_point: int, speeds: Sequence[float], n_alpha: int
+               ) -> Tuple[List[int], List[float], List[int]]:
+    """seed x platform-speed x learning-rate sweep (BASELINE config 5): global population id -> (seed, v_mp, alpha variant).
+    The mapping depends only on the GLOBAL id, so a population's trajectory is independent of how many GPUs run."""
+    seeds, v_mp, alpha = [], [], []
+    for g in population_ids:
+        point, seed = divmod(g, seeds_per_point)
+        seeds.append(seed)
+        v_mp.append(speeds[point % len(speeds)])
+        alpha.append((point // len(speeds)) % n_alpha)
+    return seeds, v_mp, alpha
+
+
+def max_over_ranks(values: Sequence[float], device: Optional[torch.device] = None) -> List[float]:
+    """Device-timed numbers are reported as the maximum over ranks."""
+    t = torch.tensor(list(values), dtype=torch.float64, device=device)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return [float(x) for x in t]
+
+
+def merge_deltas(delta: torch.Tensor) -> torch.Tensor:
+    """All-reduce (SUM) of the packed delta buffer [P, 3, CELLS] in place; returns it."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
+    return delta
+
+
+class SharedTableSync:
+    """Shared-table mode for an Engine whose populations are replicated on every rank."""
+
+    def __init__(self, engine):
+        import ctypes as C
+        from . import _ffi
+        self._C, self._ffi, self.engine = C, _ffi, engine
+        self.snapshot = engine.tables.clone()
+        self.delta = torch.zeros(engine.tables.shape, dtype=torch.float32, device=engine.device)
+
+    def sync(self):
+        """tables <- snapshot + visit-weighted mean of every replica's dQ_a; counts <- snapshot + sum of dcounts."""
+        e, C = self.engine, self._C
+        self._ffi.check(e.lib.dqlb200_shared_pack(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()), e._stream()))
+        merge_deltas(self.delta)
+        self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()), e._stream()))

@@ -241,3 +241,89 @@ def test_eval_greedy_fixture_and_oracle(golden_dir):
     assert big["episodes"] == 1 << 16 and sum(big["termination_hist"]) == 1 << 16
     assert big["termination_hist"][0] == 0 and big["termination_hist"][1] == 0
     assert big["termination_hist"][3] / big["episodes"] > 0.85
+
+
+def test_shared_table_mode_merge():
+    """Shared-table mode kernels: with one replica the sync leaves the tables bit-identical (== no-collective mode);
+    with two replicas (the all-reduce is emulated by adding the two delta buffers: the gloo test covers the
+    collective itself) Q is the visit-weighted mean of the replicas' deltas and the counts add up."""
+    from dql_multirotor_landing_b200.parallel import SharedTableSync
+    engs, syncs = [], []
+    for r in range(2):
+        e = _engine(1, 256, threads_per_block=64, seeds=[10 + r], population_ids=[r], tp=NO_PROMOTION)
+        e.reset(0)
+        engs.append(e)
+        syncs.append(SharedTableSync(e))
+    for e in engs:
+        e.train(40)
+    torch.cuda.synchronize()
+    before = [e.tables.cpu().numpy().copy() for e in engs]
+    # G = 1: pack + apply without any other replica
+    syncs[0].sync()
+    torch.cuda.synchronize()
+    assert np.array_equal(engs[0].tables.cpu().numpy(), before[0])
+    assert np.array_equal(syncs[0].snapshot.cpu().numpy(), before[0])
+    # G = 2 (fresh engines so that both start from the same snapshot)
+    engs, syncs = [], []
+    for r in range(2):
+        e = _engine(1, 256, threads_per_block=64, seeds=[10 + r], population_ids=[r], tp=NO_PROMOTION)
+        e.reset(0)
+        engs.append(e)
+        syncs.append(SharedTableSync(e))
+        e.train(40)
+    torch.cuda.synchronize()
+    tabs = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
+    lib = engs[0].lib
+    import ctypes as C
+    for e, s in zip(engs, syncs):
+        lib.dqlb200_shared_pack(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
+    total = syncs[0].delta + syncs[1].delta
+    for e, s in zip(engs, syncs):
+        s.delta.copy_(total)
+        lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
+    torch.cuda.synchronize()
+    out = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
+    assert np.array_equal(out[0], out[1])                         # replicas agree after the merge
+    cnt = [t[0, 2].astype(np.float64) for t in tabs]
+    q = [t[0, 0].view(np.float32).astype(np.float64) for t in tabs]
+    assert np.array_equal(out[0][0, 2], (cnt[0] + cnt[1]).astype(np.uint32))
+    both = (cnt[0] + cnt[1]) > 0
+    want = np.where(both, (q[0] * cnt[0] + q[1] * cnt[1]) / np.maximum(cnt[0] + cnt[1], 1), 0.0)
+    np.testing.assert_allclose(out[0][0, 0].view(np.float32), want, rtol=2e-6, atol=1e-5)
+
+
+def test_full_size_properties():
+    """BASELINE configs[4] shard at full size (740 populations x 1434 envs = 1,061,160 envs): properties that do not
+    need an oracle run -- every env-step is one counted Q-update, runs are reproducible, and a population's result is
+    independent of which other populations share the GPU (bit-identical when run alone)."""
+    from dql_multirotor_landing_b200 import parallel
+    P, n_p, steps = 740, 1434, 48
+    ids = list(range(P))
+    seeds, v_mp, aidx = parallel.sweep_axes(ids, 5, [0.4, 0.8, 1.2, 1.6], 2)
+    variants = [(0.02949, 0.51), (0.05, 0.6)]
+
+    def run(pop_ids, tpb):
+        sel = [ids.index(i) for i in pop_ids]
+        e = _engine(len(sel), n_p, threads_per_block=tpb, seeds=[seeds[i] for i in sel], population_ids=[ids[i] for i in sel],
+                    v_mp=[v_mp[i] for i in sel], alpha_variants=variants, alpha_index=[aidx[i] for i in sel], tp=NO_PROMOTION)
+        e.reset(0)
+        e.train(16)
+        e.train(steps - 16)
+        e.check_errors()
+        torch.cuda.synchronize()
+        return e.tables.cpu().numpy().view(np.uint32), e.population_state()
+
+    tab, ps = run(ids, 128)
+    assert int(ps["total_steps"].sum()) == P * n_p * steps
+    counts = tab[:, 2].astype(np.int64).sum(axis=1)
+    assert np.array_equal(counts, np.full(P, n_p * steps))                       # one Q-update per env-step
+    assert np.array_equal(ps["termination_hist"].sum(axis=1), ps["total_episodes"])
+    assert (ps["total_successes"] <= ps["total_episodes"]).all() and ps["total_episodes"].sum() > 0
+    assert np.isfinite(tab[:, 0].view(np.float32)).all() and (tab[:, 1] == 0).all()   # table B is never written (quirk Q1)
+    tab2, _ = run(ids, 128)
+    assert np.array_equal(tab, tab2)                                             # reproducible
+    probe = [0, 123, 739]
+    tab3, ps3 = run(probe, 64)                                                   # alone, other block size
+    for k, p in enumerate(probe):
+        assert np.array_equal(tab3[k], tab[p]), p
+        assert ps3[k]["total_episodes"] == ps[p]["total_episodes"] and ps3[k]["return_sum"] == ps[p]["return_sum"]
