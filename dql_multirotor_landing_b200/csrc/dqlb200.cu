@@ -53,10 +53,21 @@ struct EnvPtrs {
   uint4* c;
 };
 
-__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) {
-  const float4 A = p.a[i];
-  const uint4 B = p.b[i];
-  const uint4 Cw = p.c[i];
+struct EnvRaw {
+  float4 A;
+  uint4 B, C;
+};
+__device__ __forceinline__ EnvRaw env_fetch(const EnvPtrs& p, size_t i) {
+  EnvRaw r;
+  r.A = p.a[i];
+  r.B = p.b[i];
+  r.C = p.c[i];
+  return r;
+}
+__device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
+  const float4 A = r.A;
+  const uint4 B = r.B;
+  const uint4 Cw = r.C;
   e.b.x_d = A.x; e.b.v_d = A.y; e.b.theta = A.z; e.b.phase = __float_as_uint(A.w); e.b.a_d = 0.0f;
   e.theta_sp = __hiloint2double((int)B.y, (int)B.x);
   e.prev_rel_p = __uint_as_float(B.z);
@@ -69,6 +80,7 @@ __device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) {
   e.episode = Cw.y;
   e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
 }
+__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { env_unpack(env_fetch(p, i), e); }
 
 __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) {
   p.a[i] = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
@@ -138,6 +150,8 @@ struct TrainArgs {
 
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
 // loop, L1-resident): that keeps the footprint at ~38 KB so that five CTAs fit on one SM.
+constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it runs the batched reset pass
+
 struct Shared {
   float qa[CELLS];        // live table A
   float qs[CELLS];        // snapshot of table A at the start of the global step
@@ -149,7 +163,7 @@ struct Shared {
   dqlb200_population_state ps;
   unsigned long long n_episodes, n_success, ep_steps, hist[9];
   int promote, advance, do_advance;
-  // followed by: uint16_t reset_queue[WARPS][n_slots * 32]   (dynamic)
+  // followed by: uint16_t reset_queue[WARPS][RESET_QUEUE]   (dynamic)
 };
 
 template <int WARPS, bool TRACE>
@@ -161,7 +175,7 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
   const int pop = blockIdx.x;
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
-  uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * n_slots * 32;
+  uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
   float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
@@ -196,10 +210,32 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
     __syncthreads();
     int n_queued = 0;              // warp-uniform: envs of this warp that finished an episode in this step
 
+    // batched R1/R8: new episodes for the queued envs of this warp, all lanes busy (a warp would otherwise run
+    // the whole reset path for one or two lanes in half of its slots)
+    auto flush_resets = [&]() {
+      __syncwarp();
+      for (int base = 0; base < n_queued; base += 32) {
+        if (base + lane < n_queued) {
+          const int qv = reset_queue[base + lane];
+          const int env_r = (qv >> 5) * NT + warp * 32 + (qv & 31);
+          const size_t gr = env_base + (size_t)env_r;
+          Env e;
+          env_load(args.env, gr, e);
+          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
+          env_store(args.env, gr, e);
+        }
+      }
+      __syncwarp();
+      n_queued = 0;
+    };
+
+    EnvRaw next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));      // software prefetch of slot 0
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = env_i < n_p;
       const size_t gi = env_base + (size_t)(valid ? env_i : 0);
+      const EnvRaw cur_raw = next_raw;
+      if (slot + 1 < n_slots) next_raw = env_fetch(args.env, env_base + (size_t)min(env_i + NT, n_p - 1));   // in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -209,7 +245,7 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
       double ep_return = 0.0;
       if (valid) {
         Env e;
-        env_load(args.env, gi, e);
+        env_unpack(cur_raw, e);
         const uint32_t sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
@@ -241,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
         const uint32_t step_count = e.step_count + 1u;
         const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
         // R5
-        const DState ds = discretise_cuts(sh.cuts, sh.angle_cut, o);
+        const DState ds = discretise_cuts(sh.cuts, sh.angle_cut, o, w);
         const uint32_t sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
@@ -380,21 +416,10 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
       if (dmask) {
         if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);
         n_queued += __popc(dmask);
+        if (n_queued > RESET_QUEUE - 32) flush_resets();       // never overflows, whatever fraction of envs finishes at once
       }
     }
-    // ---------------- batched R1/R8: new episodes for the envs that finished, full lanes ---------
-    __syncwarp();
-    for (int base = 0; base < n_queued; base += 32) {
-      if (base + lane < n_queued) {
-        const int qv = reset_queue[base + lane];
-        const int env_i = (qv >> 5) * NT + warp * 32 + (qv & 31);
-        const size_t gi = env_base + (size_t)env_i;
-        Env e;
-        env_load(args.env, gi, e);
-        env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w, /*fresh_mdp=*/false);
-        env_store(args.env, gi, e);
-      }
-    }
+    flush_resets();
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
@@ -889,8 +914,8 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   {
     const int tpb_ = cfg->threads_per_block;
     const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
-    if (n_slots * 32 > 65535) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots)");
-    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * n_slots * 32 * sizeof(uint16_t);
+    if (n_slots > 2047) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots per thread)");
+    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t);
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
 #define DQL_SET_SMEM(W)                                                                                                   \

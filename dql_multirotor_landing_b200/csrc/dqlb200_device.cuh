@@ -191,12 +191,14 @@ struct DState {
 };
 
 __device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const float* __restrict__ angle_cut,
-                                                  const Obs& o) {
+                                                  const Obs& o, int w = 4) {
   int lp = 0, lv = 0;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    lp += (o.rel_p >= c.lvl_lo[0][i]) && !(o.rel_p >= c.lvl_hi[0][i]);
-    lv += (o.rel_v >= c.lvl_lo[1][i]) && !(o.rel_v >= c.lvl_hi[1][i]);
+    if (i < w) {       // levels above the working step do not exist (their cuts are NaN): skip, w is CTA-uniform
+      lp += (o.rel_p >= c.lvl_lo[0][i]) && !(o.rel_p >= c.lvl_hi[0][i]);
+      lv += (o.rel_v >= c.lvl_lo[1][i]) && !(o.rel_v >= c.lvl_hi[1][i]);
+    }
   }
   DState d;
   d.level = min(lp, lv);   // the acceleration limit is 1.0 at every level and never restricts

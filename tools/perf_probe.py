@@ -19,6 +19,6 @@ def run(P, n_p, tpb, k, reps=3):
     eng.close()
 
 if __name__ == "__main__":
-    for (P, n_p, tpb, k) in [(592, 1792, 128, 32), (740, 1434, 128, 32), (740, 1408, 128, 32), (888, 1195, 128, 32), (1480, 717, 64, 32), (370, 2868, 256, 32), (444, 2390, 256, 32),
-                             (592, 1792, 128, 1), (740, 1434, 128, 1), (1, 65536, 256, 8)]:
+    for (P, n_p, tpb, k) in [(740, 1434, 128, 32), (888, 1195, 128, 32), (888, 1184, 128, 32), (1036, 1024, 128, 32), (444, 2390, 256, 32), (1776, 598, 64, 32),
+                             (740, 1434, 128, 1), (888, 1195, 128, 1)]:
         run(P, n_p, tpb, k)
