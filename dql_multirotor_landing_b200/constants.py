@@ -85,7 +85,7 @@ class Config(C.Structure):
         ("n_sub", C.c_int32),
         ("gamma", C.c_float), ("transfer_ratio", C.c_float * MAX_CURRICULUM), ("transfer_mode", C.c_int32),
         ("window_len", C.c_int32), ("promote_successes", C.c_int32), ("max_num_episodes", C.c_int64),
-        ("n_alpha_luts", C.c_int32), ("reserved0", C.c_int32),
+        ("n_alpha_luts", C.c_int32), ("replicas_per_population", C.c_int32),
         ("eps_threshold", C.c_uint32 * EPS_LUT),
     ]
 
@@ -100,7 +100,7 @@ class PopulationState(C.Structure):
     _fields_ = [
         ("working_step", C.c_int32), ("finished", C.c_int32), ("t", C.c_uint32), ("error_flags", C.c_uint32),
         ("episodes_in_step", C.c_int64),
-        ("window_head", C.c_int32), ("window_count", C.c_int32), ("window_sum", C.c_int32), ("reserved", C.c_int32),
+        ("window_head", C.c_int32), ("window_count", C.c_int32), ("window_sum", C.c_int32), ("pending_advance", C.c_int32),
         ("window", C.c_uint8 * MAX_WINDOW),
         ("total_steps", C.c_uint64), ("total_episodes", C.c_uint64), ("total_successes", C.c_uint64),
         ("termination_hist", C.c_uint64 * 9),
@@ -113,7 +113,7 @@ class PopulationState(C.Structure):
 POPULATION_STATE_DTYPE = np.dtype([
     ("working_step", "<i4"), ("finished", "<i4"), ("t", "<u4"), ("error_flags", "<u4"),
     ("episodes_in_step", "<i8"),
-    ("window_head", "<i4"), ("window_count", "<i4"), ("window_sum", "<i4"), ("reserved", "<i4"),
+    ("window_head", "<i4"), ("window_count", "<i4"), ("window_sum", "<i4"), ("pending_advance", "<i4"),
     ("window", "u1", (MAX_WINDOW,)),
     ("total_steps", "<u8"), ("total_episodes", "<u8"), ("total_successes", "<u8"),
     ("termination_hist", "<u8", (9,)),
@@ -359,7 +359,7 @@ def platform_constants(r_mp: float, v_mp: float, f_ag: float, n_sub: int):
 
 def build_config(n_populations: int, envs_per_population: int, threads_per_block: int = 256,
                  mp: Optional[MdpParameters] = None, dp: Optional[DynamicsParameters] = None,
-                 tp: Optional[TrainerParameters] = None, n_alpha_luts: int = 1) -> Config:
+                 tp: Optional[TrainerParameters] = None, n_alpha_luts: int = 1, replicas_per_population: int = 1) -> Config:
     mp, dp, tp = mp or MdpParameters(), dp or DynamicsParameters(), tp or TrainerParameters()
     if not (1 <= tp.curriculum_steps <= MAX_CURRICULUM):
         raise ValueError("curriculum_steps must be in 1..5 (the reference's Limits hold 5 levels)")
@@ -410,6 +410,9 @@ def build_config(n_populations: int, envs_per_population: int, threads_per_block
     cfg.promote_successes = promote_threshold(tp.successive_successful_episodes, tp.success_rate)
     cfg.max_num_episodes = tp.max_num_episodes
     cfg.n_alpha_luts = n_alpha_luts
+    if replicas_per_population < 1 or n_populations % replicas_per_population:
+        raise ValueError("n_populations must be a multiple of replicas_per_population")
+    cfg.replicas_per_population = replicas_per_population
     for e in range(EPS_LUT):
         cfg.eps_threshold[e] = explore_threshold(exploration_rate(e, 0))
     return cfg

@@ -167,7 +167,7 @@ struct Shared {
 };
 
 template <int WARPS, bool TRACE>
-__global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+__global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -201,6 +201,54 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
   const dqlb200_population_params pp = sh.pp;
   const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
   uint64_t steps_done = 0;
+
+  // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
+  // fresh env + TrainingMdp for every env (PKG/trainer.py:176-189, 232-245).  All threads call it (uniform).
+  auto advance_curriculum = [&](int w, uint32_t birth) {
+    const int cs = kc.curriculum_steps;
+    int dst = -1, src = 0;
+    float ratio = 1.0f;
+    if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
+    else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
+    if (dst >= 0) {
+      for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+        sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      dqlb200_population_state& ps = sh.ps;
+      if (sh.promote) { ps.window_head = ps.window_count = ps.window_sum = 0; }
+      ps.promoted_at[w] = birth;
+      ps.episodes_in_step = 0;
+      ps.pending_advance = 0;
+      sh.promote = sh.advance = sh.do_advance = 0;
+      if (w + 1 >= cs) ps.finished = 1;
+      else {
+        ps.working_step = w + 1;
+        sh.cuts = kc.cuts[w + 1];
+      }
+    }
+    __syncthreads();
+    if (!sh.ps.finished) {
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const int env_i = slot * NT + tid;
+        if (env_i < n_p) {
+          Env e;
+          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
+          env_store(args.env, env_base + env_i, e);
+        }
+      }
+    }
+    __syncthreads();
+  };
+  // replica-merge mode: a promotion decided by replica_merge_kernel takes effect before the first step of this launch
+  if (sh.ps.pending_advance && !sh.ps.finished) {
+    if (tid == 0) sh.promote = (sh.ps.pending_advance == 1) ? 1 : 0;
+    __syncthreads();
+    advance_curriculum(sh.ps.working_step, sh.ps.t);
+  }
 
   for (int k = 0; k < args.k_steps; ++k) {
     if (sh.ps.finished) break;     // uniform: written only between barriers
@@ -396,8 +444,10 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
               ps.window_sum += ok;
               ps.window_head = (ps.window_head + 1 == kc.window_len) ? 0 : ps.window_head + 1;
               ps.episodes_in_step += 1;
-              if (ps.window_sum >= kc.promote_successes) sh.promote = 1;
-              if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
+              if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
+                if (ps.window_sum >= kc.promote_successes) sh.promote = 1;
+                if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
+              }
             }
             sh.n_episodes += (unsigned long long)__popc(dmask);
             sh.n_success += (unsigned long long)__popc(smask);
@@ -428,46 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32) train_kernel(const __grid_constant
       sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
     }
     __syncthreads();
-    if (sh.do_advance) {
-      const int cs = kc.curriculum_steps;
-      // DoubleQLearningAgent.transfer_learning (PKG/double_q_learning.py:77-89)
-      int dst = -1, src = 0;
-      float ratio = 1.0f;
-      if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
-      else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
-      if (dst >= 0) {
-        for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
-          sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
-          gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
-        }
-      }
-      __syncthreads();
-      if (tid == 0) {
-        dqlb200_population_state& ps = sh.ps;
-        if (sh.promote) { ps.window_head = ps.window_count = ps.window_sum = 0; }
-        ps.promoted_at[w] = ps.t;
-        ps.episodes_in_step = 0;
-        sh.promote = sh.advance = sh.do_advance = 0;
-        if (w + 1 >= cs) ps.finished = 1;
-        else {
-          ps.working_step = w + 1;
-          sh.cuts = kc.cuts[w + 1];
-        }
-      }
-      __syncthreads();
-      if (!sh.ps.finished) {
-        // a fresh env + TrainingMdp per curriculum step (PKG/trainer.py:176-189)
-        for (int slot = 0; slot < n_slots; ++slot) {
-          const int env_i = slot * NT + tid;
-          if (env_i < n_p) {
-            Env e;
-            env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, t + 1u, w + 1, /*fresh_mdp=*/true);
-            env_store(args.env, env_base + env_i, e);
-          }
-        }
-      }
-      __syncthreads();
-    }
+    if (sh.do_advance) advance_curriculum(w, t + 1u);
   }
 
   // ---- write back -----------------------------------------------------------------------------
@@ -807,6 +818,72 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, const floa
   snap[base + 2 * CELLS + c] = tables[base + 2 * CELLS + c];
 }
 
+// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One thread per table cell merges the
+// replicas (visit-weighted mean of their Q deltas, replica order, fp32; counts summed) and writes the result to every
+// replica and to the snapshot; thread 0 of block (0, g) pools the success windows and arms the promotion.
+__global__ void __launch_bounds__(64) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
+                                                            int R, int pooled_promote, long long max_episodes) {
+  const int g = blockIdx.y;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  uint32_t* sg = snap + (size_t)g * 3 * CELLS;
+  if (c < CELLS) {
+    const float q_snap = __uint_as_float(sg[c]);
+    const uint32_t cnt_snap = sg[2 * CELLS + c];
+    float num = 0.0f, q_single = q_snap;
+    uint32_t tot = 0;
+    int visitors = 0;
+    // loads are issued in batches of MERGE_BATCH replicas (independent, all in flight) and then accumulated strictly in
+    // replica order: the summation order is part of the semantics (bit-exact vs oracle/loop.py)
+    constexpr int MERGE_BATCH = 32;
+    for (int r0 = 0; r0 < R; r0 += MERGE_BATCH) {
+      uint32_t cn[MERGE_BATCH], qv[MERGE_BATCH];
+#pragma unroll
+      for (int j = 0; j < MERGE_BATCH; ++j) {
+        const int r = min(r0 + j, R - 1);
+        const uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
+        cn[j] = __ldcg(tr + 2 * CELLS + c);
+        qv[j] = __ldcg(tr + c);
+      }
+#pragma unroll
+      for (int j = 0; j < MERGE_BATCH; ++j) {
+        const uint32_t dc = cn[j] - cnt_snap;
+        if (r0 + j < R && dc) {
+          const float q_r = __uint_as_float(qv[j]);
+          visitors += 1;
+          q_single = q_r;
+          num = fadd(num, fmul(fsub(q_r, q_snap), __uint2float_rn(dc)));
+          tot += dc;
+        }
+      }
+    }
+    float q_new = q_snap;
+    if (visitors == 1) q_new = q_single;
+    else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
+    const uint32_t qb = tables[(size_t)(g * R) * 3 * CELLS + CELLS + c];     // table B only changes by the (identical) transfers
+    for (int r = 0; r < R; ++r) {
+      uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
+      tr[c] = __float_as_uint(q_new);
+      tr[2 * CELLS + c] = cnt_snap + tot;
+    }
+    sg[c] = __float_as_uint(q_new);
+    sg[CELLS + c] = qb;
+    sg[2 * CELLS + c] = cnt_snap + tot;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long successes = 0, episodes = 0;
+    bool live = true;
+    for (int r = 0; r < R; ++r) {
+      const dqlb200_population_state& p = ps[g * R + r];
+      successes += p.window_sum;
+      episodes += p.episodes_in_step;
+      live = live && !p.finished && !p.pending_advance;
+    }
+    const int pending = !live ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
+    if (pending)
+      for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
+  }
+}
+
 }  // namespace dql
 
 // =================================================================================================
@@ -875,6 +952,7 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   k.transfer_mode = c.transfer_mode; k.window_len = c.window_len; k.promote_successes = c.promote_successes;
   k.curriculum_steps = c.curriculum_steps; k.envs_per_population = c.envs_per_population;
   k.n_populations = c.n_populations; k.max_num_episodes = c.max_num_episodes;
+  k.replicas = c.replicas_per_population;
 }
 
 int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dqlb200_population_params* pop_params,
@@ -889,6 +967,8 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) return fail(DQLB200_ERR_ARG, "threads_per_block must be 32, 64, 128 or 256");
   if (cfg->window_len < 1 || cfg->window_len > DQLB200_MAX_WINDOW) return fail(DQLB200_ERR_ARG, "window_len out of range");
   if (cfg->n_alpha_luts < 1 || cfg->n_sub < 1) return fail(DQLB200_ERR_ARG, "n_alpha_luts / n_sub must be >= 1");
+  if (cfg->replicas_per_population < 1 || cfg->n_populations % cfg->replicas_per_population)
+    return fail(DQLB200_ERR_ARG, "n_populations must be a multiple of replicas_per_population (>= 1)");
   for (int p = 0; p < cfg->n_populations; ++p)
     if (pop_params[p].alpha_lut < 0 || pop_params[p].alpha_lut >= cfg->n_alpha_luts) return fail(DQLB200_ERR_ARG, "population alpha_lut index out of range");
   int count = 0;
@@ -1108,6 +1188,19 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
   CUDA_TRY(cudaSetDevice(h->device));
   dql::facade_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->d_cfg, working_step, ops, n, obs, contact, action,
                                                                                    mdp_state, out_state, out_code, out_reward, h->d_error);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, void* stream) {
+  if (!h || !h->tables || !h->pop_state || !snapshot) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  const int R = h->cfg.replicas_per_population;
+  if (R < 1 || h->cfg.n_populations % R) return fail(DQLB200_ERR_STATE, "n_populations is not a multiple of replicas_per_population");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const dim3 grid((DQLB200_MAX_CELLS + 63) / 64, h->cfg.n_populations / R);
+  dql::replica_merge_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
+                                                                   (dqlb200_population_state*)h->pop_state, R,
+                                                                   pooled_promote_successes, h->cfg.max_num_episodes);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

@@ -34,6 +34,7 @@ struct KC {
   int32_t timeout_steps, success_steps, n_sub;
   int32_t transfer_mode, window_len, promote_successes;
   int32_t curriculum_steps, envs_per_population, n_populations;
+  int32_t replicas;             // > 1: replica-merge mode, promotion is decided by replica_merge_kernel
   int32_t div_two_steps;        // 0 only for the exhaustively verified default divisors
   long long max_num_episodes;
 };

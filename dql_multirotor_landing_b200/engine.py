@@ -19,7 +19,7 @@ class Engine:
     def __init__(self, n_populations: int, envs_per_population: int, *, device: int = 0, threads_per_block: int = 256,
                  seeds: Optional[Sequence[int]] = None, population_ids: Optional[Sequence[int]] = None,
                  v_mp: Optional[Sequence[float]] = None, alpha_variants: Optional[Sequence[tuple]] = None,
-                 alpha_index: Optional[Sequence[int]] = None,
+                 alpha_index: Optional[Sequence[int]] = None, replicas_per_population: int = 1,
                  mp: Optional[K.MdpParameters] = None, dp: Optional[K.DynamicsParameters] = None,
                  tp: Optional[K.TrainerParameters] = None):
         if not torch.cuda.is_available():
@@ -29,8 +29,9 @@ class Engine:
         self.P, self.n_p, self.device_index = n_populations, envs_per_population, device
         self.device = torch.device("cuda", device)
         alpha_variants = list(alpha_variants or [(self.tp.alpha_min, self.tp.omega)])
+        self.R = replicas_per_population
         self.cfg = K.build_config(n_populations, envs_per_population, threads_per_block, self.mp, self.dp, self.tp,
-                                  n_alpha_luts=len(alpha_variants))
+                                  n_alpha_luts=len(alpha_variants), replicas_per_population=replicas_per_population)
         luts = np.concatenate([K.alpha_lut(a, o) for a, o in alpha_variants]).astype(np.float32)
         seeds = list(seeds) if seeds is not None else [42] * n_populations
         population_ids = list(population_ids) if population_ids is not None else list(range(n_populations))
@@ -52,6 +53,8 @@ class Engine:
             self.pop_state = torch.zeros(n_populations * C.sizeof(K.PopulationState), dtype=torch.uint8, device=self.device)
         _ffi.check(self.lib.dqlb200_bind(self.handle, self.env_state.data_ptr(), self.tables.data_ptr(), self.pop_state.data_ptr()))
         self._trace_keep = None
+        self.merge_snapshot = None       # replica-merge mode: [n_groups][3][MAX_CELLS] merged tables of the last merge
+        self.pooled_promote = K.promote_threshold(self.tp.successive_successful_episodes * self.R, self.tp.success_rate)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -104,6 +107,29 @@ class Engine:
         """End-to-end call with pinned HOST buffers (copies in, k_steps, copies out, synchronises)."""
         _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
                                                pop_state_host.data_ptr(), self._stream()))
+
+    # ------------------------------------------------------------------------------------------
+    # replica-merge mode: R consecutive populations are replicas of one agent (more envs than one CTA holds)
+    def replica_merge(self):
+        if self.merge_snapshot is None:
+            self.merge_snapshot = self.tables[:: self.R].clone().contiguous()
+        _ffi.check(self.lib.dqlb200_replica_merge(self.handle, self.merge_snapshot.data_ptr(), self.pooled_promote, self._stream()))
+
+    def train_merged(self, total_steps: int, merge_every: int = 1):
+        """total_steps global steps, merging the replicas of every agent after each `merge_every` steps."""
+        if self.merge_snapshot is None:
+            self.merge_snapshot = self.tables[:: self.R].clone().contiguous()
+        done = 0
+        while done < total_steps:
+            k = min(merge_every, total_steps - done)
+            self.train(k)
+            self.replica_merge()
+            done += k
+
+    def set_group_tables(self, group: int, qa: np.ndarray, qb: np.ndarray, count: np.ndarray):
+        for r in range(self.R):
+            self.set_tables(group * self.R + r, qa, qb, count)
+        self.merge_snapshot = None
 
     def selftest_division(self) -> int:
         """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""

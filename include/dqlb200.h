@@ -110,7 +110,8 @@ typedef struct dqlb200_config {
   int32_t promote_successes;        /* first integer s with s / window_len > success_rate */
   int64_t max_num_episodes;
   int32_t n_alpha_luts;             /* learning-rate variants for sweeps (>= 1) */
-  int32_t reserved0;
+  int32_t replicas_per_population;  /* 1 = every population is one agent; R > 1 = R consecutive populations are
+                                     * replicas of one agent merged by dqlb200_replica_merge (they never promote alone) */
   uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
 } dqlb200_config;
 
@@ -131,7 +132,8 @@ typedef struct dqlb200_population_state {
   uint32_t t;                       /* global step index (Philox counter word 1) */
   uint32_t error_flags;             /* bit 0: NaN observation */
   int64_t episodes_in_step;         /* completed episodes in this curriculum step */
-  int32_t window_head, window_count, window_sum, reserved;
+  int32_t window_head, window_count, window_sum;
+  int32_t pending_advance;          /* set by dqlb200_replica_merge: 1 = promoted, 2 = max_num_episodes reached */
   uint8_t window[DQLB200_MAX_WINDOW];
   uint64_t total_steps, total_episodes, total_successes;
   uint64_t termination_hist[9];
@@ -217,6 +219,18 @@ int dqlb200_check_errors(dqlb200_handle* h, void* stream);
  * pack:   delta <- (tables - snapshot) weighted;   apply: tables <- snapshot + reduced delta. */
 int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream);
 int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, void* stream);
+
+/* Replica-merge mode (one agent with more envs than one CTA can hold: BASELINE configs 2-3, "N envs sharing one
+ * Q-table pair").  The agent's envs are split over R = cfg.replicas_per_population consecutive populations (replicas),
+ * each running the S1 semantics on its own table copy; this call merges the R copies of every group into one table
+ * and writes it back to all replicas and to `snapshot` ([n_groups][3][DQLB200_MAX_CELLS] words, the merged tables of
+ * the previous call; initialise it with the starting tables):
+ *     dcount_r = count_r - count_snap,  Q <- Q_snap + sum_r (Q_r - Q_snap) * dcount_r / sum_r dcount_r  (replica order,
+ *     fp32),  count <- count_snap + sum_r dcount_r;  a cell only one replica visited keeps that replica's value.
+ * It also pools the replicas' success windows: when sum(window_sum) >= pooled_promote_successes or the group's finished
+ * episodes reach max_num_episodes, every replica gets pending_advance set and performs transfer + fresh restart at
+ * the start of its next dqlb200_train launch (PKG/trainer.py:232-245).  With R = 1 the tables are left untouched. */
+int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, void* stream);
 
 /* Facade kernels behind TrainingMdp / SimulationMdp / DoubleQLearningAgent single-object calls
  * (float64 observations from the host, reference comparisons in float64; PKG/mdp.py:257-541).

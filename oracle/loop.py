@@ -51,7 +51,9 @@ class TrainerParams:
 class PopulationOracle:
     def __init__(self, n_envs: int, seed: int = 42, population: int = 0, w0: int = 0,
                  tp: Optional[TrainerParams] = None, mp: Optional[MdpParams] = None,
-                 sp: Optional[StandInParams] = None, dtype=np.float32, agent: Optional[AgentOracle] = None):
+                 sp: Optional[StandInParams] = None, dtype=np.float32, agent: Optional[AgentOracle] = None,
+                 self_promote: bool = True):
+        self.self_promote = self_promote        # False: replica of a larger population (ReplicatedPopulationOracle decides)
         self.n, self.seed, self.pop = n_envs, seed, population
         self.tp = tp or TrainerParams()
         self.mp = mp or MdpParams()
@@ -135,9 +137,9 @@ class PopulationOracle:
                 self.total_successes += ok
                 self.term_hist[code] += 1
                 self.episodes_done += 1
-                if sum(self.window) / tp.successive_successful_episodes > tp.success_rate:
+                if self.self_promote and sum(self.window) / tp.successive_successful_episodes > tp.success_rate:
                     promote = True
-                if self.episodes_done >= tp.max_num_episodes:
+                if self.self_promote and self.episodes_done >= tp.max_num_episodes:
                     advance = True
                 self.ep[i] += 1
                 finished_envs.append(i)
@@ -167,6 +169,70 @@ class PopulationOracle:
             return
         self._fresh_mdps()
         self._reset_envs(range(self.n), birth=self.t + 1)
+
+
+class ReplicatedPopulationOracle:
+    """Replica-merge mode: ONE agent whose envs are split over R replicas.  Every replica runs
+    the S1 semantics on its own copy of the tables; after every `merge_every` global steps the copies are merged:
+    Q <- Q_snap + sum_r (Q_r - Q_snap) * dcount_r / sum_r dcount_r  (replica order, float32), count <- count_snap +
+    sum_r dcount_r; a cell visited by one replica only keeps that replica's value.  The success windows are pooled:
+    promotion when sum_r window_sum_r / (R * window_len) > success_rate, advance when the pooled finished episodes reach
+    max_num_episodes; both take effect before the next global step.  With R = 1 the tables are never altered."""
+
+    def __init__(self, replicas: int, envs_per_replica: int, seed: int = 42, first_population: int = 0, w0: int = 0,
+                 tp: Optional[TrainerParams] = None, sp: Optional[StandInParams] = None, merge_every: int = 1):
+        self.R, self.merge_every = replicas, merge_every
+        self.tp = tp or TrainerParams()
+        self.reps = [PopulationOracle(envs_per_replica, seed=seed, population=first_population + r, w0=w0, tp=self.tp, sp=sp,
+                                      dtype=np.float32, self_promote=False) for r in range(replicas)]
+        self.snap_q = self.reps[0].agent.qa.copy()
+        self.snap_c = self.reps[0].agent.count.copy()
+        self.steps = 0
+        self.pending = 0
+
+    def step(self):
+        if self.pending:
+            for rep in self.reps:
+                if not rep.finished:
+                    rep.t -= 1                       # _advance_curriculum uses birth = t + 1 = the next step index
+                    rep._advance_curriculum(self.pending == 1)
+                    rep.t += 1
+            self.pending = 0
+        out = [rep.step() for rep in self.reps]
+        self.steps += 1
+        if self.steps % self.merge_every == 0:
+            self.merge()
+        return out
+
+    def merge(self):
+        f32 = np.float32
+        R = self.R
+        dcs = [rep.agent.count - self.snap_c for rep in self.reps]
+        tot = sum(dcs)
+        visitors = sum((d > 0).astype(np.int64) for d in dcs)
+        num = np.zeros(self.snap_q.shape, f32)
+        single = self.snap_q.copy()
+        for rep, d in zip(self.reps, dcs):
+            hit = d > 0
+            contrib = ((rep.agent.qa - self.snap_q).astype(f32) * d.astype(f32)).astype(f32)
+            num = np.where(hit, (num + contrib).astype(f32), num)
+            single = np.where(hit, rep.agent.qa, single)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            mean = (self.snap_q + (num / tot.astype(f32)).astype(f32)).astype(f32)
+        q_new = np.where(visitors == 1, single, np.where(visitors > 1, mean, self.snap_q)).astype(f32)
+        c_new = self.snap_c + tot
+        for rep in self.reps:
+            rep.agent.qa[...] = q_new
+            rep.agent.count[...] = c_new
+        self.snap_q, self.snap_c = q_new.copy(), c_new.copy()
+        live = all((not rep.finished) for rep in self.reps)
+        if live and not self.pending:
+            successes = sum(sum(rep.window) for rep in self.reps)
+            episodes = sum(rep.episodes_done for rep in self.reps)
+            if successes / (R * self.tp.successive_successful_episodes) > self.tp.success_rate:
+                self.pending = 1
+            elif episodes >= self.tp.max_num_episodes:
+                self.pending = 2
 
 
 def eval_episode(policy, seed: int, population: int, episode_id: int, sp: StandInParams,

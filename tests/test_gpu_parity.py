@@ -327,3 +327,32 @@ def test_full_size_properties():
     for k, p in enumerate(probe):
         assert np.array_equal(tab3[k], tab[p]), p
         assert ps3[k]["total_episodes"] == ps[p]["total_episodes"] and ps3[k]["return_sum"] == ps[p]["return_sum"]
+
+
+@pytest.mark.parametrize("R,merge_every", [(4, 1), (3, 5)])
+def test_replica_merge_mode_vs_oracle(R, merge_every):
+    """One agent whose envs are spread over R CTAs (configs 2-3: many envs sharing one Q-table pair): replica tables merged
+    every `merge_every` steps, pooled promotion; tables, counts and curriculum progress identical to the oracle."""
+    from oracle.loop import ReplicatedPopulationOracle
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    n_r, steps = 40, 360
+    eng = _engine(R, n_r, threads_per_block=32, seeds=[5] * R, population_ids=list(range(R)), replicas_per_population=R, tp=kw)
+    eng.reset(0)
+    ora = ReplicatedPopulationOracle(R, n_r, seed=5, tp=TrainerParams(**kw), merge_every=merge_every)
+    eng.train_merged(steps, merge_every)
+    eng.check_errors()
+    for _ in range(steps):
+        ora.step()
+    ps = eng.population_state()
+    assert max(rep.w for rep in ora.reps) >= 2, "the test should cross at least two promotions"
+    for r in range(R):
+        qa, qb, cnt = eng.get_tables(r, np.float32)
+        rep = ora.reps[r]
+        assert np.array_equal(cnt, rep.agent.count), r
+        assert np.array_equal(qa.view(np.uint32), rep.agent.qa.view(np.uint32)), r
+        assert np.array_equal(qb.view(np.uint32), rep.agent.qb.view(np.uint32)), r
+        assert (ps[r]["working_step"], ps[r]["finished"], ps[r]["t"]) == (rep.w, int(rep.finished), rep.t)
+        assert ps[r]["total_episodes"] == rep.total_episodes and ps[r]["pending_advance"] == (0 if rep.finished else ora.pending)
+    # all replicas agree after the final merge
+    t = eng.tables.cpu().numpy()
+    assert all(np.array_equal(t[0, 0], t[r, 0]) and np.array_equal(t[0, 2], t[r, 2]) for r in range(R))
