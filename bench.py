@@ -293,6 +293,21 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
     t0 = time.perf_counter()
     res = eng.eval_greedy(pol, n_ep)
     s = time.perf_counter() - t0
+    # config 3: ONE agent, 65,536 envs sharing one Q-table pair (replica-merge mode: 512 replicas x 128 envs, merged every 16 steps)
+    try:
+        from dql_multirotor_landing_b200 import constants as K
+        from dql_multirotor_landing_b200.engine import Engine
+        R, n_r, M, steps = 512, 128, 16, 256
+        e3 = Engine(R, n_r, device=dev.index or 0, threads_per_block=128, seeds=[42] * R, population_ids=list(range(R)),
+                    replicas_per_population=R, tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+        e3.reset(0)
+        e3.train_merged(2 * M, M); torch.cuda.synchronize(dev)
+        s3 = timed(lambda: e3.train_merged(steps, M))
+        out["config3_one_agent_65536_envs"] = {"env_steps_per_s": R * n_r * steps / s3, "replicas": R, "envs_per_replica": n_r,
+                                               "merge_every_steps": M, "timing": "CUDA events, best of 3"}
+        e3.close()
+    except Exception as exc:      # never let a context measurement break the headline line
+        out["config3_one_agent_65536_envs"] = {"error": str(exc)}
     out["config2_greedy_eval"] = {"episodes": res["episodes"], "env_steps": res["steps"], "env_steps_per_s": res["steps"] / s,
                                   "landing_rate": res["termination_hist"][3] / max(res["episodes"], 1),
                                   "termination_hist": res["termination_hist"], "timing": "host wall clock incl. launch+sync"}

@@ -55,6 +55,8 @@ class Trainer:
         platform_speed: float = 1.6,
         dynamics: Optional[K.DynamicsParameters] = None,
         max_global_steps: Optional[int] = None,
+        envs_per_replica: int = 128,
+        merge_every: int = 8,
         tensorboard: bool = False,
         verbose: bool = True,
     ) -> None:
@@ -83,6 +85,13 @@ class Trainer:
         self._transfer_mode, self._platform_speed = transfer_mode, platform_speed
         self._dynamics = dynamics or K.DynamicsParameters(z_init=z_init, v_mp=platform_speed)
         self._max_global_steps = max_global_steps
+        # one agent with more envs than a CTA should hold -> replica-merge mode
+        self._replicas = 1
+        if num_populations == 1 and num_envs > 2048:
+            self._replicas = -(-num_envs // envs_per_replica)
+            self._num_envs = envs_per_replica
+            self._threads_per_block = 128 if envs_per_replica >= 128 else 32
+        self._merge_every = merge_every
         self._tensorboard, self._verbose = tensorboard, verbose
         self._engine = None
         self.history = []             # one dict per chunk (population 0)
@@ -155,10 +164,16 @@ class Trainer:
             omega=self._omega, gamma=self._gamma, scale_modification_value=self._scale_modification_value,
             transfer_mode=self._transfer_mode)
         mp = K.MdpParameters(f_ag=self._f_ag, t_max=self._t_max, p_max=self._p_max)
-        P = self._num_populations
-        eng = Engine(P, self._num_envs, device=self._device, threads_per_block=self._threads_per_block,
-                     seeds=[self._seed + p for p in range(P)], population_ids=list(range(P)),
-                     v_mp=[self._platform_speed] * P, mp=mp, dp=self._dynamics, tp=tp)
+        P, R = self._num_populations, self._replicas
+        if R > 1:
+            eng = Engine(R, self._num_envs, device=self._device, threads_per_block=self._threads_per_block,
+                         seeds=[self._seed] * R, population_ids=list(range(R)), v_mp=[self._platform_speed] * R,
+                         replicas_per_population=R, mp=mp, dp=self._dynamics, tp=tp)
+            P = R
+        else:
+            eng = Engine(P, self._num_envs, device=self._device, threads_per_block=self._threads_per_block,
+                         seeds=[self._seed + p for p in range(P)], population_ids=list(range(P)),
+                         v_mp=[self._platform_speed] * P, mp=mp, dp=self._dynamics, tp=tp)
         agent = self._double_q_learning_agent
         for p in range(P):
             eng.set_tables(p, agent.Q_table_a, agent.Q_table_b, agent.state_action_counter)
@@ -177,14 +192,17 @@ class Trainer:
         prev = eng.population_state()
         global_steps = 0
         while True:
-            eng.train(self._chunk_steps)
+            if self._replicas > 1:
+                eng.train_merged(self._chunk_steps, self._merge_every)
+            else:
+                eng.train(self._chunk_steps)
             eng.check_errors()
             global_steps += self._chunk_steps
             ps = eng.population_state()
             p0 = ps[0]
             self._working_curriculum_step = int(p0["working_step"])
-            self._current_episode = int(p0["episodes_in_step"])
-            self._curriculum_episode_count = int(p0["total_episodes"])
+            self._current_episode = int(ps["episodes_in_step"].sum()) if self._replicas > 1 else int(p0["episodes_in_step"])
+            self._curriculum_episode_count = int(ps["total_episodes"].sum()) if self._replicas > 1 else int(p0["total_episodes"])
             window = list(p0["window"][: int(p0["window_count"])])
             self._successes = deque(window, maxlen=self._successive_successful_episodes)
             d_ep = int(p0["total_episodes"] - prev[0]["total_episodes"])
@@ -197,8 +215,9 @@ class Trainer:
                 "Remaining episodes": self._max_num_episodes - self._current_episode + 1,
                 "Exploration rate": self.exploration_rate(self._current_episode // max(self._num_envs, 1), self._working_curriculum_step),
                 "Learning rate": self._alpha,
-                "Success rate": int(p0["window_sum"]) / self._successive_successful_episodes,
-                "Global steps": int(p0["t"]), "Env steps": int(p0["total_steps"]), "Episodes in chunk": d_ep,
+                "Success rate": (int(ps["window_sum"].sum()) / (self._successive_successful_episodes * self._replicas)
+                                 if self._replicas > 1 else int(p0["window_sum"]) / self._successive_successful_episodes),
+                "Global steps": int(p0["t"]), "Env steps": int(ps["total_steps"].sum()), "Episodes in chunk": d_ep,
             }
             self.history.append(dict(info, working_step=self._working_curriculum_step))
             advanced = any(int(ps[p]["working_step"]) != int(prev[p]["working_step"]) or int(ps[p]["finished"]) != int(prev[p]["finished"])

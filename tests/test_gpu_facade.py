@@ -176,3 +176,18 @@ def test_trainer_schedules_and_short_curriculum(tmp_path):
     import pickle
     again = pickle.load(open(tmp_path / "run" / "trainer.pickle", "rb"))
     assert np.array_equal(again._double_q_learning_agent.Q_table_a, agent.Q_table_a)
+
+
+def test_trainer_large_population_uses_replica_merge(tmp_path):
+    """Config 3 through the Trainer facade: one agent, 8,192 envs -> 64 replicas x 128 envs merged every 4 steps."""
+    from dql_multirotor_landing_b200.trainer import Trainer
+    tr = Trainer(save_path=tmp_path / "run", success_rate=0.5, max_num_episodes=30000, num_envs=8192, chunk_steps=64,
+                 merge_every=4, verbose=False, max_global_steps=1024)
+    tr.curriculum_training()
+    eng = tr._engine
+    assert eng.R == 64 and eng.n_p == 128
+    ps = eng.population_state()
+    agent = tr._double_q_learning_agent
+    assert agent.state_action_counter.sum() == ps["total_steps"].sum() > 0       # every env-step of every replica is in the merged counts
+    assert len(set(int(x) for x in ps["working_step"])) == 1                      # replicas move through the curriculum together
+    assert np.isfinite(agent.Q_table_a).all() and np.abs(agent.Q_table_a).max() > 0

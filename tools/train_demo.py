@@ -1,0 +1,26 @@
+"""Full-curriculum training demo (BASELINE config 3 style): prints curriculum progress and wall time per step."""
+import sys, pathlib, time, json, tempfile
+sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
+import numpy as np, torch
+from dql_multirotor_landing_b200.trainer import Trainer
+
+def main(num_envs=65536, mode="paper", max_steps=60000, merge_every=8):
+    tr = Trainer(save_path=pathlib.Path(tempfile.mkdtemp()) / "run", num_envs=num_envs, chunk_steps=256, merge_every=merge_every,
+                 transfer_mode=mode, verbose=False, max_global_steps=max_steps, max_num_episodes=50000 * num_envs)
+    t0 = time.perf_counter()
+    tr.curriculum_training()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - t0
+    ps = tr._engine.population_state()
+    last_w = -1
+    for h in tr.history:
+        if h["working_step"] != last_w:
+            print(f"  working_step {h['working_step']} reached at global step {h['Global steps']}, env steps {h['Env steps']:.3e}, success rate {h['Success rate']:.3f}")
+            last_w = h["working_step"]
+    print(json.dumps(dict(num_envs=num_envs, mode=mode, wall_s=round(wall, 2), global_steps=int(ps[0]["t"]), env_steps=int(ps["total_steps"].sum()),
+                          env_steps_per_s=f"{ps['total_steps'].sum() / wall:.3e}", finished=int(ps[0]["finished"]), working_step=int(ps[0]["working_step"]),
+                          episodes=int(ps["total_episodes"].sum()), successes=int(ps["total_successes"].sum()),
+                          promoted_at=[int(x) for x in ps[0]["promoted_at"]], final_success_rate=tr.history[-1]["Success rate"])))
+
+if __name__ == "__main__":
+    main(mode="paper", max_steps=400000)
