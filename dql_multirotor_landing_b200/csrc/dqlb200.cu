@@ -144,6 +144,7 @@ struct TrainArgs {
   const float* alpha_luts;                 // [n_luts][ALPHA_LUT]
   const uint32_t* eps_threshold;           // [EPS_LUT]
   dqlb200_trace trace;
+  uint32_t* merge_snapshot;                // replica-merge mode: [n_groups][3][CELLS] merged tables (may be null)
   int k_steps;
   long long n_total;
 };
@@ -180,11 +181,9 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
   float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
 
-  // ---- stage tables and population state in shared memory -------------------------------------
-  for (int i = tid; i < CELLS; i += NT) {
-    sh.qa[i] = __uint_as_float(gt[i]);
-    sh.cnt[i] = gt[2 * CELLS + i];
-  }
+  // ---- stage population state and the LIVE rows of the tables in shared memory --------------------
+  // At working step w only levels 0..w can be visited (a state's level never exceeds w), so only rows
+  // [0, (w+1)*567) of Q_a / count are staged, snapshotted and written back; a promotion loads the next level.
   if (tid == 0) {
     sh.pp = args.pop_params[pop];
     sh.ps = args.pop_state[pop];
@@ -195,7 +194,14 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
   if (tid < 5) sh.reward[tid] = kc.reward[tid];
   if (tid < 6) sh.angle_cut[tid] = kc.angle_cut[tid];
   __syncthreads();
-  if (tid == 0) sh.cuts = kc.cuts[sh.ps.working_step];
+  {
+    const int live = (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL;
+    for (int i = tid; i < live; i += NT) {
+      sh.qa[i] = __uint_as_float(gt[i]);
+      sh.cnt[i] = gt[2 * CELLS + i];
+    }
+    if (tid == 0) sh.cuts = kc.cuts[sh.ps.working_step];
+  }
   __syncthreads();
 
   const dqlb200_population_params pp = sh.pp;
@@ -211,9 +217,26 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
     if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
     else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
     if (dst >= 0) {
+      // replica-merge mode: the transfer acts on the MERGED table (every replica applies it identically right after a
+      // merge), so the first replica of a group also refreshes the group's merge snapshot
+      uint32_t* sg = (args.merge_snapshot && pop % kc.replicas == 0) ? args.merge_snapshot + (size_t)(pop / kc.replicas) * 3 * CELLS : nullptr;
       for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
-        sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(sh.qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
-        gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        // a source row above the working step is not staged: it is unmodified in global memory
+        const float q_src = (src <= w) ? sh.qa[src * DQLB200_CELLS_PER_LEVEL + i] : __uint_as_float(gt[src * DQLB200_CELLS_PER_LEVEL + i]);
+        const float qa_new = fmul(q_src, ratio), qb_new = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = qa_new;
+        gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = qb_new;
+        if (sg) {
+          sg[dst * DQLB200_CELLS_PER_LEVEL + i] = __float_as_uint(qa_new);
+          sg[CELLS + dst * DQLB200_CELLS_PER_LEVEL + i] = __float_as_uint(qb_new);
+        }
+      }
+    }
+    if (w + 1 < cs) {      // level w+1 becomes live: stage its rows (Q_a unless the transfer just wrote it)
+      for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+        const int c = (w + 1) * DQLB200_CELLS_PER_LEVEL + i;
+        if (dst != w + 1) sh.qa[c] = __uint_as_float(gt[c]);
+        sh.cnt[c] = gt[2 * CELLS + c];
       }
     }
     __syncthreads();
@@ -254,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
     if (sh.ps.finished) break;     // uniform: written only between barriers
     const int w = sh.ps.working_step;
     const uint32_t t = sh.ps.t;
-    for (int i = tid; i < CELLS; i += NT) sh.qs[i] = sh.qa[i];
+    for (int i = tid; i < (w + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) sh.qs[i] = sh.qa[i];
     __syncthreads();
     int n_queued = 0;              // warp-uniform: envs of this warp that finished an episode in this step
 
@@ -481,9 +504,9 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
     if (sh.do_advance) advance_curriculum(w, t + 1u);
   }
 
-  // ---- write back -----------------------------------------------------------------------------
+  // ---- write back (live rows only) ----------------------------------------------------------------
   __syncthreads();
-  for (int i = tid; i < CELLS; i += NT) {
+  for (int i = tid; i < (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) {
     gt[i] = __float_as_uint(sh.qa[i]);
     gt[2 * CELLS + i] = sh.cnt[i];
   }
@@ -818,67 +841,66 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, const floa
   snap[base + 2 * CELLS + c] = tables[base + 2 * CELLS + c];
 }
 
-// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One thread per table cell merges the
-// replicas (visit-weighted mean of their Q deltas, replica order, fp32; counts summed) and writes the result to every
-// replica and to the snapshot; thread 0 of block (0, g) pools the success windows and arms the promotion.
-__global__ void __launch_bounds__(64) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
+// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One WARP per table cell: the lanes read
+// 32 replicas at a time, the replicas that visited the cell (ballot) are accumulated strictly in replica order (the
+// summation order is part of the semantics: bit-exact vs oracle/loop.py), the merged value is written to every replica
+// and to the snapshot.  Only the live rows (levels 0..working step) can differ from the snapshot.  Thread 0 of block
+// (0, g) pools the success windows and arms the promotion.
+__global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
                                                             int R, int pooled_promote, long long max_episodes) {
   const int g = blockIdx.y;
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   uint32_t* sg = snap + (size_t)g * 3 * CELLS;
-  if (c < CELLS) {
+  const int live = (ps[g * R].working_step + 1) * DQLB200_CELLS_PER_LEVEL;
+  if (c < live) {
     const float q_snap = __uint_as_float(sg[c]);
     const uint32_t cnt_snap = sg[2 * CELLS + c];
     float num = 0.0f, q_single = q_snap;
     uint32_t tot = 0;
     int visitors = 0;
-    // loads are issued in batches of MERGE_BATCH replicas (independent, all in flight) and then accumulated strictly in
-    // replica order: the summation order is part of the semantics (bit-exact vs oracle/loop.py)
-    constexpr int MERGE_BATCH = 32;
-    for (int r0 = 0; r0 < R; r0 += MERGE_BATCH) {
-      uint32_t cn[MERGE_BATCH], qv[MERGE_BATCH];
-#pragma unroll
-      for (int j = 0; j < MERGE_BATCH; ++j) {
-        const int r = min(r0 + j, R - 1);
-        const uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
-        cn[j] = __ldcg(tr + 2 * CELLS + c);
-        qv[j] = __ldcg(tr + c);
-      }
-#pragma unroll
-      for (int j = 0; j < MERGE_BATCH; ++j) {
-        const uint32_t dc = cn[j] - cnt_snap;
-        if (r0 + j < R && dc) {
-          const float q_r = __uint_as_float(qv[j]);
-          visitors += 1;
-          q_single = q_r;
-          num = fadd(num, fmul(fsub(q_r, q_snap), __uint2float_rn(dc)));
-          tot += dc;
-        }
+    for (int r0 = 0; r0 < R; r0 += 32) {
+      const int r = r0 + lane;
+      const uint32_t* tr = tables + (size_t)(g * R + min(r, R - 1)) * 3 * CELLS;
+      const uint32_t dc = (r < R) ? (__ldcg(tr + 2 * CELLS + c) - cnt_snap) : 0u;
+      const float q_r = dc ? __uint_as_float(__ldcg(tr + c)) : 0.0f;
+      uint32_t m = __ballot_sync(FULL, dc != 0u);
+      while (m) {                                   // warp-uniform: every lane keeps the same accumulators
+        const int b = __ffs(m) - 1;
+        m &= m - 1u;
+        const uint32_t dc_b = __shfl_sync(FULL, dc, b);
+        const float q_b = __shfl_sync(FULL, q_r, b);
+        visitors += 1;
+        q_single = q_b;
+        num = fadd(num, fmul(fsub(q_b, q_snap), __uint2float_rn(dc_b)));
+        tot += dc_b;
       }
     }
     float q_new = q_snap;
     if (visitors == 1) q_new = q_single;
     else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
-    const uint32_t qb = tables[(size_t)(g * R) * 3 * CELLS + CELLS + c];     // table B only changes by the (identical) transfers
-    for (int r = 0; r < R; ++r) {
-      uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
-      tr[c] = __float_as_uint(q_new);
-      tr[2 * CELLS + c] = cnt_snap + tot;
+    if (visitors) {
+      for (int r = lane; r < R; r += 32) {
+        uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
+        tr[c] = __float_as_uint(q_new);
+        tr[2 * CELLS + c] = cnt_snap + tot;
+      }
+      if (lane == 0) {
+        sg[c] = __float_as_uint(q_new);
+        sg[2 * CELLS + c] = cnt_snap + tot;
+      }
     }
-    sg[c] = __float_as_uint(q_new);
-    sg[CELLS + c] = qb;
-    sg[2 * CELLS + c] = cnt_snap + tot;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     long long successes = 0, episodes = 0;
-    bool live = true;
+    bool alive = true;
     for (int r = 0; r < R; ++r) {
       const dqlb200_population_state& p = ps[g * R + r];
       successes += p.window_sum;
       episodes += p.episodes_in_step;
-      live = live && !p.finished && !p.pending_advance;
+      alive = alive && !p.finished && !p.pending_advance;
     }
-    const int pending = !live ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
+    const int pending = !alive ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
     if (pending)
       for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
   }
@@ -900,6 +922,7 @@ struct dqlb200_handle {
   void* env_state;
   void* tables;
   void* pop_state;
+  void* merge_snapshot;
   size_t smem_bytes;
 };
 
@@ -980,7 +1003,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   h->cfg = *cfg;
   fill_kc(*cfg, h->kc);
   h->device = device;
-  h->env_state = h->tables = h->pop_state = nullptr;
+  h->env_state = h->tables = h->pop_state = h->merge_snapshot = nullptr;
   CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
   CUDA_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(dqlb200_config), cudaMemcpyHostToDevice));
   const size_t lut_bytes = (size_t)cfg->n_alpha_luts * DQLB200_ALPHA_LUT * sizeof(float);
@@ -1059,6 +1082,7 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   a.alpha_luts = h->d_alpha;
   a.eps_threshold = h->d_cfg->eps_threshold;
   if (trace) a.trace = *trace; else memset(&a.trace, 0, sizeof(a.trace));
+  a.merge_snapshot = (h->cfg.replicas_per_population > 1) ? (uint32_t*)h->merge_snapshot : nullptr;
   a.k_steps = k_steps;
   a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
   const int grid = h->cfg.n_populations;
@@ -1192,13 +1216,22 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
   return DQLB200_OK;
 }
 
+int dqlb200_bind_merge_snapshot(dqlb200_handle* h, void* snapshot) {
+  if (!h) return fail(DQLB200_ERR_ARG, "null handle");
+  if ((uintptr_t)snapshot & 3u) return fail(DQLB200_ERR_ARG, "misaligned snapshot");
+  h->merge_snapshot = snapshot;
+  return DQLB200_OK;
+}
+
 int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, void* stream) {
   if (!h || !h->tables || !h->pop_state || !snapshot) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  if (h->cfg.replicas_per_population > 1 && snapshot != h->merge_snapshot)
+    return fail(DQLB200_ERR_STATE, "snapshot is not the one bound with dqlb200_bind_merge_snapshot (train launches keep it current across transfers)");
   const int R = h->cfg.replicas_per_population;
   if (R < 1 || h->cfg.n_populations % R) return fail(DQLB200_ERR_STATE, "n_populations is not a multiple of replicas_per_population");
   CUDA_TRY(cudaSetDevice(h->device));
-  const dim3 grid((DQLB200_MAX_CELLS + 63) / 64, h->cfg.n_populations / R);
-  dql::replica_merge_kernel<<<grid, 64, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
+  const dim3 grid((DQLB200_MAX_CELLS + 7) / 8, h->cfg.n_populations / R);       // one warp per cell, 8 warps per block
+  dql::replica_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
                                                                    (dqlb200_population_state*)h->pop_state, R,
                                                                    pooled_promote_successes, h->cfg.max_num_episodes);
   CUDA_TRY(cudaGetLastError());

@@ -110,15 +110,18 @@ class Engine:
 
     # ------------------------------------------------------------------------------------------
     # replica-merge mode: R consecutive populations are replicas of one agent (more envs than one CTA holds)
-    def replica_merge(self):
+    def _ensure_merge_snapshot(self):
         if self.merge_snapshot is None:
             self.merge_snapshot = self.tables[:: self.R].clone().contiguous()
+            _ffi.check(self.lib.dqlb200_bind_merge_snapshot(self.handle, self.merge_snapshot.data_ptr()))
+
+    def replica_merge(self):
+        self._ensure_merge_snapshot()
         _ffi.check(self.lib.dqlb200_replica_merge(self.handle, self.merge_snapshot.data_ptr(), self.pooled_promote, self._stream()))
 
     def train_merged(self, total_steps: int, merge_every: int = 1):
         """total_steps global steps, merging the replicas of every agent after each `merge_every` steps."""
-        if self.merge_snapshot is None:
-            self.merge_snapshot = self.tables[:: self.R].clone().contiguous()
+        self._ensure_merge_snapshot()
         done = 0
         while done < total_steps:
             k = min(merge_every, total_steps - done)
@@ -130,6 +133,7 @@ class Engine:
         for r in range(self.R):
             self.set_tables(group * self.R + r, qa, qb, count)
         self.merge_snapshot = None
+        _ffi.check(self.lib.dqlb200_bind_merge_snapshot(self.handle, None))
 
     def selftest_division(self) -> int:
         """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""

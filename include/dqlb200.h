@@ -229,7 +229,11 @@ int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_re
  *     fp32),  count <- count_snap + sum_r dcount_r;  a cell only one replica visited keeps that replica's value.
  * It also pools the replicas' success windows: when sum(window_sum) >= pooled_promote_successes or the group's finished
  * episodes reach max_num_episodes, every replica gets pending_advance set and performs transfer + fresh restart at
- * the start of its next dqlb200_train launch (PKG/trainer.py:232-245).  With R = 1 the tables are left untouched. */
+ * the start of its next dqlb200_train launch (PKG/trainer.py:232-245).  With R = 1 the tables are left untouched.
+ * The curriculum transfer (PKG/double_q_learning.py:77-89) acts on the merged table: every replica applies it to its copy
+ * and the first replica of a group applies it to the bound snapshot, which therefore has to be registered with
+ * dqlb200_bind_merge_snapshot before the first dqlb200_train launch of a replicated layout (NULL unbinds). */
+int dqlb200_bind_merge_snapshot(dqlb200_handle* h, void* snapshot);
 int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, void* stream);
 
 /* Facade kernels behind TrainingMdp / SimulationMdp / DoubleQLearningAgent single-object calls

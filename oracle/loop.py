@@ -197,6 +197,8 @@ class ReplicatedPopulationOracle:
                     rep.t -= 1                       # _advance_curriculum uses birth = t + 1 = the next step index
                     rep._advance_curriculum(self.pending == 1)
                     rep.t += 1
+            # the transfer acts on the merged table (all copies are identical here): the snapshot follows it
+            self.snap_q = self.reps[0].agent.qa.copy()
             self.pending = 0
         out = [rep.step() for rep in self.reps]
         self.steps += 1
