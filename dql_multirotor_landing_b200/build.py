@@ -33,7 +33,7 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, "-o", str(LIB), str(SRC)]
+    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("DQL_NVCC_EXTRA", "").split(), "-o", str(LIB), str(SRC)]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -35,13 +35,13 @@ constexpr uint32_t FULL = 0xFFFFFFFFu;
 
 // env-state word C.x layout
 constexpr uint32_t SID_BITS = 10, STEP_SHIFT = 10, STEP_BITS = 9, CC_SHIFT = 19, CC_BITS = 5;
-constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25;
+constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25, BP_SHIFT = 26;   // bits 26-27: position bin of `sid`
 
 struct Env {
   Body b;
   double theta_sp;     // NOT cleared by an episode reset while `fresh` (keeps the shaping potential, quirk Q11)
   float prev_rel_p, prev_rel_v;
-  uint32_t sid, step_count, curriculum_check;
+  uint32_t sid, bp, step_count, curriculum_check;     // bp = position bin of sid ((sid / 63) % 3, kept to avoid the division)
   bool sticky_success, fresh;
   uint32_t episode;
   double cum_reward;
@@ -76,6 +76,7 @@ __device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
   e.step_count = (Cw.x >> STEP_SHIFT) & ((1u << STEP_BITS) - 1u);
   e.curriculum_check = (Cw.x >> CC_SHIFT) & ((1u << CC_BITS) - 1u);
   e.sticky_success = (Cw.x & STICKY_BIT) != 0u;
+  e.bp = (Cw.x >> BP_SHIFT) & 3u;
   e.fresh = (Cw.x & FRESH_BIT) != 0u;
   e.episode = Cw.y;
   e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
@@ -87,7 +88,7 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
   p.b[i] = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
                       __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
   const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
-                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u);
+                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
   p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
                       (uint32_t)__double2hiint(e.cum_reward));
 }
@@ -99,7 +100,9 @@ __device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population
                                           uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
   const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
-  e.sid = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+  const DState ds0 = discretise_cuts(cuts, angle_cut, o);
+  e.sid = (uint32_t)ds0.id();
+  e.bp = (uint32_t)ds0.bp;
   e.step_count = 0;
   e.curriculum_check = 0;
   e.sticky_success = false;
@@ -153,22 +156,30 @@ struct TrainArgs {
 // loop, L1-resident): that keeps the footprint at ~38 KB so that five CTAs fit on one SM.
 constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it runs the batched reset pass
 
+constexpr int STATES = DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL;   // 945
+
 struct Shared {
   float qa[CELLS];        // live table A
-  float qs[CELLS];        // snapshot of table A at the start of the global step
   uint32_t cnt[CELLS];    // state_action_counter
+  // Snapshot of the start of the global step.  Phase A reads the tables only through two per-STATE quantities, so the
+  // snapshot is those two instead of a copy of Q_a: the greedy action argmax_a (Q_a+Q_b)/2 (R9) and max_a Q_a (R12).
+  float qmax[STATES];
+  uint8_t greedy[STATES + 3];
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
-  float angle_cut[8];
-  dqlb200_population_params pp;
   dqlb200_population_state ps;
   unsigned long long n_episodes, n_success, ep_steps, hist[9];
   int promote, advance, do_advance;
   // followed by: uint16_t reset_queue[WARPS][RESET_QUEUE]   (dynamic)
 };
 
-template <int WARPS, bool TRACE>
-__global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+#ifndef DQL_WARPS_PER_SM
+#define DQL_WARPS_PER_SM 28     // resident warps per SM the register allocation is tuned for (launch bounds)
+#endif
+// DIV2: second Markstein correction step of x / p_max, x / v_max (needed unless the divisors are the exhaustively
+// verified defaults; the trace instances always take it: both variants are correctly rounded, hence identical)
+template <int WARPS, bool TRACE, bool DIV2>
+__global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (DQL_WARPS_PER_SM / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -184,28 +195,35 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
   // ---- stage population state and the LIVE rows of the tables in shared memory --------------------
   // At working step w only levels 0..w can be visited (a state's level never exceeds w), so only rows
   // [0, (w+1)*567) of Q_a / count are staged, snapshotted and written back; a promotion loads the next level.
-  if (tid == 0) {
-    sh.pp = args.pop_params[pop];
-    sh.ps = args.pop_state[pop];
-    sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
-    for (int i = 0; i < 9; ++i) sh.hist[i] = 0ull;
-    sh.promote = sh.advance = sh.do_advance = 0;
-  }
-  if (tid < 5) sh.reward[tid] = kc.reward[tid];
-  if (tid < 6) sh.angle_cut[tid] = kc.angle_cut[tid];
-  __syncthreads();
+  // The launch prologue is ONE round trip to memory: every load below is independent of the others (the working step
+  // and the population constants are broadcast loads by every thread instead of a hop through shared memory), and the
+  // env state of slot 0 -- a cold HBM read when one global step is run per launch -- is in flight during all of it.
+  static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
+  constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
+  const dqlb200_population_params pp = args.pop_params[pop];
+  EnvRaw next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
   {
-    const int live = (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL;
+    const int w_start = args.pop_state[pop].working_step;
+    const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
+    for (int i = tid; i < PS_WORDS; i += NT) reinterpret_cast<uint32_t*>(&sh.ps)[i] = gps[i];
+    if (tid == 0) {
+      sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
+      for (int i = 0; i < 9; ++i) sh.hist[i] = 0ull;
+      sh.promote = sh.advance = sh.do_advance = 0;
+      sh.cuts = kc.cuts[w_start];
+    }
+    if (tid < 5) sh.reward[tid] = kc.reward[tid];
+    const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
     for (int i = tid; i < live; i += NT) {
       sh.qa[i] = __uint_as_float(gt[i]);
       sh.cnt[i] = gt[2 * CELLS + i];
+      if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(gqb + i));     // table B rows for the first snapshot
     }
-    if (tid == 0) sh.cuts = kc.cuts[sh.ps.working_step];
   }
   __syncthreads();
 
-  const dqlb200_population_params pp = sh.pp;
   const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
+  const float alpha_min = __ldg(alpha_lut + DQLB200_ALPHA_LUT - 1);      // alpha(count >= 1002), PKG/trainer.py:95-105
   uint64_t steps_done = 0;
 
   // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
@@ -259,7 +277,7 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         const int env_i = slot * NT + tid;
         if (env_i < n_p) {
           Env e;
-          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
+          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
           env_store(args.env, env_base + env_i, e);
         }
       }
@@ -271,13 +289,27 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
     if (tid == 0) sh.promote = (sh.ps.pending_advance == 1) ? 1 : 0;
     __syncthreads();
     advance_curriculum(sh.ps.working_step, sh.ps.t);
+    next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));     // every env was just restarted
   }
 
   for (int k = 0; k < args.k_steps; ++k) {
     if (sh.ps.finished) break;     // uniform: written only between barriers
     const int w = sh.ps.working_step;
     const uint32_t t = sh.ps.t;
-    for (int i = tid; i < (w + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) sh.qs[i] = sh.qa[i];
+    // snapshot of the step: greedy action (first max of (Q_a+Q_b)/2, PKG/double_q_learning.py:119-124) and bootstrap
+    // value max_a Q_a (:136-141) of every live state
+    for (int st = tid; st < (w + 1) * DQLB200_STATES_PER_LEVEL; st += NT) {
+      const float q0 = sh.qa[st * 3 + 0], q1 = sh.qa[st * 3 + 1], q2 = sh.qa[st * 3 + 2];
+      const float p0 = fmul(fadd(q0, gqb[st * 3 + 0]), 0.5f);
+      const float p1 = fmul(fadd(q1, gqb[st * 3 + 1]), 0.5f);
+      const float p2 = fmul(fadd(q2, gqb[st * 3 + 2]), 0.5f);
+      int a = 0;
+      float best = p0;
+      if (p1 > best) { best = p1; a = 1; }
+      if (p2 > best) { a = 2; }
+      sh.greedy[st] = (uint8_t)a;
+      sh.qmax[st] = fmaxf(fmaxf(q0, q1), q2);
+    }
     __syncthreads();
     int n_queued = 0;              // warp-uniform: envs of this warp that finished an episode in this step
 
@@ -292,7 +324,7 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
           const size_t gr = env_base + (size_t)env_r;
           Env e;
           env_load(args.env, gr, e);
-          env_reset(kc, pp, sh.cuts, sh.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
+          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
           env_store(args.env, gr, e);
         }
       }
@@ -300,13 +332,12 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
       n_queued = 0;
     };
 
-    EnvRaw next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));      // software prefetch of slot 0
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = env_i < n_p;
       const size_t gi = env_base + (size_t)(valid ? env_i : 0);
       const EnvRaw cur_raw = next_raw;
-      if (slot + 1 < n_slots) next_raw = env_fetch(args.env, env_base + (size_t)min(env_i + NT, n_p - 1));   // in flight during this slot
+      if (env_i + NT < n_p) next_raw = env_fetch(args.env, gi + NT);      // software prefetch, in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -314,19 +345,15 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
       int code = 0;
       uint32_t ep_steps = 0;
       double ep_return = 0.0;
+      Env e;
+      uint32_t c_hint = 0;
+      float a_hint = 0.0f;
       if (valid) {
-        Env e;
         env_unpack(cur_raw, e);
         const uint32_t sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
-        const float p0 = fmul(fadd(sh.qs[sid * 3 + 0], gqb[sid * 3 + 0]), 0.5f);
-        const float p1 = fmul(fadd(sh.qs[sid * 3 + 1], gqb[sid * 3 + 1]), 0.5f);
-        const float p2 = fmul(fadd(sh.qs[sid * 3 + 2], gqb[sid * 3 + 2]), 0.5f);
-        int a = 0;
-        float best = p0;
-        if (p1 > best) { best = p1; a = 1; }
-        if (p2 > best) { a = 2; }
+        int a = sh.greedy[sid];
         if (w == 0) {
           const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
@@ -348,7 +375,7 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         const uint32_t step_count = e.step_count + 1u;
         const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
         // R5
-        const DState ds = discretise_cuts(sh.cuts, sh.angle_cut, o, w);
+        const DState ds = discretise_cuts(sh.cuts, kc.angle_cut, o, w);
         const uint32_t sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
@@ -359,7 +386,7 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         else if (o.z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
         else if ((int)step_count >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
         else if (ds.bp == 1 && ds.bv == 1) {
-          if ((int)(sid / DQLB200_STATES_PER_LEVEL) == w && ds.level == w) {
+          if (sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w) {      // previous level == w (it never exceeds w)
             cc += 1u;
             code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
           } else {
@@ -371,17 +398,17 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
           atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
         // R7 (float64, reference operation order; level-dependent constants from the host)
-        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
-        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
+        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, DIV2);
+        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, DIV2);
         const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
-        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.div_two_steps != 0);
-        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.div_two_steps != 0);
+        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, DIV2);
+        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, DIV2);
         const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
         const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
         // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
-        const float qn = fmaxf(fmaxf(sh.qs[sid2 * 3 + 0], sh.qs[sid2 * 3 + 1]), sh.qs[sid2 * 3 + 2]);
-        const float changed = (((sid / 63u) % 3u) != (uint32_t)ds.bp) ? 1.0f : 0.0f;
+        const float qn = sh.qmax[sid2];
+        const float changed = (e.bp != (uint32_t)ds.bp) ? 1.0f : 0.0f;
         target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
         cell = sid * 3u + (uint32_t)a;
         if (TRACE) {
@@ -409,13 +436,17 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
           e.episode += 1u;
         } else {
           e.sid = sid2;
+          e.bp = (uint32_t)ds.bp;
           e.step_count = step_count;
           e.curriculum_check = cc;
           e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
           e.fresh = false;
           e.cum_reward = __dadd_rn(e.cum_reward, r);
         }
-        env_store(args.env, gi, e);
+        // learning-rate hint for phase B: the LUT entry of the cell's count as it is NOW (an unsynchronised peek at the
+        // live table; phase B uses it only if the count is still the same, so the result does not depend on it)
+        c_hint = min(sh.cnt[cell], (uint32_t)(DQLB200_ALPHA_LUT - 1));
+        a_hint = __ldg(alpha_lut + c_hint);
       }
       // ---------------- phase B: ordered commit (baton between warps) --------------------------
       if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
@@ -426,7 +457,9 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         const int rank = __popc(peers & ((1u << lane) - 1u));
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
-        const float alpha = alpha_lut[min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1))];   // R11 (pre-increment count)
+        const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
+        float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
+        if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
         uint32_t rem = valid ? peers : 0u;
         while (__any_sync(FULL, rem != 0u)) {
           const int src = rem ? (__ffs(rem) - 1) : lane;
@@ -485,6 +518,9 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
         __threadfence_block();
         baton_pass<WARPS>((warp + 1) % WARPS);
       }
+      // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
+      // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
+      if (valid) env_store(args.env, gi, e);
       // queue the finished envs of this warp for the batched reset (outside the baton)
       if (dmask) {
         if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);
@@ -493,6 +529,8 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
       }
     }
     flush_resets();
+    // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
+    if (k + 1 < args.k_steps) next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
@@ -501,7 +539,10 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
       sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
     }
     __syncthreads();
-    if (sh.do_advance) advance_curriculum(w, t + 1u);
+    if (sh.do_advance) {
+      advance_curriculum(w, t + 1u);
+      next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
+    }
   }
 
   // ---- write back (live rows only) ----------------------------------------------------------------
@@ -517,7 +558,11 @@ __global__ void __launch_bounds__(WARPS * 32, 24 / WARPS) train_kernel(const __g
     ps.total_successes += sh.n_success;
     ps.episode_steps_sum += sh.ep_steps;
     for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
-    args.pop_state[pop] = ps;
+  }
+  __syncthreads();
+  {
+    uint32_t* gps = reinterpret_cast<uint32_t*>(args.pop_state + pop);
+    for (int i = tid; i < PS_WORDS; i += NT) gps[i] = reinterpret_cast<const uint32_t*>(&sh.ps)[i];
   }
 }
 
@@ -566,14 +611,12 @@ __global__ void reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, dqlb200
   const int pop = blockIdx.y;
   const int env_i = blockIdx.x * blockDim.x + threadIdx.x;
   __shared__ dqlb200_cuts cuts;
-  __shared__ float angle_cut[8];
   if (threadIdx.x == 0) cuts = kc.cuts[initial_step];
-  if (threadIdx.x < 6) angle_cut[threadIdx.x] = kc.angle_cut[threadIdx.x];
   __syncthreads();
   if (env_i < kc.envs_per_population) {
     const dqlb200_population_params pp = pop_params[pop];
     Env e;
-    env_reset(kc, pp, cuts, angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true);
+    env_reset(kc, pp, cuts, kc.angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true);
     env_store(env, (size_t)pop * kc.envs_per_population + env_i, e);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -593,12 +636,10 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
                                                    dqlb200_eval_stats* stats, dqlb200_trace trace, int trace_steps) {
   __shared__ uint8_t s_policy[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
   __shared__ dqlb200_cuts cuts;
-  __shared__ float angle_cut[8];
   __shared__ unsigned long long s_hist[9], s_steps, s_eps;
   for (int i = threadIdx.x; i < DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL; i += blockDim.x) s_policy[i] = policy[i];
   if (threadIdx.x == 0) { cuts = kc.cuts[w]; s_steps = s_eps = 0ull; }
   if (threadIdx.x < 9) s_hist[threadIdx.x] = 0ull;
-  if (threadIdx.x < 6) angle_cut[threadIdx.x] = kc.angle_cut[threadIdx.x];
   __syncthreads();
   const dqlb200_population_params pp = pop_params[population];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -607,7 +648,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
     const uint4 d = philox4x32_10(make_uint4((uint32_t)ep, 0u, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
     Body b;
     Obs o = dyn_reset(kc, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim);
-    uint32_t sid = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+    uint32_t sid = (uint32_t)discretise_cuts(cuts, kc.angle_cut, o).id();
     double sp = 0.0;
     int code = DQLB200_NON_TERMINAL;
     int step = 0;
@@ -617,7 +658,7 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
       dyn_advance(kc, pp, b, (float)sp);
       step += 1;
       o = dyn_observe(kc, pp, b, step, kc.dz_sim);
-      const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, angle_cut, o).id();
+      const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, kc.angle_cut, o).id();
       if (o.contact) code = DQLB200_TERMINAL_CONTACT;
       else if (!(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
       else if (!(o.z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
@@ -1021,12 +1062,13 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
     h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t);
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
-#define DQL_SET_SMEM(W)                                                                                                   \
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes)); \
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+#define DQL_SET_SMEM1(W, T, D)                                                                                            \
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+#define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, false) DQL_SET_SMEM1(W, false, true) DQL_SET_SMEM1(W, true, true)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
 #undef DQL_SET_SMEM
+#undef DQL_SET_SMEM1
   *out = h;
   return DQLB200_OK;
 }
@@ -1089,8 +1131,9 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
 #define DQL_LAUNCH(W)                                                                        \
-  if (tracing) dql::train_kernel<W, true><<<grid, W * 32, smem, stream>>>(h->kc, a);         \
-  else dql::train_kernel<W, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
+  if (tracing) dql::train_kernel<W, true, true><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
+  else if (h->kc.div_two_steps) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
+  else dql::train_kernel<W, false, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;
     case 64: DQL_LAUNCH(2) break;

@@ -78,9 +78,11 @@ __device__ __forceinline__ void det_sincos_turns(uint32_t phase, float& s_out, f
   pc = fadd(fmul(pc, z), (float)(1.0 / 24.0));
   pc = fadd(fmul(pc, z), -0.5f);
   const float c = fadd(1.0f, fmul(z, pc));
-  const uint32_t qq = q & 3u;
-  s_out = (qq == 0u) ? s : (qq == 1u) ? c : (qq == 2u) ? -s : -c;
-  c_out = (qq == 0u) ? c : (qq == 1u) ? -s : (qq == 2u) ? -c : s;
+  // quadrant q: (sin, cos) = (s, c), (c, -s), (-s, -c), (-c, s) -- branch-free: swap on odd q, then sign bits
+  const bool odd = (q & 1u) != 0u;
+  const uint32_t sb = __float_as_uint(odd ? c : s), cb = __float_as_uint(odd ? s : c);
+  s_out = __uint_as_float(sb ^ ((q & 2u) << 30));
+  c_out = __uint_as_float(cb ^ (((q + 1u) & 2u) << 30));
 }
 
 __device__ __forceinline__ float det_tan(float x) {
@@ -122,6 +124,8 @@ __device__ __forceinline__ float det_normal(uint32_t x0, uint32_t x1) {
 
 __device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
+// np.clip for a value that is never NaN (fmin/fmax cost ~6 instructions each for their NaN rules; this is 2 compares + selects)
+__device__ __forceinline__ double clipd_finite(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 // ---------------------------------------------------------------------------------------------
 // stand-in dynamics (R4).  Body state: drone position/velocity, pitch, platform phase.
@@ -215,9 +219,14 @@ __device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const f
 
 // R3: pitch set-point integrator, float64 like the reference
 __device__ __forceinline__ double apply_action(const KC& kc, double theta_sp, int a) {
-  if (a == 0) return fmin(__dadd_rn(theta_sp, kc.delta_theta), kc.theta_max);
-  if (a == 1) return fmax(__dsub_rn(theta_sp, kc.delta_theta), -kc.theta_max);
-  return theta_sp;
+  // branch-free (the three actions diverge inside a warp): a = 2 adds 0.0 and the clamps are no-ops for |theta_sp| <= theta_max
+  const double s = __dadd_rn(theta_sp, a == 0 ? kc.delta_theta : (a == 1 ? -kc.delta_theta : 0.0));
+  // selects on the 32-bit halves (a select on a double may be compiled into a branch)
+  const bool hi = s > kc.theta_max, lo = s < -kc.theta_max;
+  const int t_hi = __double2hiint(kc.theta_max), t_lo = __double2loint(kc.theta_max);
+  const int r_hi = hi ? t_hi : (lo ? (int)((uint32_t)t_hi ^ 0x80000000u) : __double2hiint(s));
+  const int r_lo = (hi || lo) ? t_lo : __double2loint(s);
+  return __hiloint2double(r_hi, r_lo);
 }
 
 // Correctly rounded (double)x / d for a finite fp32 numerator x and a constant divisor d, rcp = RN(1/d):
@@ -252,15 +261,17 @@ __device__ __forceinline__ double div_f64_by_const(double x, double d, double rc
 
 // Shaping potential of one fp32 observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
 __device__ __forceinline__ double shaping(double w, float x, double x_max, double rcp, bool two_steps) {
-  return __dmul_rn(w, fabs(clipd(div_f32_by_const(x, x_max, rcp, two_steps), -1.0, 1.0)));
+  // |clip(q, -1, 1)| = min(|q|, 1); a NaN quotient (flagged as an error by the caller) gives 1 like fmin/fmax would
+  const double aq = fabs(div_f32_by_const(x, x_max, rcp, two_steps));
+  return __dmul_rn(w, !(aq <= 1.0) ? 1.0 : aq);
 }
 
 // R7 with the level-dependent constants pre-evaluated on the host.
 __device__ __forceinline__ double reward_f64(const KC& kc, const dqlb200_reward_level& rl, double phi_p,
                                              double phi_v, double phi_t, double prev_p, double prev_v,
                                              double prev_t, bool success) {
-  const double r_p = clipd(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
-  const double r_v = clipd(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
+  const double r_p = clipd_finite(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
+  const double r_v = clipd_finite(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
   const double r_t =
       __dmul_rn(div_f64_by_const(__dmul_rn(kc.w_theta, __dsub_rn(fabs(phi_t), fabs(prev_t))), kc.theta_max, kc.rcp_theta_max), rl.lim_v);
   const double r_term = success ? rl.r_term_succ : rl.r_term_fail;
