@@ -149,6 +149,7 @@ struct TrainArgs {
   dqlb200_trace trace;
   uint32_t* merge_snapshot;                // replica-merge mode: [n_groups][3][CELLS] merged tables (may be null)
   int k_steps;
+  int pop_offset;                          // first population of this launch (chunked host-buffer calls)
   long long n_total;
 };
 
@@ -184,7 +185,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = WARPS * 32;
-  const int pop = blockIdx.x;
+  const int pop = blockIdx.x + args.pop_offset;
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
@@ -965,6 +966,12 @@ struct dqlb200_handle {
   void* pop_state;
   void* merge_snapshot;
   size_t smem_bytes;
+  // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
+  static constexpr int MAX_HOST_CHUNKS = 8;
+  cudaStream_t chunk_stream[MAX_HOST_CHUNKS];
+  cudaEvent_t chunk_done[MAX_HOST_CHUNKS];
+  cudaEvent_t host_start;
+  bool chunk_ready;
 };
 
 static thread_local std::string g_last_error;
@@ -1045,6 +1052,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   fill_kc(*cfg, h->kc);
   h->device = device;
   h->env_state = h->tables = h->pop_state = h->merge_snapshot = nullptr;
+  h->chunk_ready = false;
   CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
   CUDA_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(dqlb200_config), cudaMemcpyHostToDevice));
   const size_t lut_bytes = (size_t)cfg->n_alpha_luts * DQLB200_ALPHA_LUT * sizeof(float);
@@ -1080,6 +1088,13 @@ int dqlb200_destroy(dqlb200_handle* h) {
   cudaFree(h->d_alpha);
   cudaFree(h->d_pop_params);
   cudaFree(h->d_error);
+  if (h->chunk_ready) {
+    for (int c = 0; c < dqlb200_handle::MAX_HOST_CHUNKS; ++c) {
+      cudaStreamDestroy(h->chunk_stream[c]);
+      cudaEventDestroy(h->chunk_done[c]);
+    }
+    cudaEventDestroy(h->host_start);
+  }
   delete h;
   return DQLB200_OK;
 }
@@ -1115,7 +1130,7 @@ int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream) {
 }
 
 static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* env_state, void* tables,
-                        void* pop_state, cudaStream_t stream) {
+                        void* pop_state, cudaStream_t stream, int pop_offset = 0, int pop_count = -1) {
   dql::TrainArgs a;
   a.env = env_ptrs(h, env_state);
   a.tables = (uint32_t*)tables;
@@ -1126,8 +1141,9 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   if (trace) a.trace = *trace; else memset(&a.trace, 0, sizeof(a.trace));
   a.merge_snapshot = (h->cfg.replicas_per_population > 1) ? (uint32_t*)h->merge_snapshot : nullptr;
   a.k_steps = k_steps;
+  a.pop_offset = pop_offset;
   a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
-  const int grid = h->cfg.n_populations;
+  const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
   const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
 #define DQL_LAUNCH(W)                                                                        \
@@ -1157,22 +1173,45 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
                        void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
   if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
+  if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
-  const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
-  const size_t env_bytes = n * DQLB200_ENV_STATE_BYTES;
-  const size_t tab_bytes = (size_t)h->cfg.n_populations * 3 * DQLB200_MAX_CELLS * 4;
-  const size_t ps_bytes = (size_t)h->cfg.n_populations * sizeof(dqlb200_population_state);
-  CUDA_TRY(cudaMemcpyAsync(h->env_state, env_state_host, env_bytes, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->tables, tables_host, tab_bytes, cudaMemcpyHostToDevice, s));
-  CUDA_TRY(cudaMemcpyAsync(h->pop_state, pop_state_host, ps_bytes, cudaMemcpyHostToDevice, s));
-  if (k_steps > 0) {
-    const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, s);
-    if (rc) return rc;
+  if (!h->chunk_ready) {
+    for (int c = 0; c < dqlb200_handle::MAX_HOST_CHUNKS; ++c) {
+      CUDA_TRY(cudaStreamCreateWithFlags(&h->chunk_stream[c], cudaStreamNonBlocking));
+      CUDA_TRY(cudaEventCreateWithFlags(&h->chunk_done[c], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventCreateWithFlags(&h->host_start, cudaEventDisableTiming));
+    h->chunk_ready = true;
   }
-  CUDA_TRY(cudaMemcpyAsync(env_state_host, h->env_state, env_bytes, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(tables_host, h->tables, tab_bytes, cudaMemcpyDeviceToHost, s));
-  CUDA_TRY(cudaMemcpyAsync(pop_state_host, h->pop_state, ps_bytes, cudaMemcpyDeviceToHost, s));
+  // Populations are independent within a launch, so the call is pipelined over chunks of populations: while chunk c
+  // trains, chunk c+1 is copied in and chunk c-1 is copied out (PCIe is full duplex, the copy engines run beside the SMs).
+  const int P = h->cfg.n_populations, n_p = h->cfg.envs_per_population;
+  const int n_chunks = P < dqlb200_handle::MAX_HOST_CHUNKS ? P : dqlb200_handle::MAX_HOST_CHUNKS;
+  const size_t n = (size_t)P * n_p;
+  const size_t tab_stride = (size_t)3 * DQLB200_MAX_CELLS * 4, ps_stride = sizeof(dqlb200_population_state);
+  CUDA_TRY(cudaEventRecord(h->host_start, s));
+  for (int c = 0; c < n_chunks; ++c) {
+    const int p0 = (int)((long long)P * c / n_chunks), p1 = (int)((long long)P * (c + 1) / n_chunks);
+    if (p1 == p0) continue;
+    cudaStream_t cs = h->chunk_stream[c];
+    CUDA_TRY(cudaStreamWaitEvent(cs, h->host_start, 0));
+    const size_t e0 = (size_t)p0 * n_p * 16, eb = (size_t)(p1 - p0) * n_p * 16;
+    for (int a = 0; a < 3; ++a)       // the three 16-byte vectors of the env-state SoA
+      CUDA_TRY(cudaMemcpyAsync((char*)h->env_state + a * 16 * n + e0, (const char*)env_state_host + a * 16 * n + e0, eb, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync((char*)h->tables + p0 * tab_stride, (const char*)tables_host + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpyAsync((char*)h->pop_state + p0 * ps_stride, (const char*)pop_state_host + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyHostToDevice, cs));
+    if (k_steps > 0) {
+      const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, cs, p0, p1 - p0);
+      if (rc) return rc;
+    }
+    for (int a = 0; a < 3; ++a)
+      CUDA_TRY(cudaMemcpyAsync((char*)env_state_host + a * 16 * n + e0, (const char*)h->env_state + a * 16 * n + e0, eb, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync((char*)tables_host + p0 * tab_stride, (const char*)h->tables + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync((char*)pop_state_host + p0 * ps_stride, (const char*)h->pop_state + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaEventRecord(h->chunk_done[c], cs));
+    CUDA_TRY(cudaStreamWaitEvent(s, h->chunk_done[c], 0));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   return DQLB200_OK;
 }

@@ -356,3 +356,26 @@ def test_replica_merge_mode_vs_oracle(R, merge_every):
     # all replicas agree after the final merge
     t = eng.tables.cpu().numpy()
     assert all(np.array_equal(t[0, 0], t[r, 0]) and np.array_equal(t[0, 2], t[r, 2]) for r in range(R))
+
+
+@pytest.mark.parametrize("P", [3, 21])
+def test_train_host_equals_device_resident_training(P):
+    """dqlb200_train_host (host buffers, chunk-pipelined copies) leaves exactly the state the device-resident entry point
+    leaves: env state, tables and trainer state bit for bit, promotions included (P = 3: fewer populations than chunks)."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    a = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=kw)
+    b = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=kw)
+    a.reset(0)
+    b.reset(0)
+    env_h = b.env_state.cpu().pin_memory()
+    tab_h = b.tables.cpu().pin_memory()
+    ps_h = b.pop_state.cpu().pin_memory()
+    b.env_state.zero_(); b.tables.zero_(); b.pop_state.zero_()        # the call must not depend on what the staging buffers hold
+    for k in (40, 1, 90):
+        a.train(k)
+        b.train_host(k, env_h, tab_h, ps_h)
+    torch.cuda.synchronize()
+    assert torch.equal(a.env_state.cpu(), env_h)
+    assert torch.equal(a.tables.cpu(), tab_h)
+    assert torch.equal(a.pop_state.cpu(), ps_h)
+    assert int(a.population_state()["working_step"].max()) >= 1
