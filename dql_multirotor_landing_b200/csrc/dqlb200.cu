@@ -169,7 +169,8 @@ struct Shared {
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   dqlb200_population_state ps;
-  unsigned long long n_episodes, n_success, ep_steps, hist[9];
+  unsigned long long n_episodes, n_success, ep_steps, hist[9];     // totals of this launch
+  uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
   int promote, advance, do_advance;
   // followed by: uint16_t reset_queue[WARPS][RESET_QUEUE]   (dynamic)
 };
@@ -209,7 +210,8 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     for (int i = tid; i < PS_WORDS; i += NT) reinterpret_cast<uint32_t*>(&sh.ps)[i] = gps[i];
     if (tid == 0) {
       sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
-      for (int i = 0; i < 9; ++i) sh.hist[i] = 0ull;
+      sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
+      for (int i = 0; i < 9; ++i) { sh.hist[i] = 0ull; sh.step_hist[i] = 0u; }
       sh.promote = sh.advance = sh.do_advance = 0;
       sh.cuts = kc.cuts[w_start];
     }
@@ -368,6 +370,12 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
             if (o >= 0) a = o;
           }
         }
+        // learning-rate hint for phase B: the LUT entry of the cell's count as it is NOW (an unsynchronised peek at the
+        // live table; phase B uses it only if the count is still the same, so the result does not depend on it).  Issued
+        // here, a whole phase A before the baton: a barrier waits for the thread's outstanding global loads too.
+        cell = sid * 3u + (uint32_t)a;
+        c_hint = min(sh.cnt[cell], (uint32_t)(DQLB200_ALPHA_LUT - 1));
+        a_hint = __ldg(alpha_lut + c_hint);
         // R3: set-point (float64).  A fresh episode starts from 0 but keeps the old value for shaping.
         const double prev_sp = e.theta_sp;
         const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
@@ -411,7 +419,6 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const float qn = sh.qmax[sid2];
         const float changed = (e.bp != (uint32_t)ds.bp) ? 1.0f : 0.0f;
         target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
-        cell = sid * 3u + (uint32_t)a;
         if (TRACE) {
           if (args.trace.obs) {
             float* po = args.trace.obs + trace_i * 5;
@@ -444,80 +451,97 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
           e.fresh = false;
           e.cum_reward = __dadd_rn(e.cum_reward, r);
         }
-        // learning-rate hint for phase B: the LUT entry of the cell's count as it is NOW (an unsynchronised peek at the
-        // live table; phase B uses it only if the count is still the same, so the result does not depend on it)
-        c_hint = min(sh.cnt[cell], (uint32_t)(DQLB200_ALPHA_LUT - 1));
-        a_hint = __ldg(alpha_lut + c_hint);
       }
       // ---------------- phase B: ordered commit (baton between warps) --------------------------
-      if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
+      // The serialised section is the critical path of a global step (n_p / 32 links per population), so everything that
+      // does not read the live table happens BEFORE the baton arrives: same-cell groups, ranks, and the reductions over
+      // the finished episodes of this warp-slot.
       const uint32_t dmask = __ballot_sync(FULL, valid && done);
+      const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
+      const uint32_t peers = __match_any_sync(FULL, key);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      uint32_t smask = 0u;
+      double ret = 0.0, last_cum = 0.0;
+      int last_steps = 0, last_code = 0;
+      if (dmask) {
+        smask = __ballot_sync(FULL, valid && success);
+        // deterministic (fixed-tree) sum of the finished episodes' returns
+        ret = (valid && done) ? ep_return : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ret = __dadd_rn(ret, __shfl_xor_sync(FULL, ret, off));
+        const int last = 31 - __clz(dmask);
+        last_steps = __shfl_sync(FULL, (int)ep_steps, last);
+        last_code = __shfl_sync(FULL, code, last);
+        last_cum = __shfl_sync(FULL, ep_return, last);
+      }
+      if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
       {
-        const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
-        const uint32_t peers = __match_any_sync(FULL, key);
-        const int rank = __popc(peers & ((1u << lane) - 1u));
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
         const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
         float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
         if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
+        // the group's updates in lane order, two members per round (their four shuffles are issued together)
         uint32_t rem = valid ? peers : 0u;
         while (__any_sync(FULL, rem != 0u)) {
-          const int src = rem ? (__ffs(rem) - 1) : lane;
-          const float a_j = __shfl_sync(FULL, alpha, src);
-          const float t_j = __shfl_sync(FULL, target, src);
-          if (rem) q = fadd(q, fmul(a_j, fsub(t_j, q)));      // q += alpha * (target - q)
-          rem &= rem - 1u;
+          const uint32_t rem1 = rem & (rem - 1u);
+          const int src0 = rem ? (__ffs(rem) - 1) : lane, src1 = rem1 ? (__ffs(rem1) - 1) : lane;
+          const float a_0 = __shfl_sync(FULL, alpha, src0), t_0 = __shfl_sync(FULL, target, src0);
+          const float a_1 = __shfl_sync(FULL, alpha, src1), t_1 = __shfl_sync(FULL, target, src1);
+          if (rem) q = fadd(q, fmul(a_0, fsub(t_0, q)));       // q += alpha * (target - q)
+          if (rem1) q = fadd(q, fmul(a_1, fsub(t_1, q)));
+          rem = rem1 & (rem1 - 1u);
         }
         if (valid && rank == 0) {
           sh.qa[cell] = q;
           sh.cnt[cell] = c0 + (uint32_t)__popc(peers);
         }
         // finished episodes, in env order: success window + promotion test after every append (R14)
-        if (dmask) {
-          const uint32_t smask = __ballot_sync(FULL, valid && success);
-          if (valid && done) {
-            atomicAdd(&sh.hist[code], 1ull);
-            atomicAdd(&sh.ep_steps, (unsigned long long)ep_steps);
+        if (dmask && lane == 0) {
+          dqlb200_population_state& ps = sh.ps;
+          int head = ps.window_head, count = ps.window_count, sum = ps.window_sum;
+          long long eps = ps.episodes_in_step;
+          bool promote = false, advance = false;
+          uint32_t m = dmask;
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1u;
+            const int ok = (smask >> b) & 1u;
+            if (count == kc.window_len) sum -= ps.window[head];
+            else count += 1;
+            ps.window[head] = (uint8_t)ok;
+            sum += ok;
+            head = (head + 1 == kc.window_len) ? 0 : head + 1;
+            eps += 1;
+            promote = promote || (sum >= kc.promote_successes);
+            advance = advance || (eps >= kc.max_num_episodes);
           }
-          // deterministic (fixed-tree) sum of the finished episodes' returns
-          double ret = (valid && done) ? ep_return : 0.0;
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1) ret = __dadd_rn(ret, __shfl_xor_sync(FULL, ret, off));
-          const int last = 31 - __clz(dmask);
-          const int last_steps = __shfl_sync(FULL, (int)ep_steps, last);
-          const int last_code = __shfl_sync(FULL, code, last);
-          const double last_cum = __shfl_sync(FULL, ep_return, last);
-          if (lane == 0) {
-            dqlb200_population_state& ps = sh.ps;
-            uint32_t m = dmask;
-            while (m) {
-              const int b = __ffs(m) - 1;
-              m &= m - 1u;
-              const int ok = (smask >> b) & 1u;
-              if (ps.window_count == kc.window_len) ps.window_sum -= ps.window[ps.window_head];
-              else ps.window_count += 1;
-              ps.window[ps.window_head] = (uint8_t)ok;
-              ps.window_sum += ok;
-              ps.window_head = (ps.window_head + 1 == kc.window_len) ? 0 : ps.window_head + 1;
-              ps.episodes_in_step += 1;
-              if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
-                if (ps.window_sum >= kc.promote_successes) sh.promote = 1;
-                if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
-              }
-            }
-            sh.n_episodes += (unsigned long long)__popc(dmask);
-            sh.n_success += (unsigned long long)__popc(smask);
-            ps.return_sum = __dadd_rn(ps.return_sum, ret);
-            ps.last_code = last_code;
-            ps.last_steps = last_steps;
-            ps.last_cumulative = last_cum;
+          ps.window_head = head; ps.window_count = count; ps.window_sum = sum;
+          ps.episodes_in_step = eps;
+          if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
+            if (promote) sh.promote = 1;
+            if (advance) sh.advance = 1;
           }
+          ps.return_sum = __dadd_rn(ps.return_sum, ret);
+          ps.last_code = last_code;
+          ps.last_steps = last_steps;
+          ps.last_cumulative = last_cum;
         }
       }
       if (WARPS > 1 && !(slot == n_slots - 1 && warp == WARPS - 1)) {
         __threadfence_block();
         baton_pass<WARPS>((warp + 1) % WARPS);
+      }
+      // order-independent episode counters: after the baton
+      if (dmask) {
+        if (valid && done) {
+          atomicAdd(&sh.step_hist[code], 1u);
+          atomicAdd(&sh.step_ep_steps, ep_steps);
+        }
+        if (lane == 0) {
+          atomicAdd(&sh.step_episodes, (uint32_t)__popc(dmask));
+          atomicAdd(&sh.step_success, (uint32_t)__popc(smask));
+        }
       }
       // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
       // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
@@ -538,7 +562,10 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     if (tid == 0) {
       sh.ps.t = t + 1u;
       sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
+      sh.n_episodes += sh.step_episodes; sh.n_success += sh.step_success; sh.ep_steps += sh.step_ep_steps;
+      sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
     }
+    if (tid < 9) { sh.hist[tid] += sh.step_hist[tid]; sh.step_hist[tid] = 0u; }
     __syncthreads();
     if (sh.do_advance) {
       advance_curriculum(w, t + 1u);
