@@ -14,7 +14,7 @@ SYMBOLS = [
     "dqlb200_abi_version", "dqlb200_config_bytes", "dqlb200_population_state_bytes", "dqlb200_last_error",
     "dqlb200_termination_string", "dqlb200_create", "dqlb200_destroy", "dqlb200_bind", "dqlb200_reset",
     "dqlb200_train", "dqlb200_train_host", "dqlb200_eval_greedy", "dqlb200_transfer", "dqlb200_check_errors",
-    "dqlb200_shared_pack", "dqlb200_shared_apply", "dqlb200_mdp_facade_step", "dqlb200_agent_facade", "dqlb200_selftest_division", "dqlb200_replica_merge", "dqlb200_bind_merge_snapshot",
+    "dqlb200_shared_pack", "dqlb200_shared_apply", "dqlb200_mdp_facade_step", "dqlb200_agent_facade", "dqlb200_selftest_division", "dqlb200_replica_merge", "dqlb200_bind_merge_snapshot", "dqlb200_eval_greedy_2d", "dqlb200_eval2d_params_bytes",
 ]
 
 OP_ACTION, OP_OBSERVE, OP_CHECK, OP_REWARD, OP_RESET, OP_SIMULATION = 1, 2, 4, 8, 16, 256
@@ -43,6 +43,7 @@ def load() -> C.CDLL:
     lib.dqlb200_abi_version.restype = C.c_int
     lib.dqlb200_config_bytes.restype = C.c_size_t
     lib.dqlb200_population_state_bytes.restype = C.c_size_t
+    lib.dqlb200_eval2d_params_bytes.restype = C.c_size_t
     lib.dqlb200_last_error.restype = C.c_char_p
     lib.dqlb200_termination_string.restype = C.c_char_p
     lib.dqlb200_termination_string.argtypes = [i32]
@@ -53,6 +54,7 @@ def load() -> C.CDLL:
     lib.dqlb200_train.argtypes = [vp, i32, C.POINTER(K.Trace), vp]
     lib.dqlb200_train_host.argtypes = [vp, i32, vp, vp, vp, vp]
     lib.dqlb200_eval_greedy.argtypes = [vp, i32, vp, i64, i64, i32, vp, C.POINTER(K.Trace), i32, vp]
+    lib.dqlb200_eval_greedy_2d.argtypes = [vp, C.POINTER(K.Eval2DParams), vp, vp, i64, i64, vp, C.POINTER(K.Trace2D), i32, vp]
     lib.dqlb200_transfer.argtypes = [vp, i32, C.c_float, vp]
     lib.dqlb200_check_errors.argtypes = [vp, vp]
     lib.dqlb200_shared_pack.argtypes = [vp, vp, vp, vp]
@@ -66,6 +68,8 @@ def load() -> C.CDLL:
         raise Dqlb200Error("libdqlb200.so ABI version mismatch; rebuild")
     if lib.dqlb200_config_bytes() != C.sizeof(K.Config) or lib.dqlb200_population_state_bytes() != C.sizeof(K.PopulationState):
         raise Dqlb200Error("struct layout mismatch between constants.py and include/dqlb200.h; rebuild")
+    if lib.dqlb200_eval2d_params_bytes() != C.sizeof(K.Eval2DParams):
+        raise Dqlb200Error("dqlb200_eval2d_params layout mismatch between constants.py and include/dqlb200.h; rebuild")
     _lib = lib
     return lib
 

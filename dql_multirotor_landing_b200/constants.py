@@ -134,6 +134,23 @@ class EvalStats(C.Structure):
     _fields_ = [("episodes", C.c_uint64), ("steps", C.c_uint64), ("termination_hist", C.c_uint64 * 9)]
 
 
+class Eval2DParams(C.Structure):
+    """dqlb200_eval2d_params (include/dqlb200.h)."""
+    _fields_ = [("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("stream_id", C.c_uint32), ("trajectory", C.c_int32),
+                ("dphase_x", C.c_uint32), ("dphase_y", C.c_uint32),
+                ("r_x", C.c_float), ("rw_x", C.c_float), ("rw2_x", C.c_float), ("r_y", C.c_float), ("rw_y", C.c_float), ("rw2_y", C.c_float),
+                ("g_x", C.c_float), ("g_y", C.c_float), ("y_action_enabled", C.c_int32), ("y_init_enabled", C.c_int32),
+                ("working_step", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Trace2D(C.Structure):
+    _fields_ = [("obs", C.c_void_p), ("action_x", C.c_void_p), ("action_y", C.c_void_p), ("code", C.c_void_p), ("done", C.c_void_p),
+                ("contact", C.c_void_p), ("state_x", C.c_void_p), ("state_y", C.c_void_p)]
+
+
+TRAJ_RECTILINEAR_X, TRAJ_RECTILINEAR_XY, TRAJ_EIGHT = 0, 1, 2
+
+
 # ------------------------------------------------------------------------------------------------
 # parameters (defaults = the reference's)
 # ------------------------------------------------------------------------------------------------
@@ -173,6 +190,38 @@ class DynamicsParameters:
     z_touch: float = 0.515           # bumper top + body       urdf/moving_platform.urdf:16,38,51,58
     half_platform: float = 0.5
     n_sub: int = 1
+
+
+@dataclass
+class TwoAxisParameters:
+    """Platform and axis conventions of the two-axis evaluator (dqlb200_eval_greedy_2d).  Defaults = the reference:
+    rectilinear periodic platform along x only (PKG/moving_platform.py:113-125), y action and y start offset disabled
+    (PKG/mdp.py:863-876, PKG/landing_simulation_env.py:336-340).  `eight` uses r = 3, v = 0.8 (PKG/moving_platform.py:92-96)."""
+    trajectory: int = 0
+    r_x: float = 2.0
+    v_x: float = 1.6
+    r_y: float = 2.0
+    v_y: float = 1.0
+    g_y_sign: float = -1.0           # a_y = -g tan(roll) in the reference's ENU frame
+    y_action_enabled: bool = False
+    y_init_enabled: bool = False
+
+
+def eval2d_params(ta: "TwoAxisParameters", dp: "DynamicsParameters", f_ag: float, seed: int, stream_id: int, working_step: int) -> Eval2DParams:
+    h = (1.0 / f_ag) / dp.n_sub
+    wx = ta.v_x / ta.r_x
+    turns = lambda w: int(round(w * h / (2.0 * math.pi) * 2.0 ** 32)) & 0xFFFFFFFF
+    f = np.float32
+    if ta.trajectory == TRAJ_EIGHT:
+        dpy, ry, rwy, rw2y = turns(wx), f(ta.r_y), f(ta.r_y * wx), f(4.0 * ta.r_y * wx * wx)
+    elif ta.trajectory == TRAJ_RECTILINEAR_XY:
+        wy = ta.v_y / ta.r_y
+        dpy, ry, rwy, rw2y = turns(wy), f(ta.r_y), f(ta.r_y * wy), f(ta.r_y * wy * wy)
+    else:
+        dpy, ry, rwy, rw2y = 0, f(0.0), f(0.0), f(0.0)
+    return Eval2DParams(seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF, stream_id, ta.trajectory, turns(wx), dpy,
+                        f(ta.r_x), f(ta.r_x * wx), f(ta.r_x * wx * wx), ry, rwy, rw2y, f(dp.g), f(ta.g_y_sign * dp.g),
+                        int(ta.y_action_enabled), int(ta.y_init_enabled), working_step, 0)
 
 
 @dataclass

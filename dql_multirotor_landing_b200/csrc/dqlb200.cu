@@ -720,6 +720,127 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
 }
 
 // -------------------------------------------------------------------------------------------------
+// two-axis greedy evaluation.  One thread per episode; pitch drives x, roll drives y (signed gravity per
+// axis), one platform under both (three trajectories).  Same operation order as oracle/dynamics.py: StandIn2D.
+// -------------------------------------------------------------------------------------------------
+struct Axis {
+  float pos, vel, ang, acc;
+};
+__device__ __forceinline__ void axis_advance(const KC& kc, Axis& b, float sp, float g) {
+  b.ang = fadd(b.ang, fmul(fsub(sp, b.ang), kc.k_theta));
+  b.acc = fsub(fmul(g, det_tan(b.ang)), fmul(kc.c_d, b.vel));
+  b.pos = fadd(fadd(b.pos, fmul(b.vel, kc.h)), fmul(b.acc, kc.half_h2));
+  b.vel = fadd(b.vel, fmul(b.acc, kc.h));
+}
+struct Platform2D {
+  float xm, um, axm, ym, vm, aym;
+};
+__device__ __forceinline__ Platform2D platform_2d(const dqlb200_eval2d_params& p, uint32_t phase_x, uint32_t phase_y) {
+  Platform2D m;
+  float sx, cx;
+  det_sincos_turns(phase_x, sx, cx);
+  if (p.trajectory == 2) {
+    const float sc = fmul(sx, cx);
+    m.xm = fmul(p.r_x, cx); m.um = -fmul(p.rw_x, sx); m.axm = -fmul(p.rw2_x, cx);
+    m.ym = fmul(p.r_y, sc); m.vm = fmul(p.rw_y, fsub(fmul(cx, cx), fmul(sx, sx))); m.aym = -fmul(p.rw2_y, sc);
+  } else {
+    float sy, cy;
+    det_sincos_turns(phase_y, sy, cy);
+    m.xm = fmul(p.r_x, sx); m.um = fmul(p.rw_x, cx); m.axm = -fmul(p.rw2_x, sx);
+    m.ym = fmul(p.r_y, sy); m.vm = fmul(p.rw_y, cy); m.aym = -fmul(p.rw2_y, sy);
+  }
+  return m;
+}
+
+__global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC kc, const __grid_constant__ dqlb200_eval2d_params p,
+                                                     const uint8_t* __restrict__ policy_x, const uint8_t* __restrict__ policy_y,
+                                                     long long first_episode, long long n_episodes, dqlb200_eval_stats* stats,
+                                                     dqlb200_trace2d trace, int trace_steps) {
+  __shared__ uint8_t s_pol_x[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL], s_pol_y[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
+  __shared__ dqlb200_cuts cuts;
+  __shared__ unsigned long long s_hist[9], s_steps, s_eps;
+  for (int i = threadIdx.x; i < DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL; i += blockDim.x) {
+    s_pol_x[i] = policy_x[i];
+    s_pol_y[i] = policy_y[i];
+  }
+  if (threadIdx.x == 0) { cuts = kc.cuts[p.working_step]; s_steps = s_eps = 0ull; }
+  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0ull;
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_episodes) {
+    const unsigned long long ep = (unsigned long long)(first_episode + i);
+    const uint4 d = philox4x32_10(make_uint4((uint32_t)ep, 0u, PURPOSE_RESET, p.stream_id), p.seed_lo, p.seed_hi);
+    // PKG/landing_simulation_env.py:327-340: uniform offsets inside the fly zone, absolute clip, random platform phase
+    const float x_init = fadd(-kc.p_max_f, fmul(kc.two_p_max_f, fmul(__uint2float_rn(d.x >> 8), (float)(1.0 / 16777216.0))));
+    const float y_init = fadd(-kc.p_max_f, fmul(kc.two_p_max_f, fmul(__uint2float_rn(d.y >> 8), (float)(1.0 / 16777216.0))));
+    uint32_t phase_x = d.z, phase_y = (p.trajectory == 2) ? d.z : d.w;
+    Platform2D m = platform_2d(p, phase_x, phase_y);
+    Axis bx, by;
+    bx.pos = clipf(fsub(m.xm, x_init), -kc.p_max_f, kc.p_max_f);
+    by.pos = p.y_init_enabled ? clipf(fsub(m.ym, y_init), -kc.p_max_f, kc.p_max_f) : 0.0f;
+    bx.vel = bx.ang = bx.acc = by.vel = by.ang = by.acc = 0.0f;
+    double sp_x = 0.0, sp_y = 0.0;
+    int code = DQLB200_NON_TERMINAL, step = -1;
+    uint32_t sid_x = 0, sid_y = 0;
+    while (code < DQLB200_TERMINAL_SUCCESS) {
+      int ax = 255, ay = 255;
+      if (step >= 0) {          // step == -1: the hover period after the reset (PKG/landing_simulation_env.py:222-224)
+        ax = s_pol_x[sid_x];
+        ay = s_pol_y[sid_y];
+        sp_x = apply_action(kc, sp_x, ax);
+        if (p.y_action_enabled) sp_y = apply_action(kc, sp_y, ay);
+      }
+      for (int k = 0; k < kc.n_sub; ++k) {
+        axis_advance(kc, bx, (float)sp_x, p.g_x);
+        axis_advance(kc, by, (float)sp_y, p.g_y);
+        phase_x += p.dphase_x;
+        phase_y += p.dphase_y;
+      }
+      step += 1;
+      m = platform_2d(p, phase_x, phase_y);
+      Obs ox, oy;
+      ox.rel_p = fsub(m.xm, bx.pos); ox.rel_v = fsub(m.um, bx.vel); ox.rel_a = fsub(m.axm, bx.acc); ox.pitch = bx.ang;
+      oy.rel_p = fsub(m.ym, by.pos); oy.rel_v = fsub(m.vm, by.vel); oy.rel_a = fsub(m.aym, by.acc); oy.pitch = by.ang;
+      const float z = fadd(kc.z_init, fmul(__int2float_rn(step), kc.dz_sim));
+      const bool contact = (z <= kc.z_touch) && (fabsf(ox.rel_p) <= kc.half_platform) && (fabsf(oy.rel_p) <= kc.half_platform);
+      sid_x = (uint32_t)discretise_cuts(cuts, kc.angle_cut, ox).id();
+      sid_y = (uint32_t)discretise_cuts(cuts, kc.angle_cut, oy).id();
+      if (step == 0) continue;          // the reset only observes (no check, PKG/landing_simulation_env.py:236-243)
+      if (contact) code = DQLB200_TERMINAL_CONTACT;
+      else if (!(ox.rel_p >= kc.fz_lo) || (ox.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
+      else if (!(oy.rel_p >= kc.fz_lo) || (oy.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_Y;
+      else if (!(z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+      else if (z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
+      else if (step >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
+      if (step <= trace_steps) {
+        const size_t ti = (size_t)(step - 1) * (size_t)n_episodes + (size_t)i;
+        if (trace.obs) {
+          float* po = trace.obs + ti * 9;
+          po[0] = ox.rel_p; po[1] = ox.rel_v; po[2] = ox.rel_a; po[3] = ox.pitch; po[4] = z;
+          po[5] = oy.rel_p; po[6] = oy.rel_v; po[7] = oy.rel_a; po[8] = oy.pitch;
+        }
+        if (trace.action_x) trace.action_x[ti] = (uint8_t)ax;
+        if (trace.action_y) trace.action_y[ti] = (uint8_t)ay;
+        if (trace.code) trace.code[ti] = (uint8_t)code;
+        if (trace.done) trace.done[ti] = (uint8_t)(code >= DQLB200_TERMINAL_SUCCESS);
+        if (trace.contact) trace.contact[ti] = (uint8_t)contact;
+        if (trace.state_x) trace.state_x[ti] = (uint16_t)sid_x;
+        if (trace.state_y) trace.state_y[ti] = (uint16_t)sid_y;
+      }
+    }
+    atomicAdd(&s_hist[code], 1ull);
+    atomicAdd(&s_steps, (unsigned long long)step);
+    atomicAdd(&s_eps, 1ull);
+  }
+  __syncthreads();
+  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x == 0) {
+    atomicAdd((unsigned long long*)&stats->steps, s_steps);
+    atomicAdd((unsigned long long*)&stats->episodes, s_eps);
+  }
+}
+
+// -------------------------------------------------------------------------------------------------
 // Facade kernel: float64 observations, the reference's comparisons in float64 (PKG/mdp.py:149-170,
 // 257-333, 335-439, 441-541, 784-845).  One thread per MDP object.
 // -------------------------------------------------------------------------------------------------
@@ -1017,6 +1138,7 @@ extern "C" {
 int dqlb200_abi_version(void) { return DQLB200_ABI_VERSION; }
 size_t dqlb200_config_bytes(void) { return sizeof(dqlb200_config); }
 size_t dqlb200_population_state_bytes(void) { return sizeof(dqlb200_population_state); }
+size_t dqlb200_eval2d_params_bytes(void) { return sizeof(dqlb200_eval2d_params); }
 const char* dqlb200_last_error(void) { return g_last_error.c_str(); }
 
 const char* dqlb200_termination_string(int code) {
@@ -1256,6 +1378,23 @@ int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy
   dql::eval_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode,
                                                                      n_episodes, working_step, (dqlb200_eval_stats*)stats_out,
                                                                      tr, trace ? trace_steps : 0);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_eval_greedy_2d(dqlb200_handle* h, const dqlb200_eval2d_params* p, const uint8_t* policy_x, const uint8_t* policy_y,
+                           int64_t first_episode, int64_t n_episodes, void* stats_out, const dqlb200_trace2d* trace, int trace_steps,
+                           void* stream) {
+  if (!h || !p || !policy_x || !policy_y || !stats_out) return fail(DQLB200_ERR_ARG, "null argument");
+  if (p->trajectory < 0 || p->trajectory > 2) return fail(DQLB200_ERR_ARG, "trajectory must be 0 (rectilinear x), 1 (rectilinear x and y) or 2 (eight)");
+  if (p->working_step < 0 || p->working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  if (n_episodes <= 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  dqlb200_trace2d tr;
+  if (trace) tr = *trace; else memset(&tr, 0, sizeof(tr));
+  const long long blocks = (n_episodes + 255) / 256;
+  dql::eval2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, *p, policy_x, policy_y, first_episode, n_episodes,
+                                                                       (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

@@ -200,11 +200,49 @@ class Engine:
         _ffi.check(self.lib.dqlb200_eval_greedy(self.handle, population, d_pol.data_ptr(), first_episode, n_episodes, working_step,
                                                 stats.data_ptr(), C.byref(tr) if tr is not None else None, trace_steps, self._stream()))
         torch.cuda.synchronize(dev)
-        st = K.EvalStats.from_buffer_copy(stats.cpu().numpy().tobytes())
-        res = dict(episodes=int(st.episodes), steps=int(st.steps), termination_hist=[int(x) for x in st.termination_hist])
-        if out is not None:
-            res["trace"] = {k: v.cpu().numpy() for k, v in out.items()}
-        return res
+        return _eval_result(K.EvalStats.from_buffer_copy(stats.cpu().numpy().tobytes()), out)
+
+    def eval_greedy_2d(self, policy_x: np.ndarray, policy_y: np.ndarray, n_episodes: int, *, two_axis: Optional[K.TwoAxisParameters] = None,
+                       seed: int = 42, stream_id: int = 0, first_episode: int = 0, working_step: int = 4, trace_steps: int = 0):
+        """Greedy two-axis SimulationMdp episodes: agent_x and agent_y both predict every step (scripts/simulation.py:48-63).
+        policy_x / policy_y: uint8 action per state id.  Defaults reproduce the reference (y action disabled)."""
+        dev = self.device
+        ta = two_axis or K.TwoAxisParameters()
+        prm = K.eval2d_params(ta, self.dp, self.mp.f_ag, seed, stream_id, working_step)
+
+        def lut(p):
+            full = np.zeros(K.MAX_CURRICULUM * K.STATES_PER_LEVEL, np.uint8)
+            full[: len(p)] = p
+            return torch.as_tensor(full, device=dev)
+
+        d_px, d_py = lut(policy_x), lut(policy_y)
+        stats = torch.zeros(C.sizeof(K.EvalStats), dtype=torch.uint8, device=dev)
+        tr, out = None, None
+        if trace_steps > 0:
+            u8 = lambda: torch.zeros((trace_steps, n_episodes), dtype=torch.uint8, device=dev)
+            i16 = lambda: torch.zeros((trace_steps, n_episodes), dtype=torch.int16, device=dev)
+            out = dict(obs=torch.zeros((trace_steps, n_episodes, 9), dtype=torch.float32, device=dev), action_x=u8(), action_y=u8(),
+                       code=u8(), done=u8(), contact=u8(), state_x=i16(), state_y=i16())
+            tr = K.Trace2D(*[out[k].data_ptr() for k in ("obs", "action_x", "action_y", "code", "done", "contact", "state_x", "state_y")])
+        _ffi.check(self.lib.dqlb200_eval_greedy_2d(self.handle, C.byref(prm), d_px.data_ptr(), d_py.data_ptr(), first_episode, n_episodes,
+                                                   stats.data_ptr(), C.byref(tr) if tr is not None else None, trace_steps, self._stream()))
+        torch.cuda.synchronize(dev)
+        return _eval_result(K.EvalStats.from_buffer_copy(stats.cpu().numpy().tobytes()), out)
+
+
+def _eval_result(st, out):
+    res = dict(episodes=int(st.episodes), steps=int(st.steps), termination_hist=[int(x) for x in st.termination_hist])
+    if out is not None:
+        res["trace"] = {k: v.cpu().numpy() for k, v in out.items()}
+    return res
+
+
+def mirrored_policy(policy: np.ndarray) -> np.ndarray:
+    """y-axis policy derived from an x policy by symmetry (a_y = -g tan(roll)): act as the x policy would in the state with
+    the mirrored angle index and swap increase/decrease.  For a y agent trained on its own (BASELINE config 4) use its own
+    greedy_policy instead."""
+    lut = np.asarray(policy, np.uint8).reshape(-1, 7)
+    return np.asarray([1, 0, 2], np.uint8)[lut[:, ::-1]].reshape(-1)
 
 
 def greedy_policy(qa: np.ndarray, qb: np.ndarray) -> np.ndarray:

@@ -160,11 +160,37 @@ typedef struct dqlb200_eval_stats {
   uint64_t termination_hist[9];
 } dqlb200_eval_stats;
 
+/* Two-axis greedy evaluation: pitch drives x, roll drives y, one platform under both.
+ * trajectory 0: x = r_x sin(w_x t), y = 0                     (PKG/moving_platform.py:113-125 with omega_y = 0)
+ *            1: x = r_x sin(w_x t), y = r_y sin(w_y t)        (the "future extension" kept in :113-125)
+ *            2: x = r_x cos(w t),  y = r_y sin(w t) cos(w t)  ("eight", PKG/moving_platform.py:92-111; rw2_y holds 4 r_y w^2)
+ * g_x / g_y are SIGNED: a = g tan(angle) - c_d v; in the reference's ENU frame g_y = -g.
+ * y_action_enabled = 0 reproduces the reference, whose roll branch is dead code (PKG/mdp.py:863-876);
+ * y_init_enabled = 0 reproduces `0 * clip(...)` (PKG/landing_simulation_env.py:336-340). */
+typedef struct dqlb200_eval2d_params {
+  uint32_t seed_lo, seed_hi, stream_id;     /* Philox key and counter word 3 */
+  int32_t trajectory;
+  uint32_t dphase_x, dphase_y;              /* platform phase advance per sub-step, uint32 turns */
+  float r_x, rw_x, rw2_x, r_y, rw_y, rw2_y;
+  float g_x, g_y;
+  int32_t y_action_enabled, y_init_enabled;
+  int32_t working_step;
+  int32_t reserved;
+} dqlb200_eval2d_params;
+
+/* Optional per-step trace of dqlb200_eval_greedy_2d: arrays [trace_steps][n_episodes], any may be NULL. */
+typedef struct dqlb200_trace2d {
+  float* obs;                       /* [..][9] rel_p_x, rel_v_x, rel_a_x, pitch, z, rel_p_y, rel_v_y, rel_a_y, roll */
+  uint8_t* action_x; uint8_t* action_y; uint8_t* code; uint8_t* done; uint8_t* contact;
+  uint16_t* state_x; uint16_t* state_y;     /* states AFTER the step */
+} dqlb200_trace2d;
+
 typedef struct dqlb200_handle dqlb200_handle;
 
 int dqlb200_abi_version(void);
 size_t dqlb200_config_bytes(void);
 size_t dqlb200_population_state_bytes(void);
+size_t dqlb200_eval2d_params_bytes(void);
 const char* dqlb200_last_error(void);
 /* CheckResult.value strings (PKG/mdp.py:69-75); NULL for non-terminal codes. */
 const char* dqlb200_termination_string(int code);
@@ -206,6 +232,14 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
 int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy, int64_t first_episode,
                         int64_t n_episodes, int working_step, void* stats_out, const dqlb200_trace* trace,
                         int trace_steps, void* stream);
+
+/* Replaces: scripts/simulation.py:48-63 with BOTH agents acting (agent_x.predict / agent_y.predict,
+ * SimulationMdp.discrete_state_x/_y PKG/mdp.py:634-782, check :784-845 incl. FLYZONE_Y and contact on both axes).
+ * policy_x / policy_y: 945-byte action LUTs (device).  Episode i uses the reset draws of (env = first_episode + i,
+ * stream p->stream_id).  stats_out: device dqlb200_eval_stats (accumulated, caller zeroes). */
+int dqlb200_eval_greedy_2d(dqlb200_handle* h, const dqlb200_eval2d_params* p, const uint8_t* policy_x,
+                           const uint8_t* policy_y, int64_t first_episode, int64_t n_episodes, void* stats_out,
+                           const dqlb200_trace2d* trace, int trace_steps, void* stream);
 
 /* Replaces: DoubleQLearningAgent.transfer_learning (PKG/double_q_learning.py:77-89) on the bound
  * tables of every population. */

@@ -246,3 +246,117 @@ def standin_f64(params: StandInParams, x_d0, phase0, theta_sp_seq):
         z = params.z_init + (i + 1) * params.v_z * (1.0 / params.f_ag)
         out.append((xm - x, vm - v, am - a, th, z))
     return np.asarray(out, dtype=np.float64)
+
+
+# ----------------------------------------------------------------------------------------
+# two-axis stand-in: pitch drives x, roll drives y, one platform for both
+# ----------------------------------------------------------------------------------------
+TRAJ_RECTILINEAR_X, TRAJ_RECTILINEAR_XY, TRAJ_EIGHT = 0, 1, 2
+
+
+@dataclass(frozen=True)
+class StandIn2DParams:
+    """Platform + axis conventions of the two-axis evaluator.
+    trajectory 0: x = r_x sin(w_x t), y = 0                       (PKG/moving_platform.py:113-125, omega_y = 0)
+    trajectory 1: x = r_x sin(w_x t), y = r_y sin(w_y t)          (the "possible future extension" of :113-125)
+    trajectory 2: x = r_x cos(w t),  y = r_y sin(w t) cos(w t)    ("eight", PKG/moving_platform.py:92-111), w = v_x / r_x
+    g_y is SIGNED: a_y = g_y tan(roll) - c_d v_y; in the reference's ENU frame a positive roll accelerates toward -y,
+    so g_y = -g; the same holds for x with g_x = +g (sign verified in SURVEY.md A.3)."""
+    base: StandInParams = StandInParams(v_z=-0.4)
+    trajectory: int = TRAJ_RECTILINEAR_X
+    r_y: float = 2.0
+    v_y: float = 1.0             # PKG/moving_platform.py t_y default
+    g_y: float = -9.81
+    y_action_enabled: bool = False   # False = the reference: the roll branch of continuous_action is dead code (PKG/mdp.py:863-876)
+    y_init_enabled: bool = False     # False = the reference: drone y = 0 * clip(...) (PKG/landing_simulation_env.py:336-340)
+
+
+def derive_2d(p: StandIn2DParams):
+    """fp32 platform constants of both axes: (dphase_x, dphase_y, r_x, rw_x, rw2_x, r_y, rw_y, rw2_y)."""
+    b = p.base
+    h = (1.0 / b.f_ag) / b.n_sub
+    wx = b.v_mp / b.r_mp
+    to_turns = lambda w: int(round(w * h / TWO_PI * 2.0 ** 32)) & 0xFFFFFFFF
+    if p.trajectory == TRAJ_EIGHT:
+        # d/dt [r_y sin cos] = r_y w (cos^2 - sin^2);  d2/dt2 = -4 r_y w^2 sin cos
+        return (to_turns(wx), to_turns(wx), f32(b.r_mp), f32(b.r_mp * wx), f32(b.r_mp * wx * wx),
+                f32(p.r_y), f32(p.r_y * wx), f32(4.0 * p.r_y * wx * wx))
+    wy = p.v_y / p.r_y if p.trajectory == TRAJ_RECTILINEAR_XY else 0.0
+    ry = p.r_y if p.trajectory == TRAJ_RECTILINEAR_XY else 0.0
+    return (to_turns(wx), to_turns(wy), f32(b.r_mp), f32(b.r_mp * wx), f32(b.r_mp * wx * wx),
+            f32(ry), f32(ry * wy), f32(ry * wy * wy))
+
+
+class StandIn2D:
+    """Deterministic fp32 two-axis stand-in, vectorised over n episodes; same operation order as eval2d_kernel."""
+
+    def __init__(self, params: StandIn2DParams, n: int):
+        self.p = params
+        self.d = derive(params.base)
+        (self.dphase_x, self.dphase_y, self.r_x, self.rw_x, self.rw2_x, self.r_y, self.rw_y, self.rw2_y) = derive_2d(params)
+        self.g = (self.d.g, f32(params.g_y))
+        z = lambda dt=f32: np.zeros(n, dt)
+        self.pos, self.vel, self.ang, self.acc = [z(), z()], [z(), z()], [z(), z()], [z(), z()]
+        self.phase = [z(np.uint32), z(np.uint32)]
+
+    def platform(self):
+        """((x_mp, u_mp, ax_mp), (y_mp, v_mp, ay_mp))"""
+        sx, cx = det_sincos_turns(self.phase[0])
+        if self.p.trajectory == TRAJ_EIGHT:
+            sc = sx * cx
+            return ((self.r_x * cx, -(self.rw_x * sx), -(self.rw2_x * cx)),
+                    (self.r_y * sc, self.rw_y * (cx * cx - sx * sx), -(self.rw2_y * sc)))
+        sy, cy = det_sincos_turns(self.phase[1])
+        return ((self.r_x * sx, self.rw_x * cx, -(self.rw2_x * sx)), (self.r_y * sy, self.rw_y * cy, -(self.rw2_y * sy)))
+
+    def reset(self, w0, w1, w2, w3):
+        """PKG/landing_simulation_env.py:327-340: uniform offsets inside the fly zone, absolute clip; random platform phase."""
+        d = self.d
+        u = lambda w: (np.asarray(w, np.uint32) >> np.uint32(8)).astype(np.float32) * f32(2.0 ** -24)
+        x_init = -d.p_max + d.two_p_max * u(w0)
+        y_init = -d.p_max + d.two_p_max * u(w1)
+        self.phase[0][:] = np.asarray(w2, np.uint32)
+        self.phase[1][:] = np.asarray(w2 if self.p.trajectory == TRAJ_EIGHT else w3, np.uint32)
+        (xm, _, _), (ym, _, _) = self.platform()
+        self.pos[0][:] = np.clip(xm - x_init, -d.p_max, d.p_max)
+        self.pos[1][:] = np.clip(ym - y_init, -d.p_max, d.p_max) if self.p.y_init_enabled else f32(0.0)
+        for a in (0, 1):
+            self.vel[a][:] = 0
+            self.ang[a][:] = 0
+            self.acc[a][:] = 0
+
+    def advance(self, sp_x, sp_y):
+        d = self.d
+        sps = (np.asarray(sp_x, np.float32), np.asarray(sp_y, np.float32))
+        for _ in range(d.n_sub):
+            for a in (0, 1):
+                th = self.ang[a] + (sps[a] - self.ang[a]) * d.k_theta
+                acc = self.g[a] * det_tan(th) - d.c_d * self.vel[a]
+                self.pos[a] = ((self.pos[a] + self.vel[a] * d.h) + acc * d.half_h2).astype(np.float32)
+                self.vel[a] = (self.vel[a] + acc * d.h).astype(np.float32)
+                self.ang[a], self.acc[a] = th.astype(np.float32), acc.astype(np.float32)
+            self.phase[0] = self.phase[0] + np.uint32(self.dphase_x)
+            self.phase[1] = self.phase[1] + np.uint32(self.dphase_y)
+
+    def observe(self, step_count):
+        """dict of fp32 arrays: rel_p/v/a for x and y, pitch, roll, z, contact."""
+        d = self.d
+        (xm, um, axm), (ym, vm, aym) = self.platform()
+        o = dict(rel_p_x=xm - self.pos[0], rel_v_x=um - self.vel[0], rel_a_x=axm - self.acc[0], pitch=self.ang[0].copy(),
+                 rel_p_y=ym - self.pos[1], rel_v_y=vm - self.vel[1], rel_a_y=aym - self.acc[1], roll=self.ang[1].copy())
+        o = {k: np.asarray(v, np.float32) for k, v in o.items()}
+        o["z"] = (d.z_init + np.asarray(step_count).astype(np.float32) * d.dz).astype(np.float32)
+        o["contact"] = (o["z"] <= d.z_touch) & (np.abs(o["rel_p_x"]) <= d.half_platform) & (np.abs(o["rel_p_y"]) <= d.half_platform)
+        return o
+
+
+def sim2d_cases():
+    """Named two-axis cases shared by the fixture generator (oracle/gen_golden.py) and the parity tests."""
+    return {
+        "reference": StandIn2DParams(trajectory=TRAJ_RECTILINEAR_X),
+        "xy": StandIn2DParams(trajectory=TRAJ_RECTILINEAR_XY, y_action_enabled=True, y_init_enabled=True, v_y=1.0),
+        "eight": StandIn2DParams(base=StandInParams(v_z=-0.4, r_mp=3.0, v_mp=0.8), trajectory=TRAJ_EIGHT, r_y=3.0,
+                                 y_action_enabled=True, y_init_enabled=True),
+        # the x policy on the y axis has the wrong sign for a_y = -g tan(roll): the drone runs away along y (FLYZONE_Y)
+        "ywrong": StandIn2DParams(trajectory=TRAJ_RECTILINEAR_XY, y_action_enabled=True, y_init_enabled=True, v_y=1.0),
+    }

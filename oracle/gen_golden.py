@@ -12,6 +12,7 @@ Fixtures:
                    Philox draws injected through np.random, float32 tables (NEP 50) and float64 tables
   schedules.npz    Trainer.alpha / exploration_rate / transfer_learning_ratio tables
   sim_trace.npz    SimulationMdp greedy episodes with the committed assets policy
+  sim2d_trace.npz  two-axis SimulationMdp episodes (x and y states, FLYZONE_Y, contact on both axes), three platform cases
 """
 from __future__ import annotations
 
@@ -307,6 +308,81 @@ def gen_sim_trace(ns, n_episodes=6, seed=5):
     print(f"sim_trace: {len(out['action'])} rows, terminal codes {dict(zip(codes.tolist(), cnt.tolist()))}")
 
 
+def gen_sim2d_trace(ns, n_episodes=4, seed=9):
+    """Two-axis greedy SimulationMdp episodes: the UNMODIFIED reference SimulationMdp discretises both axes and runs the
+    terminal chain (PKG/mdp.py:625-845) on the observations of the two-axis stand-in; pitch set-points come from the
+    reference's continuous_action, roll set-points (dead code in the reference, PKG/mdp.py:863-876) from the same
+    min/max expressions when the case enables them."""
+    from .dynamics import StandIn2D, sim2d_cases
+    from .loop import mirrored_policy
+    agent = ns.dql.DoubleQLearningAgent.load()
+    lut_x = np.asarray([agent.predict(_state_tuple(sid)) for sid in range(945)], np.uint8)
+    lut_y = mirrored_policy(lut_x)
+    theta_max, delta_theta = np.deg2rad(21.37723), np.deg2rad(7.12574)
+    cases = sim2d_cases()
+    luts_y = {"reference": lut_y, "xy": lut_y, "eight": lut_y, "ywrong": lut_x}
+    out = dict(seed=np.int64(seed), lut_x=lut_x)
+    keys = ("rel_p_x", "rel_v_x", "rel_a_x", "pitch", "z", "rel_p_y", "rel_v_y", "rel_a_y", "roll")
+    for ci, (name, p2) in enumerate(cases.items()):
+        lut_y = luts_y[name]
+        out[f"{name}_lut_y"] = lut_y
+        rec = {k: [] for k in ("obs", "contact", "action_x", "action_y", "state_x", "state_y", "code", "done", "episode")}
+        for ep in range(n_episodes):
+            dyn = StandIn2D(p2, 1)
+            mdp = ns.mdp.SimulationMdp(4, F_AG, T_MAX)
+            w = philox.draws(seed, ci, np.asarray([ep]), 0, philox.PURPOSE_RESET)
+            dyn.reset(*w)
+            mdp.reset()
+            dyn.advance(np.zeros(1, np.float32), np.zeros(1, np.float32))
+
+            def look(k):
+                o = {kk: v[0] for kk, v in dyn.observe(np.asarray([k])).items()}
+                ob = ns.Observation(rel_p_x=float(o["rel_p_x"]), rel_v_x=float(o["rel_v_x"]), rel_a_x=float(o["rel_a_x"]),
+                                    rel_p_y=float(o["rel_p_y"]), rel_v_y=float(o["rel_v_y"]), rel_a_y=float(o["rel_a_y"]),
+                                    contact=bool(o["contact"]))
+                sx, sy = mdp.discrete_state(ns.mdp.ContinuousObservation(ob, float(o["pitch"]), float(o["roll"]), float(o["z"])))
+                return o, sx, sy
+
+            def push(o, ax, ay, sx, sy, code, done):
+                rec["obs"].append([o[k] for k in keys]); rec["contact"].append(o["contact"])
+                rec["action_x"].append(ax); rec["action_y"].append(ay)
+                rec["state_x"].append(state_id(sx)); rec["state_y"].append(state_id(sy))
+                rec["code"].append(code); rec["done"].append(int(done)); rec["episode"].append(ep)
+
+            o, sx, sy = look(0)
+            push(o, 255, 255, sx, sy, 0, False)
+            roll_sp, done, k = 0.0, False, 0
+            while not done:
+                ax, ay = int(agent.predict(sx)), int(lut_y[state_id(sy)])
+                act = mdp.continuous_action(ax, ay)
+                if p2.y_action_enabled:
+                    if ay == 0:
+                        roll_sp = min((roll_sp + delta_theta, theta_max))
+                    elif ay == 1:
+                        roll_sp = max((roll_sp - delta_theta, -theta_max))
+                dyn.advance(np.asarray([act.pitch], np.float32), np.asarray([roll_sp], np.float32))
+                k += 1
+                o, sx, sy = look(k)
+                info = mdp.check()
+                done = "Termination condition" in info
+                push(o, ax, ay, sx, sy, _ref_code(mdp, ns), done)
+        out[f"{name}_obs"] = np.asarray(rec["obs"], np.float32)
+        for k2, dt in (("contact", np.uint8), ("action_x", np.uint8), ("action_y", np.uint8), ("state_x", np.uint16),
+                       ("state_y", np.uint16), ("code", np.uint8), ("done", np.uint8), ("episode", np.int32)):
+            out[f"{name}_{k2}"] = np.asarray(rec[k2], dt)
+        codes, cnt = np.unique(out[f"{name}_code"][out[f"{name}_done"] == 1], return_counts=True)
+        print(f"sim2d_trace[{name}]: {len(rec['code'])} rows, terminal codes {dict(zip(codes.tolist(), cnt.tolist()))}")
+    np.savez_compressed(GOLDEN / "sim2d_trace.npz", **out)
+
+
+def _state_tuple(sid: int):
+    th = sid % 7; sid //= 7
+    a = sid % 3; sid //= 3
+    v = sid % 3; sid //= 3
+    p = sid % 3; sid //= 3
+    return (sid, p, v, a, th)
+
+
 def main():
     ns = ref_stubs.install()
     GOLDEN.mkdir(parents=True, exist_ok=True)
@@ -327,6 +403,7 @@ def main():
     gen_replay(ns, 2, 3000, np.float32, q_init=q0)
     gen_replay(ns, 4, 3000, np.float32, q_init=q0)
     gen_sim_trace(ns)
+    gen_sim2d_trace(ns)
     total = sum(f.stat().st_size for f in GOLDEN.glob("*.npz"))
     print("golden bytes:", total)
 

@@ -263,3 +263,57 @@ def eval_episode(policy, seed: int, population: int, episode_id: int, sp: StandI
         code, done = mdp.check()
         rows.append(dict(obs=(rp, rv, ra, pit, z), contact=c, action=a, state=state_id(sx), code=code, done=int(done)))
     return rows
+
+
+def mirrored_policy(policy_lut):
+    """Policy of the y agent derived from an x policy by symmetry (roll convention a_y = -g tan(roll)): with roll' = -roll
+    the y axis obeys the x dynamics, so act as the x policy would in the state with the mirrored angle index and swap the
+    increase/decrease actions.  policy_lut: uint8[945] indexed by state id."""
+    lut = np.asarray(policy_lut, np.uint8)
+    out = np.empty_like(lut)
+    swap = np.asarray([1, 0, 2], np.uint8)
+    for sid in range(len(lut)):
+        rest, th = divmod(sid, 7)
+        out[sid] = swap[lut[rest * 7 + (6 - th)]]
+    return out
+
+
+def eval_episode_2d(policy_x, policy_y, seed: int, stream: int, episode_id: int, p2, tp: Optional[TrainerParams] = None,
+                    mp: Optional[MdpParams] = None, w: int = 4):
+    """One greedy two-axis SimulationMdp episode (scripts/simulation.py:48-63): both agents predict every step
+    (PKG/double_q_learning.py:119-124); the y action moves the roll set-point only if p2.y_action_enabled (the reference
+    has that branch disabled, PKG/mdp.py:863-876).  policy_x / policy_y: uint8[945] LUTs by state id.  Rows: per-step dicts
+    (row 0 = reset)."""
+    from .dynamics import StandIn2D
+    from .mdp_oracle import SimulationMdpOracle
+    tp = tp or TrainerParams()
+    mdp = SimulationMdpOracle(w, tp.f_ag, tp.t_max, tp.p_max, mp)
+    dyn = StandIn2D(p2, 1)
+    w0, w1, w2, w3 = philox.draws(seed, stream, np.asarray([episode_id]), 0, philox.PURPOSE_RESET)
+    dyn.reset(w0, w1, w2, w3)
+    dyn.advance(np.zeros(1, np.float32), np.zeros(1, np.float32))
+
+    def look(k):
+        o = {kk: v[0] for kk, v in dyn.observe(np.asarray([k])).items()}
+        sx, sy = mdp.observe(o["rel_p_x"], o["rel_v_x"], o["rel_a_x"], o["pitch"], o["z"], o["contact"],
+                             o["rel_p_y"], o["rel_v_y"], o["rel_a_y"], o["roll"])
+        return o, sx, sy
+
+    o, sx, sy = look(0)
+    rows = [dict(obs=o, action_x=255, action_y=255, state_x=state_id(sx), state_y=state_id(sy), code=0, done=0)]
+    sp_y, done, k = 0.0, False, 0
+    prm = mdp.prm
+    while not done:
+        ax, ay = int(policy_x[state_id(sx)]), int(policy_y[state_id(sy)])
+        sp_x = mdp.act(ax)
+        if p2.y_action_enabled:
+            if ay == 0:
+                sp_y = min(sp_y + prm.delta_theta, prm.theta_max)
+            elif ay == 1:
+                sp_y = max(sp_y - prm.delta_theta, -prm.theta_max)
+        dyn.advance(np.asarray([sp_x], np.float32), np.asarray([sp_y], np.float32))
+        k += 1
+        o, sx, sy = look(k)
+        code, done = mdp.check()
+        rows.append(dict(obs=o, action_x=ax, action_y=ay, state_x=state_id(sx), state_y=state_id(sy), code=code, done=int(done)))
+    return rows

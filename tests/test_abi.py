@@ -32,6 +32,7 @@ def test_struct_layouts_match_header():
     assert lib.dqlb200_abi_version() == K.ABI_VERSION
     assert lib.dqlb200_config_bytes() == C.sizeof(K.Config)
     assert lib.dqlb200_population_state_bytes() == C.sizeof(K.PopulationState) == 320
+    assert lib.dqlb200_eval2d_params_bytes() == C.sizeof(K.Eval2DParams) == 72
     assert lib.dqlb200_termination_string(2) == b"SUCCESS: Goal state reached"
     assert lib.dqlb200_termination_string(0) is None
     for code, text in K.TERMINATION_STRINGS.items():

@@ -379,3 +379,40 @@ def test_train_host_equals_device_resident_training(P):
     assert torch.equal(a.tables.cpu(), tab_h)
     assert torch.equal(a.pop_state.cpu(), ps_h)
     assert int(a.population_state()["working_step"].max()) >= 1
+
+
+@pytest.mark.parametrize("case", ["reference", "xy", "eight", "ywrong"])
+def test_two_axis_greedy_evaluation(golden_dir, case):
+    """eval2d_kernel against (a) the fixture the unmodified reference SimulationMdp produced on the two-axis
+    stand-in (observations, both states, codes bit-exact) and (b) the oracle for more episodes (termination histogram)."""
+    from dql_multirotor_landing_b200 import constants as K
+    from oracle.dynamics import sim2d_cases
+    from oracle.loop import eval_episode_2d
+    g = np.load(golden_dir / "sim2d_trace.npz")
+    cases = sim2d_cases()
+    p2, ci = cases[case], list(cases).index(case)
+    lut_x, lut_y = g["lut_x"], g[f"{case}_lut_y"]
+    ta = K.TwoAxisParameters(trajectory=p2.trajectory, r_x=p2.base.r_mp, v_x=p2.base.v_mp, r_y=p2.r_y, v_y=p2.v_y,
+                             y_action_enabled=p2.y_action_enabled, y_init_enabled=p2.y_init_enabled)
+    eng = _engine(1, 1, threads_per_block=32)
+    n_fix = int(g[f"{case}_episode"].max()) + 1
+    res = eng.eval_greedy_2d(lut_x, lut_y, n_fix, two_axis=ta, seed=int(g["seed"]), stream_id=ci, trace_steps=460)
+    tr = res["trace"]
+    for ep in range(n_fix):
+        sel = np.nonzero(g[f"{case}_episode"] == ep)[0][1:]           # row 0 of an episode is the reset
+        n = len(sel)
+        assert np.array_equal(tr["obs"][:n, ep].view(np.uint32), g[f"{case}_obs"][sel].view(np.uint32))
+        for k in ("action_x", "action_y", "code", "done", "contact"):
+            assert np.array_equal(tr[k][:n, ep], g[f"{case}_{k}"][sel]), k
+        assert np.array_equal(tr["state_x"][:n, ep].astype(np.uint16), g[f"{case}_state_x"][sel])
+        assert np.array_equal(tr["state_y"][:n, ep].astype(np.uint16), g[f"{case}_state_y"][sel])
+        assert tr["done"][n - 1, ep] == 1
+    # more episodes, statistics only
+    n2 = 48
+    res2 = eng.eval_greedy_2d(lut_x, lut_y, n2, two_axis=ta, seed=77, stream_id=3, first_episode=1000)
+    hist, steps = np.zeros(9, np.int64), 0
+    for ep in range(n2):
+        rows = eval_episode_2d(lut_x, lut_y, 77, 3, 1000 + ep, p2)[1:]
+        hist[rows[-1]["code"]] += 1
+        steps += len(rows)
+    assert res2["episodes"] == n2 and res2["steps"] == steps and res2["termination_hist"] == list(hist)

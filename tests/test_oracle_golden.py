@@ -120,3 +120,28 @@ def test_sim_trace(golden_dir):
 def test_state_id_roundtrip():
     for i in range(945):
         assert state_id(state_from_id(i)) == i
+
+
+@pytest.mark.parametrize("case", ["reference", "xy", "eight", "ywrong"])
+def test_two_axis_simulation_oracle_matches_reference_fixture(golden_dir, case):
+    """the two-axis restatement (x and y discretisation, contact on both axes, FLYZONE_Y) reproduces what the
+    unmodified reference SimulationMdp produced on the same two-axis stand-in trajectories (tests/golden/sim2d_trace.npz)."""
+    from oracle.dynamics import sim2d_cases
+    from oracle.loop import eval_episode_2d, mirrored_policy
+    g = np.load(golden_dir / "sim2d_trace.npz")
+    cases = sim2d_cases()
+    ci = list(cases).index(case)
+    lut_x, lut_y = g["lut_x"], g[f"{case}_lut_y"]
+    if case != "ywrong":
+        assert np.array_equal(lut_y, mirrored_policy(lut_x))
+    keys = ("rel_p_x", "rel_v_x", "rel_a_x", "pitch", "z", "rel_p_y", "rel_v_y", "rel_a_y", "roll")
+    ep_ids = g[f"{case}_episode"]
+    for ep in np.unique(ep_ids):
+        sel = np.nonzero(ep_ids == ep)[0]
+        rows = eval_episode_2d(lut_x, lut_y, int(g["seed"]), ci, int(ep), cases[case])
+        assert len(rows) == len(sel)
+        obs = np.asarray([[r["obs"][k] for k in keys] for r in rows], np.float32)
+        assert np.array_equal(obs.view(np.uint32), g[f"{case}_obs"][sel].view(np.uint32))
+        for k in ("action_x", "action_y", "state_x", "state_y", "code", "done"):
+            assert [r[k] for r in rows] == list(g[f"{case}_{k}"][sel]), k
+    assert (g["ywrong_code"][g["ywrong_done"] == 1] == 5).all()        # FLYZONE_Y is covered
