@@ -308,6 +308,20 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
         e3.close()
     except Exception as exc:      # never let a context measurement break the headline line
         out["config3_one_agent_65536_envs"] = {"error": str(exc)}
+    # config 4: decoupled x- and y-axis agents trained concurrently, 262,144 envs each (2 agents x 512 replicas x 512 envs)
+    try:
+        R, n_r, M, steps = 512, 512, 16, 128
+        e4 = Engine(2 * R, n_r, device=dev.index or 0, threads_per_block=128, seeds=[42] * (2 * R), population_ids=list(range(2 * R)),
+                    replicas_per_population=R, axes=["x"] * R + ["y"] * R,
+                    tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+        e4.reset(0)
+        e4.train_merged(2 * M, M); torch.cuda.synchronize(dev)
+        s4 = timed(lambda: e4.train_merged(steps, M))
+        out["config4_x_and_y_agents_262144_envs_each"] = {"env_steps_per_s": 2 * R * n_r * steps / s4, "replicas_per_agent": R,
+                                                         "envs_per_replica": n_r, "merge_every_steps": M, "timing": "CUDA events, best of 3"}
+        e4.close()
+    except Exception as exc:
+        out["config4_x_and_y_agents_262144_envs_each"] = {"error": str(exc)}
     out["config2_greedy_eval"] = {"episodes": res["episodes"], "env_steps": res["steps"], "env_steps_per_s": res["steps"] / s,
                                   "landing_rate": res["termination_hist"][3] / max(res["episodes"], 1),
                                   "termination_hist": res["termination_hist"], "timing": "host wall clock incl. launch+sync"}

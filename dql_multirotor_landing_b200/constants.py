@@ -34,7 +34,7 @@ ALPHA_LUT = 1003
 EPS_LUT = 2002
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 LIMITS_POSITION = [1.0, 0.64, 0.4096, 0.262144, 0.16777216]   # PKG/mdp.py:45-47
 LIMITS_VELOCITY = [1.0, 0.8, 0.64, 0.512, 0.4096]              # PKG/mdp.py:48-50
@@ -93,7 +93,7 @@ class Config(C.Structure):
 class PopulationParams(C.Structure):
     _fields_ = [("seed_lo", C.c_uint32), ("seed_hi", C.c_uint32), ("population_id", C.c_uint32),
                 ("dphase", C.c_uint32), ("r", C.c_float), ("rw", C.c_float), ("rw2", C.c_float),
-                ("alpha_lut", C.c_int32)]
+                ("alpha_lut", C.c_int32), ("g", C.c_float), ("axis", C.c_int32)]
 
 
 class PopulationState(C.Structure):

@@ -143,7 +143,7 @@ struct Obs {
 __device__ __forceinline__ void dyn_advance(const KC& kc, const dqlb200_population_params& pp, Body& b, float sp) {
   for (int i = 0; i < kc.n_sub; ++i) {
     b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
-    b.a_d = fsub(fmul(kc.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
+    b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
     b.x_d = fadd(fadd(b.x_d, fmul(b.v_d, kc.h)), fmul(b.a_d, kc.half_h2));
     b.v_d = fadd(b.v_d, fmul(b.a_d, kc.h));
     b.phase += pp.dphase;

@@ -20,6 +20,7 @@ class Engine:
                  seeds: Optional[Sequence[int]] = None, population_ids: Optional[Sequence[int]] = None,
                  v_mp: Optional[Sequence[float]] = None, alpha_variants: Optional[Sequence[tuple]] = None,
                  alpha_index: Optional[Sequence[int]] = None, replicas_per_population: int = 1,
+                 axes: Optional[Sequence[str]] = None,
                  mp: Optional[K.MdpParameters] = None, dp: Optional[K.DynamicsParameters] = None,
                  tp: Optional[K.TrainerParameters] = None):
         if not torch.cuda.is_available():
@@ -37,11 +38,17 @@ class Engine:
         population_ids = list(population_ids) if population_ids is not None else list(range(n_populations))
         v_mp = list(v_mp) if v_mp is not None else [self.dp.v_mp] * n_populations
         alpha_index = list(alpha_index) if alpha_index is not None else [0] * n_populations
+        # axis of every agent: "x" (pitch, a = +g tan) or "y" (roll, a = -g tan in the reference's ENU frame; training_y.sh)
+        axes = list(axes) if axes is not None else ["x"] * n_populations
+        if any(a not in ("x", "y") for a in axes):
+            raise ValueError("axes entries must be 'x' or 'y'")
+        self.axes = axes
         pps = (K.PopulationParams * n_populations)()
         for p in range(n_populations):
             dphase, r, rw, rw2 = K.platform_constants(self.dp.r_mp, v_mp[p], self.mp.f_ag, self.dp.n_sub)
             pps[p] = K.PopulationParams(seeds[p] & 0xFFFFFFFF, (seeds[p] >> 32) & 0xFFFFFFFF, population_ids[p], dphase,
-                                        r, rw, rw2, alpha_index[p])
+                                        r, rw, rw2, alpha_index[p], np.float32(self.dp.g if axes[p] == "x" else -self.dp.g),
+                                        0 if axes[p] == "x" else 1)
         self.handle = C.c_void_p()
         _ffi.check(self.lib.dqlb200_create(C.byref(self.cfg), luts.ctypes.data_as(C.POINTER(C.c_float)), pps, device,
                                            C.byref(self.handle)))

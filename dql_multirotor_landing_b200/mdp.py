@@ -77,7 +77,7 @@ class _FacadeHandle:
         self.cfg = K.build_config(1, 1, 32, mp)
         lut = K.alpha_lut()
         dphase, r, rw, rw2 = K.platform_constants(2.0, 1.6, mp.f_ag, 1)
-        pp = (K.PopulationParams * 1)(K.PopulationParams(0, 0, 0, dphase, r, rw, rw2, 0))
+        pp = (K.PopulationParams * 1)(K.PopulationParams(0, 0, 0, dphase, r, rw, rw2, 0, 9.81, 0))
         self.handle = C.c_void_p()
         _ffi.check(self.lib.dqlb200_create(C.byref(self.cfg), lut.ctypes.data_as(C.POINTER(C.c_float)), pp, device, C.byref(self.handle)))
 

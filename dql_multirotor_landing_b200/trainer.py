@@ -59,6 +59,7 @@ class Trainer:
         merge_every: int = 8,
         tensorboard: bool = False,
         verbose: bool = True,
+        direction: str = "x",
     ) -> None:
         np.random.seed(seed)                                        # PKG/trainer.py:45
         if not double_q_learning_agent:
@@ -93,6 +94,9 @@ class Trainer:
             self._threads_per_block = 128 if envs_per_replica >= 128 else 32
         self._merge_every = merge_every
         self._tensorboard, self._verbose = tensorboard, verbose
+        if direction not in ("x", "y"):
+            raise ValueError("direction must be 'x' or 'y' (training.launch direction:=x|y, training_x.sh / training_y.sh)")
+        self._direction = direction
         self._engine = None
         self.history = []             # one dict per chunk (population 0)
 
@@ -168,12 +172,12 @@ class Trainer:
         if R > 1:
             eng = Engine(R, self._num_envs, device=self._device, threads_per_block=self._threads_per_block,
                          seeds=[self._seed] * R, population_ids=list(range(R)), v_mp=[self._platform_speed] * R,
-                         replicas_per_population=R, mp=mp, dp=self._dynamics, tp=tp)
+                         replicas_per_population=R, axes=[self._direction] * R, mp=mp, dp=self._dynamics, tp=tp)
             P = R
         else:
             eng = Engine(P, self._num_envs, device=self._device, threads_per_block=self._threads_per_block,
                          seeds=[self._seed + p for p in range(P)], population_ids=list(range(P)),
-                         v_mp=[self._platform_speed] * P, mp=mp, dp=self._dynamics, tp=tp)
+                         v_mp=[self._platform_speed] * P, axes=[self._direction] * P, mp=mp, dp=self._dynamics, tp=tp)
         agent = self._double_q_learning_agent
         for p in range(P):
             eng.set_tables(p, agent.Q_table_a, agent.Q_table_b, agent.state_action_counter)

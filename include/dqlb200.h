@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 1
+#define DQLB200_ABI_VERSION 2
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -122,6 +122,9 @@ typedef struct dqlb200_population_params {
   uint32_t dphase;                  /* platform phase advance per sub-step, uint32 turns */
   float r, rw, rw2;                 /* platform amplitude, r*w, r*w^2 */
   int32_t alpha_lut;                /* index into the alpha LUT array */
+  float g;                          /* SIGNED gravity of the agent's axis: a_d = g tan(angle) - c_d v_d.  x agents (pitch): +g;
+                                     * y agents (roll, training_y.sh / `direction:=y`): -g in the reference's ENU frame */
+  int32_t axis;                     /* 0 = x, 1 = y (informational) */
 } dqlb200_population_params;
 
 /* Per-population mutable trainer state (device resident, 320 B).  Mirrors the Trainer fields the

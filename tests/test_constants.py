@@ -39,7 +39,7 @@ def cfg():
 def test_struct_sizes(cfg):
     assert cfg.struct_bytes == C.sizeof(K.Config)
     assert C.sizeof(K.PopulationState) == K.POPULATION_STATE_DTYPE.itemsize == 320
-    assert C.sizeof(K.PopulationParams) == 32
+    assert C.sizeof(K.PopulationParams) == 40
 
 
 def test_cut_tables_vs_reference_fixture(cfg, golden_dir):

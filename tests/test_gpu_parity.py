@@ -98,20 +98,22 @@ def test_replay_float64_reference_tolerance(golden_dir):
     np.testing.assert_allclose(qa, g["qa"], rtol=1e-6, atol=1e-6 * np.abs(g["qa"]).max())
 
 
-@pytest.mark.parametrize("tpb,n_envs", [(64, 70), (256, 300)])
-def test_multi_env_population_vs_oracle(tpb, n_envs):
+@pytest.mark.parametrize("tpb,n_envs,axes", [(64, 70, "xx"), (256, 300, "xx"), (128, 130, "xy")])
+def test_multi_env_population_vs_oracle(tpb, n_envs, axes):
     """Batched semantics S1 (oracle/loop.py): several envs share a table pair; ragged env count; two
-    populations with different seeds and platform speeds.  Traces, tables, counts, counters identical."""
+    populations with different seeds and platform speeds.  Traces, tables, counts, counters identical.
+    axes = "xy": the second population is a y-axis agent (roll; a = -g tan(angle), BASELINE config 4)."""
     steps = 120
     seeds, v_mp = [42, 7], [1.6, 0.8]
-    eng = _engine(2, n_envs, threads_per_block=tpb, seeds=seeds, v_mp=v_mp, tp=NO_PROMOTION)
+    g = [9.81 if a == "x" else -9.81 for a in axes]
+    eng = _engine(2, n_envs, threads_per_block=tpb, seeds=seeds, v_mp=v_mp, axes=list(axes), tp=NO_PROMOTION)
     eng.reset(0)
     tr = eng.train(steps, trace=True)
     eng.check_errors()
     ps = eng.population_state()
     for p in range(2):
         pop = PopulationOracle(n_envs, seed=seeds[p], population=p, w0=0, dtype=np.float32,
-                               tp=TrainerParams(**NO_PROMOTION), sp=StandInParams(v_mp=v_mp[p]))
+                               tp=TrainerParams(**NO_PROMOTION), sp=StandInParams(v_mp=v_mp[p], g=g[p]))
         sl = slice(p * n_envs, (p + 1) * n_envs)
         for t in range(steps):
             o = pop.step()
