@@ -40,6 +40,13 @@ E2E_CHUNK = 64                     # global steps per host-buffer call (about on
 ALGORITHMIC_BYTES_PER_ENV_STEP = 96   # 48 B env state read + 48 B written, one step per launch
 
 
+SHARED_SYNC_EVERY = 16             # global steps between two shared-table all-reduces (N > 1 only)
+
+
+def envs_per_gpu_shared(P: int, n_p: int) -> int:
+    return P * n_p
+
+
 def workload_config(n_gpus: int) -> dict:
     return {
         "workload": "BASELINE configs[4] per-GPU shard: independent populations (seed x platform-speed x learning-rate "
@@ -162,7 +169,20 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner on stdout when the communicator is created: send fd 1 to stderr meanwhile, so that
+        # stdout carries the ONE JSON line and nothing else
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize(dev)
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
 
     def barrier():
         if world > 1:
@@ -233,6 +253,40 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     value = world * envs_gpu * args.steps / (ms_max * 1e-3)
     e2e_value = world * envs_gpu * E2E_CHUNK * e2e_calls / (e2e_ms_max * 1e-3)
 
+    # ---- N > 1: shared-table mode (BASELINE config 5): ONE agent, ~1M envs per GPU, replicas merged on each GPU and then
+    # across GPUs by one NCCL all-reduce of the packed Q-delta/count buffer every SHARED_SYNC_EVERY global steps ------------
+    shared = None
+    if world > 1 and not args.no_extra:
+        from dql_multirotor_landing_b200.parallel import SharedTableSync
+        es = Engine(P, n_p, device=local_rank, threads_per_block=THREADS_PER_BLOCK, seeds=[42] * P,
+                    population_ids=[rank * P + p for p in range(P)], replicas_per_population=P,
+                    tp=K.TrainerParameters(max_num_episodes=10 ** 12, success_rate=2.0))
+        es.reset(0)
+        sync = SharedTableSync(es, pooled_promotion=True)
+        rounds = 8
+        for _ in range(2):
+            es.train(SHARED_SYNC_EVERY); sync.sync()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(rounds):
+            es.train(SHARED_SYNC_EVERY)
+            sync.sync()
+            launches += 4
+        b.record(stream)
+        barrier()
+        es.check_errors()
+        t_sh = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_sh, op=dist.ReduceOp.MAX)
+        agree = torch.stack([es.tables[0, 0].float().sum(), es.tables[0, 2].float().sum()]).double()
+        lo, hi = agree.clone(), agree.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        shared = {"env_steps_per_s": world * envs_per_gpu_shared(P, n_p) * SHARED_SYNC_EVERY * rounds / (float(t_sh[0]) * 1e-3),
+                  "sync_every_global_steps": SHARED_SYNC_EVERY, "envs_sharing_one_table_pair": world * P * n_p,
+                  "allreduce_bytes_per_sync": int(sync.delta.numel() * 4), "replicas_per_gpu": P,
+                  "tables_identical_on_all_ranks": bool(torch.equal(lo, hi)), "timing": "CUDA events, max over ranks"}
+        es.close()
+
     line = None
     if rank == 0:
         peak, peak_src = measured_peak_hbm()
@@ -248,6 +302,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         extra = {}
         if not args.no_extra:
             extra = extra_measurements(eng, dev, np, torch, greedy_policy)
+        if shared is not None:
+            extra["config5_shared_table_mode"] = shared
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -322,6 +378,23 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
         e4.close()
     except Exception as exc:
         out["config4_x_and_y_agents_262144_envs_each"] = {"error": str(exc)}
+    # SURVEY 8d "atomic roof": the visited cells of a real run (traced), replayed with unordered shared-memory atomics
+    try:
+        et = Engine(64, 256, device=dev.index or 0, threads_per_block=128, seeds=list(range(64)),
+                    tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+        et.reset(0)
+        et.train(2500)                                           # past the pure-exploration phase of the first episodes
+        tr = et.train(64, trace=True)
+        cells = (tr["state"].astype(np.int64) * 3 + tr["action"]).astype(np.uint16).reshape(-1)
+        rmw = et.bench_table_rmw(cells)
+        hot = np.bincount(cells, minlength=2835)
+        out["table_rmw_roof"] = {"visits_per_s": rmw["visits_per_s"], "rmw_per_s": rmw["rmw_per_s"],
+                                 "distinct_cells": int((hot > 0).sum()), "hottest_cell_share": float(hot.max() / hot.sum()),
+                                 "what": "2 unordered shared-memory atomics (red.shared.add.f32 + .u32) per recorded visit, 1036 CTAs x 128 "
+                                         "threads, tables in shared memory; an upper bound for the table update alone, NOT deterministic"}
+        et.close()
+    except Exception as exc:
+        out["table_rmw_roof"] = {"error": str(exc)}
     out["config2_greedy_eval"] = {"episodes": res["episodes"], "env_steps": res["steps"], "env_steps_per_s": res["steps"] / s,
                                   "landing_rate": res["termination_hist"][3] / max(res["episodes"], 1),
                                   "termination_hist": res["termination_hist"], "timing": "host wall clock incl. launch+sync"}

@@ -149,6 +149,7 @@ class Trace2D(C.Structure):
 
 
 TRAJ_RECTILINEAR_X, TRAJ_RECTILINEAR_XY, TRAJ_EIGHT = 0, 1, 2
+SHARED_DELTA_WORDS = 4 * MAX_CELLS + 4        # DQLB200_SHARED_DELTA_WORDS
 
 
 # ------------------------------------------------------------------------------------------------

@@ -1003,32 +1003,67 @@ __global__ void transfer_kernel(uint32_t* tables, int n_pop, int cs, int step, f
 // Shared-table mode (one agent replicated on G devices).  Each replica trains on its own envs for a few
 // steps; the replicas are then merged with a visit-weighted mean of their Q deltas and the sum of
 // their visit counts:  Q <- Q_snap + sum_g(dcount_g * dQ_g) / sum_g(dcount_g),  count <- count_snap + sum_g dcount_g.
-__global__ void shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, int n_pop) {
+// One "agent" below = a group of R = replicas_per_population consecutive populations whose tables are identical (after
+// replica_merge_kernel; R = 1: a plain population).  snap holds ONE [3][CELLS] entry per agent, delta ONE entry of
+// DQLB200_SHARED_DELTA_WORDS floats per agent: [0] sum dQ*dcount, [1] sum dcount, [2] number of ranks that visited the cell,
+// [3] sum of the visiting ranks' Q (exact when one rank visited: the value that rank keeps), then the agent's pooled trainer
+// counters: successes in the windows, finished episodes of the curriculum step, number of ranks, ranks that are alive.
+constexpr int DELTA_WORDS = DQLB200_SHARED_DELTA_WORDS;
+__global__ void shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, const dqlb200_population_state* ps,
+                                   int n_agents, int R) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_pop * CELLS) return;
-  const long long pop = i / CELLS, c = i % CELLS;
-  const size_t base = (size_t)pop * 3 * CELLS;
-  const float dc = (float)(tables[base + 2 * CELLS + c] - snap[base + 2 * CELLS + c]);
-  const float dq = fsub(__uint_as_float(tables[base + c]), __uint_as_float(snap[base + c]));
-  delta[base + c] = fmul(dq, dc);
-  delta[base + CELLS + c] = dc;
-  delta[base + 2 * CELLS + c] = 0.0f;
-}
-__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, const float* delta, int n_pop) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_pop * CELLS) return;
-  const long long pop = i / CELLS, c = i % CELLS;
-  const size_t base = (size_t)pop * 3 * CELLS;
-  const float own_dc = (float)(tables[base + 2 * CELLS + c] - snap[base + 2 * CELLS + c]);
-  const float dc = delta[base + CELLS + c];
-  if (dc != own_dc) {      // some other replica visited the cell too (dc == own_dc: keep the local value exactly)
-    const float q = fadd(__uint_as_float(snap[base + c]), __fdiv_rn(delta[base + c], dc));
-    tables[base + c] = __float_as_uint(q);
-    tables[base + 2 * CELLS + c] = snap[base + 2 * CELLS + c] + (uint32_t)__float2uint_rn(dc);
+  if (i >= (long long)n_agents * CELLS) return;
+  const long long g = i / CELLS, c = i % CELLS;
+  const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
+  float* d = delta + (size_t)g * DELTA_WORDS;
+  const uint32_t dcu = tables[tb + 2 * CELLS + c] - snap[sb + 2 * CELLS + c];
+  const float dc = (float)dcu, q = __uint_as_float(tables[tb + c]);
+  d[c] = fmul(fsub(q, __uint_as_float(snap[sb + c])), dc);
+  d[CELLS + c] = dc;
+  d[2 * CELLS + c] = dcu ? 1.0f : 0.0f;
+  d[3 * CELLS + c] = dcu ? q : 0.0f;
+  if (c < 4) {
+    long long successes = 0, episodes = 0;
+    bool alive = true;
+    for (int r = 0; r < R; ++r) {
+      const dqlb200_population_state& p = ps[g * R + r];
+      successes += p.window_sum;
+      episodes += p.episodes_in_step;
+      alive = alive && !p.finished && !p.pending_advance;
+    }
+    d[4 * CELLS + c] = c == 0 ? (float)successes : c == 1 ? (float)episodes : c == 2 ? 1.0f : (alive ? 1.0f : 0.0f);
   }
-  snap[base + c] = tables[base + c];
-  snap[base + CELLS + c] = tables[base + CELLS + c];
-  snap[base + 2 * CELLS + c] = tables[base + 2 * CELLS + c];
+}
+__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* merge_snap, const float* delta,
+                                    dqlb200_population_state* ps, int n_agents, int R, int pooled_promote, long long max_episodes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_agents * CELLS) return;
+  const long long g = i / CELLS, c = i % CELLS;
+  const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
+  const float* d = delta + (size_t)g * DELTA_WORDS;
+  const float visitors = d[2 * CELLS + c];
+  uint32_t q_bits = snap[sb + c], cnt = snap[sb + 2 * CELLS + c];
+  if (visitors == 1.0f) q_bits = __float_as_uint(d[3 * CELLS + c]);       // one rank visited: its value, bit for bit, on every rank
+  else if (visitors > 1.0f) q_bits = __float_as_uint(fadd(__uint_as_float(q_bits), __fdiv_rn(d[c], d[CELLS + c])));
+  if (visitors > 0.0f) {
+    cnt += (uint32_t)__float2uint_rn(d[CELLS + c]);
+    for (int r = 0; r < R; ++r) {
+      tables[tb + (size_t)r * 3 * CELLS + c] = q_bits;
+      tables[tb + (size_t)r * 3 * CELLS + 2 * CELLS + c] = cnt;
+    }
+  } else {          // nobody visited: the cell can still have changed by the (identical) curriculum transfers of every copy
+    q_bits = tables[tb + c];
+  }
+  const uint32_t qb_bits = tables[tb + CELLS + c];
+  snap[sb + c] = q_bits; snap[sb + CELLS + c] = qb_bits; snap[sb + 2 * CELLS + c] = cnt;
+  if (merge_snap) { merge_snap[sb + c] = q_bits; merge_snap[sb + CELLS + c] = qb_bits; merge_snap[sb + 2 * CELLS + c] = cnt; }
+  if (c == 0 && pooled_promote > 0) {      // promotion pooled over every rank's windows (same decision on every rank)
+    const float successes = d[4 * CELLS + 0], episodes = d[4 * CELLS + 1];
+    const bool alive = d[4 * CELLS + 3] == d[4 * CELLS + 2];
+    const int pending = !alive ? 0 : (successes >= (float)pooled_promote ? 1 : (episodes >= (float)max_episodes ? 2 : 0));
+    if (pending)
+      for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
+  }
 }
 
 // Replica-merge mode: R consecutive populations are replicas of ONE agent.  One WARP per table cell: the lanes read
@@ -1090,10 +1125,32 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
       episodes += p.episodes_in_step;
       alive = alive && !p.finished && !p.pending_advance;
     }
-    const int pending = !alive ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
+    const int pending = (!alive || pooled_promote <= 0) ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
     if (pending)
       for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
   }
+}
+
+// Measurement aid: the table update as UNORDERED shared-memory atomics on a recorded cell sequence (the "atomic roof").
+__global__ void table_rmw_roof_kernel(const uint16_t* __restrict__ cells, long long n_cells, int visits_per_thread,
+                                      unsigned long long* checksum) {
+  __shared__ float qa[CELLS];
+  __shared__ uint32_t cnt[CELLS];
+  for (int i = threadIdx.x; i < CELLS; i += blockDim.x) { qa[i] = 0.0f; cnt[i] = 0u; }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) % n_cells;
+  for (int k = 0; k < visits_per_thread; ++k) {
+    const uint32_t c = cells[idx];
+    atomicAdd(&qa[c], 0.015625f);
+    atomicAdd(&cnt[c], 1u);
+    idx += stride;
+    if (idx >= n_cells) idx %= n_cells;
+  }
+  __syncthreads();
+  unsigned long long sum = 0;
+  for (int i = threadIdx.x; i < CELLS; i += blockDim.x) sum += cnt[i] + (unsigned long long)qa[i];
+  if (sum) atomicAdd(checksum, sum);
 }
 
 }  // namespace dql
@@ -1429,21 +1486,27 @@ int dqlb200_check_errors(dqlb200_handle* h, void* stream) {
 }
 
 int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream) {
-  if (!h || !h->tables || !snapshot || !delta) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  if (!h || !h->tables || !h->pop_state || !snapshot || !delta) return fail(DQLB200_ERR_ARG, "null argument / not bound");
   CUDA_TRY(cudaSetDevice(h->device));
-  const long long n = (long long)h->cfg.n_populations * DQLB200_MAX_CELLS;
+  const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
+  const long long n = (long long)n_agents * DQLB200_MAX_CELLS;
   dql::shared_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)h->tables, (const uint32_t*)snapshot,
-                                                                                       (float*)delta, h->cfg.n_populations);
+                                                                                       (float*)delta, (const dqlb200_population_state*)h->pop_state,
+                                                                                       n_agents, R);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
 
-int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, void* stream) {
-  if (!h || !h->tables || !snapshot || !delta_reduced) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, int pooled_promote_successes, void* stream) {
+  if (!h || !h->tables || !h->pop_state || !snapshot || !delta_reduced) return fail(DQLB200_ERR_ARG, "null argument / not bound");
   CUDA_TRY(cudaSetDevice(h->device));
-  const long long n = (long long)h->cfg.n_populations * DQLB200_MAX_CELLS;
+  const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
+  if (R > 1 && !h->merge_snapshot) return fail(DQLB200_ERR_STATE, "replicated layout: bind the merge snapshot first (dqlb200_bind_merge_snapshot)");
+  const long long n = (long long)n_agents * DQLB200_MAX_CELLS;
   dql::shared_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
-                                                                                        (const float*)delta_reduced, h->cfg.n_populations);
+                                                                                        R > 1 ? (uint32_t*)h->merge_snapshot : nullptr,
+                                                                                        (const float*)delta_reduced, (dqlb200_population_state*)h->pop_state,
+                                                                                        n_agents, R, pooled_promote_successes, h->cfg.max_num_episodes);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
@@ -1482,6 +1545,16 @@ int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_
   dql::replica_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
                                                                    (dqlb200_population_state*)h->pop_state, R,
                                                                    pooled_promote_successes, h->cfg.max_num_episodes);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_bench_table_rmw(dqlb200_handle* h, const uint16_t* cells, int64_t n_cells, int visits_per_thread, int threads, int blocks,
+                            void* checksum_out, void* stream) {
+  if (!h || !cells || !checksum_out) return fail(DQLB200_ERR_ARG, "null argument");
+  if (n_cells < 1 || visits_per_thread < 1 || threads < 32 || threads > 1024 || blocks < 1) return fail(DQLB200_ERR_ARG, "bad launch shape");
+  CUDA_TRY(cudaSetDevice(h->device));
+  dql::table_rmw_roof_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(cells, n_cells, visits_per_thread, (unsigned long long*)checksum_out);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

@@ -142,6 +142,25 @@ class Engine:
         self.merge_snapshot = None
         _ffi.check(self.lib.dqlb200_bind_merge_snapshot(self.handle, None))
 
+    def bench_table_rmw(self, cells: np.ndarray, visits_per_thread: int = 256, threads: int = 128, blocks: int = 1036, reps: int = 5) -> dict:
+        """Measurement aid: rate of UNORDERED shared-memory read-modify-writes on a recorded sequence of visited
+        cells (uint16, cell = state * 3 + action), two RMW per visit.  Returns visits/s (CUDA events, best of reps)."""
+        dev = self.device
+        d_cells = torch.as_tensor(np.ascontiguousarray(cells, np.uint16).view(np.int16), device=dev)
+        chk = torch.zeros(1, dtype=torch.int64, device=dev)
+        best = float("inf")
+        for _ in range(reps + 1):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            _ffi.check(self.lib.dqlb200_bench_table_rmw(self.handle, d_cells.data_ptr(), d_cells.numel(), visits_per_thread, threads, blocks,
+                                                        chk.data_ptr(), self._stream()))
+            b.record()
+            torch.cuda.synchronize(dev)
+            best = min(best, a.elapsed_time(b) * 1e-3)
+        visits = visits_per_thread * threads * blocks
+        return {"visits_per_s": visits / best, "rmw_per_s": 2 * visits / best, "visits": visits, "seconds": best,
+                "threads": threads, "blocks": blocks}
+
     def selftest_division(self) -> int:
         """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""
         out = (C.c_uint64 * 3)()

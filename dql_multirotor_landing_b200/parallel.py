@@ -3,7 +3,7 @@
 The path shards by POPULATION: every rank owns a disjoint set of agents (Q-table pairs) with their envs, so the
 data path needs no collective (bench.py, `"scaling": "weak"`).  The only exchange step is the optional
 shared-table mode: one agent replicated on G ranks, merged every `sync_every` global steps by ONE all-reduce
-(SUM) of a fused [sum(dQ_a * dcount) | dcount] buffer (2 x 2835 floats per population, NCCL over NVLink on
+(SUM) of a fused [sum(dQ_a * dcount) | dcount | visitors | sum(Q_a of visitors) | counters] buffer (45 KB per agent, NCCL over NVLink on
 GPUs, gloo in the CPU tests) -- see csrc/dqlb200.cu: shared_pack_kernel / shared_apply_kernel.
 """
 from __future__ import annotations
@@ -45,25 +45,37 @@ def max_over_ranks(values: Sequence[float], device: Optional[torch.device] = Non
 
 
 def merge_deltas(delta: torch.Tensor) -> torch.Tensor:
-    """All-reduce (SUM) of the packed delta buffer [P, 3, CELLS] in place; returns it."""
+    """All-reduce (SUM) of the packed delta buffer [agents, SHARED_DELTA_WORDS] in place; returns it."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(delta, op=dist.ReduceOp.SUM)
     return delta
 
 
 class SharedTableSync:
-    """Shared-table mode for an Engine whose populations are replicated on every rank."""
+    """Shared-table mode: the agents of `engine` (groups of engine.R consecutive populations) are replicated on every rank.
+    `sync()` = local replica merge (R > 1) + ONE all-reduce of the packed [dQ*dcount | dcount | trainer counters] buffer
+    (34 KB per agent) + apply.  With `pooled_promotion` the curriculum promotion is decided from the windows of ALL ranks."""
 
-    def __init__(self, engine):
+    def __init__(self, engine, pooled_promotion: bool = False):
         import ctypes as C
         from . import _ffi
+        from . import constants as K
         self._C, self._ffi, self.engine = C, _ffi, engine
-        self.snapshot = engine.tables.clone()
-        self.delta = torch.zeros(engine.tables.shape, dtype=torch.float32, device=engine.device)
+        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.snapshot = engine.tables[:: engine.R].clone().contiguous()
+        self.delta = torch.zeros((self.snapshot.shape[0], K.SHARED_DELTA_WORDS), dtype=torch.float32, device=engine.device)
+        self.pooled_promote = 0
+        if pooled_promotion:
+            self.pooled_promote = K.promote_threshold(engine.tp.successive_successful_episodes * engine.R * self.world, engine.tp.success_rate)
+        if engine.R > 1:
+            engine._ensure_merge_snapshot()
 
     def sync(self):
-        """tables <- snapshot + visit-weighted mean of every replica's dQ_a; counts <- snapshot + sum of dcounts."""
+        """tables <- snapshot + visit-weighted mean of every rank's dQ_a; counts <- snapshot + sum of dcounts."""
         e, C = self.engine, self._C
+        if e.R > 1:      # local copies first; with pooled promotion no rank decides alone
+            self._ffi.check(e.lib.dqlb200_replica_merge(e.handle, e.merge_snapshot.data_ptr(), 0 if self.pooled_promote else e.pooled_promote, e._stream()))
         self._ffi.check(e.lib.dqlb200_shared_pack(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()), e._stream()))
         merge_deltas(self.delta)
-        self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()), e._stream()))
+        self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()),
+                                                   self.pooled_promote, e._stream()))

@@ -34,6 +34,7 @@ extern "C" {
 #define DQLB200_ALPHA_LUT 1003                /* count 0..1002; alpha(count >= 1002) == alpha_min */
 #define DQLB200_EPS_LUT 2002                  /* episode 0..2000, [2001] = every later episode */
 #define DQLB200_MAX_WINDOW 128                /* success window (Trainer successive_successful_episodes) */
+#define DQLB200_SHARED_DELTA_WORDS (4 * DQLB200_MAX_CELLS + 4)   /* floats per agent in the shared-table all-reduce buffer */
 #define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, SoA: [3][n_envs_total][16 B] */
 
 typedef enum dqlb200_status {
@@ -251,11 +252,20 @@ int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream);
 /* Checks the populations' error flags (synchronises the stream). */
 int dqlb200_check_errors(dqlb200_handle* h, void* stream);
 
-/* Shared-table mode helpers (one population replicated on G devices; NCCL all-reduce between them):
- * delta  = [3][DQLB200_MAX_CELLS] floats per population: sum_w(dQ_a * dcount), dcount, unused.
- * pack:   delta <- (tables - snapshot) weighted;   apply: tables <- snapshot + reduced delta. */
+/* Shared-table mode (one agent replicated on G devices; NCCL all-reduce between them).  An "agent" is a group of
+ * R = cfg.replicas_per_population consecutive populations (R = 1: one population; R > 1: call dqlb200_replica_merge first, so
+ * that the R local copies agree).  snapshot holds ONE [3][DQLB200_MAX_CELLS] entry per agent, delta ONE entry of
+ * DQLB200_SHARED_DELTA_WORDS floats per agent.
+ *   pack : delta <- [ (Q_a - Q_snap) * dcount | dcount | visited ? 1 : 0 | visited ? Q_a : 0 | successes, episodes, 1, alive ]
+ *   ...   the caller all-reduces delta with SUM (torch.distributed / ncclAllReduce) ...
+ *   apply: Q_a <- Q_snap + sum(dQ * dcount) / sum(dcount), count <- count_snap + sum(dcount) in every local replica, the
+ *          shared snapshot and the bound merge snapshot; a cell ONE rank visited takes that rank's value bit for bit on
+ *          every rank (so G = 1 never alters a table).  With
+ *          pooled_promote_successes > 0 the promotion / max_num_episodes decision (PKG/trainer.py:219-245) is taken from the
+ *          counters summed over all ranks and armed in every local replica (it takes effect at the next dqlb200_train);
+ *          pass the threshold for G * R * window_len episodes, and 0 to dqlb200_replica_merge so that no rank decides alone. */
 int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream);
-int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, void* stream);
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, int pooled_promote_successes, void* stream);
 
 /* Replica-merge mode (one agent with more envs than one CTA can hold: BASELINE configs 2-3, "N envs sharing one
  * Q-table pair").  The agent's envs are split over R = cfg.replicas_per_population consecutive populations (replicas),
@@ -290,6 +300,16 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
                             const double* obs, const uint8_t* contact, const int8_t* action,
                             double* mdp_state, uint16_t* out_state, uint8_t* out_code, double* out_reward,
                             void* stream);
+
+/* Measurement aid ("atomic roof"): replays a recorded sequence of visited table cells with UNORDERED
+ * shared-memory atomics -- per visit one red.shared.add.f32 on Q_a[cell] and one red.shared.add.u32 on count[cell], i.e.
+ * the two read-modify-writes of one Q update (PKG/double_q_learning.py:100,145) -- from `blocks` CTAs of `threads`
+ * threads, each thread `visits_per_thread` visits, tables in shared memory like train_kernel.  cells: device uint16
+ * [n_cells] (cell = state id * 3 + action, exported from a traced training run).  checksum_out: device uint64 (keeps the
+ * work alive).  The caller times the launch with CUDA events: visits / time = the rate an unordered-atomics design could
+ * not exceed for the table update alone; train_kernel's ordered commit is compared against it in bench.py. */
+int dqlb200_bench_table_rmw(dqlb200_handle* h, const uint16_t* cells, int64_t n_cells, int visits_per_thread, int threads,
+                            int blocks, void* checksum_out, void* stream);
 
 /* Device self-test: the 3-instruction float64 division used for fp32 numerators (x / p_max, x / v_max) against
  * the IEEE division for every finite fp32 bit pattern; mismatches_out[0] = wrong quotients of the production

@@ -282,7 +282,7 @@ def test_shared_table_mode_merge():
     total = syncs[0].delta + syncs[1].delta
     for e, s in zip(engs, syncs):
         s.delta.copy_(total)
-        lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
+        lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), 0, e._stream())
     torch.cuda.synchronize()
     out = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
     assert np.array_equal(out[0], out[1])                         # replicas agree after the merge
@@ -292,6 +292,66 @@ def test_shared_table_mode_merge():
     both = (cnt[0] + cnt[1]) > 0
     want = np.where(both, (q[0] * cnt[0] + q[1] * cnt[1]) / np.maximum(cnt[0] + cnt[1], 1), 0.0)
     np.testing.assert_allclose(out[0][0, 0].view(np.float32), want, rtol=2e-6, atol=1e-5)
+
+
+def test_shared_table_mode_with_replicas_and_pooled_promotion():
+    """BASELINE config 5 shared-table mode on top of replica-merge mode: two ranks (emulated by two engines on one device, the
+    all-reduce by adding their delta buffers; the collective itself is covered by the gloo test), each with R = 3 local
+    replicas of ONE agent.  After a sync every copy on both ranks is identical, counts add up, and the promotion is decided
+    from the windows of all ranks."""
+    import ctypes as C
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.parallel import SharedTableSync
+    R, n_r, G = 3, 64, 2
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=10 ** 9)
+    engs, syncs = [], []
+    for g in range(G):
+        e = _engine(R, n_r, threads_per_block=32, seeds=[5] * R, population_ids=[g * R + r for r in range(R)], replicas_per_population=R, tp=kw)
+        e.reset(0)
+        s = SharedTableSync(e)
+        s.pooled_promote = K.promote_threshold(6 * R * G, 0.15)          # as SharedTableSync(pooled_promotion=True) sets it with world = G
+        engs.append(e); syncs.append(s)
+    lib = engs[0].lib
+
+    def sync_all():
+        for e, s in zip(engs, syncs):
+            lib.dqlb200_replica_merge(e.handle, e.merge_snapshot.data_ptr(), 0, e._stream())
+            lib.dqlb200_shared_pack(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
+        total = syncs[0].delta + syncs[1].delta
+        for e, s in zip(engs, syncs):
+            s.delta.copy_(total)
+            lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), s.pooled_promote, e._stream())
+        torch.cuda.synchronize()
+
+    base = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
+    promoted_at = None
+    for rnd in range(40):
+        for e in engs:
+            e.train(8)
+        torch.cuda.synchronize()
+        before = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
+        ps_before = [e.population_state() for e in engs]
+        sync_all()
+        t = [e.tables.cpu().numpy().view(np.uint32) for e in engs]
+        for g in range(G):
+            assert all(np.array_equal(t[g][0], t[g][r]) for r in range(R))               # local copies agree
+            assert np.array_equal(syncs[g].snapshot.cpu().numpy().view(np.uint32)[0], t[g][0])
+            assert np.array_equal(engs[g].merge_snapshot.cpu().numpy().view(np.uint32)[0], t[g][0])
+        assert np.array_equal(t[0][0], t[1][0])                                          # ranks agree
+        # counts: every visit of every replica of every rank since the last sync is in the merged count
+        dcount = sum((before[g][r, 2].astype(np.int64) - base[g][r, 2].astype(np.int64)) for g in range(G) for r in range(R))
+        assert np.array_equal(t[0][0, 2].astype(np.int64), base[0][0, 2].astype(np.int64) + dcount)
+        base = [x.copy() for x in t]
+        pend = [int(p["pending_advance"]) for e in engs for p in e.population_state()]
+        pooled = sum(int(p["window_sum"]) for ps in ps_before for p in ps)
+        alive = all(int(p["pending_advance"]) == 0 and int(p["finished"]) == 0 for ps in ps_before for p in ps)
+        want = 1 if (alive and pooled >= syncs[0].pooled_promote) else 0
+        if alive:
+            assert pend == [want] * (G * R), (rnd, pooled, pend)
+        if want and promoted_at is None:
+            promoted_at = rnd
+    assert promoted_at is not None, "the pooled promotion should fire within the test"
+    assert all(int(p["working_step"]) >= 1 for e in engs for p in e.population_state())
 
 
 def test_full_size_properties():
