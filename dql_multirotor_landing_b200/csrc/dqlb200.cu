@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cmath>
 #include <cstring>
 #include <new>
 #include <string>
@@ -387,31 +388,30 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const DState ds = discretise_cuts(sh.cuts, kc.angle_cut, o, w);
         const uint32_t sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
+        // The priority chain of PKG/mdp.py:359-425 as selects (the ladder of branches diverges inside a warp).
+        const bool t_fx = !(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi);
+        const bool t_zmin = !(o.z >= kc.z_min_cut), t_zmax = o.z >= kc.z_max_cut;
+        const bool t_time = (int)step_count >= kc.timeout_steps;
+        const bool goal_bins = !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
+        const bool at_level = sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;   // previous level == w (it never exceeds w)
+        const uint32_t cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
-        uint32_t cc = e.curriculum_check;
-        if (o.contact) code = DQLB200_TERMINAL_CONTACT;
-        else if (!(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
-        else if (!(o.z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
-        else if (o.z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
-        else if ((int)step_count >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
-        else if (ds.bp == 1 && ds.bv == 1) {
-          if (sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w) {      // previous level == w (it never exceeds w)
-            cc += 1u;
-            code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
-          } else {
-            cc = 0u;
-          }
-        }
+        if (goal_bins && at_level) code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+        code = t_time ? DQLB200_TERMINAL_TIMEOUT : code;
+        code = t_zmax ? DQLB200_TERMINAL_FLYZONE_Z : code;
+        code = t_zmin ? DQLB200_TERMINAL_MINIMUM_ALTITUDE : code;
+        code = t_fx ? DQLB200_TERMINAL_FLYZONE_X : code;
+        code = o.contact ? DQLB200_TERMINAL_CONTACT : code;
         done = code >= DQLB200_TERMINAL_SUCCESS;
         success = code == DQLB200_TERMINAL_SUCCESS;
         if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
           atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
         // R7 (float64, reference operation order; level-dependent constants from the host)
-        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, DIV2);
-        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, DIV2);
+        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
         const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
-        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, DIV2);
-        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, DIV2);
+        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
         const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
         const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
@@ -433,24 +433,21 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
           if (args.trace.next_state) args.trace.next_state[trace_i] = (uint16_t)sid2;
           if (args.trace.episode) args.trace.episode[trace_i] = (int32_t)e.episode;
         }
-        // carry.  A finished env only gets its shaping memory and episode index written here; its new
-        // episode (R1) is set up by the batched reset pass after the slot loop.
+        // carry, without a branch on `done`: of a finished env only the shaping memory and the episode index survive -- the
+        // batched reset pass after the slot loop (R1/R8) overwrites every other field -- so all fields are written alike.
+        ep_steps = step_count;
+        ep_return = e.cum_reward;                 // quirk Q12: the last reward is not in the logged sum
         e.theta_sp = sp;
         e.prev_rel_p = o.rel_p;
         e.prev_rel_v = o.rel_v;
-        if (done) {
-          ep_steps = step_count;
-          ep_return = e.cum_reward;               // quirk Q12: the last reward is not in the logged sum
-          e.episode += 1u;
-        } else {
-          e.sid = sid2;
-          e.bp = (uint32_t)ds.bp;
-          e.step_count = step_count;
-          e.curriculum_check = cc;
-          e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
-          e.fresh = false;
-          e.cum_reward = __dadd_rn(e.cum_reward, r);
-        }
+        e.episode += done ? 1u : 0u;
+        e.sid = sid2;
+        e.bp = (uint32_t)ds.bp;
+        e.step_count = step_count;
+        e.curriculum_check = cc;
+        e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
+        e.fresh = false;
+        e.cum_reward = __dadd_rn(e.cum_reward, r);
       }
       // ---------------- phase B: ordered commit (baton between warps) --------------------------
       // The serialised section is the critical path of a global step (n_p / 32 links per population), so everything that
@@ -1211,6 +1208,15 @@ const char* dqlb200_termination_string(int code) {
   }
 }
 
+// Smallest non-negative fp32 x with RN((double)x / d) >= 1.0: np.clip(x / d, -1, 1) saturates exactly for |x| >= this cut
+// (the correctly rounded quotient is monotone in x), so the shaping potentials clip on the fp32 observation.
+static float first_f32_with_unit_quotient(double d) {
+  float x = (float)d;
+  while ((double)x / d >= 1.0) x = nextafterf(x, 0.0f);
+  while (!((double)x / d >= 1.0)) x = nextafterf(x, INFINITY);
+  return x;
+}
+
 static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   memcpy(k.cuts, c.cuts, sizeof(k.cuts));
   memcpy(k.reward, c.reward, sizeof(k.reward));
@@ -1218,6 +1224,8 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   k.w_p = c.w_p; k.w_v = c.w_v; k.w_theta = c.w_theta;
   k.rcp_p_max = 1.0 / c.p_max; k.rcp_v_max = 1.0 / c.v_max; k.rcp_theta_max = 1.0 / c.theta_max;
   k.div_two_steps = (c.p_max == 4.5 && c.v_max == 3.39411) ? 0 : 1;
+  k.clip_p_f = first_f32_with_unit_quotient(c.p_max);
+  k.clip_v_f = first_f32_with_unit_quotient(c.v_max);
   memcpy(k.angle_cut, c.angle_cut, sizeof(k.angle_cut));
   k.fz_lo = c.fz_lo; k.fz_hi = c.fz_hi; k.z_min_cut = c.z_min_cut; k.z_max_cut = c.z_max_cut;
   k.h = c.h; k.half_h2 = c.half_h2; k.k_theta = c.k_theta; k.g = c.g; k.c_d = c.c_d;

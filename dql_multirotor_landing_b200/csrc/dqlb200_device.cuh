@@ -29,6 +29,7 @@ struct KC {
   float fz_lo, fz_hi, z_min_cut, z_max_cut;
   float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
   float p_max_f, two_p_max_f, sigma_x;
+  float clip_p_f, clip_v_f;     // smallest fp32 |x| whose quotient x / p_max (x / v_max) rounds to >= 1
   float gamma;
   float transfer_ratio[DQLB200_MAX_CURRICULUM];
   int32_t timeout_steps, success_steps, n_sub;
@@ -260,10 +261,12 @@ __device__ __forceinline__ double div_f64_by_const(double x, double d, double rc
 }
 
 // Shaping potential of one fp32 observation (PKG/mdp.py:457-474): w * |clip(x / x_max, -1, 1)|
-__device__ __forceinline__ double shaping(double w, float x, double x_max, double rcp, bool two_steps) {
-  // |clip(q, -1, 1)| = min(|q|, 1); a NaN quotient (flagged as an error by the caller) gives 1 like fmin/fmax would
+__device__ __forceinline__ double shaping(double w, float x, double x_max, double rcp, float clip_cut, bool two_steps) {
+  // |clip(q, -1, 1)| = min(|q|, 1), and the quotient reaches 1 exactly when |x| >= clip_cut (host-computed, monotone
+  // rounding): the clip is one fp32 compare and a select of the halves.  NaN gives 1 like fmin/fmax would.
   const double aq = fabs(div_f32_by_const(x, x_max, rcp, two_steps));
-  return __dmul_rn(w, !(aq <= 1.0) ? 1.0 : aq);
+  const bool sat = !(fabsf(x) < clip_cut);
+  return __dmul_rn(w, __hiloint2double(sat ? 0x3FF00000 : __double2hiint(aq), sat ? 0 : __double2loint(aq)));
 }
 
 // R7 with the level-dependent constants pre-evaluated on the host.
