@@ -1063,68 +1063,114 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* 
   }
 }
 
-// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One WARP per table cell: the lanes read
-// 32 replicas at a time, the replicas that visited the cell (ballot) are accumulated strictly in replica order (the
-// summation order is part of the semantics: bit-exact vs oracle/loop.py), the merged value is written to every replica
-// and to the snapshot.  Only the live rows (levels 0..working step) can differ from the snapshot.  Thread 0 of block
-// (0, g) pools the success windows and arms the promotion.
+// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One CTA (8 warps) per tile of 32 live cells:
+//   load   : all warps stream the replicas' (count, Q_a) of the tile, lane <-> cell (128-byte coalesced rows), into shared memory,
+//            MERGE_CHUNK replicas at a time -- every load is independent of every other;
+//   reduce : warp 0 (lane <-> cell) accumulates the visitors of the chunk STRICTLY in replica order (the summation order
+//            is part of the semantics: bit-exact vs oracle/loop.py) -- the only serial part, one dependent fadd per visitor;
+//   write  : the merged value goes to every replica (all warps, coalesced) and to the snapshot.
+// Only the live rows (levels 0..working step) can differ from the snapshot.  Thread 0 of block (0, g) pools the success
+// windows and arms the promotion.
+constexpr int MERGE_CHUNK = 128;
 __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
                                                             int R, int pooled_promote, long long max_episodes) {
+  __shared__ uint32_t s_q[MERGE_CHUNK][32], s_dc[MERGE_CHUNK][32];
+  __shared__ uint32_t s_qnew[32], s_cnew[32], s_vis[32];
   const int g = blockIdx.y;
-  const int lane = threadIdx.x & 31;
-  const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
   uint32_t* sg = snap + (size_t)g * 3 * CELLS;
+  const uint32_t* tg = tables + (size_t)g * R * 3 * CELLS;
   const int live = (ps[g * R].working_step + 1) * DQLB200_CELLS_PER_LEVEL;
-  if (c < live) {
-    const float q_snap = __uint_as_float(sg[c]);
-    const uint32_t cnt_snap = sg[2 * CELLS + c];
+  if (blockIdx.x * 32 < live) {                       // block-uniform
+    const bool in = c < live;
+    const float q_snap = in ? __uint_as_float(sg[c]) : 0.0f;
+    const uint32_t cnt_snap = in ? sg[2 * CELLS + c] : 0u;
     float num = 0.0f, q_single = q_snap;
     uint32_t tot = 0;
     int visitors = 0;
-    for (int r0 = 0; r0 < R; r0 += 32) {
-      const int r = r0 + lane;
-      const uint32_t* tr = tables + (size_t)(g * R + min(r, R - 1)) * 3 * CELLS;
-      const uint32_t dc = (r < R) ? (__ldcg(tr + 2 * CELLS + c) - cnt_snap) : 0u;
-      const float q_r = dc ? __uint_as_float(__ldcg(tr + c)) : 0.0f;
-      uint32_t m = __ballot_sync(FULL, dc != 0u);
-      while (m) {                                   // warp-uniform: every lane keeps the same accumulators
-        const int b = __ffs(m) - 1;
-        m &= m - 1u;
-        const uint32_t dc_b = __shfl_sync(FULL, dc, b);
-        const float q_b = __shfl_sync(FULL, q_r, b);
-        visitors += 1;
-        q_single = q_b;
-        num = fadd(num, fmul(fsub(q_b, q_snap), __uint2float_rn(dc_b)));
-        tot += dc_b;
+    for (int r0 = 0; r0 < R; r0 += MERGE_CHUNK) {
+      const int n = min(MERGE_CHUNK, R - r0);
+      {   // MERGE_CHUNK / 8 replicas per warp: all their loads are issued before the first one is consumed
+        uint32_t cv[MERGE_CHUNK / 8], qv[MERGE_CHUNK / 8];
+#pragma unroll
+        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
+          const int j = warp + 8 * i;
+          const uint32_t* tr = tg + (size_t)(r0 + min(j, n - 1)) * 3 * CELLS;
+          cv[i] = in ? __ldcg(tr + 2 * CELLS + c) : cnt_snap;
+          qv[i] = in ? __ldcg(tr + c) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
+          const int j = warp + 8 * i;
+          if (j < n) {
+            s_dc[j][lane] = cv[i] - cnt_snap;
+            s_q[j][lane] = qv[i];
+          }
+        }
       }
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) {
+          const uint32_t dc = s_dc[j][lane];
+          const float q_r = __uint_as_float(s_q[j][lane]);
+          const float term = fmul(fsub(q_r, q_snap), __uint2float_rn(dc));      // off the dependent chain
+          if (dc) {
+            visitors += 1;
+            q_single = q_r;
+            num = fadd(num, term);
+            tot += dc;
+          }
+        }
+      }
+      __syncthreads();
     }
-    float q_new = q_snap;
-    if (visitors == 1) q_new = q_single;
-    else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
-    if (visitors) {
-      for (int r = lane; r < R; r += 32) {
-        uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
-        tr[c] = __float_as_uint(q_new);
-        tr[2 * CELLS + c] = cnt_snap + tot;
-      }
-      if (lane == 0) {
+    if (warp == 0) {
+      float q_new = q_snap;
+      if (visitors == 1) q_new = q_single;
+      else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
+      s_qnew[lane] = __float_as_uint(q_new);
+      s_cnew[lane] = cnt_snap + tot;
+      s_vis[lane] = (uint32_t)visitors;
+      if (in && visitors) {
         sg[c] = __float_as_uint(q_new);
         sg[2 * CELLS + c] = cnt_snap + tot;
       }
     }
-  }
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    long long successes = 0, episodes = 0;
-    bool alive = true;
-    for (int r = 0; r < R; ++r) {
-      const dqlb200_population_state& p = ps[g * R + r];
-      successes += p.window_sum;
-      episodes += p.episodes_in_step;
-      alive = alive && !p.finished && !p.pending_advance;
+    __syncthreads();
+    if (in && s_vis[lane]) {
+      const uint32_t qn = s_qnew[lane], cn = s_cnew[lane];
+      for (int r = warp; r < R; r += 8) {
+        uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
+        tr[c] = qn;
+        tr[2 * CELLS + c] = cn;
+      }
     }
-    const int pending = (!alive || pooled_promote <= 0) ? 0 : (successes >= pooled_promote ? 1 : (episodes >= max_episodes ? 2 : 0));
+  }
+  if (blockIdx.x == 0) {          // pooled trainer counters of the group: block-wide reduction over the R replicas
+    __shared__ unsigned long long s_succ, s_eps;
+    __shared__ int s_dead, s_pending;
+    if (threadIdx.x == 0) { s_succ = s_eps = 0ull; s_dead = 0; s_pending = 0; }
+    __syncthreads();
+    unsigned long long successes = 0, episodes = 0;
+    int dead = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      const dqlb200_population_state& p = ps[g * R + r];
+      successes += (unsigned long long)p.window_sum;
+      episodes += (unsigned long long)p.episodes_in_step;
+      dead |= (p.finished || p.pending_advance) ? 1 : 0;
+    }
+    if (successes) atomicAdd(&s_succ, successes);
+    if (episodes) atomicAdd(&s_eps, episodes);
+    if (dead) atomicOr(&s_dead, 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_pending = (s_dead || pooled_promote <= 0) ? 0 : ((long long)s_succ >= pooled_promote ? 1 : ((long long)s_eps >= max_episodes ? 2 : 0));
+    __syncthreads();
+    const int pending = s_pending;
     if (pending)
-      for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
+      for (int r = threadIdx.x; r < R; r += blockDim.x) ps[g * R + r].pending_advance = pending;
   }
 }
 
@@ -1174,6 +1220,12 @@ struct dqlb200_handle {
   cudaEvent_t chunk_done[MAX_HOST_CHUNKS];
   cudaEvent_t host_start;
   bool chunk_ready;
+  // dqlb200_train_merged replays ONE captured CUDA graph (train launch of `merged_k` steps + replica merge) on its own stream
+  cudaStream_t merged_stream;
+  cudaEvent_t merged_in, merged_out;
+  cudaGraphExec_t merged_exec;
+  int merged_k, merged_promote;
+  bool merged_ready;
 };
 
 static thread_local std::string g_last_error;
@@ -1267,6 +1319,10 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   h->device = device;
   h->env_state = h->tables = h->pop_state = h->merge_snapshot = nullptr;
   h->chunk_ready = false;
+  h->merged_ready = false;
+  h->merged_exec = nullptr;
+  h->merged_k = 0;
+  h->merged_promote = 0;
   CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
   CUDA_TRY(cudaMemcpy(h->d_cfg, cfg, sizeof(dqlb200_config), cudaMemcpyHostToDevice));
   const size_t lut_bytes = (size_t)cfg->n_alpha_luts * DQLB200_ALPHA_LUT * sizeof(float);
@@ -1309,6 +1365,12 @@ int dqlb200_destroy(dqlb200_handle* h) {
     }
     cudaEventDestroy(h->host_start);
   }
+  if (h->merged_exec) cudaGraphExecDestroy(h->merged_exec);
+  if (h->merged_ready) {
+    cudaStreamDestroy(h->merged_stream);
+    cudaEventDestroy(h->merged_in);
+    cudaEventDestroy(h->merged_out);
+  }
   delete h;
   return DQLB200_OK;
 }
@@ -1320,6 +1382,7 @@ int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_sta
   h->env_state = env_state;
   h->tables = tables;
   h->pop_state = pop_state;
+  h->merged_k = 0;                 // a captured graph holds the old pointers
   return DQLB200_OK;
 }
 
@@ -1539,6 +1602,16 @@ int dqlb200_bind_merge_snapshot(dqlb200_handle* h, void* snapshot) {
   if (!h) return fail(DQLB200_ERR_ARG, "null handle");
   if ((uintptr_t)snapshot & 3u) return fail(DQLB200_ERR_ARG, "misaligned snapshot");
   h->merge_snapshot = snapshot;
+  h->merged_k = 0;
+  return DQLB200_OK;
+}
+
+static int launch_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, cudaStream_t stream) {
+  const int R = h->cfg.replicas_per_population;
+  const dim3 grid((DQLB200_MAX_CELLS + 31) / 32, h->cfg.n_populations / R);     // one CTA per tile of 32 cells
+  dql::replica_merge_kernel<<<grid, 256, 0, stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot, (dqlb200_population_state*)h->pop_state, R,
+                                                     pooled_promote_successes, h->cfg.max_num_episodes);
+  CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
 
@@ -1549,11 +1622,49 @@ int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_
   const int R = h->cfg.replicas_per_population;
   if (R < 1 || h->cfg.n_populations % R) return fail(DQLB200_ERR_STATE, "n_populations is not a multiple of replicas_per_population");
   CUDA_TRY(cudaSetDevice(h->device));
-  const dim3 grid((DQLB200_MAX_CELLS + 7) / 8, h->cfg.n_populations / R);       // one warp per cell, 8 warps per block
-  dql::replica_merge_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
-                                                                   (dqlb200_population_state*)h->pop_state, R,
-                                                                   pooled_promote_successes, h->cfg.max_num_episodes);
-  CUDA_TRY(cudaGetLastError());
+  return launch_merge(h, snapshot, pooled_promote_successes, (cudaStream_t)stream);
+}
+
+int dqlb200_train_merged(dqlb200_handle* h, int total_steps, int merge_every, int pooled_promote_successes, void* stream) {
+  if (!h || !h->env_state || !h->tables || !h->pop_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (!h->merge_snapshot) return fail(DQLB200_ERR_STATE, "bind the merge snapshot first (dqlb200_bind_merge_snapshot)");
+  if (total_steps < 0 || merge_every < 1) return fail(DQLB200_ERR_ARG, "total_steps >= 0 and merge_every >= 1 required");
+  if (total_steps == 0) return DQLB200_OK;
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (!h->merged_ready) {
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->merged_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->merged_in, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->merged_out, cudaEventDisableTiming));
+    h->merged_ready = true;
+  }
+  cudaStream_t ms = h->merged_stream, cs = (cudaStream_t)stream;
+  const int n_full = total_steps / merge_every, rem = total_steps % merge_every;
+  if (n_full > 0 && (h->merged_k != merge_every || h->merged_promote != pooled_promote_successes || !h->merged_exec)) {
+    // (train launch of merge_every steps, replica merge) captured once and replayed: the pair is launch-bound for
+    // populations of a few thousand CTAs (two ~5 us launches around ~10 us of work), a graph launch is one submission
+    if (h->merged_exec) { cudaGraphExecDestroy(h->merged_exec); h->merged_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CUDA_TRY(cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal));
+    int rc = launch_train(h, merge_every, nullptr, h->env_state, h->tables, h->pop_state, ms);
+    if (!rc) rc = launch_merge(h, h->merge_snapshot, pooled_promote_successes, ms);
+    const cudaError_t ce = cudaStreamEndCapture(ms, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    CUDA_TRY(ce);
+    CUDA_TRY(cudaGraphInstantiate(&h->merged_exec, graph, 0));
+    CUDA_TRY(cudaGraphDestroy(graph));
+    h->merged_k = merge_every;
+    h->merged_promote = pooled_promote_successes;
+  }
+  CUDA_TRY(cudaEventRecord(h->merged_in, cs));
+  CUDA_TRY(cudaStreamWaitEvent(ms, h->merged_in, 0));
+  for (int i = 0; i < n_full; ++i) CUDA_TRY(cudaGraphLaunch(h->merged_exec, ms));
+  if (rem) {
+    int rc = launch_train(h, rem, nullptr, h->env_state, h->tables, h->pop_state, ms);
+    if (!rc) rc = launch_merge(h, h->merge_snapshot, pooled_promote_successes, ms);
+    if (rc) return rc;
+  }
+  CUDA_TRY(cudaEventRecord(h->merged_out, ms));
+  CUDA_TRY(cudaStreamWaitEvent(cs, h->merged_out, 0));
   return DQLB200_OK;
 }
 

@@ -126,9 +126,14 @@ class Engine:
         self._ensure_merge_snapshot()
         _ffi.check(self.lib.dqlb200_replica_merge(self.handle, self.merge_snapshot.data_ptr(), self.pooled_promote, self._stream()))
 
-    def train_merged(self, total_steps: int, merge_every: int = 1):
-        """total_steps global steps, merging the replicas of every agent after each `merge_every` steps."""
+    def train_merged(self, total_steps: int, merge_every: int = 1, graph: bool = True):
+        """total_steps global steps, merging the replicas of every agent after each `merge_every` steps.  graph=True submits
+        the whole loop from C as replays of one captured CUDA graph (dqlb200_train_merged); graph=False alternates the two
+        entry points from Python (same result, one ctypes call per launch)."""
         self._ensure_merge_snapshot()
+        if graph:
+            _ffi.check(self.lib.dqlb200_train_merged(self.handle, total_steps, merge_every, self.pooled_promote, self._stream()))
+            return
         done = 0
         while done < total_steps:
             k = min(merge_every, total_steps - done)

@@ -56,7 +56,7 @@ class Trainer:
         dynamics: Optional[K.DynamicsParameters] = None,
         max_global_steps: Optional[int] = None,
         envs_per_replica: int = 128,
-        merge_every: int = 8,
+        merge_every: int = 1,
         tensorboard: bool = False,
         verbose: bool = True,
         direction: str = "x",

@@ -282,6 +282,11 @@ int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_re
  * dqlb200_bind_merge_snapshot before the first dqlb200_train launch of a replicated layout (NULL unbinds). */
 int dqlb200_bind_merge_snapshot(dqlb200_handle* h, void* snapshot);
 int dqlb200_replica_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, void* stream);
+/* total_steps global steps with a replica merge after every `merge_every` of them (the loop Trainer.curriculum_training runs
+ * in replica-merge mode), submitted from C: the (train launch, merge) pair is captured ONCE as a CUDA graph and replayed on
+ * an internal stream that is ordered after / before `stream` by events.  Equivalent to alternating dqlb200_train(h,
+ * merge_every) and dqlb200_replica_merge on the bound merge snapshot. */
+int dqlb200_train_merged(dqlb200_handle* h, int total_steps, int merge_every, int pooled_promote_successes, void* stream);
 
 /* Facade kernels behind TrainingMdp / SimulationMdp / DoubleQLearningAgent single-object calls
  * (float64 observations from the host, reference comparisons in float64; PKG/mdp.py:257-541).

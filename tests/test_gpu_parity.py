@@ -478,3 +478,20 @@ def test_two_axis_greedy_evaluation(golden_dir, case):
         hist[rows[-1]["code"]] += 1
         steps += len(rows)
     assert res2["episodes"] == n2 and res2["steps"] == steps and res2["termination_hist"] == list(hist)
+
+
+def test_train_merged_graph_replay_equals_python_loop():
+    """dqlb200_train_merged (one captured CUDA graph replayed from C, remainder launched directly) leaves exactly the state
+    the Python loop over dqlb200_train / dqlb200_replica_merge leaves, promotions included."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    out = []
+    for graph in (True, False):
+        e = _engine(4, 40, threads_per_block=32, seeds=[5] * 4, population_ids=list(range(4)), replicas_per_population=4, tp=kw)
+        e.reset(0)
+        e.train_merged(203, 5, graph=graph)          # 40 graph replays + a remainder of 3 steps
+        e.train_merged(60, 1, graph=graph)           # a different interval re-captures the graph
+        e.check_errors()
+        out.append((e.tables.cpu(), e.env_state.cpu(), e.pop_state.cpu(), e.merge_snapshot.cpu()))
+        assert int(e.population_state()["working_step"].max()) >= 1
+    for a, b in zip(*out):
+        assert torch.equal(a, b)

@@ -21,6 +21,6 @@ def run(total_envs, R, tpb, M, steps=256):
     eng.close()
 
 if __name__ == "__main__":
-    for args in [(65536, 512, 128, 1), (65536, 512, 128, 4), (65536, 512, 128, 16), (65536, 256, 128, 4), (65536, 888, 64, 4),
-                 (262144, 888, 128, 4), (262144, 888, 128, 16), (65536, 1, 256, 64)]:
+    for args in [(65536, 512, 128, 1), (65536, 512, 128, 4), (65536, 512, 128, 16), (65536, 1024, 64, 1), (65536, 2048, 32, 1),
+                 (262144, 1024, 128, 1), (262144, 1024, 128, 16)]:
         run(*args)
