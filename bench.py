@@ -33,8 +33,8 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "env_steps_per_sec_incl_q_updates"
 UNIT = "env-steps/s"
-POPULATIONS_PER_GPU = 1036         # 7 CTAs per SM x 148 SMs (shared-memory and register limit of train_kernel<4>)
-ENVS_PER_POPULATION = 1024         # 8 full slots of 128 threads; 1036 * 1024 = 1,060,864 envs per GPU  (BASELINE config 5: "1M envs per GPU")
+POPULATIONS_PER_GPU = 888          # 6 CTAs per SM x 148 SMs (shared-memory limit of train_kernel<4>: 35 KB per population)
+ENVS_PER_POPULATION = 1280         # 10 full slots of 128 threads; 888 * 1280 = 1,136,640 envs per GPU  (BASELINE config 5: "1M envs per GPU")
 THREADS_PER_BLOCK = 128
 E2E_CHUNK = 64                     # global steps per host-buffer call (about one episode, the reference's save interval)
 ALGORITHMIC_BYTES_PER_ENV_STEP = 96   # 48 B env state read + 48 B written, one step per launch

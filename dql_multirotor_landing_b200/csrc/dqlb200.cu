@@ -65,6 +65,25 @@ __device__ __forceinline__ EnvRaw env_fetch(const EnvPtrs& p, size_t i) {
   r.C = p.c[i];
   return r;
 }
+// Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
+// unlike a register prefetch it holds no registers while in flight and cannot be consumed early by the scheduler's copies.
+__device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, uint4* stage, int nt, int tid) {
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(stage + tid);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(p.a + i) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16u * nt), "l"(p.b + i) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 32u * nt), "l"(p.c + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ EnvRaw env_prefetch_take(const uint4* stage, int nt, int tid) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  EnvRaw r;
+  const uint4 a = stage[tid];
+  r.A = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+  r.B = stage[nt + tid];
+  r.C = stage[2 * nt + tid];
+  return r;
+}
+
 __device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
   const float4 A = r.A;
   const uint4 B = r.B;
@@ -177,7 +196,7 @@ struct Shared {
 };
 
 #ifndef DQL_WARPS_PER_SM
-#define DQL_WARPS_PER_SM 28     // resident warps per SM the register allocation is tuned for (launch bounds)
+#define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
 // DIV2: second Markstein correction step of x / p_max, x / v_max (needed unless the divisors are the exhaustively
 // verified defaults; the trace instances always take it: both variants are correctly rounded, hence identical)
@@ -191,6 +210,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT]
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
   float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
@@ -204,7 +224,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
   static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
   constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
   const dqlb200_population_params pp = args.pop_params[pop];
-  EnvRaw next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
+  env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
   {
     const int w_start = args.pop_state[pop].working_step;
     const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
@@ -293,7 +313,8 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     if (tid == 0) sh.promote = (sh.ps.pending_advance == 1) ? 1 : 0;
     __syncthreads();
     advance_curriculum(sh.ps.working_step, sh.ps.t);
-    next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));     // every env was just restarted
+    (void)env_prefetch_take(stage, NT, tid);
+    env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);     // every env was just restarted
   }
 
   for (int k = 0; k < args.k_steps; ++k) {
@@ -340,8 +361,8 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       const int env_i = slot * NT + tid;
       const bool valid = env_i < n_p;
       const size_t gi = env_base + (size_t)(valid ? env_i : 0);
-      const EnvRaw cur_raw = next_raw;
-      if (env_i + NT < n_p) next_raw = env_fetch(args.env, gi + NT);      // software prefetch, in flight during this slot
+      const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
+      if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage, NT, tid);      // in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -552,7 +573,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     }
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
-    if (k + 1 < args.k_steps) next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
+    if (k + 1 < args.k_steps) env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
@@ -566,11 +587,13 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     __syncthreads();
     if (sh.do_advance) {
       advance_curriculum(w, t + 1u);
-      next_raw = env_fetch(args.env, env_base + (size_t)min(tid, n_p - 1));
+      (void)env_prefetch_take(stage, NT, tid);
+      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
     }
   }
 
   // ---- write back (live rows only) ----------------------------------------------------------------
+  asm volatile("cp.async.wait_all;" ::: "memory");      // a prefetch issued for a step that did not run
   __syncthreads();
   for (int i = tid; i < (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) {
     gt[i] = __float_as_uint(sh.qa[i]);
@@ -1337,7 +1360,8 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
     const int tpb_ = cfg->threads_per_block;
     const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
     if (n_slots > 2047) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots per thread)");
-    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t);
+    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t) +
+                    (size_t)3 * tpb_ * 16;          // + the cp.async staging slots of the env prefetch
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \
