@@ -740,6 +740,112 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
 }
 
 // -------------------------------------------------------------------------------------------------
+// Un-fused environment entry points (the gym surface of the reference: TrainingLandingEnv / SimulationLandingEnv reset()
+// and step(), PKG/landing_simulation_env.py:167-282, 327-400): the caller supplies the actions, no agent, no table.  Same
+// device functions and the same operation order as phase A of train_kernel; tests/test_gpu_facade.py holds the two
+// bit-identical (a traced train launch with forced actions == a sequence of env steps).
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) env_reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, const dqlb200_population_params* pop_params,
+                                                        int w, uint32_t birth, const uint8_t* __restrict__ mask, int fresh_mdp, int simulation,
+                                                        uint16_t* out_state) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_total = (long long)kc.n_populations * kc.envs_per_population;
+  if (i >= n_total) return;
+  Env e;
+  env_load(env, (size_t)i, e);
+  if (!mask || mask[i]) {
+    const int pop = (int)(i / kc.envs_per_population);
+    const uint32_t env_i = (uint32_t)(i % kc.envs_per_population);
+    const dqlb200_population_params pp = pop_params[pop];
+    if (simulation) {      // SimulationLandingEnv.reset (PKG/landing_simulation_env.py:327-340) + SimulationMdp.reset (PKG/mdp.py:879-886)
+      const uint4 d = philox4x32_10(make_uint4(env_i, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
+      const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim);
+      const DState ds = discretise_cuts(kc.cuts[w], kc.angle_cut, o);
+      e.sid = (uint32_t)ds.id(); e.bp = (uint32_t)ds.bp;
+      e.step_count = 0; e.curriculum_check = 0; e.sticky_success = false; e.fresh = true; e.cum_reward = 0.0;
+      e.theta_sp = 0.0; e.prev_rel_p = 0.0f; e.prev_rel_v = 0.0f;
+      if (fresh_mdp) e.episode = 0;
+    } else {
+      env_reset(kc, pp, kc.cuts[w], kc.angle_cut, e, env_i, birth, w, fresh_mdp != 0);
+    }
+    env_store(env, (size_t)i, e);
+  }
+  if (out_state) out_state[i] = (uint16_t)e.sid;
+}
+
+template <bool DIV2>
+__global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ KC kc, EnvPtrs env, const dqlb200_population_params* pop_params,
+                                                       int w, uint32_t t, const int8_t* __restrict__ actions, int auto_reset, int simulation,
+                                                       uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done,
+                                                       float* out_obs, uint32_t* out_steps, double* out_cumulative, uint32_t* error_flag) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_total = (long long)kc.n_populations * kc.envs_per_population;
+  if (i >= n_total) return;
+  const int pop = (int)(i / kc.envs_per_population);
+  const uint32_t env_i = (uint32_t)(i % kc.envs_per_population);
+  const dqlb200_population_params pp = pop_params[pop];
+  const dqlb200_cuts& cuts = kc.cuts[w];
+  Env e;
+  env_load(env, (size_t)i, e);
+  const int a = actions[i];
+  // R3 .. R8 in the order of TrainingLandingEnv.step (PKG/landing_simulation_env.py:245-282)
+  const double prev_sp = e.theta_sp;
+  const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
+  dyn_advance(kc, pp, e.b, (float)sp);
+  const uint32_t step_count = e.step_count + 1u;
+  const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train);
+  const DState ds = discretise_cuts(cuts, kc.angle_cut, o, w);
+  const uint32_t sid2 = (uint32_t)ds.id();
+  const bool t_fx = !(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi);
+  const bool t_zmin = !(o.z >= kc.z_min_cut), t_zmax = o.z >= kc.z_max_cut;
+  const bool t_time = (int)step_count >= kc.timeout_steps;
+  const bool goal_bins = !simulation && !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
+  const bool at_level = e.sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;
+  const uint32_t cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
+  int code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
+  if (goal_bins && at_level) code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+  code = t_time ? DQLB200_TERMINAL_TIMEOUT : code;
+  code = t_zmax ? DQLB200_TERMINAL_FLYZONE_Z : code;
+  code = t_zmin ? DQLB200_TERMINAL_MINIMUM_ALTITUDE : code;
+  code = t_fx ? DQLB200_TERMINAL_FLYZONE_X : code;
+  code = o.contact ? DQLB200_TERMINAL_CONTACT : code;
+  const bool done = code >= DQLB200_TERMINAL_SUCCESS;
+  if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
+    atomicOr(error_flag, 1u);
+  double r = 0.0;
+  if (!simulation) {
+    const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+    const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+    const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
+    const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+    const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+    const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
+    const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
+    r = reward_f64(kc, kc.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
+  }
+  if (out_reward) out_reward[i] = r;
+  if (out_code) out_code[i] = (uint8_t)code;
+  if (out_done) out_done[i] = (uint8_t)done;
+  if (out_obs) { float* po = out_obs + i * 5; po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z; }
+  if (out_steps) out_steps[i] = step_count;
+  if (out_cumulative) out_cumulative[i] = e.cum_reward;          // quirk Q12: without this step's reward
+  e.theta_sp = sp;
+  e.prev_rel_p = o.rel_p;
+  e.prev_rel_v = o.rel_v;
+  e.episode += done ? 1u : 0u;
+  e.sid = sid2;
+  e.bp = (uint32_t)ds.bp;
+  e.step_count = step_count;
+  e.curriculum_check = cc;
+  e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
+  e.fresh = false;
+  e.cum_reward = __dadd_rn(e.cum_reward, r);
+  if (done && auto_reset && !simulation) env_reset(kc, pp, cuts, kc.angle_cut, e, env_i, t + 1u, w, /*fresh_mdp=*/false);
+  if (out_state) out_state[i] = (uint16_t)e.sid;       // of a finished env with auto_reset: the first state of its next episode
+  env_store(env, (size_t)i, e);
+}
+
+// -------------------------------------------------------------------------------------------------
 // two-axis greedy evaluation.  One thread per episode; pitch drives x, roll drives y (signed gravity per
 // axis), one platform under both (three trajectories).  Same operation order as oracle/dynamics.py: StandIn2D.
 // -------------------------------------------------------------------------------------------------
@@ -1530,6 +1636,37 @@ int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy
   dql::eval_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode,
                                                                      n_episodes, working_step, (dqlb200_eval_stats*)stats_out,
                                                                      tr, trace ? trace_steps : 0);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_env_reset(dqlb200_handle* h, int working_step, uint32_t birth, const uint8_t* mask, int fresh_mdp, int simulation,
+                      uint16_t* out_state, void* stream) {
+  if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
+  dql::env_reset_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step,
+                                                                                     birth, mask, fresh_mdp, simulation, out_state);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8_t* actions, int auto_reset, int simulation,
+                     uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done, float* out_obs, uint32_t* out_steps,
+                     double* out_cumulative, void* stream) {
+  if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (!actions) return fail(DQLB200_ERR_ARG, "actions required");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  if (h->kc.div_two_steps)
+    dql::env_step_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step, t, actions, auto_reset,
+                                                                       simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, h->d_error);
+  else
+    dql::env_step_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step, t, actions, auto_reset,
+                                                                        simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, h->d_error);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

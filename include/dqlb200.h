@@ -237,6 +237,25 @@ int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy
                         int64_t n_episodes, int working_step, void* stats_out, const dqlb200_trace* trace,
                         int trace_steps, void* stream);
 
+/* Un-fused environment entry points: the gym surface of the reference with caller-supplied actions, no agent, no table.
+ *   dqlb200_env_reset  replaces TrainingLandingEnv.reset / SimulationLandingEnv.reset (PKG/landing_simulation_env.py:167-243,
+ *                      327-400) + mdp.reset() for the envs whose mask byte is non-zero (mask NULL = all).  fresh_mdp != 0 also
+ *                      clears what only a NEW TrainingMdp clears (shaping memory, quirk Q11; episode index).  birth = Philox
+ *                      counter word 1 of the reset draws.  out_state (nullable): the state of EVERY env after the call.
+ *   dqlb200_env_step   replaces TrainingLandingEnv.step (PKG/landing_simulation_env.py:245-282: continuous_action -> physics
+ *                      -> discrete_state -> check -> reward) for every env; actions: int8 [n_envs_total].  auto_reset != 0 starts
+ *                      the next episode of a finished env inside the call (birth t + 1, like dqlb200_train); simulation != 0
+ *                      selects SimulationMdp semantics (v_z = -0.4, no goal logic, reward 0, PKG/mdp.py:784-877).  Outputs
+ *                      (all nullable, device, [n_envs_total]): state after the step (auto_reset: of a finished env the first state of
+ *                      its next episode), float64 reward, CheckResult code, done,
+ *                      obs [..][5], "Number of steps", "Cumulative reward" (without this step's reward, quirk Q12).
+ * Both work on the bound env_state; they neither read nor write tables or trainer state. */
+int dqlb200_env_reset(dqlb200_handle* h, int working_step, uint32_t birth, const uint8_t* mask, int fresh_mdp, int simulation,
+                      uint16_t* out_state, void* stream);
+int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8_t* actions, int auto_reset, int simulation,
+                     uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done, float* out_obs,
+                     uint32_t* out_steps, double* out_cumulative, void* stream);
+
 /* Replaces: scripts/simulation.py:48-63 with BOTH agents acting (agent_x.predict / agent_y.predict,
  * SimulationMdp.discrete_state_x/_y PKG/mdp.py:634-782, check :784-845 incl. FLYZONE_Y and contact on both axes).
  * policy_x / policy_y: 945-byte action LUTs (device).  Episode i uses the reset draws of (env = first_episode + i,

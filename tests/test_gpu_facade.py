@@ -191,3 +191,93 @@ def test_trainer_large_population_uses_replica_merge(tmp_path):
     assert agent.state_action_counter.sum() == ps["total_steps"].sum() > 0       # every env-step of every replica is in the merged counts
     assert len(set(int(x) for x in ps["working_step"])) == 1                      # replicas move through the curriculum together
     assert np.isfinite(agent.Q_table_a).all() and np.abs(agent.Q_table_a).max() > 0
+
+
+@pytest.mark.parametrize("name", ["w0", "w2", "w4", "lowz"])
+def test_training_env_gym_surface_against_reference_fixture(golden_dir, name):
+    """TrainingLandingEnv (num_envs = 1, the reference's calling convention): reset() / step(a) reproduce the fixture the
+    unmodified reference TrainingMdp produced on the stand-in -- state tuples, float64 rewards, done flags, info strings."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.landing_simulation_env import make
+    from dql_multirotor_landing_b200.mdp import state_tuple
+    g = np.load(golden_dir / f"mdp_trace_{name}.npz")
+    env = make("Landing-Training-v0", initial_curriculum_step=int(g["w"]), z_init=float(g["z_init"]), seed=int(g["seed"]),
+               dynamics=K.DynamicsParameters(z_init=float(g["z_init"]), v_z_train=float(g["v_z"]), v_mp=float(g["v_mp"])))
+    n = len(g["action"])
+    i = 0
+    while i < n:
+        assert g["action"][i] == 255                      # a reset row
+        s = env.reset()
+        assert s == state_tuple(int(g["state"][i]))
+        i += 1
+        done = False
+        while not done:
+            s, r, done, info = env.step(int(g["action"][i]))
+            assert s == state_tuple(int(g["state"][i])) and r == float(g["reward"][i]) and done == bool(g["done"][i]), i
+            assert np.array_equal(env.observation[0].view(np.uint32), g["obs"][i].view(np.uint32))
+            if done:
+                assert info["Termination condition"] == K.TERMINATION_STRINGS[int(g["code"][i])]
+                assert info["Cumulative reward"] == float(g["cum"][i - 1])     # check() runs before reward(): quirk Q12
+            else:
+                assert "Termination condition" not in info
+            assert info["Current reward"] == r
+            i += 1
+    env.close()
+
+
+def test_batched_env_steps_equal_fused_training_trace():
+    """The un-fused entry points (dqlb200_env_reset / dqlb200_env_step, auto-reset on) walk exactly the trajectory the fused
+    train_kernel walks when it is forced to take the same actions: observations, states, rewards, codes, episode ends."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.engine import Engine
+    from dql_multirotor_landing_b200.landing_simulation_env import TrainingLandingEnv
+    n, steps = 300, 150
+    rng = np.random.default_rng(3)
+    acts = rng.integers(0, 3, size=(steps, n)).astype(np.int8)
+    eng = Engine(1, n, threads_per_block=128, seeds=[11], tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+    eng.reset(0)
+    tr = eng.train(steps, trace=True, action_override=acts)
+    env = TrainingLandingEnv(0, num_envs=n, seed=11, auto_reset=True)
+    env.reset()
+    for t in range(steps):
+        s, r, done, info = env.step(acts[t])
+        assert np.array_equal(env.observation.view(np.uint32), tr["obs"][t].view(np.uint32)), t
+        assert np.array_equal(r, tr["reward"][t]) and np.array_equal(done, tr["done"][t].astype(bool)), t
+        assert np.array_equal(info["code"], tr["code"][t]), t
+        ids = (((s[:, 0] * 3 + s[:, 1]) * 3 + s[:, 2]) * 3 + s[:, 3]) * 7 + s[:, 4]
+        nd = ~done                     # a finished env already shows the first state of its next episode (auto-reset)
+        assert np.array_equal(ids[nd], tr["next_state"][t][nd].astype(np.int64)), t
+        if t + 1 < steps:
+            assert np.array_equal(ids, tr["state"][t + 1].astype(np.int64)), t
+    assert tr["done"].sum() > 50
+    torch.cuda.synchronize()
+    assert torch.equal(env._engine.env_state, eng.env_state)
+    env.close()
+
+
+def test_simulation_env_gym_surface(golden_dir):
+    """SimulationLandingEnv: reset() -> (state_x, state_y), step(ax, ay) -> (state_x, state_y, done, info) on the fixture of the
+    unmodified reference SimulationMdp (greedy episodes of the committed policy)."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.landing_simulation_env import make
+    from dql_multirotor_landing_b200.mdp import state_tuple
+    g = np.load(golden_dir / "sim_trace.npz")
+    # episode ep of the fixture used the reset draws of env index ep, birth 0: three envs replay its first three episodes
+    env = make("Landing-Simulation-v0", seed=int(g["seed"]), num_envs=3)
+    sx, sy = env.reset()
+    for ep in range(3):
+        rows = np.nonzero(g["episode"] == ep)[0]
+        assert tuple(sx[ep]) == state_tuple(int(g["state"][rows[0]])) and tuple(sy[ep]) == (4, 1, 1, 1, 3)
+    lens = [int((g["episode"] == ep).sum()) - 1 for ep in range(3)]
+    finished = np.zeros(3, bool)
+    for k in range(max(lens)):
+        a = np.asarray([int(g["action"][np.nonzero(g["episode"] == ep)[0][min(k + 1, lens[ep])]]) for ep in range(3)], np.int8)
+        sx, sy, done, info = env.step(a)
+        for ep in range(3):
+            if k < lens[ep]:
+                row = np.nonzero(g["episode"] == ep)[0][k + 1]
+                assert tuple(sx[ep]) == state_tuple(int(g["state"][row])) and bool(done[ep]) == bool(g["done"][row]), (ep, k)
+                assert int(info["code"][ep]) == int(g["code"][row])
+                if done[ep]:
+                    assert info["Termination condition"][ep] == K.TERMINATION_STRINGS[int(g["code"][row])]
+    env.close()
