@@ -381,6 +381,29 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
         e4.close()
     except Exception as exc:
         out["config4_x_and_y_agents_262144_envs_each"] = {"error": str(exc)}
+    # SURVEY 8d streaming case: env state far larger than L2 (888 x 5,120 envs = 218 MB), ONE global step per launch, launches
+    # back to back without any flush (every launch has to stream the whole state from and to HBM)
+    try:
+        n_big = 5120
+        eb = Engine(POPULATIONS_PER_GPU, n_big, device=dev.index or 0, threads_per_block=THREADS_PER_BLOCK, seeds=list(range(POPULATIONS_PER_GPU)),
+                    tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+        eb.reset(0)
+        eb.train(64); torch.cuda.synchronize(dev)
+        reps = 40
+        def many():
+            for _ in range(reps):
+                eb.train(1)
+        sb = timed(many)
+        rate = eb.n_total * reps / sb
+        peak, _src = measured_peak_hbm()
+        out["streaming_case_state_larger_than_l2"] = {
+            "envs_per_gpu": eb.n_total, "env_state_bytes": eb.n_total * 48, "global_steps_per_launch": 1, "launches_timed_back_to_back": reps,
+            "env_steps_per_s": rate, "algorithmic_gb_per_s": rate * ALGORITHMIC_BYTES_PER_ENV_STEP / 1e9,
+            "frac_of_measured_hbm_peak": rate * ALGORITHMIC_BYTES_PER_ENV_STEP / 1e9 / peak, "l2": "no flush needed: 218 MB of state per launch vs 126 MB of L2",
+            "timing": "CUDA events around 40 launches, best of 3"}
+        eb.close()
+    except Exception as exc:
+        out["streaming_case_state_larger_than_l2"] = {"error": str(exc)}
     # SURVEY 8d "atomic roof": the visited cells of a real run (traced), replayed with unordered shared-memory atomics
     try:
         et = Engine(64, 256, device=dev.index or 0, threads_per_block=128, seeds=list(range(64)),
