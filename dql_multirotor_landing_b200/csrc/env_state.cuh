@@ -1,0 +1,115 @@
+// env_state.cuh -- the 48-byte environment state (SoA of three 16-byte vectors): pack/unpack, reset law, asynchronous prefetch
+// Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
+#pragma once
+#include "dqlb200_device.cuh"
+
+namespace dql {
+
+
+constexpr int CELLS = DQLB200_MAX_CELLS;
+constexpr uint32_t FULL = 0xFFFFFFFFu;
+
+// env-state word C.x layout
+constexpr uint32_t SID_BITS = 10, STEP_SHIFT = 10, STEP_BITS = 9, CC_SHIFT = 19, CC_BITS = 5;
+constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25, BP_SHIFT = 26;   // bits 26-27: position bin of `sid`
+
+struct Env {
+  Body b;
+  double theta_sp;     // NOT cleared by an episode reset while `fresh` (keeps the shaping potential, quirk Q11)
+  float prev_rel_p, prev_rel_v;
+  uint32_t sid, bp, step_count, curriculum_check;     // bp = position bin of sid ((sid / 63) % 3, kept to avoid the division)
+  bool sticky_success, fresh;
+  uint32_t episode;
+  double cum_reward;
+};
+
+struct EnvPtrs {
+  float4* a;
+  uint4* b;
+  uint4* c;
+};
+
+struct EnvRaw {
+  float4 A;
+  uint4 B, C;
+};
+__device__ __forceinline__ EnvRaw env_fetch(const EnvPtrs& p, size_t i) {
+  EnvRaw r;
+  r.A = p.a[i];
+  r.B = p.b[i];
+  r.C = p.c[i];
+  return r;
+}
+// Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
+// unlike a register prefetch it holds no registers while in flight and cannot be consumed early by the scheduler's copies.
+__device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, uint4* stage, int nt, int tid) {
+  const unsigned s0 = (unsigned)__cvta_generic_to_shared(stage + tid);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(p.a + i) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16u * nt), "l"(p.b + i) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 32u * nt), "l"(p.c + i) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ EnvRaw env_prefetch_take(const uint4* stage, int nt, int tid) {
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  EnvRaw r;
+  const uint4 a = stage[tid];
+  r.A = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+  r.B = stage[nt + tid];
+  r.C = stage[2 * nt + tid];
+  return r;
+}
+
+__device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
+  const float4 A = r.A;
+  const uint4 B = r.B;
+  const uint4 Cw = r.C;
+  e.b.x_d = A.x; e.b.v_d = A.y; e.b.theta = A.z; e.b.phase = __float_as_uint(A.w); e.b.a_d = 0.0f;
+  e.theta_sp = __hiloint2double((int)B.y, (int)B.x);
+  e.prev_rel_p = __uint_as_float(B.z);
+  e.prev_rel_v = __uint_as_float(B.w);
+  e.sid = Cw.x & ((1u << SID_BITS) - 1u);
+  e.step_count = (Cw.x >> STEP_SHIFT) & ((1u << STEP_BITS) - 1u);
+  e.curriculum_check = (Cw.x >> CC_SHIFT) & ((1u << CC_BITS) - 1u);
+  e.sticky_success = (Cw.x & STICKY_BIT) != 0u;
+  e.bp = (Cw.x >> BP_SHIFT) & 3u;
+  e.fresh = (Cw.x & FRESH_BIT) != 0u;
+  e.episode = Cw.y;
+  e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
+}
+__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { env_unpack(env_fetch(p, i), e); }
+
+__device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) {
+  p.a[i] = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
+  p.b[i] = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
+                      __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
+                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
+  p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
+                      (uint32_t)__double2hiint(e.cum_reward));
+}
+
+// R1 + R8: new episode.  `fresh_mdp` additionally clears what only a NEW TrainingMdp clears
+// (shaping potentials, PKG/trainer.py:176 + quirk Q11) and the per-step episode index.
+__device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population_params& pp,
+                                          const dqlb200_cuts& cuts, const float* angle_cut, Env& e,
+                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
+  const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
+  const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
+  const DState ds0 = discretise_cuts(cuts, angle_cut, o);
+  e.sid = (uint32_t)ds0.id();
+  e.bp = (uint32_t)ds0.bp;
+  e.step_count = 0;
+  e.curriculum_check = 0;
+  e.sticky_success = false;
+  e.fresh = true;
+  e.cum_reward = 0.0;
+  if (fresh_mdp) {
+    e.theta_sp = 0.0;
+    e.prev_rel_p = 0.0f;
+    e.prev_rel_v = 0.0f;
+    e.episode = 0;
+  }
+}
+
+
+}  // namespace dql

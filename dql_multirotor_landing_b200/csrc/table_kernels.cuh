@@ -1,0 +1,220 @@
+// table_kernels.cuh -- kernels on the Q/count tables: transfer, shared-table pack/apply, replica merge, atomic-roof micro-benchmark
+// Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
+#pragma once
+#include "env_state.cuh"
+
+namespace dql {
+
+// -------------------------------------------------------------------------------------------------
+__global__ void transfer_kernel(uint32_t* tables, int n_pop, int cs, int step, float ratio) {
+  const int pop = blockIdx.x;
+  float* qa = reinterpret_cast<float*>(tables + (size_t)pop * 3 * CELLS);
+  float* qb = qa + CELLS;
+  const int src = (step - 1 + cs) % cs;
+  for (int i = threadIdx.x; i < DQLB200_CELLS_PER_LEVEL; i += blockDim.x) {
+    qa[step * DQLB200_CELLS_PER_LEVEL + i] = fmul(qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+    qb[step * DQLB200_CELLS_PER_LEVEL + i] = fmul(qb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+  }
+}
+
+// Shared-table mode (one agent replicated on G devices).  Each replica trains on its own envs for a few
+// steps; the replicas are then merged with a visit-weighted mean of their Q deltas and the sum of
+// their visit counts:  Q <- Q_snap + sum_g(dcount_g * dQ_g) / sum_g(dcount_g),  count <- count_snap + sum_g dcount_g.
+// One "agent" below = a group of R = replicas_per_population consecutive populations whose tables are identical (after
+// replica_merge_kernel; R = 1: a plain population).  snap holds ONE [3][CELLS] entry per agent, delta ONE entry of
+// DQLB200_SHARED_DELTA_WORDS floats per agent: [0] sum dQ*dcount, [1] sum dcount, [2] number of ranks that visited the cell,
+// [3] sum of the visiting ranks' Q (exact when one rank visited: the value that rank keeps), then the agent's pooled trainer
+// counters: successes in the windows, finished episodes of the curriculum step, number of ranks, ranks that are alive.
+constexpr int DELTA_WORDS = DQLB200_SHARED_DELTA_WORDS;
+__global__ void shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, const dqlb200_population_state* ps,
+                                   int n_agents, int R) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_agents * CELLS) return;
+  const long long g = i / CELLS, c = i % CELLS;
+  const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
+  float* d = delta + (size_t)g * DELTA_WORDS;
+  const uint32_t dcu = tables[tb + 2 * CELLS + c] - snap[sb + 2 * CELLS + c];
+  const float dc = (float)dcu, q = __uint_as_float(tables[tb + c]);
+  d[c] = fmul(fsub(q, __uint_as_float(snap[sb + c])), dc);
+  d[CELLS + c] = dc;
+  d[2 * CELLS + c] = dcu ? 1.0f : 0.0f;
+  d[3 * CELLS + c] = dcu ? q : 0.0f;
+  if (c < 4) {
+    long long successes = 0, episodes = 0;
+    bool alive = true;
+    for (int r = 0; r < R; ++r) {
+      const dqlb200_population_state& p = ps[g * R + r];
+      successes += p.window_sum;
+      episodes += p.episodes_in_step;
+      alive = alive && !p.finished && !p.pending_advance;
+    }
+    d[4 * CELLS + c] = c == 0 ? (float)successes : c == 1 ? (float)episodes : c == 2 ? 1.0f : (alive ? 1.0f : 0.0f);
+  }
+}
+__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* merge_snap, const float* delta,
+                                    dqlb200_population_state* ps, int n_agents, int R, int pooled_promote, long long max_episodes) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)n_agents * CELLS) return;
+  const long long g = i / CELLS, c = i % CELLS;
+  const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
+  const float* d = delta + (size_t)g * DELTA_WORDS;
+  const float visitors = d[2 * CELLS + c];
+  uint32_t q_bits = snap[sb + c], cnt = snap[sb + 2 * CELLS + c];
+  if (visitors == 1.0f) q_bits = __float_as_uint(d[3 * CELLS + c]);       // one rank visited: its value, bit for bit, on every rank
+  else if (visitors > 1.0f) q_bits = __float_as_uint(fadd(__uint_as_float(q_bits), __fdiv_rn(d[c], d[CELLS + c])));
+  if (visitors > 0.0f) {
+    cnt += (uint32_t)__float2uint_rn(d[CELLS + c]);
+    for (int r = 0; r < R; ++r) {
+      tables[tb + (size_t)r * 3 * CELLS + c] = q_bits;
+      tables[tb + (size_t)r * 3 * CELLS + 2 * CELLS + c] = cnt;
+    }
+  } else {          // nobody visited: the cell can still have changed by the (identical) curriculum transfers of every copy
+    q_bits = tables[tb + c];
+  }
+  const uint32_t qb_bits = tables[tb + CELLS + c];
+  snap[sb + c] = q_bits; snap[sb + CELLS + c] = qb_bits; snap[sb + 2 * CELLS + c] = cnt;
+  if (merge_snap) { merge_snap[sb + c] = q_bits; merge_snap[sb + CELLS + c] = qb_bits; merge_snap[sb + 2 * CELLS + c] = cnt; }
+  if (c == 0 && pooled_promote > 0) {      // promotion pooled over every rank's windows (same decision on every rank)
+    const float successes = d[4 * CELLS + 0], episodes = d[4 * CELLS + 1];
+    const bool alive = d[4 * CELLS + 3] == d[4 * CELLS + 2];
+    const int pending = !alive ? 0 : (successes >= (float)pooled_promote ? 1 : (episodes >= (float)max_episodes ? 2 : 0));
+    if (pending)
+      for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
+  }
+}
+
+// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One CTA (8 warps) per tile of 32 live cells:
+//   load   : all warps stream the replicas' (count, Q_a) of the tile, lane <-> cell (128-byte coalesced rows), into shared memory,
+//            MERGE_CHUNK replicas at a time -- every load is independent of every other;
+//   reduce : warp 0 (lane <-> cell) accumulates the visitors of the chunk STRICTLY in replica order (the summation order
+//            is part of the semantics: bit-exact vs oracle/loop.py) -- the only serial part, one dependent fadd per visitor;
+//   write  : the merged value goes to every replica (all warps, coalesced) and to the snapshot.
+// Only the live rows (levels 0..working step) can differ from the snapshot.  Thread 0 of block (0, g) pools the success
+// windows and arms the promotion.
+constexpr int MERGE_CHUNK = 128;
+__global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
+                                                            int R, int pooled_promote, long long max_episodes) {
+  __shared__ uint32_t s_q[MERGE_CHUNK][32], s_dc[MERGE_CHUNK][32];
+  __shared__ uint32_t s_qnew[32], s_cnew[32], s_vis[32];
+  const int g = blockIdx.y;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane;
+  uint32_t* sg = snap + (size_t)g * 3 * CELLS;
+  const uint32_t* tg = tables + (size_t)g * R * 3 * CELLS;
+  const int live = (ps[g * R].working_step + 1) * DQLB200_CELLS_PER_LEVEL;
+  if (blockIdx.x * 32 < live) {                       // block-uniform
+    const bool in = c < live;
+    const float q_snap = in ? __uint_as_float(sg[c]) : 0.0f;
+    const uint32_t cnt_snap = in ? sg[2 * CELLS + c] : 0u;
+    float num = 0.0f, q_single = q_snap;
+    uint32_t tot = 0;
+    int visitors = 0;
+    for (int r0 = 0; r0 < R; r0 += MERGE_CHUNK) {
+      const int n = min(MERGE_CHUNK, R - r0);
+      {   // MERGE_CHUNK / 8 replicas per warp: all their loads are issued before the first one is consumed
+        uint32_t cv[MERGE_CHUNK / 8], qv[MERGE_CHUNK / 8];
+#pragma unroll
+        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
+          const int j = warp + 8 * i;
+          const uint32_t* tr = tg + (size_t)(r0 + min(j, n - 1)) * 3 * CELLS;
+          cv[i] = in ? __ldcg(tr + 2 * CELLS + c) : cnt_snap;
+          qv[i] = in ? __ldcg(tr + c) : 0u;
+        }
+#pragma unroll
+        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
+          const int j = warp + 8 * i;
+          if (j < n) {
+            s_dc[j][lane] = cv[i] - cnt_snap;
+            s_q[j][lane] = qv[i];
+          }
+        }
+      }
+      __syncthreads();
+      if (warp == 0) {
+#pragma unroll 8
+        for (int j = 0; j < n; ++j) {
+          const uint32_t dc = s_dc[j][lane];
+          const float q_r = __uint_as_float(s_q[j][lane]);
+          const float term = fmul(fsub(q_r, q_snap), __uint2float_rn(dc));      // off the dependent chain
+          if (dc) {
+            visitors += 1;
+            q_single = q_r;
+            num = fadd(num, term);
+            tot += dc;
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (warp == 0) {
+      float q_new = q_snap;
+      if (visitors == 1) q_new = q_single;
+      else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
+      s_qnew[lane] = __float_as_uint(q_new);
+      s_cnew[lane] = cnt_snap + tot;
+      s_vis[lane] = (uint32_t)visitors;
+      if (in && visitors) {
+        sg[c] = __float_as_uint(q_new);
+        sg[2 * CELLS + c] = cnt_snap + tot;
+      }
+    }
+    __syncthreads();
+    if (in && s_vis[lane]) {
+      const uint32_t qn = s_qnew[lane], cn = s_cnew[lane];
+      for (int r = warp; r < R; r += 8) {
+        uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
+        tr[c] = qn;
+        tr[2 * CELLS + c] = cn;
+      }
+    }
+  }
+  if (blockIdx.x == 0) {          // pooled trainer counters of the group: block-wide reduction over the R replicas
+    __shared__ unsigned long long s_succ, s_eps;
+    __shared__ int s_dead, s_pending;
+    if (threadIdx.x == 0) { s_succ = s_eps = 0ull; s_dead = 0; s_pending = 0; }
+    __syncthreads();
+    unsigned long long successes = 0, episodes = 0;
+    int dead = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      const dqlb200_population_state& p = ps[g * R + r];
+      successes += (unsigned long long)p.window_sum;
+      episodes += (unsigned long long)p.episodes_in_step;
+      dead |= (p.finished || p.pending_advance) ? 1 : 0;
+    }
+    if (successes) atomicAdd(&s_succ, successes);
+    if (episodes) atomicAdd(&s_eps, episodes);
+    if (dead) atomicOr(&s_dead, 1);
+    __syncthreads();
+    if (threadIdx.x == 0)
+      s_pending = (s_dead || pooled_promote <= 0) ? 0 : ((long long)s_succ >= pooled_promote ? 1 : ((long long)s_eps >= max_episodes ? 2 : 0));
+    __syncthreads();
+    const int pending = s_pending;
+    if (pending)
+      for (int r = threadIdx.x; r < R; r += blockDim.x) ps[g * R + r].pending_advance = pending;
+  }
+}
+
+// Measurement aid: the table update as UNORDERED shared-memory atomics on a recorded cell sequence (the "atomic roof").
+__global__ void table_rmw_roof_kernel(const uint16_t* __restrict__ cells, long long n_cells, int visits_per_thread,
+                                      unsigned long long* checksum) {
+  __shared__ float qa[CELLS];
+  __shared__ uint32_t cnt[CELLS];
+  for (int i = threadIdx.x; i < CELLS; i += blockDim.x) { qa[i] = 0.0f; cnt[i] = 0u; }
+  __syncthreads();
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  long long idx = ((long long)blockIdx.x * blockDim.x + threadIdx.x) % n_cells;
+  for (int k = 0; k < visits_per_thread; ++k) {
+    const uint32_t c = cells[idx];
+    atomicAdd(&qa[c], 0.015625f);
+    atomicAdd(&cnt[c], 1u);
+    idx += stride;
+    if (idx >= n_cells) idx %= n_cells;
+  }
+  __syncthreads();
+  unsigned long long sum = 0;
+  for (int i = threadIdx.x; i < CELLS; i += blockDim.x) sum += cnt[i] + (unsigned long long)qa[i];
+  if (sum) atomicAdd(checksum, sum);
+}
+
+
+}  // namespace dql

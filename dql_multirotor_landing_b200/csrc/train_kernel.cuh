@@ -1,0 +1,487 @@
+// train_kernel.cuh -- the fused training kernel (one CTA per population): phase A per env, ordered commit, auto-reset, curriculum
+// Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
+#pragma once
+#include "env_state.cuh"
+
+namespace dql {
+
+// Baton between the warps of a CTA: warp w waits on named barrier 1+w (its 32 threads + the 32 arriving
+// threads of the previous warp).  The ids are IMMEDIATES so that ptxas allocates WARPS+1 barriers per CTA;
+// with a register id it reserves all 16 and the 64-barriers-per-SM limit caps occupancy at 4 CTAs
+// (ncu launch__occupancy_limit_barriers).
+#define DQL_BAR_CASE(OP, ID) case (ID - 1): if (WARPS >= ID) asm volatile("barrier." OP " " #ID ", 64;" ::: "memory"); break;
+template <int WARPS>
+__device__ __forceinline__ void baton_wait(int warp) {
+  switch (warp) {
+    DQL_BAR_CASE("sync", 1) DQL_BAR_CASE("sync", 2) DQL_BAR_CASE("sync", 3) DQL_BAR_CASE("sync", 4)
+    DQL_BAR_CASE("sync", 5) DQL_BAR_CASE("sync", 6) DQL_BAR_CASE("sync", 7) DQL_BAR_CASE("sync", 8)
+    default: break;
+  }
+}
+template <int WARPS>
+__device__ __forceinline__ void baton_pass(int next_warp) {
+  switch (next_warp) {
+    DQL_BAR_CASE("arrive", 1) DQL_BAR_CASE("arrive", 2) DQL_BAR_CASE("arrive", 3) DQL_BAR_CASE("arrive", 4)
+    DQL_BAR_CASE("arrive", 5) DQL_BAR_CASE("arrive", 6) DQL_BAR_CASE("arrive", 7) DQL_BAR_CASE("arrive", 8)
+    default: break;
+  }
+}
+#undef DQL_BAR_CASE
+
+struct TrainArgs {
+  EnvPtrs env;
+  uint32_t* tables;                        // [P][3][CELLS]
+  dqlb200_population_state* pop_state;     // [P]
+  const dqlb200_population_params* pop_params;
+  const float* alpha_luts;                 // [n_luts][ALPHA_LUT]
+  const uint32_t* eps_threshold;           // [EPS_LUT]
+  dqlb200_trace trace;
+  uint32_t* merge_snapshot;                // replica-merge mode: [n_groups][3][CELLS] merged tables (may be null)
+  int k_steps;
+  int pop_offset;                          // first population of this launch (chunked host-buffer calls)
+  long long n_total;
+};
+
+// Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
+// loop, L1-resident): that keeps the footprint at ~38 KB so that five CTAs fit on one SM.
+constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it runs the batched reset pass
+
+constexpr int STATES = DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL;   // 945
+
+struct Shared {
+  float qa[CELLS];        // live table A
+  uint32_t cnt[CELLS];    // state_action_counter
+  // Snapshot of the start of the global step.  Phase A reads the tables only through two per-STATE quantities, so the
+  // snapshot is those two instead of a copy of Q_a: the greedy action argmax_a (Q_a+Q_b)/2 (R9) and max_a Q_a (R12).
+  float qmax[STATES];
+  uint8_t greedy[STATES + 3];
+  dqlb200_cuts cuts;
+  dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
+  dqlb200_population_state ps;
+  unsigned long long n_episodes, n_success, ep_steps, hist[9];     // totals of this launch
+  uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
+  int promote, advance, do_advance;
+  // followed by: uint16_t reset_queue[WARPS][RESET_QUEUE]   (dynamic)
+};
+
+#ifndef DQL_WARPS_PER_SM
+#define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
+#endif
+// DIV2: second Markstein correction step of x / p_max, x / v_max (needed unless the divisors are the exhaustively
+// verified defaults; the trace instances always take it: both variants are correctly rounded, hence identical)
+template <int WARPS, bool TRACE, bool DIV2>
+__global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (DQL_WARPS_PER_SM / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NT = WARPS * 32;
+  const int pop = blockIdx.x + args.pop_offset;
+  const int n_p = kc.envs_per_population;
+  const int n_slots = (n_p + NT - 1) / NT;
+  uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT]
+  const size_t env_base = (size_t)pop * n_p;
+  uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
+  float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
+
+  // ---- stage population state and the LIVE rows of the tables in shared memory --------------------
+  // At working step w only levels 0..w can be visited (a state's level never exceeds w), so only rows
+  // [0, (w+1)*567) of Q_a / count are staged, snapshotted and written back; a promotion loads the next level.
+  // The launch prologue is ONE round trip to memory: every load below is independent of the others (the working step
+  // and the population constants are broadcast loads by every thread instead of a hop through shared memory), and the
+  // env state of slot 0 -- a cold HBM read when one global step is run per launch -- is in flight during all of it.
+  static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
+  constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
+  const dqlb200_population_params pp = args.pop_params[pop];
+  env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+  {
+    const int w_start = args.pop_state[pop].working_step;
+    const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
+    for (int i = tid; i < PS_WORDS; i += NT) reinterpret_cast<uint32_t*>(&sh.ps)[i] = gps[i];
+    if (tid == 0) {
+      sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
+      sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
+      for (int i = 0; i < 9; ++i) { sh.hist[i] = 0ull; sh.step_hist[i] = 0u; }
+      sh.promote = sh.advance = sh.do_advance = 0;
+      sh.cuts = kc.cuts[w_start];
+    }
+    if (tid < 5) sh.reward[tid] = kc.reward[tid];
+    const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
+    for (int i = tid; i < live; i += NT) {
+      sh.qa[i] = __uint_as_float(gt[i]);
+      sh.cnt[i] = gt[2 * CELLS + i];
+      if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(gqb + i));     // table B rows for the first snapshot
+    }
+  }
+  __syncthreads();
+
+  const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
+  const float alpha_min = __ldg(alpha_lut + DQLB200_ALPHA_LUT - 1);      // alpha(count >= 1002), PKG/trainer.py:95-105
+  uint64_t steps_done = 0;
+
+  // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
+  // fresh env + TrainingMdp for every env (PKG/trainer.py:176-189, 232-245).  All threads call it (uniform).
+  auto advance_curriculum = [&](int w, uint32_t birth) {
+    const int cs = kc.curriculum_steps;
+    int dst = -1, src = 0;
+    float ratio = 1.0f;
+    if (kc.transfer_mode == 0) { dst = w; src = (w - 1 + cs) % cs; ratio = kc.transfer_ratio[w]; }
+    else if (w + 1 < cs) { dst = w + 1; src = w; ratio = kc.transfer_ratio[w + 1]; }
+    if (dst >= 0) {
+      // replica-merge mode: the transfer acts on the MERGED table (every replica applies it identically right after a
+      // merge), so the first replica of a group also refreshes the group's merge snapshot
+      uint32_t* sg = (args.merge_snapshot && pop % kc.replicas == 0) ? args.merge_snapshot + (size_t)(pop / kc.replicas) * 3 * CELLS : nullptr;
+      for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+        // a source row above the working step is not staged: it is unmodified in global memory
+        const float q_src = (src <= w) ? sh.qa[src * DQLB200_CELLS_PER_LEVEL + i] : __uint_as_float(gt[src * DQLB200_CELLS_PER_LEVEL + i]);
+        const float qa_new = fmul(q_src, ratio), qb_new = fmul(gqb[src * DQLB200_CELLS_PER_LEVEL + i], ratio);
+        sh.qa[dst * DQLB200_CELLS_PER_LEVEL + i] = qa_new;
+        gqb[dst * DQLB200_CELLS_PER_LEVEL + i] = qb_new;
+        if (sg) {
+          sg[dst * DQLB200_CELLS_PER_LEVEL + i] = __float_as_uint(qa_new);
+          sg[CELLS + dst * DQLB200_CELLS_PER_LEVEL + i] = __float_as_uint(qb_new);
+        }
+      }
+    }
+    if (w + 1 < cs) {      // level w+1 becomes live: stage its rows (Q_a unless the transfer just wrote it)
+      for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
+        const int c = (w + 1) * DQLB200_CELLS_PER_LEVEL + i;
+        if (dst != w + 1) sh.qa[c] = __uint_as_float(gt[c]);
+        sh.cnt[c] = gt[2 * CELLS + c];
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      dqlb200_population_state& ps = sh.ps;
+      if (sh.promote) { ps.window_head = ps.window_count = ps.window_sum = 0; }
+      ps.promoted_at[w] = birth;
+      ps.episodes_in_step = 0;
+      ps.pending_advance = 0;
+      sh.promote = sh.advance = sh.do_advance = 0;
+      if (w + 1 >= cs) ps.finished = 1;
+      else {
+        ps.working_step = w + 1;
+        sh.cuts = kc.cuts[w + 1];
+      }
+    }
+    __syncthreads();
+    if (!sh.ps.finished) {
+      for (int slot = 0; slot < n_slots; ++slot) {
+        const int env_i = slot * NT + tid;
+        if (env_i < n_p) {
+          Env e;
+          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
+          env_store(args.env, env_base + env_i, e);
+        }
+      }
+    }
+    __syncthreads();
+  };
+  // replica-merge mode: a promotion decided by replica_merge_kernel takes effect before the first step of this launch
+  if (sh.ps.pending_advance && !sh.ps.finished) {
+    if (tid == 0) sh.promote = (sh.ps.pending_advance == 1) ? 1 : 0;
+    __syncthreads();
+    advance_curriculum(sh.ps.working_step, sh.ps.t);
+    (void)env_prefetch_take(stage, NT, tid);
+    env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);     // every env was just restarted
+  }
+
+  for (int k = 0; k < args.k_steps; ++k) {
+    if (sh.ps.finished) break;     // uniform: written only between barriers
+    const int w = sh.ps.working_step;
+    const uint32_t t = sh.ps.t;
+    // snapshot of the step: greedy action (first max of (Q_a+Q_b)/2, PKG/double_q_learning.py:119-124) and bootstrap
+    // value max_a Q_a (:136-141) of every live state
+    for (int st = tid; st < (w + 1) * DQLB200_STATES_PER_LEVEL; st += NT) {
+      const float q0 = sh.qa[st * 3 + 0], q1 = sh.qa[st * 3 + 1], q2 = sh.qa[st * 3 + 2];
+      const float p0 = fmul(fadd(q0, gqb[st * 3 + 0]), 0.5f);
+      const float p1 = fmul(fadd(q1, gqb[st * 3 + 1]), 0.5f);
+      const float p2 = fmul(fadd(q2, gqb[st * 3 + 2]), 0.5f);
+      int a = 0;
+      float best = p0;
+      if (p1 > best) { best = p1; a = 1; }
+      if (p2 > best) { a = 2; }
+      sh.greedy[st] = (uint8_t)a;
+      sh.qmax[st] = fmaxf(fmaxf(q0, q1), q2);
+    }
+    __syncthreads();
+    int n_queued = 0;              // warp-uniform: envs of this warp that finished an episode in this step
+
+    // batched R1/R8: new episodes for the queued envs of this warp, all lanes busy (a warp would otherwise run
+    // the whole reset path for one or two lanes in half of its slots)
+    auto flush_resets = [&]() {
+      __syncwarp();
+      for (int base = 0; base < n_queued; base += 32) {
+        if (base + lane < n_queued) {
+          const int qv = reset_queue[base + lane];
+          const int env_r = (qv >> 5) * NT + warp * 32 + (qv & 31);
+          const size_t gr = env_base + (size_t)env_r;
+          Env e;
+          env_load(args.env, gr, e);
+          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
+          env_store(args.env, gr, e);
+        }
+      }
+      __syncwarp();
+      n_queued = 0;
+    };
+
+    for (int slot = 0; slot < n_slots; ++slot) {
+      const int env_i = slot * NT + tid;
+      const bool valid = env_i < n_p;
+      const size_t gi = env_base + (size_t)(valid ? env_i : 0);
+      const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
+      if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage, NT, tid);      // in flight during this slot
+      // ---------------- phase A: everything that only reads the snapshot ----------------------
+      uint32_t cell = 0;
+      float target = 0.0f;
+      bool done = false, success = false;
+      int code = 0;
+      uint32_t ep_steps = 0;
+      double ep_return = 0.0;
+      Env e;
+      uint32_t c_hint = 0;
+      float a_hint = 0.0f;
+      if (valid) {
+        env_unpack(cur_raw, e);
+        const uint32_t sid = e.sid;
+        // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
+        // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
+        int a = sh.greedy[sid];
+        if (w == 0) {
+          const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
+          const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+          if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+        }
+        size_t trace_i = 0;
+        if (TRACE) {
+          trace_i = (size_t)k * (size_t)args.n_total + gi;
+          if (args.trace.action_override) {
+            const int o = args.trace.action_override[trace_i];
+            if (o >= 0) a = o;
+          }
+        }
+        // learning-rate hint for phase B: the LUT entry of the cell's count as it is NOW (an unsynchronised peek at the
+        // live table; phase B uses it only if the count is still the same, so the result does not depend on it).  Issued
+        // here, a whole phase A before the baton: a barrier waits for the thread's outstanding global loads too.
+        cell = sid * 3u + (uint32_t)a;
+        c_hint = min(sh.cnt[cell], (uint32_t)(DQLB200_ALPHA_LUT - 1));
+        a_hint = __ldg(alpha_lut + c_hint);
+        // R3: set-point (float64).  A fresh episode starts from 0 but keeps the old value for shaping.
+        const double prev_sp = e.theta_sp;
+        const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
+        // R4
+        dyn_advance(kc, pp, e.b, (float)sp);
+        const uint32_t step_count = e.step_count + 1u;
+        const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
+        // R5
+        const DState ds = discretise_cuts(sh.cuts, kc.angle_cut, o, w);
+        const uint32_t sid2 = (uint32_t)ds.id();
+        // R6 (sticky result: only ever set, quirk Q9)
+        // The priority chain of PKG/mdp.py:359-425 as selects (the ladder of branches diverges inside a warp).
+        const bool t_fx = !(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi);
+        const bool t_zmin = !(o.z >= kc.z_min_cut), t_zmax = o.z >= kc.z_max_cut;
+        const bool t_time = (int)step_count >= kc.timeout_steps;
+        const bool goal_bins = !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
+        const bool at_level = sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;   // previous level == w (it never exceeds w)
+        const uint32_t cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
+        code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
+        if (goal_bins && at_level) code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+        code = t_time ? DQLB200_TERMINAL_TIMEOUT : code;
+        code = t_zmax ? DQLB200_TERMINAL_FLYZONE_Z : code;
+        code = t_zmin ? DQLB200_TERMINAL_MINIMUM_ALTITUDE : code;
+        code = t_fx ? DQLB200_TERMINAL_FLYZONE_X : code;
+        code = o.contact ? DQLB200_TERMINAL_CONTACT : code;
+        done = code >= DQLB200_TERMINAL_SUCCESS;
+        success = code == DQLB200_TERMINAL_SUCCESS;
+        if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
+          atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
+        // R7 (float64, reference operation order; level-dependent constants from the host)
+        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+        const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
+        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
+        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+        const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
+        const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
+        const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
+        // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
+        const float qn = sh.qmax[sid2];
+        const float changed = (e.bp != (uint32_t)ds.bp) ? 1.0f : 0.0f;
+        target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
+        if (TRACE) {
+          if (args.trace.obs) {
+            float* po = args.trace.obs + trace_i * 5;
+            po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z;
+          }
+          if (args.trace.reward) args.trace.reward[trace_i] = r;
+          if (args.trace.action) args.trace.action[trace_i] = (uint8_t)a;
+          if (args.trace.code) args.trace.code[trace_i] = (uint8_t)code;
+          if (args.trace.done) args.trace.done[trace_i] = (uint8_t)done;
+          if (args.trace.contact) args.trace.contact[trace_i] = (uint8_t)o.contact;
+          if (args.trace.state) args.trace.state[trace_i] = (uint16_t)sid;
+          if (args.trace.next_state) args.trace.next_state[trace_i] = (uint16_t)sid2;
+          if (args.trace.episode) args.trace.episode[trace_i] = (int32_t)e.episode;
+        }
+        // carry, without a branch on `done`: of a finished env only the shaping memory and the episode index survive -- the
+        // batched reset pass after the slot loop (R1/R8) overwrites every other field -- so all fields are written alike.
+        ep_steps = step_count;
+        ep_return = e.cum_reward;                 // quirk Q12: the last reward is not in the logged sum
+        e.theta_sp = sp;
+        e.prev_rel_p = o.rel_p;
+        e.prev_rel_v = o.rel_v;
+        e.episode += done ? 1u : 0u;
+        e.sid = sid2;
+        e.bp = (uint32_t)ds.bp;
+        e.step_count = step_count;
+        e.curriculum_check = cc;
+        e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
+        e.fresh = false;
+        e.cum_reward = __dadd_rn(e.cum_reward, r);
+      }
+      // ---------------- phase B: ordered commit (baton between warps) --------------------------
+      // The serialised section is the critical path of a global step (n_p / 32 links per population), so everything that
+      // does not read the live table happens BEFORE the baton arrives: same-cell groups, ranks, and the reductions over
+      // the finished episodes of this warp-slot.
+      const uint32_t dmask = __ballot_sync(FULL, valid && done);
+      const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
+      const uint32_t peers = __match_any_sync(FULL, key);
+      const int rank = __popc(peers & ((1u << lane) - 1u));
+      uint32_t smask = 0u;
+      double ret = 0.0, last_cum = 0.0;
+      int last_steps = 0, last_code = 0;
+      if (dmask) {
+        smask = __ballot_sync(FULL, valid && success);
+        // deterministic (fixed-tree) sum of the finished episodes' returns
+        ret = (valid && done) ? ep_return : 0.0;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) ret = __dadd_rn(ret, __shfl_xor_sync(FULL, ret, off));
+        const int last = 31 - __clz(dmask);
+        last_steps = __shfl_sync(FULL, (int)ep_steps, last);
+        last_code = __shfl_sync(FULL, code, last);
+        last_cum = __shfl_sync(FULL, ep_return, last);
+      }
+      if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
+      {
+        float q = valid ? sh.qa[cell] : 0.0f;
+        const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
+        const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
+        float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
+        if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
+        // the group's updates in lane order, two members per round (their four shuffles are issued together)
+        uint32_t rem = valid ? peers : 0u;
+        while (__any_sync(FULL, rem != 0u)) {
+          const uint32_t rem1 = rem & (rem - 1u);
+          const int src0 = rem ? (__ffs(rem) - 1) : lane, src1 = rem1 ? (__ffs(rem1) - 1) : lane;
+          const float a_0 = __shfl_sync(FULL, alpha, src0), t_0 = __shfl_sync(FULL, target, src0);
+          const float a_1 = __shfl_sync(FULL, alpha, src1), t_1 = __shfl_sync(FULL, target, src1);
+          if (rem) q = fadd(q, fmul(a_0, fsub(t_0, q)));       // q += alpha * (target - q)
+          if (rem1) q = fadd(q, fmul(a_1, fsub(t_1, q)));
+          rem = rem1 & (rem1 - 1u);
+        }
+        if (valid && rank == 0) {
+          sh.qa[cell] = q;
+          sh.cnt[cell] = c0 + (uint32_t)__popc(peers);
+        }
+        // finished episodes, in env order: success window + promotion test after every append (R14)
+        if (dmask && lane == 0) {
+          dqlb200_population_state& ps = sh.ps;
+          int head = ps.window_head, count = ps.window_count, sum = ps.window_sum;
+          long long eps = ps.episodes_in_step;
+          bool promote = false, advance = false;
+          uint32_t m = dmask;
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1u;
+            const int ok = (smask >> b) & 1u;
+            if (count == kc.window_len) sum -= ps.window[head];
+            else count += 1;
+            ps.window[head] = (uint8_t)ok;
+            sum += ok;
+            head = (head + 1 == kc.window_len) ? 0 : head + 1;
+            eps += 1;
+            promote = promote || (sum >= kc.promote_successes);
+            advance = advance || (eps >= kc.max_num_episodes);
+          }
+          ps.window_head = head; ps.window_count = count; ps.window_sum = sum;
+          ps.episodes_in_step = eps;
+          if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
+            if (promote) sh.promote = 1;
+            if (advance) sh.advance = 1;
+          }
+          ps.return_sum = __dadd_rn(ps.return_sum, ret);
+          ps.last_code = last_code;
+          ps.last_steps = last_steps;
+          ps.last_cumulative = last_cum;
+        }
+      }
+      if (WARPS > 1 && !(slot == n_slots - 1 && warp == WARPS - 1)) {
+        __threadfence_block();
+        baton_pass<WARPS>((warp + 1) % WARPS);
+      }
+      // order-independent episode counters: after the baton
+      if (dmask) {
+        if (valid && done) {
+          atomicAdd(&sh.step_hist[code], 1u);
+          atomicAdd(&sh.step_ep_steps, ep_steps);
+        }
+        if (lane == 0) {
+          atomicAdd(&sh.step_episodes, (uint32_t)__popc(dmask));
+          atomicAdd(&sh.step_success, (uint32_t)__popc(smask));
+        }
+      }
+      // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
+      // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
+      if (valid) env_store(args.env, gi, e);
+      // queue the finished envs of this warp for the batched reset (outside the baton)
+      if (dmask) {
+        if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);
+        n_queued += __popc(dmask);
+        if (n_queued > RESET_QUEUE - 32) flush_resets();       // never overflows, whatever fraction of envs finishes at once
+      }
+    }
+    flush_resets();
+    // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
+    if (k + 1 < args.k_steps) env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+    __syncthreads();
+    // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
+    steps_done += (uint64_t)n_p;
+    if (tid == 0) {
+      sh.ps.t = t + 1u;
+      sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
+      sh.n_episodes += sh.step_episodes; sh.n_success += sh.step_success; sh.ep_steps += sh.step_ep_steps;
+      sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
+    }
+    if (tid < 9) { sh.hist[tid] += sh.step_hist[tid]; sh.step_hist[tid] = 0u; }
+    __syncthreads();
+    if (sh.do_advance) {
+      advance_curriculum(w, t + 1u);
+      (void)env_prefetch_take(stage, NT, tid);
+      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+    }
+  }
+
+  // ---- write back (live rows only) ----------------------------------------------------------------
+  asm volatile("cp.async.wait_all;" ::: "memory");      // a prefetch issued for a step that did not run
+  __syncthreads();
+  for (int i = tid; i < (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) {
+    gt[i] = __float_as_uint(sh.qa[i]);
+    gt[2 * CELLS + i] = sh.cnt[i];
+  }
+  if (tid == 0) {
+    dqlb200_population_state& ps = sh.ps;
+    ps.total_steps += steps_done;
+    ps.total_episodes += sh.n_episodes;
+    ps.total_successes += sh.n_success;
+    ps.episode_steps_sum += sh.ep_steps;
+    for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
+  }
+  __syncthreads();
+  {
+    uint32_t* gps = reinterpret_cast<uint32_t*>(args.pop_state + pop);
+    for (int i = tid; i < PS_WORDS; i += NT) gps[i] = reinterpret_cast<const uint32_t*>(&sh.ps)[i];
+  }
+}
+
+
+}  // namespace dql

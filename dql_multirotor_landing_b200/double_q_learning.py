@@ -2,7 +2,7 @@
 
 Same constructor, attributes (`Q_table_a`, `Q_table_b`, `state_action_counter`: float64 NumPy arrays of shape
 (curriculum_steps, 3, 3, 3, 7, 3)), methods and `.npy` files.  The arithmetic of `predict` / `update` /
-`transfer_learning` runs on the GPU in float64 (csrc/dqlb200.cu: agent_facade_kernel); the NumPy arrays are
+`transfer_learning` runs on the GPU in float64 (csrc/facade_kernels.cuh: agent_facade_kernel); the NumPy arrays are
 host mirrors, kept coherent lazily.  The batched trainer (`trainer.Trainer`) uses float32 device tables
 instead and writes its result back into these attributes.
 """

@@ -1,7 +1,7 @@
 """Batched device driver: owns the torch tensors (device memory handles) and calls the C-ABI.
 
 One ``Engine`` = one CUDA device = ``n_populations`` independent agents (Q-table pairs), each with
-``envs_per_population`` environments; one CTA per population (csrc/dqlb200.cu: train_kernel).
+``envs_per_population`` environments; one CTA per population (csrc/train_kernel.cuh: train_kernel).
 This replaces the `while not done` loop of Trainer.curriculum_training (PKG/trainer.py:187-245)."""
 from __future__ import annotations
 

@@ -5,7 +5,7 @@ convention (``reset() -> state``, ``step(action) -> (state, reward, done, info)`
 ``reset() -> (state_x, state_y)``, ``step(ax, ay) -> (state_x, state_y, done, info)``), and add ``num_envs``: with the default
 ``num_envs=1`` states are 5-tuples, rewards floats and ``info`` holds the reference's keys, exactly like the reference; with
 ``num_envs > 1`` every quantity is a NumPy array over the environments.  Gazebo/ROS is replaced by the analytic stand-in
-inside ``dqlb200_env_reset`` / ``dqlb200_env_step`` (csrc/dqlb200.cu: env_reset_kernel, env_step_kernel) -- the same device
+inside ``dqlb200_env_reset`` / ``dqlb200_env_step`` (csrc/env_kernels.cuh: env_reset_kernel, env_step_kernel) -- the same device
 functions, in the same order, as the fused training kernel.  ``make("Landing-Training-v0", ...)`` /
 ``make("Landing-Simulation-v0", ...)`` stand in for ``gym.make`` (the ids are registered at PKG/landing_simulation_env.py:432-440).
 """

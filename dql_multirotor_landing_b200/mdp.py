@@ -2,7 +2,7 @@
 
 Same class names, constructor signatures, method names, return types and ValueErrors as
 PKG/mdp.py:11-886; the numerics run on the GPU in float64 through ``dqlb200_mdp_facade_step``
-(csrc/dqlb200.cu: facade_kernel) -- there is no CPU implementation here.  These objects exist so that code
+(csrc/facade_kernels.cuh: facade_kernel) -- there is no CPU implementation here.  These objects exist so that code
 written against the reference (and parity tests that read like reference tests) keep working; the
 throughput path is ``Trainer`` / ``Engine`` (one fused kernel for thousands of envs).
 """

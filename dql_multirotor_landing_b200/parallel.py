@@ -4,7 +4,7 @@ The path shards by POPULATION: every rank owns a disjoint set of agents (Q-table
 data path needs no collective (bench.py, `"scaling": "weak"`).  The only exchange step is the optional
 shared-table mode: one agent replicated on G ranks, merged every `sync_every` global steps by ONE all-reduce
 (SUM) of a fused [sum(dQ_a * dcount) | dcount | visitors | sum(Q_a of visitors) | counters] buffer (45 KB per agent, NCCL over NVLink on
-GPUs, gloo in the CPU tests) -- see csrc/dqlb200.cu: shared_pack_kernel / shared_apply_kernel.
+GPUs, gloo in the CPU tests) -- see csrc/table_kernels.cuh: shared_pack_kernel / shared_apply_kernel.
 """
 from __future__ import annotations
 

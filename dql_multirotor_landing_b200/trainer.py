@@ -4,7 +4,7 @@
 keyword-only extras (`num_envs`, `num_populations`, `device`, `chunk_steps`, `transfer_mode`, platform/dynamics
 parameters).  `curriculum_training()` replaces the Python `for episode: while not done:` loop (PKG/trainer.py:
 169-245) by `Engine.train(chunk_steps)` launches: the select -> step -> update -> auto-reset -> promotion -> transfer
-cycle runs inside one CUDA kernel for all envs (csrc/dqlb200.cu: train_kernel); the host only reads the
+cycle runs inside one CUDA kernel for all envs (csrc/train_kernel.cuh: train_kernel); the host only reads the
 320-byte population state between launches to log, checkpoint and stop.
 """
 from __future__ import annotations

@@ -9,7 +9,7 @@ from dql_multirotor_landing_b200 import constants as K
 
 
 def cut_discretise(cfg, w, obs):
-    """What the kernel does with the cut tables (csrc/dqlb200.cu: discretise_cuts)."""
+    """What the kernel does with the cut tables (csrc/dqlb200_device.cuh: discretise_cuts)."""
     c = cfg.cuts[w]
     x = [obs[:, 0], obs[:, 1], obs[:, 2]]
     with np.errstate(invalid="ignore"):
