@@ -364,7 +364,7 @@ int dqlb200_env_reset(dqlb200_handle* h, int working_step, uint32_t birth, const
 
 int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8_t* actions, int auto_reset, int simulation,
                      uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done, float* out_obs, uint32_t* out_steps,
-                     double* out_cumulative, void* stream) {
+                     double* out_cumulative, uint16_t* out_next_state, void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
   if (!actions) return fail(DQLB200_ERR_ARG, "actions required");
   if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
@@ -373,10 +373,34 @@ int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8
   const unsigned blocks = (unsigned)((n + 127) / 128);
   if (h->kc.div_two_steps)
     dql::env_step_kernel<true><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step, t, actions, auto_reset,
-                                                                       simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, h->d_error);
+                                                                       simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, out_next_state, h->d_error);
   else
     dql::env_step_kernel<false><<<blocks, 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step, t, actions, auto_reset,
-                                                                        simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, h->d_error);
+                                                                        simulation, out_state, out_reward, out_code, out_done, out_obs, out_steps, out_cumulative, out_next_state, h->d_error);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_agent_select(dqlb200_handle* h, int working_step, uint32_t t, uint8_t* out_actions, uint16_t* out_states, void* stream) {
+  if (!h || !h->env_state || !h->tables) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (!out_actions) return fail(DQLB200_ERR_ARG, "out_actions required");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long n = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
+  dql::agent_select_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), (const uint32_t*)h->tables,
+                                                                                        h->d_pop_params, h->d_cfg->eps_threshold, working_step, t,
+                                                                                        out_actions, out_states);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_agent_update(dqlb200_handle* h, const uint16_t* states, const uint8_t* actions, const uint16_t* next_states, const double* rewards,
+                         void* stream) {
+  if (!h || !h->tables) return fail(DQLB200_ERR_STATE, "buffers not bound");
+  if (!states || !actions || !next_states || !rewards) return fail(DQLB200_ERR_ARG, "null argument");
+  CUDA_TRY(cudaSetDevice(h->device));
+  dql::agent_update_kernel<<<h->cfg.n_populations, 32, 0, (cudaStream_t)stream>>>(h->kc, (uint32_t*)h->tables, h->d_pop_params, h->d_alpha, states, actions,
+                                                                                next_states, rewards);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

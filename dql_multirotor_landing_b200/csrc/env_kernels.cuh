@@ -129,7 +129,7 @@ template <bool DIV2>
 __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ KC kc, EnvPtrs env, const dqlb200_population_params* pop_params,
                                                        int w, uint32_t t, const int8_t* __restrict__ actions, int auto_reset, int simulation,
                                                        uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done,
-                                                       float* out_obs, uint32_t* out_steps, double* out_cumulative, uint32_t* error_flag) {
+                                                       float* out_obs, uint32_t* out_steps, double* out_cumulative, uint16_t* out_next_state, uint32_t* error_flag) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long n_total = (long long)kc.n_populations * kc.envs_per_population;
   if (i >= n_total) return;
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
     r = reward_f64(kc, kc.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
   }
   if (out_reward) out_reward[i] = r;
+  if (out_next_state) out_next_state[i] = (uint16_t)sid2;
   if (out_code) out_code[i] = (uint8_t)code;
   if (out_done) out_done[i] = (uint8_t)done;
   if (out_obs) { float* po = out_obs + i * 5; po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z; }

@@ -1,7 +1,7 @@
 // table_kernels.cuh -- kernels on the Q/count tables: transfer, shared-table pack/apply, replica merge, atomic-roof micro-benchmark
 // Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
 #pragma once
-#include "env_state.cuh"
+#include "train_kernel.cuh"
 
 namespace dql {
 
@@ -192,6 +192,82 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
     if (pending)
       for (int r = threadIdx.x; r < R; r += blockDim.x) ps[g * R + r].pending_advance = pending;
   }
+}
+
+// -------------------------------------------------------------------------------------------------
+// Un-fused agent entry points on the float32 device tables (the batched DoubleQLearningAgent.guess / update,
+// PKG/double_q_learning.py:91-146, with the trainer's schedules PKG/trainer.py:88-126): same arithmetic, same draws and the
+// same ordering ("S1") as the select / commit phases of train_kernel -- tests hold a loop of agent_select -> env_step ->
+// agent_update bit-identical to the fused kernel.
+// -------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) agent_select_kernel(const __grid_constant__ KC kc, EnvPtrs env, const uint32_t* __restrict__ tables,
+                                                           const dqlb200_population_params* pop_params, const uint32_t* __restrict__ eps_threshold,
+                                                           int w, uint32_t t, uint8_t* out_action, uint16_t* out_state) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long n_total = (long long)kc.n_populations * kc.envs_per_population;
+  if (i >= n_total) return;
+  const int pop = (int)(i / kc.envs_per_population);
+  const uint32_t env_i = (uint32_t)(i % kc.envs_per_population);
+  const dqlb200_population_params pp = pop_params[pop];
+  const uint4 Cw = env.c[i];
+  const uint32_t sid = Cw.x & ((1u << SID_BITS) - 1u), episode = Cw.y;
+  const float* qa = reinterpret_cast<const float*>(tables + (size_t)pop * 3 * CELLS);
+  const float* qb = qa + CELLS;
+  const float p0 = fmul(fadd(qa[sid * 3 + 0], qb[sid * 3 + 0]), 0.5f);
+  const float p1 = fmul(fadd(qa[sid * 3 + 1], qb[sid * 3 + 1]), 0.5f);
+  const float p2 = fmul(fadd(qa[sid * 3 + 2], qb[sid * 3 + 2]), 0.5f);
+  int a = 0;
+  float best = p0;
+  if (p1 > best) { best = p1; a = 1; }
+  if (p2 > best) { a = 2; }
+  if (w == 0) {        // exploration_rate is 0 for every later working step (PKG/trainer.py:112-126)
+    const uint32_t thr = eps_threshold[min(episode, (uint32_t)(DQLB200_EPS_LUT - 1))];
+    const uint4 d = philox4x32_10(make_uint4(env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+    if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+  }
+  out_action[i] = (uint8_t)a;
+  if (out_state) out_state[i] = (uint16_t)sid;
+}
+
+// One warp per population: the updates of its envs are applied in env-index order, 32 at a time (same-cell groups inside a
+// chunk by __match_any_sync, lane order), against the bootstrap values of the tables as they were when the call started.
+__global__ void __launch_bounds__(32) agent_update_kernel(const __grid_constant__ KC kc, uint32_t* tables, const dqlb200_population_params* pop_params,
+                                                          const float* __restrict__ alpha_luts, const uint16_t* __restrict__ state,
+                                                          const uint8_t* __restrict__ action, const uint16_t* __restrict__ next_state,
+                                                          const double* __restrict__ reward) {
+  __shared__ float qa[CELLS], qmax[STATES];
+  __shared__ uint32_t cnt[CELLS];
+  const int pop = blockIdx.x, lane = threadIdx.x, n_p = kc.envs_per_population;
+  uint32_t* gt = tables + (size_t)pop * 3 * CELLS;
+  const float* __restrict__ alpha_lut = alpha_luts + (size_t)pop_params[pop].alpha_lut * DQLB200_ALPHA_LUT;
+  for (int i = lane; i < CELLS; i += 32) { qa[i] = __uint_as_float(gt[i]); cnt[i] = gt[2 * CELLS + i]; }
+  __syncwarp();
+  for (int st = lane; st < STATES; st += 32) qmax[st] = fmaxf(fmaxf(qa[st * 3], qa[st * 3 + 1]), qa[st * 3 + 2]);
+  __syncwarp();
+  const size_t base = (size_t)pop * n_p;
+  for (int e0 = 0; e0 < n_p; e0 += 32) {
+    const bool valid = e0 + lane < n_p;
+    const size_t gi = base + (size_t)min(e0 + lane, n_p - 1);
+    const uint32_t s = state[gi], s2 = next_state[gi], a = action[gi];
+    const uint32_t cell = s * 3u + a;
+    const float changed = (((s / 63u) % 3u) != ((s2 / 63u) % 3u)) ? 1.0f : 0.0f;
+    const float target = fadd((float)reward[gi], fmul(fmul(kc.gamma, qmax[s2]), changed));
+    const uint32_t peers = __match_any_sync(FULL, valid ? cell : (0x80000000u | (uint32_t)lane));
+    const int rank = __popc(peers & ((1u << lane) - 1u));
+    float q = valid ? qa[cell] : 0.0f;
+    const uint32_t c0 = valid ? cnt[cell] : 0u;
+    const float alpha = alpha_lut[min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1))];      // R11: pre-increment count
+    uint32_t rem = valid ? peers : 0u;
+    while (__any_sync(FULL, rem != 0u)) {
+      const int src = rem ? (__ffs(rem) - 1) : lane;
+      const float a_j = __shfl_sync(FULL, alpha, src), t_j = __shfl_sync(FULL, target, src);
+      if (rem) q = fadd(q, fmul(a_j, fsub(t_j, q)));
+      rem &= rem - 1u;
+    }
+    if (valid && rank == 0) { qa[cell] = q; cnt[cell] = c0 + (uint32_t)__popc(peers); }
+    __syncwarp();
+  }
+  for (int i = lane; i < CELLS; i += 32) { gt[i] = __float_as_uint(qa[i]); gt[2 * CELLS + i] = cnt[i]; }
 }
 
 // Measurement aid: the table update as UNORDERED shared-memory atomics on a recorded cell sequence (the "atomic roof").

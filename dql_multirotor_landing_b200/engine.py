@@ -166,6 +166,39 @@ class Engine:
         return {"visits_per_s": visits / best, "rmw_per_s": 2 * visits / best, "visits": visits, "seconds": best,
                 "threads": threads, "blocks": blocks}
 
+    # ------------------------------------------------------------------------------------------
+    # un-fused entry points: the reference's loop body as separate operators (PKG/trainer.py:191-212)
+    def env_reset(self, working_step: int = 0, birth: int = 0, fresh_mdp: bool = True):
+        """env.reset() for every env (dqlb200_env_reset); returns the states (int16 tensor)."""
+        st = torch.zeros(self.n_total, dtype=torch.int16, device=self.device)
+        _ffi.check(self.lib.dqlb200_env_reset(self.handle, working_step, birth, None, int(fresh_mdp), 0, st.data_ptr(), self._stream()))
+        return st
+
+    def agent_select(self, working_step: int, t: int):
+        """agent.guess(state, exploration_rate(episode, step)) for every env; returns (actions uint8, states int16)."""
+        act = torch.zeros(self.n_total, dtype=torch.uint8, device=self.device)
+        st = torch.zeros(self.n_total, dtype=torch.int16, device=self.device)
+        _ffi.check(self.lib.dqlb200_agent_select(self.handle, working_step, t, act.data_ptr(), st.data_ptr(), self._stream()))
+        return act, st
+
+    def env_step(self, working_step: int, t: int, actions: torch.Tensor, auto_reset: bool = True):
+        """env.step(action) for every env (dqlb200_env_step); returns dict(state, next_state, reward, code, done) of tensors."""
+        dev, n = self.device, self.n_total
+        out = dict(state=torch.zeros(n, dtype=torch.int16, device=dev), next_state=torch.zeros(n, dtype=torch.int16, device=dev),
+                   reward=torch.zeros(n, dtype=torch.float64, device=dev), code=torch.zeros(n, dtype=torch.uint8, device=dev),
+                   done=torch.zeros(n, dtype=torch.uint8, device=dev))
+        a8 = actions.to(torch.int8)
+        _ffi.check(self.lib.dqlb200_env_step(self.handle, working_step, t, a8.data_ptr(), int(auto_reset), 0, out["state"].data_ptr(),
+                                             out["reward"].data_ptr(), out["code"].data_ptr(), out["done"].data_ptr(), None, None, None,
+                                             out["next_state"].data_ptr(), self._stream()))
+        self._keep = a8
+        return out
+
+    def agent_update(self, states: torch.Tensor, actions: torch.Tensor, next_states: torch.Tensor, rewards: torch.Tensor):
+        """agent.update(state + (action,), next_state, alpha(count), gamma, reward) for every env, S1 order (dqlb200_agent_update)."""
+        _ffi.check(self.lib.dqlb200_agent_update(self.handle, states.data_ptr(), actions.data_ptr(), next_states.data_ptr(), rewards.data_ptr(),
+                                                 self._stream()))
+
     def selftest_division(self) -> int:
         """Exhaustive device check of the fast float64 division (all fp32 numerators); returns the mismatch count."""
         out = (C.c_uint64 * 3)()

@@ -80,7 +80,7 @@ class AbstractLandingEnv:
         self._actions.copy_(torch.from_numpy(np.array(a, dtype=np.int8)))
         _ffi.check(e.lib.dqlb200_env_step(e.handle, self._working_curriculum_step, self._t, self._actions.data_ptr(), int(self._auto_reset),
                                           int(self._simulation), self._state.data_ptr(), self._reward.data_ptr(), self._code.data_ptr(),
-                                          self._done.data_ptr(), self._obs.data_ptr(), self._steps.data_ptr(), self._cum.data_ptr(), e._stream()))
+                                          self._done.data_ptr(), self._obs.data_ptr(), self._steps.data_ptr(), self._cum.data_ptr(), None, e._stream()))
         e.check_errors()
         self._t += 1
 

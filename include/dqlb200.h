@@ -248,13 +248,29 @@ int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy
  *                      selects SimulationMdp semantics (v_z = -0.4, no goal logic, reward 0, PKG/mdp.py:784-877).  Outputs
  *                      (all nullable, device, [n_envs_total]): state after the step (auto_reset: of a finished env the first state of
  *                      its next episode), float64 reward, CheckResult code, done,
- *                      obs [..][5], "Number of steps", "Cumulative reward" (without this step's reward, quirk Q12).
+ *                      obs [..][5], "Number of steps", "Cumulative reward" (without this step's reward, quirk Q12), and
+ *                      out_next_state: the state the step ENDED in (differs from out_state only for an auto-reset env).
  * Both work on the bound env_state; they neither read nor write tables or trainer state. */
 int dqlb200_env_reset(dqlb200_handle* h, int working_step, uint32_t birth, const uint8_t* mask, int fresh_mdp, int simulation,
                       uint16_t* out_state, void* stream);
 int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8_t* actions, int auto_reset, int simulation,
                      uint16_t* out_state, double* out_reward, uint8_t* out_code, uint8_t* out_done, float* out_obs,
-                     uint32_t* out_steps, double* out_cumulative, void* stream);
+                     uint32_t* out_steps, double* out_cumulative, uint16_t* out_next_state, void* stream);
+
+/* Un-fused agent entry points on the bound float32 tables (batched DoubleQLearningAgent.guess / update with the trainer's
+ * schedules; PKG/double_q_learning.py:91-146, PKG/trainer.py:88-126, 191-209):
+ *   dqlb200_agent_select  for every env: epsilon-greedy action of its CURRENT state (read from the bound env state, like its
+ *                         per-curriculum-step episode index that drives epsilon): greedy = first max of (Q_a + Q_b) / 2; both
+ *                         draws of guess() come from Philox (env, t, step, population) -- the draws dqlb200_train uses at global
+ *                         step t.  out_actions uint8 [n_envs_total]; out_states (nullable) the states acted on.
+ *   dqlb200_agent_update  count[sa] += 1; Q_a[sa] += alpha(count before) * (r + (gamma * max_a' Q_a[s'][a']) * [p-bin changed]
+ *                         - Q_a[sa]) for every env, applied per population in env-index order against the bootstrap values of the
+ *                         tables as they were when the call started (the "S1" semantics of dqlb200_train).
+ * A loop of agent_select -> env_step(auto_reset) -> agent_update leaves tables and env state bit-identical to dqlb200_train
+ * (tests/test_gpu_facade.py); promotion / transfer stay with the caller (dqlb200_transfer). */
+int dqlb200_agent_select(dqlb200_handle* h, int working_step, uint32_t t, uint8_t* out_actions, uint16_t* out_states, void* stream);
+int dqlb200_agent_update(dqlb200_handle* h, const uint16_t* states, const uint8_t* actions, const uint16_t* next_states,
+                         const double* rewards, void* stream);
 
 /* Replaces: scripts/simulation.py:48-63 with BOTH agents acting (agent_x.predict / agent_y.predict,
  * SimulationMdp.discrete_state_x/_y PKG/mdp.py:634-782, check :784-845 incl. FLYZONE_Y and contact on both axes).

@@ -281,3 +281,28 @@ def test_simulation_env_gym_surface(golden_dir):
                 if done[ep]:
                     assert info["Termination condition"][ep] == K.TERMINATION_STRINGS[int(g["code"][row])]
     env.close()
+
+
+def test_unfused_select_step_update_loop_equals_fused_kernel():
+    """The reference's loop body as separate device operators -- agent_select (guess + exploration_rate), env_step
+    (TrainingLandingEnv.step, auto-reset), agent_update (alpha + update) -- leaves tables, counts and env state bit-identical
+    to the fused train_kernel (two populations, ragged env count, epsilon phase of curriculum step 0)."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.engine import Engine
+    P, n, steps = 2, 150, 120
+    kw = dict(success_rate=2.0, max_num_episodes=10 ** 12)
+    mk = lambda: Engine(P, n, threads_per_block=64, seeds=[42, 7], v_mp=[1.6, 0.8], tp=K.TrainerParameters(**kw))
+    fused, loop = mk(), mk()
+    fused.reset(0)
+    fused.set_episode_index(1400)          # epsilon = 0.505: exploration and greedy actions both occur
+    fused.train(steps)
+    loop.env_reset(0, birth=0, fresh_mdp=True)
+    loop.set_episode_index(1400)
+    for t in range(steps):
+        act, st = loop.agent_select(0, t)
+        out = loop.env_step(0, t, act, auto_reset=True)
+        loop.agent_update(st, act, out["next_state"], out["reward"])
+    torch.cuda.synchronize()
+    assert torch.equal(fused.tables, loop.tables)
+    assert torch.equal(fused.env_state, loop.env_state)
+    assert int(fused.tables[:, 2].sum()) == P * n * steps
