@@ -34,7 +34,7 @@ ALPHA_LUT = 1003
 EPS_LUT = 2002
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 LIMITS_POSITION = [1.0, 0.64, 0.4096, 0.262144, 0.16777216]   # PKG/mdp.py:45-47
 LIMITS_VELOCITY = [1.0, 0.8, 0.64, 0.512, 0.4096]              # PKG/mdp.py:48-50
@@ -86,6 +86,7 @@ class Config(C.Structure):
         ("gamma", C.c_float), ("transfer_ratio", C.c_float * MAX_CURRICULUM), ("transfer_mode", C.c_int32),
         ("window_len", C.c_int32), ("promote_successes", C.c_int32), ("max_num_episodes", C.c_int64),
         ("n_alpha_luts", C.c_int32), ("replicas_per_population", C.c_int32),
+        ("noise_pos_sd", C.c_float), ("noise_vel_sd", C.c_float),
         ("eps_threshold", C.c_uint32 * EPS_LUT),
     ]
 
@@ -191,6 +192,8 @@ class DynamicsParameters:
     z_touch: float = 0.515           # bumper top + body       urdf/moving_platform.urdf:16,38,51,58
     half_platform: float = 0.5
     n_sub: int = 1
+    noise_pos_sd: float = 0.0        # Gaussian noise on the observed rel. position   PKG/observation_utils.py:127-129 (launch: 0)
+    noise_vel_sd: float = 0.0        # ... and velocity (manager_node defaults 0.25 / 0.1, launch/environment.launch:56-57 sets 0)
 
 
 @dataclass
@@ -452,6 +455,7 @@ def build_config(n_populations: int, envs_per_population: int, threads_per_block
     cfg.z_init, cfg.z_touch, cfg.half_platform = dp.z_init, dp.z_touch, dp.half_platform
     cfg.p_max_f, cfg.two_p_max_f, cfg.sigma_x = mp.p_max, 2.0 * mp.p_max, mp.p_max / 3.0
     cfg.n_sub = dp.n_sub
+    cfg.noise_pos_sd, cfg.noise_vel_sd = dp.noise_pos_sd, dp.noise_vel_sd
     cfg.gamma = tp.gamma
     for k in range(MAX_CURRICULUM):
         cfg.transfer_ratio[k] = transfer_learning_ratio(k, tp.scale_modification_value)

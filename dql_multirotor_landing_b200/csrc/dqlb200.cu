@@ -123,6 +123,8 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   k.dz_train = c.dz_train; k.dz_sim = c.dz_sim; k.z_init = c.z_init; k.z_touch = c.z_touch;
   k.half_platform = c.half_platform; k.p_max_f = c.p_max_f; k.two_p_max_f = c.two_p_max_f; k.sigma_x = c.sigma_x;
   k.gamma = c.gamma;
+  k.noise_pos_sd = c.noise_pos_sd; k.noise_vel_sd = c.noise_vel_sd;
+  k.noise_enabled = (c.noise_pos_sd != 0.0f || c.noise_vel_sd != 0.0f) ? 1 : 0;
   memcpy(k.transfer_ratio, c.transfer_ratio, sizeof(k.transfer_ratio));
   k.timeout_steps = c.timeout_steps; k.success_steps = c.success_steps; k.n_sub = c.n_sub;
   k.transfer_mode = c.transfer_mode; k.window_len = c.window_len; k.promote_successes = c.promote_successes;
@@ -265,7 +267,7 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const bool tracing = trace != nullptr;
 #define DQL_LAUNCH(W)                                                                        \
   if (tracing) dql::train_kernel<W, true, true><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
-  else if (h->kc.div_two_steps) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
+  else if (h->kc.div_two_steps || h->kc.noise_enabled) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
   else dql::train_kernel<W, false, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;

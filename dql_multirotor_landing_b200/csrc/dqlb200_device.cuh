@@ -30,6 +30,8 @@ struct KC {
   float h, half_h2, k_theta, g, c_d, dz_train, dz_sim, z_init, z_touch, half_platform;
   float p_max_f, two_p_max_f, sigma_x;
   float clip_p_f, clip_v_f;     // smallest fp32 |x| whose quotient x / p_max (x / v_max) rounds to >= 1
+  float noise_pos_sd, noise_vel_sd;
+  int32_t noise_enabled;        // either standard deviation is non-zero
   float gamma;
   float transfer_ratio[DQLB200_MAX_CURRICULUM];
   int32_t timeout_steps, success_steps, n_sub;
@@ -58,7 +60,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint32_t k0, uint32_t k1
   }
   return c;
 }
-constexpr uint32_t PURPOSE_STEP = 0u, PURPOSE_RESET = 1u;
+constexpr uint32_t PURPOSE_STEP = 0u, PURPOSE_RESET = 1u, PURPOSE_RESET_NOISE = 2u;
 
 // ---------------------------------------------------------------------------------------------
 // deterministic fp32 math
@@ -123,6 +125,16 @@ __device__ __forceinline__ float det_normal(uint32_t x0, uint32_t x1) {
   return fmul(rad, c);
 }
 
+// Both Box-Muller normals of one (u1, angle) pair.
+__device__ __forceinline__ void det_normal_pair(uint32_t x0, uint32_t x1, float& n0, float& n1) {
+  const float u1 = fmul(fadd(__uint2float_rn(x0 >> 8), 1.0f), (float)(1.0 / 16777216.0));
+  const float rad = __fsqrt_rn(fmul(-2.0f, det_log(u1)));
+  float s, c;
+  det_sincos_turns(x1, s, c);
+  n0 = fmul(rad, c);
+  n1 = fmul(rad, s);
+}
+
 __device__ __forceinline__ float clipf(float x, float lo, float hi) { return fminf(fmaxf(x, lo), hi); }
 __device__ __forceinline__ double clipd(double x, double lo, double hi) { return fmin(fmax(x, lo), hi); }
 // np.clip for a value that is never NaN (fmin/fmax cost ~6 instructions each for their NaN rules; this is 2 compares + selects)
@@ -163,6 +175,15 @@ __device__ __forceinline__ Obs dyn_observe(const KC& kc, const dqlb200_populatio
   o.z = fadd(kc.z_init, fmul(__int2float_rn(step_count), dz));
   o.contact = (o.z <= kc.z_touch) && (fabsf(o.rel_p) <= kc.half_platform);
   return o;
+}
+
+// Observation noise (PKG/observation_utils.py:127-129): what the MDP sees is the true relative position / velocity plus
+// independent Gaussians; contact (a bumper in the reference) and the physical state are untouched.
+__device__ __forceinline__ void add_observation_noise(const KC& kc, Obs& o, uint32_t w0, uint32_t w1) {
+  float n0, n1;
+  det_normal_pair(w0, w1, n0, n1);
+  o.rel_p = fadd(o.rel_p, fmul(kc.noise_pos_sd, n0));
+  o.rel_v = fadd(o.rel_v, fmul(kc.noise_vel_sd, n1));
 }
 
 // R1 (PKG/landing_simulation_env.py:181-216) and R15 (:327-340), then one hover period (:222-224).

@@ -145,7 +145,11 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
   dyn_advance(kc, pp, e.b, (float)sp);
   const uint32_t step_count = e.step_count + 1u;
-  const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train);
+  Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train);
+  if (kc.noise_enabled && !simulation) {      // the words the fused kernel uses at global step t
+    const uint4 d = philox4x32_10(make_uint4(env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+    add_observation_noise(kc, o, d.z, d.w);
+  }
   const DState ds = discretise_cuts(cuts, kc.angle_cut, o, w);
   const uint32_t sid2 = (uint32_t)ds.id();
   const bool t_fx = !(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi);

@@ -94,7 +94,11 @@ __device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population
                                           const dqlb200_cuts& cuts, const float* angle_cut, Env& e,
                                           uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
-  const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
+  Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
+  if (kc.noise_enabled) {
+    const uint4 dn = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET_NOISE, pp.population_id), pp.seed_lo, pp.seed_hi);
+    add_observation_noise(kc, o, dn.x, dn.y);
+  }
   const DState ds0 = discretise_cuts(cuts, angle_cut, o);
   e.sid = (uint32_t)ds0.id();
   e.bp = (uint32_t)ds0.bp;

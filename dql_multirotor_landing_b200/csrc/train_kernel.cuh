@@ -67,9 +67,11 @@ struct Shared {
 #ifndef DQL_WARPS_PER_SM
 #define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
-// DIV2: second Markstein correction step of x / p_max, x / v_max (needed unless the divisors are the exhaustively
-// verified defaults; the trace instances always take it: both variants are correctly rounded, hence identical)
-template <int WARPS, bool TRACE, bool DIV2>
+// GENERIC = false is the production instance of the reference's default configuration; GENERIC = true adds what only
+// non-default configurations need: the second Markstein correction step of x / p_max, x / v_max (required unless the
+// divisors are the exhaustively verified defaults) and the observation-noise option.  The trace instances are generic
+// (both division variants are correctly rounded, hence identical).
+template <int WARPS, bool TRACE, bool GENERIC>
 __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (DQL_WARPS_PER_SM / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
@@ -248,10 +250,14 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
         int a = sh.greedy[sid];
-        if (w == 0) {
-          const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
+        uint32_t noise_w0 = 0u, noise_w1 = 0u;      // words z, w of the step draw feed the observation noise (off by default)
+        if (w == 0 || (GENERIC && kc.noise_enabled)) {
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
-          if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+          if (w == 0) {
+            const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
+            if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
+          }
+          if (GENERIC) { noise_w0 = d.z; noise_w1 = d.w; }
         }
         size_t trace_i = 0;
         if (TRACE) {
@@ -273,7 +279,8 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         // R4
         dyn_advance(kc, pp, e.b, (float)sp);
         const uint32_t step_count = e.step_count + 1u;
-        const Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
+        Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
+        if (GENERIC && kc.noise_enabled) add_observation_noise(kc, o, noise_w0, noise_w1);
         // R5
         const DState ds = discretise_cuts(sh.cuts, kc.angle_cut, o, w);
         const uint32_t sid2 = (uint32_t)ds.id();
@@ -297,11 +304,11 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
           atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
         // R7 (float64, reference operation order; level-dependent constants from the host)
-        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
-        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, GENERIC);
+        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, GENERIC);
         const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
-        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, DIV2);
-        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, DIV2);
+        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, GENERIC);
+        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, GENERIC);
         const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
         const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 2
+#define DQLB200_ABI_VERSION 3
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -113,6 +113,10 @@ typedef struct dqlb200_config {
   int32_t n_alpha_luts;             /* learning-rate variants for sweeps (>= 1) */
   int32_t replicas_per_population;  /* 1 = every population is one agent; R > 1 = R consecutive populations are
                                      * replicas of one agent merged by dqlb200_replica_merge (they never promote alone) */
+  /* ---- observation realism: Gaussian noise on the observed relative position / velocity
+   * (PKG/observation_utils.py:127-129, manager_node parameters noise_pos_sd / noise_vel_sd; launch default 0 = off).
+   * Applied to what the MDP sees (discretisation, fly-zone check, shaping); the physical state and `contact` stay exact. */
+  float noise_pos_sd, noise_vel_sd;
   uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
 } dqlb200_config;
 

@@ -50,6 +50,8 @@ class StandInParams:
     half_platform: float = 0.5
     p_max: float = 4.5
     n_sub: int = 1
+    noise_pos_sd: float = 0.0    # PKG/observation_utils.py:127-129 (launch/environment.launch:56-57 sets both to 0)
+    noise_vel_sd: float = 0.0
 
 
 @dataclass(frozen=True)
@@ -156,6 +158,21 @@ def det_normal(x0, x1):
     rad = np.sqrt(f32(-2.0) * det_log(u1)).astype(np.float32)
     _, c = det_sincos_turns(x1)
     return (rad * c).astype(np.float32)
+
+
+def det_normal_pair(x0, x1):
+    """Both Box-Muller normals of one (u1, angle) pair (rad * cos, rad * sin)."""
+    u1 = ((np.atleast_1d(np.asarray(x0, dtype=np.uint32)) >> np.uint32(8)).astype(np.float32) + ONE) * f32(2.0 ** -24)
+    rad = np.sqrt(f32(-2.0) * det_log(u1)).astype(np.float32)
+    s, c = det_sincos_turns(x1)
+    return (rad * c).astype(np.float32), (rad * s).astype(np.float32)
+
+
+def add_observation_noise(p: "StandInParams", rel_p, rel_v, w0, w1):
+    """What the MDP sees: true relative position / velocity plus independent Gaussians (PKG/observation_utils.py:127-129)."""
+    n0, n1 = det_normal_pair(w0, w1)
+    return ((np.asarray(rel_p, np.float32) + f32(p.noise_pos_sd) * n0).astype(np.float32),
+            (np.asarray(rel_v, np.float32) + f32(p.noise_vel_sd) * n1).astype(np.float32))
 
 
 class StandInDet:

@@ -28,7 +28,7 @@ import numpy as np
 
 from . import philox
 from .agent_oracle import AgentOracle, exploration_rate, explore_threshold, state_id, transfer_ratio
-from .dynamics import StandInDet, StandInParams
+from .dynamics import StandInDet, StandInParams, add_observation_noise
 from .mdp_oracle import (MdpParams, TERMINAL_SUCCESS, TrainingMdpOracle)
 
 
@@ -89,6 +89,9 @@ class PopulationOracle:
         self.dyn.reset(idx, w0, w1, w2, normal_init=(self.w == 0))
         self.dyn.advance(np.zeros(idx.size, np.float32), idx)
         rel_p, rel_v, rel_a, pitch, z, contact = self.dyn.observe(np.zeros(idx.size), idx)
+        if self.sp.noise_pos_sd or self.sp.noise_vel_sd:
+            n0, n1, _, _ = philox.draws(self.seed, self.pop, idx, birth, philox.PURPOSE_RESET_NOISE)
+            rel_p, rel_v = add_observation_noise(self.sp, rel_p, rel_v, n0, n1)
         for k, i in enumerate(idx):
             m = self.mdps[i]
             m.reset()
@@ -106,7 +109,8 @@ class PopulationOracle:
         if self.finished:
             return tr
         env = np.arange(n)
-        d0, d1, _d2, _ = philox.draws(self.seed, self.pop, env, self.t, philox.PURPOSE_STEP)
+        d0, d1, d2, d3 = philox.draws(self.seed, self.pop, env, self.t, philox.PURPOSE_STEP)
+        noisy = bool(self.sp.noise_pos_sd or self.sp.noise_vel_sd)
         snap_a, snap_b = ag.qa.copy(), ag.qb.copy()
         promote = advance = False
         finished_envs = []
@@ -121,6 +125,8 @@ class PopulationOracle:
             th_sp = m.act(a)
             self.dyn.advance(np.asarray([th_sp], np.float32), np.asarray([i]))
             rel_p, rel_v, rel_a, pitch, z, contact = (x[0] for x in self.dyn.observe(np.asarray([m.step_count + 1]), np.asarray([i])))
+            if noisy:       # words z, w of the step draw (the table-pick draw of update() is consumed and ignored, quirk Q1)
+                rel_p, rel_v = (x[0] for x in add_observation_noise(self.sp, rel_p, rel_v, d2[i:i + 1], d3[i:i + 1]))
             s2 = m.observe(rel_p, rel_v, rel_a, pitch, z, contact)
             code, done = m.check()
             r = m.reward()

@@ -26,6 +26,7 @@ MASK = np.uint64(0xFFFFFFFF)
 
 PURPOSE_STEP = 0
 PURPOSE_RESET = 1
+PURPOSE_RESET_NOISE = 2
 
 
 def philox4x32_10(c0, c1, c2, c3, k0, k1):

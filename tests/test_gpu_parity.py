@@ -130,6 +130,41 @@ def test_multi_env_population_vs_oracle(tpb, n_envs, axes):
         assert ps[p]["window_sum"] == sum(pop.window) and ps[p]["window_count"] == len(pop.window)
 
 
+def test_observation_noise_option_vs_oracle():
+    """Gaussian noise on the observed relative position / velocity (PKG/observation_utils.py:127-129, the
+    manager_node defaults 0.25 m / 0.1 m/s).  The MDP sees the noisy values (states, fly-zone exits, shaping rewards), the
+    physical state stays exact; with promotions (w > 0: no exploration draws, the noise still needs the Philox call)."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    noise = dict(noise_pos_sd=0.25, noise_vel_sd=0.1)
+    n_envs, steps = 70, 260
+    eng = _engine(1, n_envs, threads_per_block=64, seeds=[3], tp=kw, dp=noise)
+    eng.reset(0)
+    tr = eng.train(steps, trace=True)
+    eng.check_errors()
+    pop = PopulationOracle(n_envs, seed=3, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw), sp=StandInParams(**noise))
+    clean = PopulationOracle(n_envs, seed=3, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw))
+    differs = False
+    for t in range(steps):
+        o = pop.step()
+        assert np.array_equal(tr["obs"][t].view(np.uint32), o["obs"].view(np.uint32)), t
+        for key in ("action", "code", "done"):
+            assert np.array_equal(tr[key][t], o[key]), (t, key)
+        assert np.array_equal(tr["next_state"][t].astype(np.uint16), o["next_state"]), t
+        assert np.array_equal(tr["reward"][t], o["reward"]), t
+        if t < 5:
+            differs = differs or not np.array_equal(clean.step()["obs"], o["obs"])
+    assert differs, "the noise must actually change the observations"
+    qa, _, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(cnt, pop.agent.count) and np.array_equal(qa.view(np.uint32), pop.agent.qa.view(np.uint32))
+    ps = eng.population_state()[0]
+    assert int(ps["working_step"]) == pop.w >= 1
+    # the production (non-trace) generic instance
+    eng2 = _engine(1, n_envs, threads_per_block=64, seeds=[3], tp=kw, dp=noise)
+    eng2.reset(0)
+    eng2.train(steps)
+    assert torch.equal(eng2.tables, eng.tables) and torch.equal(eng2.env_state, eng.env_state)
+
+
 @pytest.mark.parametrize("mode", ["reference", "paper"])
 def test_curriculum_promotion_and_transfer(mode):
     """R13/R14: success window, promotion latch, max_num_episodes advance, transfer (quirk Q7 and the
