@@ -42,8 +42,10 @@ __device__ __forceinline__ EnvRaw env_fetch(const EnvPtrs& p, size_t i) {
 }
 // Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
 // unlike a register prefetch it holds no registers while in flight and cannot be consumed early by the scheduler's copies.
-__device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, uint4* stage, int nt, int tid) {
-  const unsigned s0 = (unsigned)__cvta_generic_to_shared(stage + tid);
+// stage_addr = shared-state-space address of the thread's first staging slot (__cvta_generic_to_shared(stage + tid), hoisted
+// out of the slot loop by the caller: the conversion reads a special register).
+__device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, unsigned stage_addr, int nt) {
+  const unsigned s0 = stage_addr;
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(p.a + i) : "memory");
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16u * nt), "l"(p.b + i) : "memory");
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 32u * nt), "l"(p.c + i) : "memory");

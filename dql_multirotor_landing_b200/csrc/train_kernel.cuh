@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
   const int n_slots = (n_p + NT - 1) / NT;
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
   uint4* stage = reinterpret_cast<uint4*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT]
+  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage + tid);
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
   float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
   static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
   constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
   const dqlb200_population_params pp = args.pop_params[pop];
-  env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+  env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
   {
     const int w_start = args.pop_state[pop].working_step;
     const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
@@ -185,7 +186,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     __syncthreads();
     advance_curriculum(sh.ps.working_step, sh.ps.t);
     (void)env_prefetch_take(stage, NT, tid);
-    env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);     // every env was just restarted
+    env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);     // every env was just restarted
   }
 
   for (int k = 0; k < args.k_steps; ++k) {
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       const bool valid = env_i < n_p;
       const size_t gi = env_base + (size_t)(valid ? env_i : 0);
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
-      if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage, NT, tid);      // in flight during this slot
+      if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage_addr, NT);      // in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -449,7 +450,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     }
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
-    if (k + 1 < args.k_steps) env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+    if (k + 1 < args.k_steps) env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
@@ -464,7 +465,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     if (sh.do_advance) {
       advance_curriculum(w, t + 1u);
       (void)env_prefetch_take(stage, NT, tid);
-      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage, NT, tid);
+      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
     }
   }
 

@@ -20,7 +20,7 @@ class Engine:
                  seeds: Optional[Sequence[int]] = None, population_ids: Optional[Sequence[int]] = None,
                  v_mp: Optional[Sequence[float]] = None, alpha_variants: Optional[Sequence[tuple]] = None,
                  alpha_index: Optional[Sequence[int]] = None, replicas_per_population: int = 1,
-                 axes: Optional[Sequence[str]] = None,
+                 axes: Optional[Sequence[str]] = None, r_mp: Optional[Sequence[float]] = None,
                  mp: Optional[K.MdpParameters] = None, dp: Optional[K.DynamicsParameters] = None,
                  tp: Optional[K.TrainerParameters] = None):
         if not torch.cuda.is_available():
@@ -37,6 +37,10 @@ class Engine:
         seeds = list(seeds) if seeds is not None else [42] * n_populations
         population_ids = list(population_ids) if population_ids is not None else list(range(n_populations))
         v_mp = list(v_mp) if v_mp is not None else [self.dp.v_mp] * n_populations
+        # platform amplitude per population (default: DynamicsParameters.r_mp).  Decoupled per-axis training under the
+        # reference's "eight" trajectory (PKG/moving_platform.py:92-111: x = r cos wt, y = r sin wt cos wt = (r/2) sin 2wt)
+        # is a parameter choice: x agent (r, v), y agent (r / 2, v) -- see eight_axis_platforms().
+        r_mp = list(r_mp) if r_mp is not None else [self.dp.r_mp] * n_populations
         alpha_index = list(alpha_index) if alpha_index is not None else [0] * n_populations
         # axis of every agent: "x" (pitch, a = +g tan) or "y" (roll, a = -g tan in the reference's ENU frame; training_y.sh)
         axes = list(axes) if axes is not None else ["x"] * n_populations
@@ -45,7 +49,7 @@ class Engine:
         self.axes = axes
         pps = (K.PopulationParams * n_populations)()
         for p in range(n_populations):
-            dphase, r, rw, rw2 = K.platform_constants(self.dp.r_mp, v_mp[p], self.mp.f_ag, self.dp.n_sub)
+            dphase, r, rw, rw2 = K.platform_constants(r_mp[p], v_mp[p], self.mp.f_ag, self.dp.n_sub)
             pps[p] = K.PopulationParams(seeds[p] & 0xFFFFFFFF, (seeds[p] >> 32) & 0xFFFFFFFF, population_ids[p], dphase,
                                         r, rw, rw2, alpha_index[p], np.float32(self.dp.g if axes[p] == "x" else -self.dp.g),
                                         0 if axes[p] == "x" else 1)
@@ -292,6 +296,14 @@ class Engine:
                                                    stats.data_ptr(), C.byref(tr) if tr is not None else None, trace_steps, self._stream()))
         torch.cuda.synchronize(dev)
         return _eval_result(K.EvalStats.from_buffer_copy(stats.cpu().numpy().tobytes()), out)
+
+
+def eight_axis_platforms(r: float = 3.0, v: float = 0.8):
+    """(r_mp, v_mp) of the x and the y agent for decoupled training under the reference's "eight" platform trajectory
+    (PKG/moving_platform.py:92-111, r_x = r_y = 3, t_x = 0.8): each axis sees a sinusoid -- x: amplitude r, peak speed
+    v = r w; y: r sin(wt) cos(wt) = (r / 2) sin(2 w t), amplitude r / 2, peak speed (r / 2)(2 w) = v.  The start phase is
+    random per episode, so cos versus sin makes no difference."""
+    return (r, v), (r / 2.0, v)
 
 
 def _eval_result(st, out):

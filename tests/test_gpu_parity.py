@@ -106,14 +106,15 @@ def test_multi_env_population_vs_oracle(tpb, n_envs, axes):
     steps = 120
     seeds, v_mp = [42, 7], [1.6, 0.8]
     g = [9.81 if a == "x" else -9.81 for a in axes]
-    eng = _engine(2, n_envs, threads_per_block=tpb, seeds=seeds, v_mp=v_mp, axes=list(axes), tp=NO_PROMOTION)
+    r_mp = [2.0, 2.0] if axes == "xx" else [3.0, 1.5]          # "xy": the two axes of the reference's eight trajectory
+    eng = _engine(2, n_envs, threads_per_block=tpb, seeds=seeds, v_mp=v_mp, r_mp=r_mp, axes=list(axes), tp=NO_PROMOTION)
     eng.reset(0)
     tr = eng.train(steps, trace=True)
     eng.check_errors()
     ps = eng.population_state()
     for p in range(2):
         pop = PopulationOracle(n_envs, seed=seeds[p], population=p, w0=0, dtype=np.float32,
-                               tp=TrainerParams(**NO_PROMOTION), sp=StandInParams(v_mp=v_mp[p], g=g[p]))
+                               tp=TrainerParams(**NO_PROMOTION), sp=StandInParams(v_mp=v_mp[p], r_mp=r_mp[p], g=g[p]))
         sl = slice(p * n_envs, (p + 1) * n_envs)
         for t in range(steps):
             o = pop.step()
