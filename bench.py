@@ -238,7 +238,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t0 = time.perf_counter()
     for _ in range(e2e_calls):
         eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h)          # synchronises inside
-        launches += 1
+        launches += min(8, P)                                   # one train_kernel launch per pipelined chunk of populations
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
@@ -313,7 +313,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu,
                          "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 6 and profiles/"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
-                    "global_steps_per_call": E2E_CHUNK, "calls": e2e_calls, "api": "dqlb200_train_host (pinned host buffers)"},
+                    "global_steps_per_call": E2E_CHUNK, "calls": e2e_calls, "api": "dqlb200_train_host (pinned host buffers)",
+                    "step": "one e2e step = one dqlb200_train_host call: env state + tables + trainer state copied in, 64 global steps, all copied back"},
             "gpu_launches": launches, "clocks": clocks, "total_env_steps_counted_on_device": steps_done,
             "cpu_baseline": cpu_baseline() if not args.no_cpu else None,
             "extra": extra,

@@ -15,8 +15,8 @@ batched semantics the CUDA kernel must reproduce ("S1"):
     promotion test runs after every append (PKG/trainer.py:219-236) and takes
     effect at the end of the global step (all envs restart with a fresh MDP).
 
-Pure Python: use small n_envs * steps (the C restatement oracle/c covers
-large cases and is pinned against this file).
+Pure Python / NumPy: use small n_envs * steps (seconds); the full-size runs are
+checked through size-independent properties (tests/test_gpu_parity.py).
 """
 from __future__ import annotations
 
