@@ -266,5 +266,10 @@ class Trainer:
         shown["Termination condition"] = shown["Termination condition"].replace("FAILURE", "\x1b[1;31mFAILURE\x1b[0m")
         for k, v in shown.items():
             print(f"{k}: {v}")
-        if not clean:
+        print("Press Ctrl-C to exit...")
+        if clean:
+            print("\x1b[0;0f", end="")
+            print("\x1b[J", end="")
+            print("\x1b[0m", end="")
+        else:
             print("=" * 80)

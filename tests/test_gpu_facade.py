@@ -306,3 +306,22 @@ def test_unfused_select_step_update_loop_equals_fused_kernel():
     assert torch.equal(fused.tables, loop.tables)
     assert torch.equal(fused.env_state, loop.env_state)
     assert int(fused.tables[:, 2].sum()) == P * n * steps
+
+
+def test_trainer_log_writes_the_reference_tensorboard_tags(tmp_path, capsys):
+    """Trainer.log (PKG/trainer.py:247-303): the same scalar / text tags under <save_path>/logs and the same console layout."""
+    pytest.importorskip("tensorboard")
+    from tensorboard.backend.event_processing.event_accumulator import EventAccumulator
+    from dql_multirotor_landing_b200.trainer import Trainer
+    tr = Trainer(save_path=tmp_path / "run", successive_successful_episodes=5, success_rate=0.2, max_num_episodes=60,
+                 num_envs=64, chunk_steps=32, threads_per_block=64, verbose=False, max_global_steps=256, tensorboard=True)
+    info = tr.curriculum_training()
+    tr.log(info)
+    out = capsys.readouterr().out
+    assert "Curiculum step:" in out and "Current episode:" in out and "Press Ctrl-C to exit..." in out
+    acc = EventAccumulator(str(tmp_path / "run" / "logs"))
+    acc.Reload()
+    tags = set(acc.Tags()["scalars"])
+    assert {"Episode/Success Rate", "Episode/Cumulative Reward", "Episode/Exploration Rate", "Episode/Learning Rate",
+            "Episode/Mean reward"} <= tags
+    assert any("Episode/Termination Condition" in t for t in acc.Tags()["tensors"])
