@@ -190,6 +190,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         torch.cuda.synchronize(dev)
 
     from dql_multirotor_landing_b200 import parallel
+    numa_node = parallel.bind_to_gpu_numa_node(local_rank) if world > 1 else None     # pinned e2e buffers next to the GPU
     P, n_p = POPULATIONS_PER_GPU, ENVS_PER_POPULATION
     speeds = [0.4, 0.8, 1.2, 1.6]
     variants = [(0.02949, 0.51), (0.05, 0.6)]
@@ -314,6 +315,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 6 and profiles/"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
                     "global_steps_per_call": E2E_CHUNK, "calls": e2e_calls, "api": "dqlb200_train_host (pinned host buffers)",
+                    "host_numa_node_rank0": numa_node,
                     "step": "one e2e step = one dqlb200_train_host call: env state + tables + trainer state copied in, 64 global steps, all copied back"},
             "gpu_launches": launches, "clocks": clocks, "total_env_steps_counted_on_device": steps_done,
             "cpu_baseline": cpu_baseline() if not args.no_cpu else None,

@@ -155,6 +155,10 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   CUDA_TRY(cudaSetDevice(device));
   dqlb200_handle* h = new (std::nothrow) dqlb200_handle();
   if (!h) return fail(DQLB200_ERR_STATE, "out of host memory");
+  struct Guard {       // every early return below releases what has been allocated so far
+    dqlb200_handle* h;
+    ~Guard() { if (h) dqlb200_destroy(h); }
+  } guard{h};
   h->cfg = *cfg;
   fill_kc(*cfg, h->kc);
   h->device = device;
@@ -189,6 +193,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
 #undef DQL_SET_SMEM
 #undef DQL_SET_SMEM1
+  guard.h = nullptr;
   *out = h;
   return DQLB200_OK;
 }

@@ -36,6 +36,37 @@ def sweep_axes(population_ids: Sequence[int], seeds_per_point: int, speeds: Sequ
     return seeds, v_mp, alpha
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host buffers allocated
+    afterwards are first-touched on that node and the host<->device copies of the ranks do not cross sockets.  Returns the
+    node id, or None when the topology cannot be read (nothing is changed then)."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
+        if bus is None:
+            import ctypes
+            rt = ctypes.CDLL("libcudart.so.12")
+            buf = ctypes.create_string_buffer(32)
+            if rt.cudaDeviceGetPCIBusId(buf, 32, device_index) != 0:
+                return None
+            bus = buf.value.decode()
+        node_file = f"/sys/bus/pci/devices/{bus.lower()}/numa_node"
+        node = int(open(node_file).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = set(cpus) & os.sched_getaffinity(0)
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:
+        return None
+
+
 def max_over_ranks(values: Sequence[float], device: Optional[torch.device] = None) -> List[float]:
     """Device-timed numbers are reported as the maximum over ranks."""
     t = torch.tensor(list(values), dtype=torch.float64, device=device)
