@@ -120,7 +120,9 @@ def cpu_baseline(seconds: float = 12.0) -> dict:
         t += s
     return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port",
             "sample": f"{steps} env-steps of the single-env reference loop (oracle port, float64 tables, analytic stand-in), "
-                      f"{t:.1f} s on 1 of {os.cpu_count()} host cores"}
+                      f"{t:.1f} s on 1 of {os.cpu_count()} host cores",
+            "context": "the unmodified reference loop measures 6.9-7.5e3 env-steps/s per core on the same stand-in (BASELINE.md section 2); "
+                       "the reference's own Gazebo-locked training ran at 20.3 env-steps/s"}
 
 
 # ----------------------------------------------------------------------------------------------------
