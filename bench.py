@@ -354,6 +354,20 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
     t0 = time.perf_counter()
     res = eng.eval_greedy(pol, n_ep)
     s = time.perf_counter() - t0
+    # config 2, both axes: the same policy on x, its mirror image on y, "eight" platform (PKG/moving_platform.py:92-111)
+    try:
+        from dql_multirotor_landing_b200 import constants as K2
+        from dql_multirotor_landing_b200.engine import mirrored_policy
+        ta = K2.TwoAxisParameters(trajectory=K2.TRAJ_EIGHT, r_x=3.0, v_x=0.8, r_y=3.0, y_action_enabled=True, y_init_enabled=True)
+        eng.eval_greedy_2d(pol, mirrored_policy(pol), 4096, two_axis=ta)
+        t0 = time.perf_counter()
+        r2 = eng.eval_greedy_2d(pol, mirrored_policy(pol), n_ep, two_axis=ta)
+        s2 = time.perf_counter() - t0
+        out["config2_two_axis_eval_eight_trajectory"] = {"episodes": r2["episodes"], "env_steps": r2["steps"], "env_steps_per_s": r2["steps"] / s2,
+                                                         "landing_rate": r2["termination_hist"][3] / max(r2["episodes"], 1),
+                                                         "termination_hist": r2["termination_hist"], "timing": "host wall clock incl. launch+sync"}
+    except Exception as exc:
+        out["config2_two_axis_eval_eight_trajectory"] = {"error": str(exc)}
     # config 3: ONE agent, 65,536 envs sharing one Q-table pair (replica-merge mode: 512 replicas x 128 envs, merged every 16 steps)
     try:
         from dql_multirotor_landing_b200 import constants as K
