@@ -52,6 +52,7 @@ struct dqlb200_handle {
   void* tables;
   void* pop_state;
   void* merge_snapshot;
+  bool kc_default;              // the configuration equals the compile-time defaults: the production instance may run
   size_t smem_bytes;
   // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
   static constexpr int MAX_HOST_CHUNKS = 8;
@@ -161,6 +162,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   } guard{h};
   h->cfg = *cfg;
   fill_kc(*cfg, h->kc);
+  h->kc_default = dql::kdef_matches(h->kc);
   h->device = device;
   h->env_state = h->tables = h->pop_state = h->merge_snapshot = nullptr;
   h->chunk_ready = false;
@@ -197,6 +199,8 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   *out = h;
   return DQLB200_OK;
 }
+
+int dqlb200_uses_default_instance(dqlb200_handle* h) { return (h && h->kc_default) ? 1 : 0; }
 
 int dqlb200_destroy(dqlb200_handle* h) {
   if (!h) return DQLB200_OK;
@@ -272,7 +276,7 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const bool tracing = trace != nullptr;
 #define DQL_LAUNCH(W)                                                                        \
   if (tracing) dql::train_kernel<W, true, true><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
-  else if (h->kc.div_two_steps || h->kc.noise_enabled) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
+  else if (!h->kc_default) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
   else dql::train_kernel<W, false, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;

@@ -42,6 +42,45 @@ struct KC {
   long long max_num_episodes;
 };
 
+// The reference-default configuration as COMPILE-TIME constants (MdpParameters / DynamicsParameters defaults of constants.py;
+// PKG/mdp.py:214-235, PKG/trainer.py:41-44).  sm_100a has no constant-bank operands: a run-time constant costs
+// a uniform-register load next to its use (about 70 of them per env-step); literals are encoded in the instructions.  The
+// production instance of train_kernel uses this type; dqlb200_create checks every value below against the run-time
+// configuration bit for bit and falls back to the generic instance (run-time KC) when anything differs.
+struct KDef {
+  static constexpr float h = 0x1.656ac8p-5f, half_h2 = 0x1.f302fcp-11f, k_theta = 0x1.0d7ec4p-2f, c_d = 0x1.99999ap-3f;
+  static constexpr float dz_train = -0x1.1def06p-8f, dz_sim = -0x1.1def06p-6f, z_init = 4.0f, z_touch = 0x1.07ae14p-1f;
+  static constexpr float half_platform = 0.5f, p_max_f = 4.5f, two_p_max_f = 9.0f, sigma_x = 1.5f, gamma = 0x1.fae148p-1f;
+  static constexpr float fz_lo = -4.5f, fz_hi = 0x1.200002p+2f, z_min_cut = 0x1.99999ap-3f, z_max_cut = 0x1.200002p+2f;
+  static constexpr float clip_p_f = 4.5f, clip_v_f = 0x1.b27234p+1f;
+  static constexpr double p_max = 4.5, v_max = 0x1.b272324c83665p+1, theta_max = 0x1.7e0eb9bca0a66p-2, delta_theta = 0x1.fd68e8083ba2ep-4;
+  static constexpr double w_p = -100.0, w_v = -10.0, w_theta = -0x1.8cccccccccccdp+0;
+  static constexpr double rcp_p_max = 1.0 / p_max, rcp_v_max = 1.0 / v_max, rcp_theta_max = 1.0 / theta_max;
+  static constexpr int32_t timeout_steps = 459, success_steps = 23, n_sub = 1;
+  static constexpr int32_t noise_enabled = 0;
+  static constexpr float noise_pos_sd = 0.0f, noise_vel_sd = 0.0f;
+  struct AngleCut {          // constant-index reads fold into literals
+    __host__ __device__ constexpr float operator[](int i) const {
+      return i == 0 ? -0x1.3e619ap-2f : i == 1 ? -0x1.7e0eb8p-3f : i == 2 ? -0x1.fd68f6p-5f : i == 3 ? 0x1.fd68f8p-5f : i == 4 ? 0x1.7e0ebap-3f : 0x1.3e619cp-2f;
+    }
+  };
+  AngleCut angle_cut;       // an (empty) member: passed by reference to discretise_cuts
+};
+// true when every compile-time value of KDef equals the run-time configuration (host side, dqlb200_create)
+inline bool kdef_matches(const KC& k) {
+  bool ok = k.h == KDef::h && k.half_h2 == KDef::half_h2 && k.k_theta == KDef::k_theta && k.c_d == KDef::c_d && k.dz_train == KDef::dz_train &&
+            k.dz_sim == KDef::dz_sim && k.z_init == KDef::z_init && k.z_touch == KDef::z_touch && k.half_platform == KDef::half_platform &&
+            k.p_max_f == KDef::p_max_f && k.two_p_max_f == KDef::two_p_max_f && k.sigma_x == KDef::sigma_x && k.gamma == KDef::gamma &&
+            k.fz_lo == KDef::fz_lo && k.fz_hi == KDef::fz_hi && k.z_min_cut == KDef::z_min_cut && k.z_max_cut == KDef::z_max_cut &&
+            k.clip_p_f == KDef::clip_p_f && k.clip_v_f == KDef::clip_v_f && k.p_max == KDef::p_max && k.v_max == KDef::v_max &&
+            k.theta_max == KDef::theta_max && k.delta_theta == KDef::delta_theta && k.w_p == KDef::w_p && k.w_v == KDef::w_v &&
+            k.w_theta == KDef::w_theta && k.rcp_p_max == KDef::rcp_p_max && k.rcp_v_max == KDef::rcp_v_max && k.rcp_theta_max == KDef::rcp_theta_max &&
+            k.timeout_steps == KDef::timeout_steps && k.success_steps == KDef::success_steps && k.n_sub == KDef::n_sub && k.noise_enabled == 0 &&
+            k.div_two_steps == 0;
+  for (int i = 0; i < 6; ++i) ok = ok && k.angle_cut[i] == KDef::AngleCut{}[i];
+  return ok;
+}
+
 __device__ __forceinline__ float fmul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float fadd(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fsub(float a, float b) { return __fsub_rn(a, b); }
@@ -153,7 +192,8 @@ struct Obs {
   bool contact;
 };
 
-__device__ __forceinline__ void dyn_advance(const KC& kc, const dqlb200_population_params& pp, Body& b, float sp) {
+template <class KT>
+__device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_population_params& pp, Body& b, float sp) {
   for (int i = 0; i < kc.n_sub; ++i) {
     b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
     b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
@@ -163,7 +203,8 @@ __device__ __forceinline__ void dyn_advance(const KC& kc, const dqlb200_populati
   }
 }
 
-__device__ __forceinline__ Obs dyn_observe(const KC& kc, const dqlb200_population_params& pp, const Body& b,
+template <class KT>
+__device__ __forceinline__ Obs dyn_observe(const KT& kc, const dqlb200_population_params& pp, const Body& b,
                                            int step_count, float dz) {
   float s, c;
   det_sincos_turns(b.phase, s, c);
@@ -179,7 +220,8 @@ __device__ __forceinline__ Obs dyn_observe(const KC& kc, const dqlb200_populatio
 
 // Observation noise (PKG/observation_utils.py:127-129): what the MDP sees is the true relative position / velocity plus
 // independent Gaussians; contact (a bumper in the reference) and the physical state are untouched.
-__device__ __forceinline__ void add_observation_noise(const KC& kc, Obs& o, uint32_t w0, uint32_t w1) {
+template <class KT>
+__device__ __forceinline__ void add_observation_noise(const KT& kc, Obs& o, uint32_t w0, uint32_t w1) {
   float n0, n1;
   det_normal_pair(w0, w1, n0, n1);
   o.rel_p = fadd(o.rel_p, fmul(kc.noise_pos_sd, n0));
@@ -187,7 +229,8 @@ __device__ __forceinline__ void add_observation_noise(const KC& kc, Obs& o, uint
 }
 
 // R1 (PKG/landing_simulation_env.py:181-216) and R15 (:327-340), then one hover period (:222-224).
-__device__ __forceinline__ Obs dyn_reset(const KC& kc, const dqlb200_population_params& pp, Body& b, uint4 w,
+template <class KT>
+__device__ __forceinline__ Obs dyn_reset(const KT& kc, const dqlb200_population_params& pp, Body& b, uint4 w,
                                          bool normal_init, bool simulation, float dz) {
   float x_init;
   if (normal_init) {
@@ -217,7 +260,8 @@ struct DState {
   __device__ __forceinline__ int id() const { return (((level * 3 + bp) * 3 + bv) * 3 + ba) * 7 + bt; }
 };
 
-__device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const float* __restrict__ angle_cut,
+template <class AC>
+__device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const AC& angle_cut,
                                                   const Obs& o, int w = 4) {
   int lp = 0, lv = 0;
 #pragma unroll
@@ -240,7 +284,8 @@ __device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const f
 }
 
 // R3: pitch set-point integrator, float64 like the reference
-__device__ __forceinline__ double apply_action(const KC& kc, double theta_sp, int a) {
+template <class KT>
+__device__ __forceinline__ double apply_action(const KT& kc, double theta_sp, int a) {
   // branch-free (the three actions diverge inside a warp): a = 2 adds 0.0 and the clamps are no-ops for |theta_sp| <= theta_max
   const double s = __dadd_rn(theta_sp, a == 0 ? kc.delta_theta : (a == 1 ? -kc.delta_theta : 0.0));
   // selects on the 32-bit halves (a select on a double may be compiled into a branch)
@@ -291,7 +336,8 @@ __device__ __forceinline__ double shaping(double w, float x, double x_max, doubl
 }
 
 // R7 with the level-dependent constants pre-evaluated on the host.
-__device__ __forceinline__ double reward_f64(const KC& kc, const dqlb200_reward_level& rl, double phi_p,
+template <class KT>
+__device__ __forceinline__ double reward_f64(const KT& kc, const dqlb200_reward_level& rl, double phi_p,
                                              double phi_v, double phi_t, double prev_p, double prev_v,
                                              double prev_t, bool success) {
   const double r_p = clipd_finite(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);

@@ -92,8 +92,9 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
 
 // R1 + R8: new episode.  `fresh_mdp` additionally clears what only a NEW TrainingMdp clears
 // (shaping potentials, PKG/trainer.py:176 + quirk Q11) and the per-step episode index.
-__device__ __forceinline__ void env_reset(const KC& kc, const dqlb200_population_params& pp,
-                                          const dqlb200_cuts& cuts, const float* angle_cut, Env& e,
+template <class KT, class AC>
+__device__ __forceinline__ void env_reset(const KT& kc, const dqlb200_population_params& pp,
+                                          const dqlb200_cuts& cuts, const AC& angle_cut, Env& e,
                                           uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
   Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);

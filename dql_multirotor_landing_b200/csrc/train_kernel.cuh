@@ -67,14 +67,24 @@ struct Shared {
 #ifndef DQL_WARPS_PER_SM
 #define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
+template <bool GENERIC_> struct ConstsOf;
+template <> struct ConstsOf<true> {
+  __device__ __forceinline__ static const KC& get(const KC& kc) { return kc; }
+};
+template <> struct ConstsOf<false> {
+  __device__ __forceinline__ static KDef get(const KC&) { return KDef{}; }
+};
+
 // GENERIC = false is the production instance of the reference's default configuration; GENERIC = true adds what only
-// non-default configurations need: the second Markstein correction step of x / p_max, x / v_max (required unless the
-// divisors are the exhaustively verified defaults) and the observation-noise option.  The trace instances are generic
+// non-default configurations need: run-time constants instead of the compile-time defaults (KDef), the second Markstein
+// correction step of x / p_max, x / v_max (required unless the divisors are the exhaustively verified defaults) and the
+// observation-noise option.  The trace instances are generic
 // (both division variants are correctly rounded, hence identical).
 template <int WARPS, bool TRACE, bool GENERIC>
 __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (DQL_WARPS_PER_SM / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+  const auto& kk = ConstsOf<GENERIC>::get(kc);       // run-time KC (generic) or the compile-time defaults KDef (production)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = WARPS * 32;
   const int pop = blockIdx.x + args.pop_offset;
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const int env_i = slot * NT + tid;
         if (env_i < n_p) {
           Env e;
-          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
           env_store(args.env, env_base + env_i, e);
         }
       }
@@ -221,7 +231,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
           const size_t gr = env_base + (size_t)env_r;
           Env e;
           env_load(args.env, gr, e);
-          env_reset(kc, pp, sh.cuts, kc.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
           env_store(args.env, gr, e);
         }
       }
@@ -252,7 +262,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
         int a = sh.greedy[sid];
         uint32_t noise_w0 = 0u, noise_w1 = 0u;      // words z, w of the step draw feed the observation noise (off by default)
-        if (w == 0 || (GENERIC && kc.noise_enabled)) {
+        if (w == 0 || (GENERIC && kk.noise_enabled)) {
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
           if (w == 0) {
             const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
@@ -276,25 +286,25 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         a_hint = __ldg(alpha_lut + c_hint);
         // R3: set-point (float64).  A fresh episode starts from 0 but keeps the old value for shaping.
         const double prev_sp = e.theta_sp;
-        const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
+        const double sp = apply_action(kk, e.fresh ? 0.0 : e.theta_sp, a);
         // R4
-        dyn_advance(kc, pp, e.b, (float)sp);
+        dyn_advance(kk, pp, e.b, (float)sp);
         const uint32_t step_count = e.step_count + 1u;
-        Obs o = dyn_observe(kc, pp, e.b, (int)step_count, kc.dz_train);
-        if (GENERIC && kc.noise_enabled) add_observation_noise(kc, o, noise_w0, noise_w1);
+        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train);
+        if (GENERIC && kk.noise_enabled) add_observation_noise(kk, o, noise_w0, noise_w1);
         // R5
-        const DState ds = discretise_cuts(sh.cuts, kc.angle_cut, o, w);
+        const DState ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
         const uint32_t sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
         // The priority chain of PKG/mdp.py:359-425 as selects (the ladder of branches diverges inside a warp).
-        const bool t_fx = !(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi);
-        const bool t_zmin = !(o.z >= kc.z_min_cut), t_zmax = o.z >= kc.z_max_cut;
-        const bool t_time = (int)step_count >= kc.timeout_steps;
+        const bool t_fx = !(o.rel_p >= kk.fz_lo) || (o.rel_p >= kk.fz_hi);
+        const bool t_zmin = !(o.z >= kk.z_min_cut), t_zmax = o.z >= kk.z_max_cut;
+        const bool t_time = (int)step_count >= kk.timeout_steps;
         const bool goal_bins = !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
         const bool at_level = sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;   // previous level == w (it never exceeds w)
         const uint32_t cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
-        if (goal_bins && at_level) code = ((int)cc >= kc.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
+        if (goal_bins && at_level) code = ((int)cc >= kk.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
         code = t_time ? DQLB200_TERMINAL_TIMEOUT : code;
         code = t_zmax ? DQLB200_TERMINAL_FLYZONE_Z : code;
         code = t_zmin ? DQLB200_TERMINAL_MINIMUM_ALTITUDE : code;
@@ -305,18 +315,18 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
           atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
         // R7 (float64, reference operation order; level-dependent constants from the host)
-        const double phi_p = shaping(kc.w_p, o.rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, GENERIC);
-        const double phi_v = shaping(kc.w_v, o.rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, GENERIC);
-        const double phi_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(sp, kc.theta_max, kc.rcp_theta_max)));
-        const double prev_p = shaping(kc.w_p, e.prev_rel_p, kc.p_max, kc.rcp_p_max, kc.clip_p_f, GENERIC);
-        const double prev_v = shaping(kc.w_v, e.prev_rel_v, kc.v_max, kc.rcp_v_max, kc.clip_v_f, GENERIC);
-        const double prev_t = __dmul_rn(kc.w_theta, fabs(div_f64_by_const(prev_sp, kc.theta_max, kc.rcp_theta_max)));
+        const double phi_p = shaping(kk.w_p, o.rel_p, kk.p_max, kk.rcp_p_max, kk.clip_p_f, GENERIC);
+        const double phi_v = shaping(kk.w_v, o.rel_v, kk.v_max, kk.rcp_v_max, kk.clip_v_f, GENERIC);
+        const double phi_t = __dmul_rn(kk.w_theta, fabs(div_f64_by_const(sp, kk.theta_max, kk.rcp_theta_max)));
+        const double prev_p = shaping(kk.w_p, e.prev_rel_p, kk.p_max, kk.rcp_p_max, kk.clip_p_f, GENERIC);
+        const double prev_v = shaping(kk.w_v, e.prev_rel_v, kk.v_max, kk.rcp_v_max, kk.clip_v_f, GENERIC);
+        const double prev_t = __dmul_rn(kk.w_theta, fabs(div_f64_by_const(prev_sp, kk.theta_max, kk.rcp_theta_max)));
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
-        const double r = reward_f64(kc, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
+        const double r = reward_f64(kk, sh.reward[ds.level], phi_p, phi_v, phi_t, prev_p, prev_v, prev_t, succ_reward);
         // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
         const float qn = sh.qmax[sid2];
         const float changed = (e.bp != (uint32_t)ds.bp) ? 1.0f : 0.0f;
-        target = fadd((float)r, fmul(fmul(kc.gamma, qn), changed));
+        target = fadd((float)r, fmul(fmul(kk.gamma, qn), changed));
         if (TRACE) {
           if (args.trace.obs) {
             float* po = args.trace.obs + trace_i * 5;

@@ -208,6 +208,10 @@ const char* dqlb200_termination_string(int code);
 int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts,
                    const dqlb200_population_params* pop_params, int device, dqlb200_handle** out);
 int dqlb200_destroy(dqlb200_handle* h);
+/* 1 when the handle's configuration equals the reference-default configuration bit for bit, so that dqlb200_train runs the
+ * production instance whose MDP / dynamics constants are compile-time literals; 0: the generic instance (run-time constants,
+ * observation noise, any divisor).  Both instances produce identical results for the default configuration. */
+int dqlb200_uses_default_instance(dqlb200_handle* h);
 
 /* Borrow device buffers.
  *   env_state : DQLB200_ENV_STATE_BYTES * n_populations * envs_per_population bytes, 16-B aligned

@@ -531,3 +531,26 @@ def test_train_merged_graph_replay_equals_python_loop():
         assert int(e.population_state()["working_step"].max()) >= 1
     for a, b in zip(*out):
         assert torch.equal(a, b)
+
+
+def test_default_and_generic_instances_agree():
+    """The production instance of train_kernel has the reference-default MDP / dynamics constants compiled in (KDef); the generic
+    instance reads them at run time.  dqlb200_create picks the production instance only for a bit-identical configuration; the
+    trace instance is always generic, and both leave the same tables and env state."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    a = _engine(2, 150, threads_per_block=64, seeds=[1, 2], tp=kw)
+    assert a.lib.dqlb200_uses_default_instance(a.handle) == 1
+    c = _engine(2, 150, threads_per_block=64, seeds=[1, 2], tp=kw)
+    for e, trace in ((a, False), (c, True)):
+        e.reset(0)
+        e.train(300, trace=trace)
+    torch.cuda.synchronize()
+    assert torch.equal(a.tables, c.tables) and torch.equal(a.env_state, c.env_state) and torch.equal(a.pop_state, c.pop_state)
+    assert int(a.population_state()["working_step"].max()) >= 1
+    # per-population constants (platform amplitude / speed, axis) are run-time values: the production instance stays
+    d = _engine(1, 8, threads_per_block=32, dp=dict(r_mp=3.0, v_mp=0.8))
+    assert d.lib.dqlb200_uses_default_instance(d.handle) == 1
+    # anything that changes a compiled-in constant selects the generic instance
+    for dp in (dict(c_d=0.25), dict(z_init=3.0), dict(noise_pos_sd=0.1), dict(n_sub=2)):
+        e = _engine(1, 8, threads_per_block=32, dp=dp)
+        assert e.lib.dqlb200_uses_default_instance(e.handle) == 0, dp

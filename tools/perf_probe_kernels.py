@@ -30,3 +30,5 @@ o = eng.env_step(0, 10, act, auto_reset=True)
 s = timed(lambda: eng.agent_update(st, act, o["next_state"], o["reward"]))
 out["agent_update_kernel"] = dict(envs=n, populations=P, us=round(s * 1e6, 1), updates_per_s=f"{n / s:.3e}")
 print(json.dumps(out))
+s = timed(lambda: eng.env_step(0, 11, act, auto_reset=False))
+print(json.dumps(dict(env_step_no_auto_reset_us=round(s * 1e6, 1), env_steps_per_s=f"{n / s:.3e}")))
