@@ -264,11 +264,13 @@ template <class AC>
 __device__ __forceinline__ DState discretise_cuts(const dqlb200_cuts& c, const AC& angle_cut,
                                                   const Obs& o, int w = 4) {
   int lp = 0, lv = 0;
+  if (w > 0) {         // one uniform branch at working step 0 (the only level there); w is CTA-uniform
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    if (i < w) {       // levels above the working step do not exist (their cuts are NaN): skip, w is CTA-uniform
-      lp += (o.rel_p >= c.lvl_lo[0][i]) && !(o.rel_p >= c.lvl_hi[0][i]);
-      lv += (o.rel_v >= c.lvl_lo[1][i]) && !(o.rel_v >= c.lvl_hi[1][i]);
+    for (int i = 0; i < 4; ++i) {
+      if (i < w) {     // levels above the working step do not exist (their cuts are NaN): skip
+        lp += (o.rel_p >= c.lvl_lo[0][i]) && !(o.rel_p >= c.lvl_hi[0][i]);
+        lv += (o.rel_v >= c.lvl_lo[1][i]) && !(o.rel_v >= c.lvl_hi[1][i]);
+      }
     }
   }
   DState d;

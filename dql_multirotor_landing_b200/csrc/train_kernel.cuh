@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = env_i < n_p;
-      const size_t gi = env_base + (size_t)(valid ? env_i : 0);
+      const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
       if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage_addr, NT);      // in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
