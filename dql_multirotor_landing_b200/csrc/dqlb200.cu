@@ -354,9 +354,12 @@ int dqlb200_eval_greedy(dqlb200_handle* h, int population, const uint8_t* policy
   dqlb200_trace tr;
   if (trace) tr = *trace; else memset(&tr, 0, sizeof(tr));
   const long long blocks = (n_episodes + 255) / 256;
-  dql::eval_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode,
-                                                                     n_episodes, working_step, (dqlb200_eval_stats*)stats_out,
-                                                                     tr, trace ? trace_steps : 0);
+  if (h->kc_default)
+    dql::eval_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode, n_episodes,
+                                                                              working_step, (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
+  else
+    dql::eval_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, h->d_pop_params, population, policy, first_episode, n_episodes,
+                                                                             working_step, (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
@@ -427,8 +430,12 @@ int dqlb200_eval_greedy_2d(dqlb200_handle* h, const dqlb200_eval2d_params* p, co
   dqlb200_trace2d tr;
   if (trace) tr = *trace; else memset(&tr, 0, sizeof(tr));
   const long long blocks = (n_episodes + 255) / 256;
-  dql::eval2d_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, *p, policy_x, policy_y, first_episode, n_episodes,
-                                                                       (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
+  if (h->kc_default)
+    dql::eval2d_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, *p, policy_x, policy_y, first_episode, n_episodes,
+                                                                                (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
+  else
+    dql::eval2d_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(h->kc, *p, policy_x, policy_y, first_episode, n_episodes,
+                                                                               (dqlb200_eval_stats*)stats_out, tr, trace ? trace_steps : 0);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }

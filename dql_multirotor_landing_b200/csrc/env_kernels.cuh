@@ -1,7 +1,7 @@
 // env_kernels.cuh -- reset, greedy evaluation (one and two axes) and the un-fused gym-surface kernels
 // Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
 #pragma once
-#include "env_state.cuh"
+#include "train_kernel.cuh"
 
 namespace dql {
 
@@ -30,10 +30,12 @@ __global__ void reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, dqlb200
 // -------------------------------------------------------------------------------------------------
 // R15: greedy evaluation, SimulationMdp semantics (PKG/mdp.py:784-886, scripts/simulation.py:48-63)
 // -------------------------------------------------------------------------------------------------
+template <bool GENERIC>
 __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc, const dqlb200_population_params* pop_params,
                                                    int population, const uint8_t* __restrict__ policy,
                                                    long long first_episode, long long n_episodes, int w,
                                                    dqlb200_eval_stats* stats, dqlb200_trace trace, int trace_steps) {
+  const auto& kk = ConstsOf<GENERIC>::get(kc);
   __shared__ uint8_t s_policy[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
   __shared__ dqlb200_cuts cuts;
   __shared__ unsigned long long s_hist[9], s_steps, s_eps;
@@ -47,23 +49,23 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
     const unsigned long long ep = (unsigned long long)(first_episode + i);
     const uint4 d = philox4x32_10(make_uint4((uint32_t)ep, 0u, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
     Body b;
-    Obs o = dyn_reset(kc, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim);
-    uint32_t sid = (uint32_t)discretise_cuts(cuts, kc.angle_cut, o).id();
+    Obs o = dyn_reset(kk, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kk.dz_sim);
+    uint32_t sid = (uint32_t)discretise_cuts(cuts, kk.angle_cut, o).id();
     double sp = 0.0;
     int code = DQLB200_NON_TERMINAL;
     int step = 0;
     while (code < DQLB200_TERMINAL_SUCCESS) {
       const int a = s_policy[sid];
-      sp = apply_action(kc, sp, a);
-      dyn_advance(kc, pp, b, (float)sp);
+      sp = apply_action(kk, sp, a);
+      dyn_advance(kk, pp, b, (float)sp);
       step += 1;
-      o = dyn_observe(kc, pp, b, step, kc.dz_sim);
-      const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, kc.angle_cut, o).id();
+      o = dyn_observe(kk, pp, b, step, kk.dz_sim);
+      const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, kk.angle_cut, o).id();
       if (o.contact) code = DQLB200_TERMINAL_CONTACT;
-      else if (!(o.rel_p >= kc.fz_lo) || (o.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
-      else if (!(o.z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
-      else if (o.z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
-      else if (step >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
+      else if (!(o.rel_p >= kk.fz_lo) || (o.rel_p >= kk.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
+      else if (!(o.z >= kk.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+      else if (o.z >= kk.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
+      else if (step >= kk.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
       if (step <= trace_steps) {
         const size_t ti = (size_t)(step - 1) * (size_t)n_episodes + (size_t)i;
         if (trace.obs) {
@@ -209,7 +211,8 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
 struct Axis {
   float pos, vel, ang, acc;
 };
-__device__ __forceinline__ void axis_advance(const KC& kc, Axis& b, float sp, float g) {
+template <class KT>
+__device__ __forceinline__ void axis_advance(const KT& kc, Axis& b, float sp, float g) {
   b.ang = fadd(b.ang, fmul(fsub(sp, b.ang), kc.k_theta));
   b.acc = fsub(fmul(g, det_tan(b.ang)), fmul(kc.c_d, b.vel));
   b.pos = fadd(fadd(b.pos, fmul(b.vel, kc.h)), fmul(b.acc, kc.half_h2));
@@ -235,10 +238,12 @@ __device__ __forceinline__ Platform2D platform_2d(const dqlb200_eval2d_params& p
   return m;
 }
 
+template <bool GENERIC>
 __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC kc, const __grid_constant__ dqlb200_eval2d_params p,
                                                      const uint8_t* __restrict__ policy_x, const uint8_t* __restrict__ policy_y,
                                                      long long first_episode, long long n_episodes, dqlb200_eval_stats* stats,
                                                      dqlb200_trace2d trace, int trace_steps) {
+  const auto& kk = ConstsOf<GENERIC>::get(kc);
   __shared__ uint8_t s_pol_x[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL], s_pol_y[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
   __shared__ dqlb200_cuts cuts;
   __shared__ unsigned long long s_hist[9], s_steps, s_eps;
@@ -254,13 +259,13 @@ __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC 
     const unsigned long long ep = (unsigned long long)(first_episode + i);
     const uint4 d = philox4x32_10(make_uint4((uint32_t)ep, 0u, PURPOSE_RESET, p.stream_id), p.seed_lo, p.seed_hi);
     // PKG/landing_simulation_env.py:327-340: uniform offsets inside the fly zone, absolute clip, random platform phase
-    const float x_init = fadd(-kc.p_max_f, fmul(kc.two_p_max_f, fmul(__uint2float_rn(d.x >> 8), (float)(1.0 / 16777216.0))));
-    const float y_init = fadd(-kc.p_max_f, fmul(kc.two_p_max_f, fmul(__uint2float_rn(d.y >> 8), (float)(1.0 / 16777216.0))));
+    const float x_init = fadd(-kk.p_max_f, fmul(kk.two_p_max_f, fmul(__uint2float_rn(d.x >> 8), (float)(1.0 / 16777216.0))));
+    const float y_init = fadd(-kk.p_max_f, fmul(kk.two_p_max_f, fmul(__uint2float_rn(d.y >> 8), (float)(1.0 / 16777216.0))));
     uint32_t phase_x = d.z, phase_y = (p.trajectory == 2) ? d.z : d.w;
     Platform2D m = platform_2d(p, phase_x, phase_y);
     Axis bx, by;
-    bx.pos = clipf(fsub(m.xm, x_init), -kc.p_max_f, kc.p_max_f);
-    by.pos = p.y_init_enabled ? clipf(fsub(m.ym, y_init), -kc.p_max_f, kc.p_max_f) : 0.0f;
+    bx.pos = clipf(fsub(m.xm, x_init), -kk.p_max_f, kk.p_max_f);
+    by.pos = p.y_init_enabled ? clipf(fsub(m.ym, y_init), -kk.p_max_f, kk.p_max_f) : 0.0f;
     bx.vel = bx.ang = bx.acc = by.vel = by.ang = by.acc = 0.0f;
     double sp_x = 0.0, sp_y = 0.0;
     int code = DQLB200_NON_TERMINAL, step = -1;
@@ -270,12 +275,12 @@ __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC 
       if (step >= 0) {          // step == -1: the hover period after the reset (PKG/landing_simulation_env.py:222-224)
         ax = s_pol_x[sid_x];
         ay = s_pol_y[sid_y];
-        sp_x = apply_action(kc, sp_x, ax);
-        if (p.y_action_enabled) sp_y = apply_action(kc, sp_y, ay);
+        sp_x = apply_action(kk, sp_x, ax);
+        if (p.y_action_enabled) sp_y = apply_action(kk, sp_y, ay);
       }
-      for (int k = 0; k < kc.n_sub; ++k) {
-        axis_advance(kc, bx, (float)sp_x, p.g_x);
-        axis_advance(kc, by, (float)sp_y, p.g_y);
+      for (int k = 0; k < kk.n_sub; ++k) {
+        axis_advance(kk, bx, (float)sp_x, p.g_x);
+        axis_advance(kk, by, (float)sp_y, p.g_y);
         phase_x += p.dphase_x;
         phase_y += p.dphase_y;
       }
@@ -284,17 +289,17 @@ __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC 
       Obs ox, oy;
       ox.rel_p = fsub(m.xm, bx.pos); ox.rel_v = fsub(m.um, bx.vel); ox.rel_a = fsub(m.axm, bx.acc); ox.pitch = bx.ang;
       oy.rel_p = fsub(m.ym, by.pos); oy.rel_v = fsub(m.vm, by.vel); oy.rel_a = fsub(m.aym, by.acc); oy.pitch = by.ang;
-      const float z = fadd(kc.z_init, fmul(__int2float_rn(step), kc.dz_sim));
-      const bool contact = (z <= kc.z_touch) && (fabsf(ox.rel_p) <= kc.half_platform) && (fabsf(oy.rel_p) <= kc.half_platform);
-      sid_x = (uint32_t)discretise_cuts(cuts, kc.angle_cut, ox).id();
-      sid_y = (uint32_t)discretise_cuts(cuts, kc.angle_cut, oy).id();
+      const float z = fadd(kk.z_init, fmul(__int2float_rn(step), kk.dz_sim));
+      const bool contact = (z <= kk.z_touch) && (fabsf(ox.rel_p) <= kk.half_platform) && (fabsf(oy.rel_p) <= kk.half_platform);
+      sid_x = (uint32_t)discretise_cuts(cuts, kk.angle_cut, ox).id();
+      sid_y = (uint32_t)discretise_cuts(cuts, kk.angle_cut, oy).id();
       if (step == 0) continue;          // the reset only observes (no check, PKG/landing_simulation_env.py:236-243)
       if (contact) code = DQLB200_TERMINAL_CONTACT;
-      else if (!(ox.rel_p >= kc.fz_lo) || (ox.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
-      else if (!(oy.rel_p >= kc.fz_lo) || (oy.rel_p >= kc.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_Y;
-      else if (!(z >= kc.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
-      else if (z >= kc.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
-      else if (step >= kc.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
+      else if (!(ox.rel_p >= kk.fz_lo) || (ox.rel_p >= kk.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
+      else if (!(oy.rel_p >= kk.fz_lo) || (oy.rel_p >= kk.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_Y;
+      else if (!(z >= kk.z_min_cut)) code = DQLB200_TERMINAL_MINIMUM_ALTITUDE;
+      else if (z >= kk.z_max_cut) code = DQLB200_TERMINAL_FLYZONE_Z;
+      else if (step >= kk.timeout_steps) code = DQLB200_TERMINAL_TIMEOUT;
       if (step <= trace_steps) {
         const size_t ti = (size_t)(step - 1) * (size_t)n_episodes + (size_t)i;
         if (trace.obs) {
