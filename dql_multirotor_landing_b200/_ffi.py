@@ -14,7 +14,7 @@ SYMBOLS = [
     "dqlb200_abi_version", "dqlb200_config_bytes", "dqlb200_population_state_bytes", "dqlb200_last_error",
     "dqlb200_termination_string", "dqlb200_create", "dqlb200_destroy", "dqlb200_bind", "dqlb200_reset",
     "dqlb200_train", "dqlb200_train_host", "dqlb200_eval_greedy", "dqlb200_transfer", "dqlb200_check_errors",
-    "dqlb200_shared_pack", "dqlb200_shared_apply", "dqlb200_mdp_facade_step", "dqlb200_agent_facade", "dqlb200_selftest_division", "dqlb200_replica_merge", "dqlb200_bind_merge_snapshot", "dqlb200_eval_greedy_2d", "dqlb200_eval2d_params_bytes", "dqlb200_bench_table_rmw", "dqlb200_train_merged", "dqlb200_env_reset", "dqlb200_env_step", "dqlb200_agent_select", "dqlb200_agent_update", "dqlb200_uses_default_instance",
+    "dqlb200_shared_pack", "dqlb200_shared_apply", "dqlb200_mdp_facade_step", "dqlb200_agent_facade", "dqlb200_selftest_division", "dqlb200_replica_merge", "dqlb200_bind_merge_snapshot", "dqlb200_eval_greedy_2d", "dqlb200_eval2d_params_bytes", "dqlb200_bench_table_rmw", "dqlb200_train_merged", "dqlb200_env_reset", "dqlb200_env_step", "dqlb200_agent_select", "dqlb200_agent_update", "dqlb200_uses_default_instance", "dqlb200_config_is_default",
 ]
 
 OP_ACTION, OP_OBSERVE, OP_CHECK, OP_REWARD, OP_RESET, OP_SIMULATION = 1, 2, 4, 8, 16, 256
@@ -50,6 +50,7 @@ def load() -> C.CDLL:
     lib.dqlb200_create.argtypes = [C.POINTER(K.Config), C.POINTER(C.c_float), C.POINTER(K.PopulationParams), i32, C.POINTER(vp)]
     lib.dqlb200_destroy.argtypes = [vp]
     lib.dqlb200_uses_default_instance.argtypes = [vp]
+    lib.dqlb200_config_is_default.argtypes = [C.POINTER(K.Config)]
     lib.dqlb200_bind.argtypes = [vp, vp, vp, vp]
     lib.dqlb200_reset.argtypes = [vp, i32, vp]
     lib.dqlb200_train.argtypes = [vp, i32, C.POINTER(K.Trace), vp]

@@ -202,6 +202,13 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
 
 int dqlb200_uses_default_instance(dqlb200_handle* h) { return (h && h->kc_default) ? 1 : 0; }
 
+int dqlb200_config_is_default(const dqlb200_config* cfg) {
+  if (!cfg || cfg->struct_bytes != sizeof(dqlb200_config)) return fail(DQLB200_ERR_ARG, "dqlb200_config size mismatch");
+  dql::KC k;
+  fill_kc(*cfg, k);
+  return dql::kdef_matches(k) ? 1 : 0;
+}
+
 int dqlb200_destroy(dqlb200_handle* h) {
   if (!h) return DQLB200_OK;
   cudaSetDevice(h->device);

@@ -212,6 +212,8 @@ int dqlb200_destroy(dqlb200_handle* h);
  * production instance whose MDP / dynamics constants are compile-time literals; 0: the generic instance (run-time constants,
  * observation noise, any divisor).  Both instances produce identical results for the default configuration. */
 int dqlb200_uses_default_instance(dqlb200_handle* h);
+/* The same test on a configuration, host only (no device needed): 1 / 0, negative on a malformed struct. */
+int dqlb200_config_is_default(const dqlb200_config* cfg);
 
 /* Borrow device buffers.
  *   env_state : DQLB200_ENV_STATE_BYTES * n_populations * envs_per_population bytes, 16-B aligned

@@ -74,3 +74,16 @@ def test_npy_layout_of_committed_assets():
     for name in ("Q_table_a.npy", "Q_table_b.npy", "state_action_count.npy"):
         a = np.load(ROOT / "assets" / name)
         assert a.shape == (5, 3, 3, 3, 7, 3) and a.dtype == np.float64 and a.flags["C_CONTIGUOUS"]
+
+
+def test_compiled_in_defaults_match_constants_py():
+    """The production kernel instances carry the reference-default constants as literals (csrc/dqlb200_device.cuh: KDef).  They
+    must equal what constants.py derives for the default parameters bit for bit -- otherwise every default run would silently
+    fall back to the slower generic instance.  Host-only check, no GPU needed."""
+    import ctypes as C
+    lib = _ffi.load()
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128))) == 1
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(c_d=0.21)))) == 0
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, mp=K.MdpParameters(p_max=4.0)))) == 0
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(noise_vel_sd=0.1)))) == 0
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(v_mp=0.8, r_mp=3.0)))) == 1
