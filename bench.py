@@ -435,7 +435,7 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
         hot = np.bincount(cells, minlength=2835)
         out["table_rmw_roof"] = {"visits_per_s": rmw["visits_per_s"], "rmw_per_s": rmw["rmw_per_s"],
                                  "distinct_cells": int((hot > 0).sum()), "hottest_cell_share": float(hot.max() / hot.sum()),
-                                 "what": "2 unordered shared-memory atomics (red.shared.add.f32 + .u32) per recorded visit, 1036 CTAs x 128 "
+                                 "what": "2 unordered shared-memory atomics (red.shared.add.f32 + .u32) per recorded visit, 888 CTAs x 128 "
                                          "threads, tables in shared memory; an upper bound for the table update alone, NOT deterministic"}
         et.close()
     except Exception as exc:

@@ -151,7 +151,7 @@ class Engine:
         self.merge_snapshot = None
         _ffi.check(self.lib.dqlb200_bind_merge_snapshot(self.handle, None))
 
-    def bench_table_rmw(self, cells: np.ndarray, visits_per_thread: int = 256, threads: int = 128, blocks: int = 1036, reps: int = 5) -> dict:
+    def bench_table_rmw(self, cells: np.ndarray, visits_per_thread: int = 256, threads: int = 128, blocks: int = 888, reps: int = 5) -> dict:
         """Measurement aid: rate of UNORDERED shared-memory read-modify-writes on a recorded sequence of visited
         cells (uint16, cell = state * 3 + action), two RMW per visit.  Returns visits/s (CUDA events, best of reps)."""
         dev = self.device
