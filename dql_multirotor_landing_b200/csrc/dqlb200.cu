@@ -598,6 +598,15 @@ int dqlb200_bench_table_rmw(dqlb200_handle* h, const uint16_t* cells, int64_t n_
   return DQLB200_OK;
 }
 
+int dqlb200_bench_launch_floor(dqlb200_handle* h, int blocks, int threads, int smem_bytes, void* stream) {
+  if (!h || blocks < 1 || threads < 32 || threads > 1024 || smem_bytes < 0 || smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "bad launch shape");
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaFuncSetAttribute(dql::launch_floor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+  dql::launch_floor_kernel<<<blocks, threads, smem_bytes, (cudaStream_t)stream>>>(h->kc, (int*)h->d_error);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
 int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void* stream) {
   if (!h || !mismatches_out) return fail(DQLB200_ERR_ARG, "null argument");
   CUDA_TRY(cudaSetDevice(h->device));

@@ -361,6 +361,10 @@ int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_
 int dqlb200_bench_table_rmw(dqlb200_handle* h, const uint16_t* cells, int64_t n_cells, int visits_per_thread, int threads,
                             int blocks, void* checksum_out, void* stream);
 
+/* Measurement aid: launches an empty kernel with train_kernel's launch shape (grid, block, dynamic shared memory, by-value
+ * parameter block); timed by the caller to separate the cost of launching from the cost of the work. */
+int dqlb200_bench_launch_floor(dqlb200_handle* h, int blocks, int threads, int smem_bytes, void* stream);
+
 /* Device self-test: the 3-instruction float64 division used for fp32 numerators (x / p_max, x / v_max) against
  * the IEEE division for every finite fp32 bit pattern; mismatches_out[0] = wrong quotients of the production
  * routine (must be 0), [1] = of the one-correction-step variant (diagnostic), [2] = of the float64-numerator

@@ -14,7 +14,7 @@ def timed(fn, flush, reps=7):
         best = min(best, e0.elapsed_time(e1))
     return round(best * 1e3, 1)
 
-P, n_p, tpb = 1036, 1152, 128
+P, n_p, tpb = 888, 1280, 128
 eng = Engine(P, n_p, threads_per_block=tpb, seeds=list(range(P)), tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10**12))
 eng.reset(0); eng.train(300); torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
@@ -28,4 +28,10 @@ ps[:, off:off + 4] = torch.tensor(np.frombuffer(np.int32(1).tobytes(), np.uint8)
 out["train_k1_finished_populations_us"] = timed(lambda: eng.train(1), flush)
 ps.copy_(saved)
 out["train_k1_again_us"] = timed(lambda: eng.train(1), flush)
+import ctypes as C
+lib, hnd = eng.lib, eng.handle
+st = lambda: C.c_void_p(torch.cuda.current_stream().cuda_stream)
+out["empty_kernel_888x128_35KB_smem_us"] = timed(lambda: lib.dqlb200_bench_launch_floor(hnd, 888, 128, 36000, st()), flush)
+out["empty_kernel_888x128_no_smem_us"] = timed(lambda: lib.dqlb200_bench_launch_floor(hnd, 888, 128, 0, st()), flush)
+out["empty_kernel_148x128_no_smem_us"] = timed(lambda: lib.dqlb200_bench_launch_floor(hnd, 148, 128, 0, st()), flush)
 print(json.dumps(out))
