@@ -34,7 +34,7 @@ ALPHA_LUT = 1003
 EPS_LUT = 2002
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 LIMITS_POSITION = [1.0, 0.64, 0.4096, 0.262144, 0.16777216]   # PKG/mdp.py:45-47
 LIMITS_VELOCITY = [1.0, 0.8, 0.64, 0.512, 0.4096]              # PKG/mdp.py:48-50
@@ -87,6 +87,7 @@ class Config(C.Structure):
         ("window_len", C.c_int32), ("promote_successes", C.c_int32), ("max_num_episodes", C.c_int64),
         ("n_alpha_luts", C.c_int32), ("replicas_per_population", C.c_int32),
         ("noise_pos_sd", C.c_float), ("noise_vel_sd", C.c_float),
+        ("accel_mode", C.c_int32), ("kf_q", C.c_float), ("kf_r", C.c_float),
         ("eps_threshold", C.c_uint32 * EPS_LUT),
     ]
 
@@ -178,6 +179,9 @@ class MdpParameters:
     minimum_altitude: float = 0.2
 
 
+ACCEL_MODES = {"exact": 0, "kalman_reference": 1, "kalman": 2}
+
+
 @dataclass
 class DynamicsParameters:
     """Analytic stand-in for the Gazebo/RotorS path (parameters traced in SURVEY.md A.3)."""
@@ -194,6 +198,11 @@ class DynamicsParameters:
     n_sub: int = 1
     noise_pos_sd: float = 0.0        # Gaussian noise on the observed rel. position   PKG/observation_utils.py:127-129 (launch: 0)
     noise_vel_sd: float = 0.0        # ... and velocity (manager_node defaults 0.25 / 0.1, launch/environment.launch:56-57 sets 0)
+    # relative acceleration seen by the MDP: "exact" (analytic), "kalman_reference" (PKG/filters.py:4-80 over the finite
+    # difference against the FIRST sample, as PKG/observation_utils.py:137-150 is written), "kalman" (consecutive samples)
+    accel_mode: str = "exact"
+    kf_process_variance: float = 1e-4      # scripts/manager_node.py:96-98
+    kf_measurement_sd: float = 0.1         # manager_node passes noise_vel_sd (default 0.1); R = sd ** 2 (PKG/filters.py:50-52)
 
 
 @dataclass
@@ -456,6 +465,8 @@ def build_config(n_populations: int, envs_per_population: int, threads_per_block
     cfg.p_max_f, cfg.two_p_max_f, cfg.sigma_x = mp.p_max, 2.0 * mp.p_max, mp.p_max / 3.0
     cfg.n_sub = dp.n_sub
     cfg.noise_pos_sd, cfg.noise_vel_sd = dp.noise_pos_sd, dp.noise_vel_sd
+    cfg.accel_mode = ACCEL_MODES[dp.accel_mode]
+    cfg.kf_q, cfg.kf_r = dp.kf_process_variance, dp.kf_measurement_sd ** 2
     cfg.gamma = tp.gamma
     for k in range(MAX_CURRICULUM):
         cfg.transfer_ratio[k] = transfer_learning_ratio(k, tp.scale_modification_value)

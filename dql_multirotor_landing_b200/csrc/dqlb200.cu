@@ -52,6 +52,7 @@ struct dqlb200_handle {
   void* tables;
   void* pop_state;
   void* merge_snapshot;
+  void* filter_state;       // accel_mode != 0: [n_total] x 16 B estimator state (dqlb200_bind_filter_state)
   bool kc_default;              // the configuration equals the compile-time defaults: the production instance may run
   size_t smem_bytes;
   // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
@@ -126,6 +127,7 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   k.gamma = c.gamma;
   k.noise_pos_sd = c.noise_pos_sd; k.noise_vel_sd = c.noise_vel_sd;
   k.noise_enabled = (c.noise_pos_sd != 0.0f || c.noise_vel_sd != 0.0f) ? 1 : 0;
+  k.accel_mode = c.accel_mode; k.kf_q = c.kf_q; k.kf_r = c.kf_r;
   memcpy(k.transfer_ratio, c.transfer_ratio, sizeof(k.transfer_ratio));
   k.timeout_steps = c.timeout_steps; k.success_steps = c.success_steps; k.n_sub = c.n_sub;
   k.transfer_mode = c.transfer_mode; k.window_len = c.window_len; k.promote_successes = c.promote_successes;
@@ -146,6 +148,9 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) return fail(DQLB200_ERR_ARG, "threads_per_block must be 32, 64, 128 or 256");
   if (cfg->window_len < 1 || cfg->window_len > DQLB200_MAX_WINDOW) return fail(DQLB200_ERR_ARG, "window_len out of range");
   if (cfg->n_alpha_luts < 1 || cfg->n_sub < 1) return fail(DQLB200_ERR_ARG, "n_alpha_luts / n_sub must be >= 1");
+  if (cfg->accel_mode < 0 || cfg->accel_mode > 2) return fail(DQLB200_ERR_ARG, "accel_mode must be 0 (exact), 1 (reference filter) or 2 (consecutive-sample filter)");
+  if (cfg->accel_mode != 0 && (!(cfg->kf_q >= 0.0f) || !(cfg->kf_r >= 0.0f) || !(cfg->kf_q + cfg->kf_r > 0.0f)))
+    return fail(DQLB200_ERR_ARG, "acceleration filter needs non-negative variances, not both zero");
   if (cfg->replicas_per_population < 1 || cfg->n_populations % cfg->replicas_per_population)
     return fail(DQLB200_ERR_ARG, "n_populations must be a multiple of replicas_per_population (>= 1)");
   for (int p = 0; p < cfg->n_populations; ++p)
@@ -164,7 +169,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   fill_kc(*cfg, h->kc);
   h->kc_default = dql::kdef_matches(h->kc);
   h->device = device;
-  h->env_state = h->tables = h->pop_state = h->merge_snapshot = nullptr;
+  h->env_state = h->tables = h->pop_state = h->merge_snapshot = h->filter_state = nullptr;
   h->chunk_ready = false;
   h->merged_ready = false;
   h->merged_exec = nullptr;
@@ -244,18 +249,33 @@ int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_sta
   return DQLB200_OK;
 }
 
+int dqlb200_bind_filter_state(dqlb200_handle* h, void* filter_state) {
+  if (!h) return fail(DQLB200_ERR_ARG, "null handle");
+  if ((uintptr_t)filter_state & 15u) return fail(DQLB200_ERR_ARG, "misaligned filter_state (needs 16 B)");
+  h->filter_state = filter_state;
+  h->merged_k = 0;                 // a captured graph holds the old pointer
+  return DQLB200_OK;
+}
+
+// accel_mode != 0 and no estimator state bound: refuse instead of computing with the exact acceleration
+static bool filter_missing(const dqlb200_handle* h) { return h->cfg.accel_mode != 0 && !h->filter_state; }
+#define DQL_NEED_FILTER(h) \
+  if (filter_missing(h)) return fail(DQLB200_ERR_STATE, "accel_mode != 0 needs dqlb200_bind_filter_state()")
+
 static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
   const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
   dql::EnvPtrs p;
   p.a = reinterpret_cast<float4*>(base);
   p.b = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 16 * n);
   p.c = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 32 * n);
+  p.d = h->cfg.accel_mode != 0 ? reinterpret_cast<uint4*>(h->filter_state) : nullptr;
   return p;
 }
 
 int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
   if (initial_step < 0 || initial_step >= h->cfg.curriculum_steps) return fail(DQLB200_ERR_ARG, "initial_step out of range");
+  DQL_NEED_FILTER(h);
   CUDA_TRY(cudaSetDevice(h->device));
   const dim3 grid((h->cfg.envs_per_population + 255) / 256, h->cfg.n_populations);
   dql::reset_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state),
@@ -300,6 +320,7 @@ int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, vo
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
   if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
   if (k_steps == 0) return DQLB200_OK;
+  DQL_NEED_FILTER(h);
   CUDA_TRY(cudaSetDevice(h->device));
   return launch_train(h, k_steps, trace, h->env_state, h->tables, h->pop_state, (cudaStream_t)stream);
 }
@@ -308,6 +329,7 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
                        void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
   if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
+  if (h->cfg.accel_mode != 0) return fail(DQLB200_ERR_ARG, "dqlb200_train_host does not carry the estimator state (accel_mode != 0): use dqlb200_train on bound device buffers");
   if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
@@ -375,6 +397,7 @@ int dqlb200_env_reset(dqlb200_handle* h, int working_step, uint32_t birth, const
                       uint16_t* out_state, void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
   if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  DQL_NEED_FILTER(h);
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
   dql::env_reset_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(h->kc, env_ptrs(h, h->env_state), h->d_pop_params, working_step,
@@ -389,6 +412,7 @@ int dqlb200_env_step(dqlb200_handle* h, int working_step, uint32_t t, const int8
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound");
   if (!actions) return fail(DQLB200_ERR_ARG, "actions required");
   if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  DQL_NEED_FILTER(h);
   CUDA_TRY(cudaSetDevice(h->device));
   const long long n = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
   const unsigned blocks = (unsigned)((n + 127) / 128);
@@ -550,6 +574,7 @@ int dqlb200_train_merged(dqlb200_handle* h, int total_steps, int merge_every, in
   if (!h->merge_snapshot) return fail(DQLB200_ERR_STATE, "bind the merge snapshot first (dqlb200_bind_merge_snapshot)");
   if (total_steps < 0 || merge_every < 1) return fail(DQLB200_ERR_ARG, "total_steps >= 0 and merge_every >= 1 required");
   if (total_steps == 0) return DQLB200_OK;
+  DQL_NEED_FILTER(h);
   CUDA_TRY(cudaSetDevice(h->device));
   if (!h->merged_ready) {
     CUDA_TRY(cudaStreamCreateWithFlags(&h->merged_stream, cudaStreamNonBlocking));

@@ -32,6 +32,8 @@ struct KC {
   float clip_p_f, clip_v_f;     // smallest fp32 |x| whose quotient x / p_max (x / v_max) rounds to >= 1
   float noise_pos_sd, noise_vel_sd;
   int32_t noise_enabled;        // either standard deviation is non-zero
+  int32_t accel_mode;           // 0 exact, 1 / 2 Kalman-filtered finite difference (dqlb200_config.accel_mode)
+  float kf_q, kf_r;
   float gamma;
   float transfer_ratio[DQLB200_MAX_CURRICULUM];
   int32_t timeout_steps, success_steps, n_sub;
@@ -57,7 +59,8 @@ struct KDef {
   static constexpr double w_p = -100.0, w_v = -10.0, w_theta = -0x1.8cccccccccccdp+0;
   static constexpr double rcp_p_max = 1.0 / p_max, rcp_v_max = 1.0 / v_max, rcp_theta_max = 1.0 / theta_max;
   static constexpr int32_t timeout_steps = 459, success_steps = 23, n_sub = 1;
-  static constexpr int32_t noise_enabled = 0;
+  static constexpr int32_t noise_enabled = 0, accel_mode = 0;
+  static constexpr float kf_q = 0.0f, kf_r = 0.0f;
   static constexpr float noise_pos_sd = 0.0f, noise_vel_sd = 0.0f;
   struct AngleCut {          // constant-index reads fold into literals
     __host__ __device__ constexpr float operator[](int i) const {
@@ -76,7 +79,7 @@ inline bool kdef_matches(const KC& k) {
             k.theta_max == KDef::theta_max && k.delta_theta == KDef::delta_theta && k.w_p == KDef::w_p && k.w_v == KDef::w_v &&
             k.w_theta == KDef::w_theta && k.rcp_p_max == KDef::rcp_p_max && k.rcp_v_max == KDef::rcp_v_max && k.rcp_theta_max == KDef::rcp_theta_max &&
             k.timeout_steps == KDef::timeout_steps && k.success_steps == KDef::success_steps && k.n_sub == KDef::n_sub && k.noise_enabled == 0 &&
-            k.div_two_steps == 0;
+            k.accel_mode == 0 && k.div_two_steps == 0;
   for (int i = 0; i < 6; ++i) ok = ok && k.angle_cut[i] == KDef::AngleCut{}[i];
   return ok;
 }
@@ -192,26 +195,56 @@ struct Obs {
   bool contact;
 };
 
+// Acceleration estimator of the reference's observation node: KalmanFilter1D (PKG/filters.py:4-37) fed with a
+// finite difference of the TRUE relative velocity (PKG/filters.py:54-80, PKG/observation_utils.py:134-150).  fp32, every operation
+// rounded separately (oracle/dynamics.py: KalmanAccel is the same arithmetic in NumPy float32).
+struct Kf {
+  float x, P, v_ref;      // estimate, variance, anchor (mode 1: first sample ever) or previous (mode 2) relative velocity
+  uint32_t n;             // samples seen (mode 2: 0 or 1)
+};
 template <class KT>
-__device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_population_params& pp, Body& b, float sp) {
+__device__ __forceinline__ void kf_sample(const KT& kc, Kf& f, float rel_v) {
+  if (f.n == 0u) {        // PKG/observation_utils.py:137-143: the first sample only sets the anchor, the filter is not touched
+    f.v_ref = rel_v;
+    f.n = 1u;
+    return;
+  }
+  const float dt = (kc.accel_mode == 1) ? fmul(__uint2float_rn(f.n), kc.h) : kc.h;
+  const float raw = __fdiv_rn(fsub(rel_v, f.v_ref), dt);
+  f.P = fadd(f.P, kc.kf_q);                                   // PKG/filters.py:31-35
+  const float K = __fdiv_rn(f.P, fadd(f.P, kc.kf_r));
+  f.x = fadd(f.x, fmul(K, fsub(raw, f.x)));
+  f.P = fmul(f.P, fsub(1.0f, K));
+  if (kc.accel_mode == 1) f.n += 1u;      // quirk Q13: the anchor is never refreshed, the time base keeps growing
+  else f.v_ref = rel_v;
+}
+
+template <class KT>
+__device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_population_params& pp, Body& b, float sp, Kf* kf = nullptr) {
   for (int i = 0; i < kc.n_sub; ++i) {
     b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
     b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
     b.x_d = fadd(fadd(b.x_d, fmul(b.v_d, kc.h)), fmul(b.a_d, kc.half_h2));
     b.v_d = fadd(b.v_d, fmul(b.a_d, kc.h));
     b.phase += pp.dphase;
+    if (kc.accel_mode != 0 && kf) {       // one estimator sample per sub-step (the node publishes at the sub-step rate)
+      float s, c;
+      det_sincos_turns(b.phase, s, c);
+      kf_sample(kc, *kf, fsub(fmul(pp.rw, c), b.v_d));
+    }
   }
 }
 
 template <class KT>
 __device__ __forceinline__ Obs dyn_observe(const KT& kc, const dqlb200_population_params& pp, const Body& b,
-                                           int step_count, float dz) {
+                                           int step_count, float dz, const Kf* kf = nullptr) {
   float s, c;
   det_sincos_turns(b.phase, s, c);
   Obs o;
   o.rel_p = fsub(fmul(pp.r, s), b.x_d);
   o.rel_v = fsub(fmul(pp.rw, c), b.v_d);
   o.rel_a = fsub(-fmul(pp.rw2, s), b.a_d);
+  if (kc.accel_mode != 0 && kf) o.rel_a = kf->x;
   o.pitch = b.theta;
   o.z = fadd(kc.z_init, fmul(__int2float_rn(step_count), dz));
   o.contact = (o.z <= kc.z_touch) && (fabsf(o.rel_p) <= kc.half_platform);
@@ -231,7 +264,7 @@ __device__ __forceinline__ void add_observation_noise(const KT& kc, Obs& o, uint
 // R1 (PKG/landing_simulation_env.py:181-216) and R15 (:327-340), then one hover period (:222-224).
 template <class KT>
 __device__ __forceinline__ Obs dyn_reset(const KT& kc, const dqlb200_population_params& pp, Body& b, uint4 w,
-                                         bool normal_init, bool simulation, float dz) {
+                                         bool normal_init, bool simulation, float dz, Kf* kf = nullptr) {
   float x_init;
   if (normal_init) {
     x_init = fmul(kc.sigma_x, det_normal(w.x, w.y));
@@ -248,8 +281,8 @@ __device__ __forceinline__ Obs dyn_reset(const KT& kc, const dqlb200_population_
   b.v_d = 0.0f;
   b.theta = 0.0f;
   b.a_d = 0.0f;
-  dyn_advance(kc, pp, b, 0.0f);
-  return dyn_observe(kc, pp, b, 0, dz);
+  dyn_advance(kc, pp, b, 0.0f, kf);       // the estimator keeps sampling through the teleport and the hover period
+  return dyn_observe(kc, pp, b, 0, dz, kf);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -27,7 +27,16 @@ struct EnvPtrs {
   float4* a;
   uint4* b;
   uint4* c;
+  uint4* d;      // acceleration-estimator state (accel_mode != 0 only, else null): {x, P, v_ref, n}
 };
+__device__ __forceinline__ Kf kf_load(const EnvPtrs& p, size_t i) {
+  const uint4 v = p.d[i];
+  return Kf{__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), v.w};
+}
+__device__ __forceinline__ void kf_store(const EnvPtrs& p, size_t i, const Kf& f) {
+  p.d[i] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.P), __float_as_uint(f.v_ref), f.n);
+}
+__device__ __forceinline__ Kf kf_initial() { return Kf{0.0f, 1.0f, 0.0f, 0u}; }      // PKG/filters.py:15-16
 
 struct EnvRaw {
   float4 A;
@@ -95,9 +104,9 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
 template <class KT, class AC>
 __device__ __forceinline__ void env_reset(const KT& kc, const dqlb200_population_params& pp,
                                           const dqlb200_cuts& cuts, const AC& angle_cut, Env& e,
-                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp) {
+                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp, Kf* kf = nullptr) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
-  Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train);
+  Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train, kf);
   if (kc.noise_enabled) {
     const uint4 dn = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET_NOISE, pp.population_id), pp.seed_lo, pp.seed_hi);
     add_observation_noise(kc, o, dn.x, dn.y);

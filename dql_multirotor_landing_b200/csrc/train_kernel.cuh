@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
 
   const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
   const float alpha_min = __ldg(alpha_lut + DQLB200_ALPHA_LUT - 1);      // alpha(count >= 1002), PKG/trainer.py:95-105
+  const bool filt = GENERIC && kk.accel_mode != 0;      // acceleration estimator: 16 more bytes per env, generic instance only
   uint64_t steps_done = 0;
 
   // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
@@ -183,8 +184,11 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const int env_i = slot * NT + tid;
         if (env_i < n_p) {
           Env e;
-          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true);
+          Kf kf;
+          if (filt) kf = kf_load(args.env, env_base + env_i);       // the estimator outlives the curriculum step
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true, filt ? &kf : nullptr);
           env_store(args.env, env_base + env_i, e);
+          if (filt) kf_store(args.env, env_base + env_i, kf);
         }
       }
     }
@@ -231,8 +235,11 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
           const size_t gr = env_base + (size_t)env_r;
           Env e;
           env_load(args.env, gr, e);
-          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false);
+          Kf kf;
+          if (filt) kf = kf_load(args.env, gr);
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr);
           env_store(args.env, gr, e);
+          if (filt) kf_store(args.env, gr, kf);
         }
       }
       __syncwarp();
@@ -253,10 +260,12 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       uint32_t ep_steps = 0;
       double ep_return = 0.0;
       Env e;
+      Kf kf;
       uint32_t c_hint = 0;
       float a_hint = 0.0f;
       if (valid) {
         env_unpack(cur_raw, e);
+        if (filt) kf = kf_load(args.env, gi);
         const uint32_t sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
@@ -288,9 +297,9 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const double prev_sp = e.theta_sp;
         const double sp = apply_action(kk, e.fresh ? 0.0 : e.theta_sp, a);
         // R4
-        dyn_advance(kk, pp, e.b, (float)sp);
+        dyn_advance(kk, pp, e.b, (float)sp, filt ? &kf : nullptr);
         const uint32_t step_count = e.step_count + 1u;
-        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train);
+        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr);
         if (GENERIC && kk.noise_enabled) add_observation_noise(kk, o, noise_w0, noise_w1);
         // R5
         const DState ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
@@ -451,6 +460,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
       // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
       if (valid) env_store(args.env, gi, e);
+      if (filt && valid) kf_store(args.env, gi, kf);
       // queue the finished envs of this warp for the batched reset (outside the baton)
       if (dmask) {
         if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);

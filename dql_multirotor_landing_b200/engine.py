@@ -63,6 +63,13 @@ class Engine:
             self.tables = torch.zeros((n_populations, 3, K.MAX_CELLS), dtype=torch.int32, device=self.device)
             self.pop_state = torch.zeros(n_populations * C.sizeof(K.PopulationState), dtype=torch.uint8, device=self.device)
         _ffi.check(self.lib.dqlb200_bind(self.handle, self.env_state.data_ptr(), self.tables.data_ptr(), self.pop_state.data_ptr()))
+        self.filter_state = None
+        if self.cfg.accel_mode != 0:      # per-env state of the acceleration estimator {x, P, v_ref, n}, 16 B/env
+            with torch.cuda.device(self.device):
+                fs = torch.zeros((n, 4), dtype=torch.int32, device=self.device)
+                fs[:, 1] = 0x3F800000     # P = 1.0f (PKG/filters.py:16): a simulator that has not published yet
+            self.filter_state = fs
+            _ffi.check(self.lib.dqlb200_bind_filter_state(self.handle, fs.data_ptr()))
         self._trace_keep = None
         self.merge_snapshot = None       # replica-merge mode: [n_groups][3][MAX_CELLS] merged tables of the last merge
         self.pooled_promote = K.promote_threshold(self.tp.successive_successful_episodes * self.R, self.tp.success_rate)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 3
+#define DQLB200_ABI_VERSION 4
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -117,6 +117,17 @@ typedef struct dqlb200_config {
    * (PKG/observation_utils.py:127-129, manager_node parameters noise_pos_sd / noise_vel_sd; launch default 0 = off).
    * Applied to what the MDP sees (discretisation, fly-zone check, shaping); the physical state and `contact` stay exact. */
   float noise_pos_sd, noise_vel_sd;
+  /* ---- observation realism: the relative acceleration the MDP sees.
+   *   0 = exact (the stand-in's analytic acceleration, default)
+   *   1 = the reference's estimator as written: a scalar Kalman filter (PKG/filters.py:4-37, Q = kf_q, R = kf_r) over the
+   *       finite difference (v_now - v_first) / (t_now - t_first), the anchor sample being the FIRST observation the node ever
+   *       made (PKG/observation_utils.py:137-150 never refreshes last_velocity / last_timestep) -- one update per sub-step
+   *       (n_sub = 4 is the 100 Hz publish rate of manager_node, scripts/manager_node.py:78-80); the filter and its anchor
+   *       live as long as the simulator: they survive episode resets and curriculum steps
+   *   2 = the estimator as evidently intended: the same filter over consecutive samples (v_now - v_prev) / h
+   * Needs dqlb200_bind_filter_state(). */
+  int32_t accel_mode;
+  float kf_q, kf_r;                 /* process variance (1e-4), measurement variance (noise_vel_sd^2, scripts/manager_node.py:96-98) */
   uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
 } dqlb200_config;
 
@@ -222,6 +233,12 @@ int dqlb200_config_is_default(const dqlb200_config* cfg);
  *               (curriculum, p, v, a, theta, action) like the .npy files (PKG/double_q_learning.py:38-53)
  *   pop_state : n_populations x dqlb200_population_state */
 int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_state);
+
+/* Borrow the per-env state of the acceleration estimator (accel_mode != 0): n_populations * envs_per_population x 16 bytes
+ * {x (f32 estimate), P (f32 variance), v_ref (f32 anchor / previous velocity), n (u32 samples seen)}, 16-B aligned.
+ * Replaces: ObservationUtils.filter / last_velocity / last_timestep (PKG/observation_utils.py:44-50).  dqlb200_reset()
+ * initialises it (x = 0, P = 1, PKG/filters.py:15-16); nothing else ever clears it. */
+int dqlb200_bind_filter_state(dqlb200_handle* h, void* filter_state);
 
 /* Replaces: env.reset() for every env + a fresh TrainingMdp (PKG/landing_simulation_env.py:167-243,
  * PKG/trainer.py:176-189).  Sets every population to working step `initial_step`, t = 0. */

@@ -52,6 +52,10 @@ class StandInParams:
     n_sub: int = 1
     noise_pos_sd: float = 0.0    # PKG/observation_utils.py:127-129 (launch/environment.launch:56-57 sets both to 0)
     noise_vel_sd: float = 0.0
+    # relative acceleration the MDP sees: "exact" | "kalman_reference" | "kalman" -- see KalmanAccel
+    accel_mode: str = "exact"
+    kf_process_variance: float = 1e-4     # scripts/manager_node.py:96-98
+    kf_measurement_sd: float = 0.1        # manager_node hands noise_vel_sd (default 0.1) to KalmanFilter3D; R = sd ** 2 (PKG/filters.py:50-52)
 
 
 @dataclass(frozen=True)
@@ -175,6 +179,49 @@ def add_observation_noise(p: "StandInParams", rel_p, rel_v, w0, w1):
             (np.asarray(rel_v, np.float32) + f32(p.noise_vel_sd) * n1).astype(np.float32))
 
 
+class KalmanAccel:
+    """The acceleration estimator of the reference's observation node, vectorised over envs, fp32 with one rounding per
+    operation (the CUDA kernels' kf_sample is the same arithmetic): KalmanFilter1D (PKG/filters.py:4-37; x = 0, P = 1, Q = process
+    variance, R = measurement_sd ** 2) fed by KalmanFilter3D.filter (PKG/filters.py:54-80) with the finite difference of the TRUE
+    relative velocity (PKG/observation_utils.py:134-150 passes rel_vel, not the noisy copy).
+
+    mode "kalman_reference" reproduces the node as written: last_velocity / last_timestep are set by the first observation and
+    never refreshed (PKG/observation_utils.py:137-139 is their only assignment), so raw = (v_now - v_first) / (t_now - t_first)
+    with an ever-growing time base (quirk Q13); the first observation reports 0 and does not touch the filter (:140-143).
+    mode "kalman" is the evident intention: raw = (v_now - v_prev) / h.
+    The filter belongs to the node, not to the episode: nothing resets it (no reset path in scripts/manager_node.py touches
+    self.utils), so it runs through teleports, hover periods and curriculum steps."""
+
+    def __init__(self, n: int, mode: str, h: np.float32, q: float, r: float):
+        assert mode in ("kalman_reference", "kalman")
+        self.mode, self.h, self.q, self.r = mode, f32(h), f32(q), f32(r)
+        self.x = np.zeros(n, f32)
+        self.P = np.ones(n, f32)
+        self.v_ref = np.zeros(n, f32)
+        self.n = np.zeros(n, np.uint32)
+
+    def sample(self, idx, rel_v):
+        idx = np.asarray(idx)
+        rel_v = np.asarray(rel_v, f32)
+        first = self.n[idx] == 0
+        x, P, v_ref, n = self.x[idx], self.P[idx], self.v_ref[idx], self.n[idx]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            dt = (n.astype(np.float32) * self.h) if self.mode == "kalman_reference" else np.full(n.shape, self.h, f32)
+            raw = ((rel_v - v_ref) / dt).astype(np.float32)
+            P1 = (P + self.q).astype(np.float32)
+            K = (P1 / (P1 + self.r)).astype(np.float32)
+            x1 = (x + K * (raw - x)).astype(np.float32)
+            P2 = (P1 * (ONE - K)).astype(np.float32)
+        self.x[idx] = np.where(first, x, x1)
+        self.P[idx] = np.where(first, P, P2)
+        if self.mode == "kalman_reference":
+            self.v_ref[idx] = np.where(first, rel_v, v_ref)
+            self.n[idx] = n + np.uint32(1)
+        else:
+            self.v_ref[idx] = rel_v
+            self.n[idx] = np.uint32(1)
+
+
 class StandInDet:
     """Vectorised (over envs) deterministic fp32 stand-in.  State arrays are np.float32/uint32."""
 
@@ -187,6 +234,9 @@ class StandInDet:
         self.theta = np.zeros(n, f32)
         self.phase = np.zeros(n, np.uint32)
         self.a_d = np.zeros(n, f32)
+        self.kf = None
+        if params.accel_mode != "exact":
+            self.kf = KalmanAccel(n, params.accel_mode, self.d.h, params.kf_process_variance, params.kf_measurement_sd ** 2)
 
     # R1 (PKG/landing_simulation_env.py:181-216) / R15 (:327-340)
     def reset(self, idx, w0, w1, w2, *, normal_init: bool, simulation: bool = False):
@@ -226,6 +276,9 @@ class StandInDet:
             x = (x + v * d.h) + a * d.half_h2
             v = v + a * d.h
             ph = ph + np.uint32(d.dphase)
+            if self.kf is not None:       # one estimator sample per sub-step
+                _, c = det_sincos_turns(ph)
+                self.kf.sample(np.arange(self.n) if idx is None else idx, d.rw * c - v)
         self.x_d[sl], self.v_d[sl], self.theta[sl], self.phase[sl], self.a_d[sl] = x, v, th, ph, a
 
     def observe(self, step_count, idx=None):
@@ -236,6 +289,8 @@ class StandInDet:
         rel_p = d.r * s - self.x_d[sl]
         rel_v = d.rw * c - self.v_d[sl]
         rel_a = -(d.rw2 * s) - self.a_d[sl]
+        if self.kf is not None:
+            rel_a = self.kf.x[sl].copy()
         z = d.z_init + np.asarray(step_count).astype(np.float32) * d.dz
         contact = (z <= d.z_touch) & (np.abs(rel_p) <= d.half_platform)
         return (rel_p.astype(np.float32), rel_v.astype(np.float32), rel_a.astype(np.float32),

@@ -13,6 +13,7 @@ Fixtures:
   schedules.npz    Trainer.alpha / exploration_rate / transfer_learning_ratio tables
   sim_trace.npz    SimulationMdp greedy episodes with the committed assets policy
   sim2d_trace.npz  two-axis SimulationMdp episodes (x and y states, FLYZONE_Y, contact on both axes), three platform cases
+  kalman_accel.npz the reference KalmanFilter3D (PKG/filters.py) driven the way ObservationUtils drives it, on stand-in velocities
 """
 from __future__ import annotations
 
@@ -375,6 +376,73 @@ def gen_sim2d_trace(ns, n_episodes=4, seed=9):
     np.savez_compressed(GOLDEN / "sim2d_trace.npz", **out)
 
 
+def gen_kalman(n_steps=700, seed=11):
+    """PKG/filters.py:4-80 (unmodified, imported with a stub for geometry_msgs.msg.Vector3Stamped) called with the protocol of
+    PKG/observation_utils.py:134-150: the first sample sets last_velocity / last_timestep and reports 0; every later sample
+    calls filter(current, t, last_velocity, last_timestep) -- and nothing ever refreshes the anchor ("anchor" outputs).  The
+    "consecutive" outputs come from the same reference class with the anchor refreshed after every call (the evident
+    intention).  Inputs: the true relative velocity of the stand-in at every 100 Hz sub-step (n_sub = 4) over several
+    episodes with random set-points, teleport resets included; y carries the same signal negated, z is constant."""
+    import importlib
+    import sys
+    import types
+    gm = types.ModuleType("geometry_msgs")
+    gmm = types.ModuleType("geometry_msgs.msg")
+
+    class _V3:
+        def __init__(self, x=0.0, y=0.0, z=0.0):
+            self.x, self.y, self.z = x, y, z
+
+    class Vector3Stamped:
+        def __init__(self):
+            self.vector = _V3()
+
+    gmm.Vector3Stamped = Vector3Stamped
+    gm.msg = gmm
+    sys.modules.setdefault("geometry_msgs", gm)
+    sys.modules.setdefault("geometry_msgs.msg", gmm)
+    ref_stubs.install()
+    filters = importlib.import_module("dql_multirotor_landing.filters")
+
+    rng = np.random.default_rng(seed)
+    sp = StandInParams(n_sub=4, accel_mode="kalman_reference")
+    dyn = StandInDet(sp, 1)
+    samples = []
+    orig = dyn.kf.sample
+    dyn.kf.sample = lambda idx, rel_v: (samples.append(np.float32(np.asarray(rel_v).reshape(-1)[0])), orig(idx, rel_v))[1]
+    idx = np.arange(1)
+    step = 0
+    while step < n_steps:
+        w = rng.integers(0, 2 ** 32, size=3, dtype=np.uint64).astype(np.uint32)
+        dyn.reset(idx, w[0:1], w[1:2], w[2:3], normal_init=True)
+        dyn.advance(np.zeros(1, np.float32), idx)
+        theta = 0.0
+        for _ in range(int(rng.integers(40, 200))):
+            theta = float(np.clip(theta + rng.choice([-1, 0, 1]) * np.deg2rad(7.12574), -0.3731, 0.3731))
+            dyn.advance(np.asarray([theta], np.float32), idx)
+            step += 1
+    v = np.asarray(samples, np.float32)
+    h = float(dyn.d.h)
+    out = dict(rel_v=v, h=np.float32(h), q=np.float64(1e-4))
+    for sd in (0.1, 0.25):
+        for mode in ("anchor", "consecutive"):
+            kf = filters.KalmanFilter3D(process_variance=1e-4, measurement_variance=sd)      # scripts/manager_node.py:96-98
+            last_v, last_t, acc = None, None, []
+            for k, vk in enumerate(v):
+                cur, t = _V3(float(vk), -float(vk), 0.5), k * h
+                if last_v is None:
+                    last_v, last_t = cur, t
+                    acc.append((0.0, 0.0, 0.0))
+                    continue
+                a = kf.filter(current_rel_v=cur, timestep=t, last_vel=last_v, last_timestep=last_t)
+                acc.append((a.vector.x, a.vector.y, a.vector.z))
+                if mode == "consecutive":
+                    last_v, last_t = cur, t
+            out[f"{mode}_sd{sd}"] = np.asarray(acc, np.float64)
+    np.savez_compressed(GOLDEN / "kalman_accel.npz", **out)
+    print("kalman_accel:", len(v), "samples")
+
+
 def _state_tuple(sid: int):
     th = sid % 7; sid //= 7
     a = sid % 3; sid //= 3
@@ -404,6 +472,7 @@ def main():
     gen_replay(ns, 4, 3000, np.float32, q_init=q0)
     gen_sim_trace(ns)
     gen_sim2d_trace(ns)
+    gen_kalman()
     total = sum(f.stat().st_size for f in GOLDEN.glob("*.npz"))
     print("golden bytes:", total)
 

@@ -86,4 +86,5 @@ def test_compiled_in_defaults_match_constants_py():
     assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(c_d=0.21)))) == 0
     assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, mp=K.MdpParameters(p_max=4.0)))) == 0
     assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(noise_vel_sd=0.1)))) == 0
+    assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(accel_mode="kalman", n_sub=4)))) == 0
     assert lib.dqlb200_config_is_default(C.byref(K.build_config(4, 100, 128, dp=K.DynamicsParameters(v_mp=0.8, r_mp=3.0)))) == 1

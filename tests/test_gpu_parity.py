@@ -166,6 +166,63 @@ def test_observation_noise_option_vs_oracle():
     assert torch.equal(eng2.tables, eng.tables) and torch.equal(eng2.env_state, eng.env_state)
 
 
+@pytest.mark.parametrize("accel_mode", ["kalman_reference", "kalman"])
+def test_kalman_acceleration_option_vs_oracle(accel_mode):
+    """the MDP sees the reference's acceleration estimate (KalmanFilter3D over a finite difference of the true
+    relative velocity, PKG/filters.py:4-80 + PKG/observation_utils.py:134-150) instead of the analytic value; sampled at the
+    100 Hz sub-step rate (n_sub = 4), combined with the observation noise, through episode resets and promotions (the
+    estimator is never reset).  Bit-exact against oracle KalmanAccel, which tests/test_oracle_golden.py pins to the
+    unmodified reference filter."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    dyn = dict(accel_mode=accel_mode, n_sub=4, kf_measurement_sd=0.1, noise_pos_sd=0.25, noise_vel_sd=0.1)
+    n_envs, steps = 70, 260
+    eng = _engine(1, n_envs, threads_per_block=64, seeds=[5], tp=kw, dp=dyn)
+    eng.reset(0)
+    tr = eng.train(steps, trace=True)
+    eng.check_errors()
+    pop = PopulationOracle(n_envs, seed=5, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw), sp=StandInParams(**dyn))
+    exact = PopulationOracle(n_envs, seed=5, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw),
+                             sp=StandInParams(**{**dyn, "accel_mode": "exact"}))
+    differs = False
+    for t in range(steps):
+        o = pop.step()
+        assert np.array_equal(tr["obs"][t].view(np.uint32), o["obs"].view(np.uint32)), t
+        for key in ("action", "code", "done"):
+            assert np.array_equal(tr[key][t], o[key]), (t, key)
+        assert np.array_equal(tr["next_state"][t].astype(np.uint16), o["next_state"]), t
+        assert np.array_equal(tr["reward"][t], o["reward"]), t
+        if t < 5:
+            differs = differs or not np.array_equal(exact.step()["obs"][:, 2], o["obs"][:, 2])
+    assert differs, "the estimate must differ from the analytic acceleration"
+    qa, _, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(cnt, pop.agent.count) and np.array_equal(qa.view(np.uint32), pop.agent.qa.view(np.uint32))
+    assert int(eng.population_state()[0]["working_step"]) == pop.w >= 1
+    # the estimator state itself: {x, P, v_ref, n}
+    fs = eng.filter_state.cpu().numpy()
+    assert np.array_equal(fs[:, 0].view(np.float32).view(np.uint32), pop.dyn.kf.x.view(np.uint32))
+    assert np.array_equal(fs[:, 1].view(np.float32).view(np.uint32), pop.dyn.kf.P.view(np.uint32))
+    assert np.array_equal(fs[:, 2].view(np.float32).view(np.uint32), pop.dyn.kf.v_ref.view(np.uint32))
+    assert np.array_equal(fs[:, 3].view(np.uint32), pop.dyn.kf.n)
+    # the production (non-trace) generic instance, and the un-fused env operators under the same actions
+    eng2 = _engine(1, n_envs, threads_per_block=64, seeds=[5], tp=kw, dp=dyn)
+    eng2.reset(0)
+    eng2.train(steps)
+    assert torch.equal(eng2.tables, eng.tables) and torch.equal(eng2.env_state, eng.env_state)
+    assert torch.equal(eng2.filter_state, eng.filter_state)
+
+
+def test_kalman_acceleration_needs_its_state_buffer():
+    """accel_mode != 0 without the estimator buffer is refused (no silent fall-back to the analytic acceleration), and the
+    host-buffer call, which does not carry that buffer, says so."""
+    from dql_multirotor_landing_b200 import _ffi
+    eng = _engine(1, 32, threads_per_block=32, seeds=[1], dp=dict(accel_mode="kalman", n_sub=4))
+    _ffi.check(eng.lib.dqlb200_bind_filter_state(eng.handle, None))
+    with pytest.raises(RuntimeError, match="dqlb200_bind_filter_state"):
+        eng.reset(0)
+    with pytest.raises(RuntimeError, match="dqlb200_bind_filter_state"):
+        eng.train(1)
+
+
 @pytest.mark.parametrize("mode", ["reference", "paper"])
 def test_curriculum_promotion_and_transfer(mode):
     """R13/R14: success window, promotion latch, max_num_episodes advance, transfer (quirk Q7 and the

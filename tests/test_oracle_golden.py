@@ -145,3 +145,27 @@ def test_two_axis_simulation_oracle_matches_reference_fixture(golden_dir, case):
         for k in ("action_x", "action_y", "state_x", "state_y", "code", "done"):
             assert [r[k] for r in rows] == list(g[f"{case}_{k}"][sel]), k
     assert (g["ywrong_code"][g["ywrong_done"] == 1] == 5).all()        # FLYZONE_Y is covered
+
+
+@pytest.mark.parametrize("mode,key", [("kalman_reference", "anchor"), ("kalman", "consecutive")])
+@pytest.mark.parametrize("sd", [0.1, 0.25])
+def test_kalman_acceleration_estimator_matches_reference_filter(golden_dir, mode, key, sd):
+    """the fp32 estimator (oracle KalmanAccel == kf_sample of the kernels) against the UNMODIFIED reference
+    KalmanFilter3D (PKG/filters.py:4-80, float64) driven with the call protocol of PKG/observation_utils.py:134-150 on the same
+    velocity samples (tests/golden/kalman_accel.npz).  Tolerance 2e-5 m/s^2 absolute (measured 8e-6; fp32 vs float64 over 3 364 updates; the
+    filter is a contraction, errors do not accumulate), i.e. 1.6e-5 of a_max = 1.28."""
+    from oracle.dynamics import KalmanAccel
+    g = np.load(golden_dir / "kalman_accel.npz")
+    v, ref = g["rel_v"], g[f"{key}_sd{sd}"]
+    kf = KalmanAccel(2, mode, g["h"], float(g["q"]), sd ** 2)
+    out = np.zeros((len(v), 2), np.float32)
+    for k, vk in enumerate(v):
+        kf.sample(np.arange(2), np.asarray([vk, -vk], np.float32))
+        out[k] = kf.x
+    assert out[0, 0] == 0.0 and ref[0, 0] == 0.0            # the first observation reports 0 (observation_utils.py:140-143)
+    assert np.array_equal(out[:, 0], -out[:, 1])            # the y channel of the fixture is the negated signal
+    assert np.abs(ref[:, 2]).max() == 0.0                   # constant z velocity -> zero acceleration
+    err = np.abs(out.astype(np.float64) - ref[:, :2]).max()
+    assert err < 2e-5, err
+    if key == "anchor":       # quirk Q13: against the growing time base the estimate decays toward the mean acceleration since start
+        assert np.abs(ref[-200:, 0]).max() < 0.25 * np.abs(g["consecutive_sd0.1"][-200:, 0]).max()
