@@ -34,7 +34,7 @@ ALPHA_LUT = 1003
 EPS_LUT = 2002
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 LIMITS_POSITION = [1.0, 0.64, 0.4096, 0.262144, 0.16777216]   # PKG/mdp.py:45-47
 LIMITS_VELOCITY = [1.0, 0.8, 0.64, 0.512, 0.4096]              # PKG/mdp.py:48-50
@@ -88,6 +88,11 @@ class Config(C.Structure):
         ("n_alpha_luts", C.c_int32), ("replicas_per_population", C.c_int32),
         ("noise_pos_sd", C.c_float), ("noise_vel_sd", C.c_float),
         ("accel_mode", C.c_int32), ("kf_q", C.c_float), ("kf_r", C.c_float),
+        ("dynamics_model", C.c_int32), ("pid_ticks", C.c_int32),
+        ("att_kr", C.c_float), ("att_kw", C.c_float), ("inv_m", C.c_float), ("inv_mg", C.c_float), ("g_abs", C.c_float),
+        ("pid_kp", C.c_float), ("pid_ki", C.c_float), ("pid_lo", C.c_float), ("pid_hi", C.c_float), ("pid_windup", C.c_float),
+        ("pid_dt", C.c_float), ("pid_i0", C.c_float), ("bw_inv_denom", C.c_float), ("bw_k2", C.c_float),
+        ("vz_train", C.c_float), ("vz_sim", C.c_float),
         ("eps_threshold", C.c_uint32 * EPS_LUT),
     ]
 
@@ -180,6 +185,7 @@ class MdpParameters:
 
 
 ACCEL_MODES = {"exact": 0, "kalman_reference": 1, "kalman": 2}
+DYNAMICS_MODELS = {"first_order": 0, "second_order": 1}
 
 
 @dataclass
@@ -203,6 +209,19 @@ class DynamicsParameters:
     accel_mode: str = "exact"
     kf_process_variance: float = 1e-4      # scripts/manager_node.py:96-98
     kf_measurement_sd: float = 0.1         # manager_node passes noise_vel_sd (default 0.1); R = sd ** 2 (PKG/filters.py:50-52)
+    # "first_order" (the stand-in of SURVEY A.3) or "second_order": attitude as torque on inertia under the geometric controller
+    # (PKG/attitude_controller.py:86-87,124-156) + the vertical PID node (PKG/pid.py:62-104, launch/drone.launch:33-46)
+    dynamics_model: str = "first_order"
+    mass: float = 0.68                     # PKG/attitude_controller.py:57, hummingbird.xacro:29
+    inertia: float = 0.007                 # PKG/attitude_controller.py:59 (Ixx = Iyy)
+    k_R: float = 0.7                       # PKG/attitude_controller.py:86
+    k_omega: float = 0.1                   # PKG/attitude_controller.py:87
+    pid_kp: float = 5.0                    # launch/drone.launch:35-40
+    pid_ki: float = 10.0
+    pid_lower: float = 0.0
+    pid_upper: float = 10.0
+    pid_windup: float = 10.0
+    pid_ticks: int = 10                    # PID node iterations per sub-step (rate_hz 1000 against the 100 Hz state topic, PKG/pid.py:14)
 
 
 @dataclass
@@ -467,6 +486,16 @@ def build_config(n_populations: int, envs_per_population: int, threads_per_block
     cfg.noise_pos_sd, cfg.noise_vel_sd = dp.noise_pos_sd, dp.noise_vel_sd
     cfg.accel_mode = ACCEL_MODES[dp.accel_mode]
     cfg.kf_q, cfg.kf_r = dp.kf_process_variance, dp.kf_measurement_sd ** 2
+    cfg.dynamics_model = DYNAMICS_MODELS[dp.dynamics_model]
+    cfg.pid_ticks = dp.pid_ticks
+    g_abs = abs(dp.g)
+    cfg.att_kr, cfg.att_kw = dp.k_R / dp.inertia, dp.k_omega / dp.inertia
+    cfg.inv_m, cfg.inv_mg, cfg.g_abs = 1.0 / dp.mass, 1.0 / (dp.mass * g_abs), g_abs
+    cfg.pid_kp, cfg.pid_ki, cfg.pid_lo, cfg.pid_hi, cfg.pid_windup = dp.pid_kp, dp.pid_ki, dp.pid_lower, dp.pid_upper, dp.pid_windup
+    cfg.pid_dt = h / max(dp.pid_ticks, 1)
+    cfg.pid_i0 = dp.mass * g_abs / dp.pid_ki if dp.pid_ki else 0.0
+    cfg.bw_inv_denom, cfg.bw_k2 = 1.0 / (1 + 1.0 ** 2 + 1.414 * 1.0), 1.0 ** 2 - 1.414 * 1.0 + 1      # PKG/filters.py:92-93,103 with c = 1
+    cfg.vz_train, cfg.vz_sim = dp.v_z_train, dp.v_z_sim
     cfg.gamma = tp.gamma
     for k in range(MAX_CURRICULUM):
         cfg.transfer_ratio[k] = transfer_learning_ratio(k, tp.scale_modification_value)

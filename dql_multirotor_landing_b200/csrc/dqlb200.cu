@@ -5,7 +5,7 @@
 //   dqlb200_device.cuh   Philox4x32-10, deterministic fp32 math, stand-in dynamics (R4), cut-table discretisation (R5),
 //                        set-point (R3), exact float64 divisions, reward (R7)
 //   env_state.cuh        the 48-byte env state: pack/unpack, reset law (R1/R8), cp.async prefetch
-//   train_kernel.cuh     train_kernel<WARPS, TRACE, DIV2>: one CTA per population (agent), K fused global steps per launch.
+//   train_kernel.cuh     train_kernel<WARPS, TRACE, VARIANT>: one CTA per population (agent), K fused global steps per launch.
 //                        Per step and env: epsilon-greedy select (R9/R10), set-point, dynamics, discretise, check (R6),
 //                        reward, learning rate (R11), table update (R12), auto-reset, success window / promotion /
 //                        transfer (R13/R14).  Q_a / count live in shared memory for the whole launch.
@@ -53,6 +53,7 @@ struct dqlb200_handle {
   void* pop_state;
   void* merge_snapshot;
   void* filter_state;       // accel_mode != 0: [n_total] x 16 B estimator state (dqlb200_bind_filter_state)
+  void* dynamics_state;     // dynamics_model != 0: [2][n_total] x 16 B second-order model state (dqlb200_bind_dynamics_state)
   bool kc_default;              // the configuration equals the compile-time defaults: the production instance may run
   size_t smem_bytes;
   // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
@@ -128,6 +129,11 @@ static void fill_kc(const dqlb200_config& c, dql::KC& k) {
   k.noise_pos_sd = c.noise_pos_sd; k.noise_vel_sd = c.noise_vel_sd;
   k.noise_enabled = (c.noise_pos_sd != 0.0f || c.noise_vel_sd != 0.0f) ? 1 : 0;
   k.accel_mode = c.accel_mode; k.kf_q = c.kf_q; k.kf_r = c.kf_r;
+  k.dynamics_model = c.dynamics_model; k.pid_ticks = c.pid_ticks;
+  k.att_kr = c.att_kr; k.att_kw = c.att_kw; k.inv_m = c.inv_m; k.inv_mg = c.inv_mg; k.g_abs = c.g_abs;
+  k.pid_kp = c.pid_kp; k.pid_ki = c.pid_ki; k.pid_lo = c.pid_lo; k.pid_hi = c.pid_hi; k.pid_windup = c.pid_windup;
+  k.pid_dt = c.pid_dt; k.pid_i0 = c.pid_i0; k.bw_inv_denom = c.bw_inv_denom; k.bw_k2 = c.bw_k2;
+  k.vz_train = c.vz_train; k.vz_sim = c.vz_sim;
   memcpy(k.transfer_ratio, c.transfer_ratio, sizeof(k.transfer_ratio));
   k.timeout_steps = c.timeout_steps; k.success_steps = c.success_steps; k.n_sub = c.n_sub;
   k.transfer_mode = c.transfer_mode; k.window_len = c.window_len; k.promote_successes = c.promote_successes;
@@ -149,6 +155,9 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   if (cfg->window_len < 1 || cfg->window_len > DQLB200_MAX_WINDOW) return fail(DQLB200_ERR_ARG, "window_len out of range");
   if (cfg->n_alpha_luts < 1 || cfg->n_sub < 1) return fail(DQLB200_ERR_ARG, "n_alpha_luts / n_sub must be >= 1");
   if (cfg->accel_mode < 0 || cfg->accel_mode > 2) return fail(DQLB200_ERR_ARG, "accel_mode must be 0 (exact), 1 (reference filter) or 2 (consecutive-sample filter)");
+  if (cfg->dynamics_model < 0 || cfg->dynamics_model > 1) return fail(DQLB200_ERR_ARG, "dynamics_model must be 0 (first order) or 1 (second order)");
+  if (cfg->dynamics_model != 0 && (cfg->pid_ticks < 2 || cfg->pid_ticks > 64 || !(cfg->inv_m > 0.0f) || !(cfg->pid_hi >= cfg->pid_lo)))
+    return fail(DQLB200_ERR_ARG, "second-order model: pid_ticks in 2..64, positive mass and pid_hi >= pid_lo required");
   if (cfg->accel_mode != 0 && (!(cfg->kf_q >= 0.0f) || !(cfg->kf_r >= 0.0f) || !(cfg->kf_q + cfg->kf_r > 0.0f)))
     return fail(DQLB200_ERR_ARG, "acceleration filter needs non-negative variances, not both zero");
   if (cfg->replicas_per_population < 1 || cfg->n_populations % cfg->replicas_per_population)
@@ -169,7 +178,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   fill_kc(*cfg, h->kc);
   h->kc_default = dql::kdef_matches(h->kc);
   h->device = device;
-  h->env_state = h->tables = h->pop_state = h->merge_snapshot = h->filter_state = nullptr;
+  h->env_state = h->tables = h->pop_state = h->merge_snapshot = h->filter_state = h->dynamics_state = nullptr;
   h->chunk_ready = false;
   h->merged_ready = false;
   h->merged_exec = nullptr;
@@ -196,7 +205,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-#define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, false) DQL_SET_SMEM1(W, false, true) DQL_SET_SMEM1(W, true, true)
+#define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, true, 2)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
 #undef DQL_SET_SMEM
 #undef DQL_SET_SMEM1
@@ -257,10 +266,18 @@ int dqlb200_bind_filter_state(dqlb200_handle* h, void* filter_state) {
   return DQLB200_OK;
 }
 
-// accel_mode != 0 and no estimator state bound: refuse instead of computing with the exact acceleration
-static bool filter_missing(const dqlb200_handle* h) { return h->cfg.accel_mode != 0 && !h->filter_state; }
-#define DQL_NEED_FILTER(h) \
-  if (filter_missing(h)) return fail(DQLB200_ERR_STATE, "accel_mode != 0 needs dqlb200_bind_filter_state()")
+int dqlb200_bind_dynamics_state(dqlb200_handle* h, void* dynamics_state) {
+  if (!h) return fail(DQLB200_ERR_ARG, "null handle");
+  if ((uintptr_t)dynamics_state & 15u) return fail(DQLB200_ERR_ARG, "misaligned dynamics_state (needs 16 B)");
+  h->dynamics_state = dynamics_state;
+  h->merged_k = 0;
+  return DQLB200_OK;
+}
+
+// an option that needs its own per-env buffer and has none bound: refuse instead of computing with the default model
+#define DQL_NEED_FILTER(h)                                                                                                          \
+  if ((h)->cfg.accel_mode != 0 && !(h)->filter_state) return fail(DQLB200_ERR_STATE, "accel_mode != 0 needs dqlb200_bind_filter_state()"); \
+  if ((h)->cfg.dynamics_model != 0 && !(h)->dynamics_state) return fail(DQLB200_ERR_STATE, "dynamics_model != 0 needs dqlb200_bind_dynamics_state()")
 
 static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
   const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
@@ -269,6 +286,8 @@ static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
   p.b = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 16 * n);
   p.c = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 32 * n);
   p.d = h->cfg.accel_mode != 0 ? reinterpret_cast<uint4*>(h->filter_state) : nullptr;
+  p.e = h->cfg.dynamics_model != 0 ? reinterpret_cast<uint4*>(h->dynamics_state) : nullptr;
+  p.n = n;
   return p;
 }
 
@@ -301,10 +320,12 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
   const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
+  const bool extended = h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0;      // options with extra per-env state
 #define DQL_LAUNCH(W)                                                                        \
-  if (tracing) dql::train_kernel<W, true, true><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
-  else if (!h->kc_default) dql::train_kernel<W, false, true><<<grid, W * 32, smem, stream>>>(h->kc, a);    \
-  else dql::train_kernel<W, false, false><<<grid, W * 32, smem, stream>>>(h->kc, a);
+  if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
+  else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);            \
+  else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32, smem, stream>>>(h->kc, a);      \
+  else dql::train_kernel<W, false, 0><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;
     case 64: DQL_LAUNCH(2) break;
@@ -329,7 +350,8 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
                        void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
   if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
-  if (h->cfg.accel_mode != 0) return fail(DQLB200_ERR_ARG, "dqlb200_train_host does not carry the estimator state (accel_mode != 0): use dqlb200_train on bound device buffers");
+  if (h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0)
+    return fail(DQLB200_ERR_ARG, "dqlb200_train_host does not carry the estimator / second-order state (accel_mode, dynamics_model != 0): use dqlb200_train on bound device buffers");
   if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;

@@ -34,6 +34,13 @@ struct KC {
   int32_t noise_enabled;        // either standard deviation is non-zero
   int32_t accel_mode;           // 0 exact, 1 / 2 Kalman-filtered finite difference (dqlb200_config.accel_mode)
   float kf_q, kf_r;
+  // second-order attitude + vertical PID model (dqlb200_config.dynamics_model == 1)
+  int32_t dynamics_model, pid_ticks;
+  float att_kr, att_kw;         // k_R / J, k_omega / J
+  float inv_m, inv_mg, g_abs;   // 1 / m, 1 / (m g), |g|
+  float pid_kp, pid_ki, pid_lo, pid_hi, pid_windup, pid_dt, pid_i0;
+  float bw_inv_denom, bw_k2;    // ButterworthFilter (c = 1): 1 / (1 + c^2 + 1.414 c), c^2 - 1.414 c + 1
+  float vz_train, vz_sim;       // vertical-velocity set-points (PKG/mdp.py:212, 580)
   float gamma;
   float transfer_ratio[DQLB200_MAX_CURRICULUM];
   int32_t timeout_steps, success_steps, n_sub;
@@ -61,6 +68,9 @@ struct KDef {
   static constexpr int32_t timeout_steps = 459, success_steps = 23, n_sub = 1;
   static constexpr int32_t noise_enabled = 0, accel_mode = 0;
   static constexpr float kf_q = 0.0f, kf_r = 0.0f;
+  static constexpr int32_t dynamics_model = 0, pid_ticks = 0;
+  static constexpr float att_kr = 0.0f, att_kw = 0.0f, inv_m = 0.0f, inv_mg = 0.0f, g_abs = 0.0f, pid_kp = 0.0f, pid_ki = 0.0f, pid_lo = 0.0f,
+                         pid_hi = 0.0f, pid_windup = 0.0f, pid_dt = 0.0f, pid_i0 = 0.0f, bw_inv_denom = 0.0f, bw_k2 = 0.0f, vz_train = 0.0f, vz_sim = 0.0f;
   static constexpr float noise_pos_sd = 0.0f, noise_vel_sd = 0.0f;
   struct AngleCut {          // constant-index reads fold into literals
     __host__ __device__ constexpr float operator[](int i) const {
@@ -79,7 +89,7 @@ inline bool kdef_matches(const KC& k) {
             k.theta_max == KDef::theta_max && k.delta_theta == KDef::delta_theta && k.w_p == KDef::w_p && k.w_v == KDef::w_v &&
             k.w_theta == KDef::w_theta && k.rcp_p_max == KDef::rcp_p_max && k.rcp_v_max == KDef::rcp_v_max && k.rcp_theta_max == KDef::rcp_theta_max &&
             k.timeout_steps == KDef::timeout_steps && k.success_steps == KDef::success_steps && k.n_sub == KDef::n_sub && k.noise_enabled == 0 &&
-            k.accel_mode == 0 && k.div_two_steps == 0;
+            k.accel_mode == 0 && k.dynamics_model == 0 && k.div_two_steps == 0;
   for (int i = 0; i < 6; ++i) ok = ok && k.angle_cut[i] == KDef::AngleCut{}[i];
   return ok;
 }
@@ -139,6 +149,25 @@ __device__ __forceinline__ float det_tan(float x) {
   p = fadd(fmul(p, z), (float)(2.0 / 15.0));
   p = fadd(fmul(p, z), (float)(1.0 / 3.0));
   return fadd(x, fmul(x, fmul(z, p)));
+}
+
+// sin / cos of a small angle in radians (|x| <= ~0.8: attitude angles and attitude errors), Taylor polynomials in Horner form
+__device__ __forceinline__ float det_sin_small(float x) {
+  const float z = fmul(x, x);
+  float p = (float)(1.0 / 362880.0);
+  p = fadd(fmul(p, z), (float)(-1.0 / 5040.0));
+  p = fadd(fmul(p, z), (float)(1.0 / 120.0));
+  p = fadd(fmul(p, z), (float)(-1.0 / 6.0));
+  return fadd(x, fmul(x, fmul(z, p)));
+}
+__device__ __forceinline__ float det_cos_small(float x) {
+  const float z = fmul(x, x);
+  float p = (float)(-1.0 / 3628800.0);
+  p = fadd(fmul(p, z), (float)(1.0 / 40320.0));
+  p = fadd(fmul(p, z), (float)(-1.0 / 720.0));
+  p = fadd(fmul(p, z), (float)(1.0 / 24.0));
+  p = fadd(fmul(p, z), -0.5f);
+  return fadd(1.0f, fmul(z, p));
 }
 
 __device__ __forceinline__ float det_log(float u) {
@@ -219,11 +248,56 @@ __device__ __forceinline__ void kf_sample(const KT& kc, Kf& f, float rel_v) {
   else f.v_ref = rel_v;
 }
 
+// Second-order attitude + vertical PID model, the state the first-order stand-in does not have:
+// pitch (roll) rate, altitude, vertical velocity, and the PID node's memory (integral, the Butterworth filter's previous input
+// and three previous outputs).  The PID memory belongs to the node: like the acceleration estimator it survives episode resets.
+// The filter's two previous inputs are equal at every sub-step boundary (the error is held for pid_ticks >= 2 node
+// iterations), so one word holds both.
+struct Ext {
+  float omega, z, v_z, integ;
+  float e1, f1, f2, f3;
+};
+// One sub-step of the vertical loop (PKG/pid.py:62-104 with the gains of launch/drone.launch:33-46, Kd = 0): the node runs
+// `pid_ticks` times per sub-step on the held error (1 kHz against the 100 Hz state topic); returns the thrust [N].
 template <class KT>
-__device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_population_params& pp, Body& b, float sp, Kf* kf = nullptr) {
+__device__ __forceinline__ float pid_thrust(const KT& kc, Ext& x, float vz_sp) {
+  const float e = fsub(vz_sp, x.v_z);
+  float thrust = 0.0f, e1 = x.e1, e2 = x.e1;
+  for (int k = 0; k < kc.pid_ticks; ++k) {
+    x.integ = clipf(fadd(x.integ, fmul(e, kc.pid_dt)), -kc.pid_windup, kc.pid_windup);            // PKG/pid.py:85-86
+    // ButterworthFilter.update (PKG/filters.py:96-108) with c = 1, as written: the new input is pushed BEFORE the sum, the new
+    // output after it, so the output taps are one sample older than the input taps (quirk Q14): y_k = (x_k-2 + 2 x_k-1 + x_k
+    // - (c^2 - 1.414 c + 1) y_k-3 - (-2 c^2 + 2) y_k-2) / denom, and the last coefficient is zero
+    const float f = fmul(kc.bw_inv_denom, fsub(fadd(fadd(e2, fmul(2.0f, e1)), e), fmul(kc.bw_k2, x.f3)));
+    e2 = e1; e1 = e;
+    x.f3 = x.f2; x.f2 = x.f1; x.f1 = f;
+    thrust = clipf(fadd(fmul(kc.pid_kp, f), fmul(kc.pid_ki, x.integ)), kc.pid_lo, kc.pid_hi);    // PKG/pid.py:97-103
+  }
+  x.e1 = e;
+  return thrust;
+}
+
+template <class KT>
+__device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_population_params& pp, Body& b, float sp, Kf* kf = nullptr,
+                                            Ext* ext = nullptr, float vz_sp = 0.0f) {
   for (int i = 0; i < kc.n_sub; ++i) {
-    b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
-    b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
+    if (kc.dynamics_model != 0 && ext) {
+      Ext& x = *ext;
+      const float thrust = pid_thrust(kc, x, vz_sp);
+      // geometric attitude controller reduced to one axis (PKG/attitude_controller.py:124-156): M = -k_R sin(theta - theta_sp)
+      // - k_w omega is applied as a torque (:107-113), theta'' = M / J; semi-implicit Euler
+      const float alpha = fsub(-fmul(kc.att_kr, det_sin_small(fsub(b.theta, sp))), fmul(kc.att_kw, x.omega));
+      x.omega = fadd(x.omega, fmul(alpha, kc.h));
+      b.theta = fadd(b.theta, fmul(x.omega, kc.h));
+      // thrust along the body z axis: horizontal and vertical components (pp.g carries the sign of the axis)
+      b.a_d = fsub(fmul(fmul(pp.g, fmul(thrust, kc.inv_mg)), det_sin_small(b.theta)), fmul(kc.c_d, b.v_d));
+      const float a_z = fsub(fmul(fmul(thrust, det_cos_small(b.theta)), kc.inv_m), kc.g_abs);
+      x.z = fadd(fadd(x.z, fmul(x.v_z, kc.h)), fmul(a_z, kc.half_h2));
+      x.v_z = fadd(x.v_z, fmul(a_z, kc.h));
+    } else {
+      b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
+      b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
+    }
     b.x_d = fadd(fadd(b.x_d, fmul(b.v_d, kc.h)), fmul(b.a_d, kc.half_h2));
     b.v_d = fadd(b.v_d, fmul(b.a_d, kc.h));
     b.phase += pp.dphase;
@@ -237,7 +311,7 @@ __device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_populati
 
 template <class KT>
 __device__ __forceinline__ Obs dyn_observe(const KT& kc, const dqlb200_population_params& pp, const Body& b,
-                                           int step_count, float dz, const Kf* kf = nullptr) {
+                                           int step_count, float dz, const Kf* kf = nullptr, const Ext* ext = nullptr) {
   float s, c;
   det_sincos_turns(b.phase, s, c);
   Obs o;
@@ -247,6 +321,7 @@ __device__ __forceinline__ Obs dyn_observe(const KT& kc, const dqlb200_populatio
   if (kc.accel_mode != 0 && kf) o.rel_a = kf->x;
   o.pitch = b.theta;
   o.z = fadd(kc.z_init, fmul(__int2float_rn(step_count), dz));
+  if (kc.dynamics_model != 0 && ext) o.z = ext->z;
   o.contact = (o.z <= kc.z_touch) && (fabsf(o.rel_p) <= kc.half_platform);
   return o;
 }
@@ -264,7 +339,7 @@ __device__ __forceinline__ void add_observation_noise(const KT& kc, Obs& o, uint
 // R1 (PKG/landing_simulation_env.py:181-216) and R15 (:327-340), then one hover period (:222-224).
 template <class KT>
 __device__ __forceinline__ Obs dyn_reset(const KT& kc, const dqlb200_population_params& pp, Body& b, uint4 w,
-                                         bool normal_init, bool simulation, float dz, Kf* kf = nullptr) {
+                                         bool normal_init, bool simulation, float dz, Kf* kf = nullptr, Ext* ext = nullptr) {
   float x_init;
   if (normal_init) {
     x_init = fmul(kc.sigma_x, det_normal(w.x, w.y));
@@ -281,8 +356,13 @@ __device__ __forceinline__ Obs dyn_reset(const KT& kc, const dqlb200_population_
   b.v_d = 0.0f;
   b.theta = 0.0f;
   b.a_d = 0.0f;
-  dyn_advance(kc, pp, b, 0.0f, kf);       // the estimator keeps sampling through the teleport and the hover period
-  return dyn_observe(kc, pp, b, 0, dz, kf);
+  if (kc.dynamics_model != 0 && ext) {    // teleport with zero twist (PKG/landing_simulation_env.py:203-216); the PID memory stays
+    ext->omega = 0.0f;
+    ext->z = kc.z_init;
+    ext->v_z = 0.0f;
+  }
+  dyn_advance(kc, pp, b, 0.0f, kf, ext, 0.0f);       // hover period: all set-points zero (scripts/manager_node.py:328)
+  return dyn_observe(kc, pp, b, 0, dz, kf, ext);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -16,10 +16,12 @@ __global__ void reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, dqlb200
   if (env_i < kc.envs_per_population) {
     const dqlb200_population_params pp = pop_params[pop];
     Env e;
-    Kf kf = kf_initial();       // a new simulator: the only place the estimator is ever cleared
-    env_reset(kc, pp, cuts, kc.angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true, env.d ? &kf : nullptr);
+    Kf kf = kf_initial();       // a new simulator: the only place the estimator and the PID memory are ever cleared
+    Ext ex = ext_initial(kc);
+    env_reset(kc, pp, cuts, kc.angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true, env.d ? &kf : nullptr, env.e ? &ex : nullptr);
     env_store(env, (size_t)pop * kc.envs_per_population + env_i, e);
     if (kc.accel_mode != 0 && env.d) kf_store(env, (size_t)pop * kc.envs_per_population + env_i, kf);
+    if (kc.dynamics_model != 0 && env.e) ext_store(env, (size_t)pop * kc.envs_per_population + env_i, ex);
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     dqlb200_population_state ps;
@@ -53,7 +55,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
     Body b;
     Kf kf = kf_initial();       // accel_mode != 0: every evaluation episode runs on a freshly started simulator
     Kf* const kfp = (GENERIC && kk.accel_mode != 0) ? &kf : nullptr;
-    Obs o = dyn_reset(kk, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kk.dz_sim, kfp);
+    Ext ex = ext_initial(kk);
+    Ext* const exp_ = (GENERIC && kk.dynamics_model != 0) ? &ex : nullptr;
+    Obs o = dyn_reset(kk, pp, b, d, /*normal_init=*/false, /*simulation=*/true, kk.dz_sim, kfp, exp_);
     uint32_t sid = (uint32_t)discretise_cuts(cuts, kk.angle_cut, o).id();
     double sp = 0.0;
     int code = DQLB200_NON_TERMINAL;
@@ -61,9 +65,9 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
     while (code < DQLB200_TERMINAL_SUCCESS) {
       const int a = s_policy[sid];
       sp = apply_action(kk, sp, a);
-      dyn_advance(kk, pp, b, (float)sp, kfp);
+      dyn_advance(kk, pp, b, (float)sp, kfp, exp_, kk.vz_sim);
       step += 1;
-      o = dyn_observe(kk, pp, b, step, kk.dz_sim, kfp);
+      o = dyn_observe(kk, pp, b, step, kk.dz_sim, kfp, exp_);
       const uint32_t sid2 = (uint32_t)discretise_cuts(cuts, kk.angle_cut, o).id();
       if (o.contact) code = DQLB200_TERMINAL_CONTACT;
       else if (!(o.rel_p >= kk.fz_lo) || (o.rel_p >= kk.fz_hi)) code = DQLB200_TERMINAL_FLYZONE_X;
@@ -112,25 +116,29 @@ __global__ void __launch_bounds__(128) env_reset_kernel(const __grid_constant__ 
   Env e;
   env_load(env, (size_t)i, e);
   const bool filt = kc.accel_mode != 0 && env.d;
+  const bool so = kc.dynamics_model != 0 && env.e;
   Kf kf;
+  Ext ex;
   if (filt) kf = kf_load(env, (size_t)i);
+  if (so) ex = ext_load(env, (size_t)i);
   if (!mask || mask[i]) {
     const int pop = (int)(i / kc.envs_per_population);
     const uint32_t env_i = (uint32_t)(i % kc.envs_per_population);
     const dqlb200_population_params pp = pop_params[pop];
     if (simulation) {      // SimulationLandingEnv.reset (PKG/landing_simulation_env.py:327-340) + SimulationMdp.reset (PKG/mdp.py:879-886)
       const uint4 d = philox4x32_10(make_uint4(env_i, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
-      const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim, filt ? &kf : nullptr);
+      const Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/false, /*simulation=*/true, kc.dz_sim, filt ? &kf : nullptr, so ? &ex : nullptr);
       const DState ds = discretise_cuts(kc.cuts[w], kc.angle_cut, o);
       e.sid = (uint32_t)ds.id(); e.bp = (uint32_t)ds.bp;
       e.step_count = 0; e.curriculum_check = 0; e.sticky_success = false; e.fresh = true; e.cum_reward = 0.0;
       e.theta_sp = 0.0; e.prev_rel_p = 0.0f; e.prev_rel_v = 0.0f;
       if (fresh_mdp) e.episode = 0;
     } else {
-      env_reset(kc, pp, kc.cuts[w], kc.angle_cut, e, env_i, birth, w, fresh_mdp != 0, filt ? &kf : nullptr);
+      env_reset(kc, pp, kc.cuts[w], kc.angle_cut, e, env_i, birth, w, fresh_mdp != 0, filt ? &kf : nullptr, so ? &ex : nullptr);
     }
     env_store(env, (size_t)i, e);
     if (filt) kf_store(env, (size_t)i, kf);
+    if (so) ext_store(env, (size_t)i, ex);
   }
   if (out_state) out_state[i] = (uint16_t)e.sid;
 }
@@ -150,15 +158,18 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   Env e;
   env_load(env, (size_t)i, e);
   const bool filt = kc.accel_mode != 0 && env.d;
+  const bool so = kc.dynamics_model != 0 && env.e;
   Kf kf;
+  Ext ex;
   if (filt) kf = kf_load(env, (size_t)i);
+  if (so) ex = ext_load(env, (size_t)i);
   const int a = actions[i];
   // R3 .. R8 in the order of TrainingLandingEnv.step (PKG/landing_simulation_env.py:245-282)
   const double prev_sp = e.theta_sp;
   const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
-  dyn_advance(kc, pp, e.b, (float)sp, filt ? &kf : nullptr);
+  dyn_advance(kc, pp, e.b, (float)sp, filt ? &kf : nullptr, so ? &ex : nullptr, simulation ? kc.vz_sim : kc.vz_train);
   const uint32_t step_count = e.step_count + 1u;
-  Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train, filt ? &kf : nullptr);
+  Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
   if (kc.noise_enabled && !simulation) {      // the words the fused kernel uses at global step t
     const uint4 d = philox4x32_10(make_uint4(env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
     add_observation_noise(kc, o, d.z, d.w);
@@ -210,10 +221,11 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
   e.fresh = false;
   e.cum_reward = __dadd_rn(e.cum_reward, r);
-  if (done && auto_reset && !simulation) env_reset(kc, pp, cuts, kc.angle_cut, e, env_i, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr);
+  if (done && auto_reset && !simulation) env_reset(kc, pp, cuts, kc.angle_cut, e, env_i, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr, so ? &ex : nullptr);
   if (out_state) out_state[i] = (uint16_t)e.sid;       // of a finished env with auto_reset: the first state of its next episode
   env_store(env, (size_t)i, e);
   if (filt) kf_store(env, (size_t)i, kf);
+  if (so) ext_store(env, (size_t)i, ex);
 }
 
 // -------------------------------------------------------------------------------------------------

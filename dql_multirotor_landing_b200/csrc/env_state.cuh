@@ -28,7 +28,21 @@ struct EnvPtrs {
   uint4* b;
   uint4* c;
   uint4* d;      // acceleration-estimator state (accel_mode != 0 only, else null): {x, P, v_ref, n}
+  uint4* e;      // second-order model state (dynamics_model != 0 only, else null): [2][n] {omega, z, v_z, integral}, {e1, f1, f2, f3}
+  size_t n;      // envs in the SoA (stride of `e`)
 };
+__device__ __forceinline__ Ext ext_load(const EnvPtrs& p, size_t i) {
+  const uint4 u = p.e[i], v = p.e[p.n + i];
+  return Ext{__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w),
+             __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+}
+__device__ __forceinline__ void ext_store(const EnvPtrs& p, size_t i, const Ext& x) {
+  p.e[i] = make_uint4(__float_as_uint(x.omega), __float_as_uint(x.z), __float_as_uint(x.v_z), __float_as_uint(x.integ));
+  p.e[p.n + i] = make_uint4(__float_as_uint(x.e1), __float_as_uint(x.f1), __float_as_uint(x.f2), __float_as_uint(x.f3));
+}
+// a simulator that has been hovering: the integral holds the hover thrust (m g / Ki), the filter memory is empty
+template <class KT>
+__device__ __forceinline__ Ext ext_initial(const KT& kc) { return Ext{0.0f, kc.z_init, 0.0f, kc.pid_i0, 0.0f, 0.0f, 0.0f, 0.0f}; }
 __device__ __forceinline__ Kf kf_load(const EnvPtrs& p, size_t i) {
   const uint4 v = p.d[i];
   return Kf{__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), v.w};
@@ -104,9 +118,9 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
 template <class KT, class AC>
 __device__ __forceinline__ void env_reset(const KT& kc, const dqlb200_population_params& pp,
                                           const dqlb200_cuts& cuts, const AC& angle_cut, Env& e,
-                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp, Kf* kf = nullptr) {
+                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp, Kf* kf = nullptr, Ext* ext = nullptr) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
-  Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train, kf);
+  Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train, kf, ext);
   if (kc.noise_enabled) {
     const uint4 dn = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET_NOISE, pp.population_id), pp.seed_lo, pp.seed_hi);
     add_observation_noise(kc, o, dn.x, dn.y);

@@ -67,6 +67,9 @@ struct Shared {
 #ifndef DQL_WARPS_PER_SM
 #define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
+#ifndef DQL_WARPS_PER_SM_GENERIC
+#define DQL_WARPS_PER_SM_GENERIC 20     // the extended instance carries the estimator and the second-order model: 5 CTAs/SM, 102 registers
+#endif
 template <bool GENERIC_> struct ConstsOf;
 template <> struct ConstsOf<true> {
   __device__ __forceinline__ static const KC& get(const KC& kc) { return kc; }
@@ -80,8 +83,11 @@ template <> struct ConstsOf<false> {
 // correction step of x / p_max, x / v_max (required unless the divisors are the exhaustively verified defaults) and the
 // observation-noise option.  The trace instances are generic
 // (both division variants are correctly rounded, hence identical).
-template <int WARPS, bool TRACE, bool GENERIC>
-__global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (DQL_WARPS_PER_SM / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+// VARIANT 0 = production, 1 = generic, 2 = extended: generic plus the options that carry extra per-env state (acceleration
+// estimator, second-order model) -- a separate instance so that the generic one does not pay for their branches and registers.
+template <int WARPS, bool TRACE, int VARIANT>
+__global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_GENERIC : DQL_WARPS_PER_SM) / WARPS) > 0 ? ((VARIANT == 2 ? DQL_WARPS_PER_SM_GENERIC : DQL_WARPS_PER_SM) / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
+  constexpr bool GENERIC = VARIANT >= 1, EXT = VARIANT == 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const auto& kk = ConstsOf<GENERIC>::get(kc);       // run-time KC (generic) or the compile-time defaults KDef (production)
@@ -130,7 +136,8 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
 
   const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
   const float alpha_min = __ldg(alpha_lut + DQLB200_ALPHA_LUT - 1);      // alpha(count >= 1002), PKG/trainer.py:95-105
-  const bool filt = GENERIC && kk.accel_mode != 0;      // acceleration estimator: 16 more bytes per env, generic instance only
+  const bool filt = EXT && kc.accel_mode != 0;      // acceleration estimator: 16 more bytes per env, extended instance only
+  const bool so = EXT && kc.dynamics_model != 0;    // second-order attitude + vertical PID: 32 more bytes per env
   uint64_t steps_done = 0;
 
   // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
@@ -185,10 +192,13 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         if (env_i < n_p) {
           Env e;
           Kf kf;
+          Ext ex;
           if (filt) kf = kf_load(args.env, env_base + env_i);       // the estimator outlives the curriculum step
-          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true, filt ? &kf : nullptr);
+          if (so) ex = ext_load(args.env, env_base + env_i);
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true, filt ? &kf : nullptr, so ? &ex : nullptr);
           env_store(args.env, env_base + env_i, e);
           if (filt) kf_store(args.env, env_base + env_i, kf);
+          if (so) ext_store(args.env, env_base + env_i, ex);
         }
       }
     }
@@ -236,10 +246,13 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
           Env e;
           env_load(args.env, gr, e);
           Kf kf;
+          Ext ex;
           if (filt) kf = kf_load(args.env, gr);
-          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr);
+          if (so) ex = ext_load(args.env, gr);
+          env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr, so ? &ex : nullptr);
           env_store(args.env, gr, e);
           if (filt) kf_store(args.env, gr, kf);
+          if (so) ext_store(args.env, gr, ex);
         }
       }
       __syncwarp();
@@ -261,11 +274,13 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       double ep_return = 0.0;
       Env e;
       Kf kf;
+      Ext ex;
       uint32_t c_hint = 0;
       float a_hint = 0.0f;
       if (valid) {
         env_unpack(cur_raw, e);
         if (filt) kf = kf_load(args.env, gi);
+        if (so) ex = ext_load(args.env, gi);
         const uint32_t sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
@@ -297,9 +312,9 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
         const double prev_sp = e.theta_sp;
         const double sp = apply_action(kk, e.fresh ? 0.0 : e.theta_sp, a);
         // R4
-        dyn_advance(kk, pp, e.b, (float)sp, filt ? &kf : nullptr);
+        dyn_advance(kk, pp, e.b, (float)sp, filt ? &kf : nullptr, so ? &ex : nullptr, kk.vz_train);
         const uint32_t step_count = e.step_count + 1u;
-        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr);
+        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
         if (GENERIC && kk.noise_enabled) add_observation_noise(kk, o, noise_w0, noise_w1);
         // R5
         const DState ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
@@ -461,6 +476,7 @@ __global__ void __launch_bounds__(WARPS * 32, (DQL_WARPS_PER_SM / WARPS) > 0 ? (
       // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
       if (valid) env_store(args.env, gi, e);
       if (filt && valid) kf_store(args.env, gi, kf);
+      if (so && valid) ext_store(args.env, gi, ex);
       // queue the finished envs of this warp for the batched reset (outside the baton)
       if (dmask) {
         if (valid && done) reset_queue[n_queued + __popc(dmask & ((1u << lane) - 1u))] = (uint16_t)(slot * 32 + lane);

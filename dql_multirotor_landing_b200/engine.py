@@ -70,6 +70,13 @@ class Engine:
                 fs[:, 1] = 0x3F800000     # P = 1.0f (PKG/filters.py:16): a simulator that has not published yet
             self.filter_state = fs
             _ffi.check(self.lib.dqlb200_bind_filter_state(self.handle, fs.data_ptr()))
+        self.dynamics_state = None
+        if self.cfg.dynamics_model != 0:  # [2][n] x 16 B {omega, z, v_z, integral}, {e1, f1, f2, f3}; dqlb200_reset initialises it
+            with torch.cuda.device(self.device):
+                self.dynamics_state = torch.zeros((2, n, 4), dtype=torch.float32, device=self.device)
+                self.dynamics_state[0, :, 1] = float(self.cfg.z_init)
+                self.dynamics_state[0, :, 3] = float(self.cfg.pid_i0)
+            _ffi.check(self.lib.dqlb200_bind_dynamics_state(self.handle, self.dynamics_state.data_ptr()))
         self._trace_keep = None
         self.merge_snapshot = None       # replica-merge mode: [n_groups][3][MAX_CELLS] merged tables of the last merge
         self.pooled_promote = K.promote_threshold(self.tp.successive_successful_episodes * self.R, self.tp.success_rate)

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 4
+#define DQLB200_ABI_VERSION 5
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -128,6 +128,18 @@ typedef struct dqlb200_config {
    * Needs dqlb200_bind_filter_state(). */
   int32_t accel_mode;
   float kf_q, kf_r;                 /* process variance (1e-4), measurement variance (noise_vel_sd^2, scripts/manager_node.py:96-98) */
+  /* ---- higher-fidelity per-env model; 0 = the first-order stand-in (default), 1 = second order:
+   *   attitude: the geometric controller of PKG/attitude_controller.py:124-156 reduced to one axis, torque M = -k_R sin(theta -
+   *     theta_sp) - k_w omega on the inertia J (att_kr = k_R / J = 0.7 / 0.007, att_kw = k_w / J = 0.1 / 0.007)
+   *   vertical: the v_z PID node (PKG/pid.py:62-104, gains launch/drone.launch:33-46: Kp 5, Ki 10, Kd 0, effort in [0, 10] N,
+   *     wind-up 10) with its Butterworth error filter (PKG/filters.py:83-108), `pid_ticks` (2..64) node iterations per sub-step;
+   *     thrust along the body axis: a_x = sign * (T / m) sin(theta) - c_d v, a_z = (T / m) cos(theta) - g  (m = 0.68)
+   * Altitude becomes state (the first-order model derives it from the step count).  Needs dqlb200_bind_dynamics_state(). */
+  int32_t dynamics_model, pid_ticks;
+  float att_kr, att_kw, inv_m, inv_mg, g_abs;
+  float pid_kp, pid_ki, pid_lo, pid_hi, pid_windup, pid_dt, pid_i0 /* m g / Ki: the integral of a hovering simulator */;
+  float bw_inv_denom, bw_k2;        /* 1 / (1 + c^2 + 1.414 c), c^2 - 1.414 c + 1 with c = 1 (PKG/filters.py:92-93,103) */
+  float vz_train, vz_sim;           /* v_z set-points -0.1 / -0.4 (PKG/mdp.py:212, 580) */
   uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
 } dqlb200_config;
 
@@ -239,6 +251,11 @@ int dqlb200_bind(dqlb200_handle* h, void* env_state, void* tables, void* pop_sta
  * Replaces: ObservationUtils.filter / last_velocity / last_timestep (PKG/observation_utils.py:44-50).  dqlb200_reset()
  * initialises it (x = 0, P = 1, PKG/filters.py:15-16); nothing else ever clears it. */
 int dqlb200_bind_filter_state(dqlb200_handle* h, void* filter_state);
+
+/* Borrow the per-env state of the second-order model (dynamics_model != 0): 32 bytes per env as [2][n] 16-byte vectors
+ * {omega, z, v_z, PID integral}, {e1, f1, f2, f3 (Butterworth memory: previous input, three previous outputs)}, 16-B aligned.  Replaces: the Gazebo body state the
+ * first-order model does not carry and the memory of the pid_v_z node (PKG/pid.py:14-23).  dqlb200_reset() initialises it. */
+int dqlb200_bind_dynamics_state(dqlb200_handle* h, void* dynamics_state);
 
 /* Replaces: env.reset() for every env + a fresh TrainingMdp (PKG/landing_simulation_env.py:167-243,
  * PKG/trainer.py:176-189).  Sets every population to working step `initial_step`, t = 0. */

@@ -56,6 +56,18 @@ class StandInParams:
     accel_mode: str = "exact"
     kf_process_variance: float = 1e-4     # scripts/manager_node.py:96-98
     kf_measurement_sd: float = 0.1        # manager_node hands noise_vel_sd (default 0.1) to KalmanFilter3D; R = sd ** 2 (PKG/filters.py:50-52)
+    # "first_order" | "second_order" (SURVEY 8f-4): see SecondOrder
+    dynamics_model: str = "first_order"
+    mass: float = 0.68                    # PKG/attitude_controller.py:57
+    inertia: float = 0.007                # PKG/attitude_controller.py:59
+    k_R: float = 0.7                      # PKG/attitude_controller.py:86
+    k_omega: float = 0.1                  # PKG/attitude_controller.py:87
+    pid_kp: float = 5.0                   # launch/drone.launch:35-40
+    pid_ki: float = 10.0
+    pid_lower: float = 0.0
+    pid_upper: float = 10.0
+    pid_windup: float = 10.0
+    pid_ticks: int = 10                   # PKG/pid.py:14 rate_hz = 1000 against the 100 Hz state topic
 
 
 @dataclass(frozen=True)
@@ -179,6 +191,61 @@ def add_observation_noise(p: "StandInParams", rel_p, rel_v, w0, w1):
             (np.asarray(rel_v, np.float32) + f32(p.noise_vel_sd) * n1).astype(np.float32))
 
 
+_SS = [f32(-1.0 / 6.0), f32(1.0 / 120.0), f32(-1.0 / 5040.0), f32(1.0 / 362880.0)]
+
+
+def det_sin_small(x):
+    """sin(x), |x| <= ~0.8 rad (Taylor to x**9, Horner, no FMA) -- the kernels' det_sin_small."""
+    x = np.asarray(x, np.float32)
+    z = x * x
+    p = _SS[3]
+    for c in (_SS[2], _SS[1], _SS[0]):
+        p = p * z + c
+    return (x + x * (z * p)).astype(np.float32)
+
+
+def det_cos_small(x):
+    """cos(x), |x| <= ~0.8 rad (Taylor to x**10) -- the kernels' det_cos_small."""
+    x = np.asarray(x, np.float32)
+    z = x * x
+    p = _C[4]
+    for c in (_C[3], _C[2], _C[1], _C[0]):
+        p = p * z + c
+    return (ONE + z * p).astype(np.float32)
+
+
+class VerticalPid:
+    """The pid_v_z node (PKG/pid.py:62-104; gains launch/drone.launch:33-46, Kd = 0) in fp32, vectorised over envs: integral
+    with wind-up clip (:85-86), ButterworthFilter on the error (PKG/filters.py:83-108, c = 1), effort = clip(Kp f + Ki I, lower,
+    upper) (:97-103).  The filter as written pushes the new input BEFORE the sum and the new output after it, so its output
+    taps are one sample older than its input taps (quirk Q14): y_k = (x_k-2 + 2 x_k-1 + x_k - 0.586 y_k-3 - 0 * y_k-2) / 3.414.  `ticks` node iterations per call on a
+    held error (the node spins at 1 kHz, its state topic arrives at 100 Hz); dt = h / ticks.  The memory is the node's: it
+    survives episode resets.  A simulator that has been hovering starts with I = m g / Ki."""
+
+    def __init__(self, n: int, p: "StandInParams", h: float):
+        self.kp, self.ki = f32(p.pid_kp), f32(p.pid_ki)
+        self.lo, self.hi, self.windup = f32(p.pid_lower), f32(p.pid_upper), f32(p.pid_windup)
+        self.ticks, self.dt = p.pid_ticks, f32(h / p.pid_ticks)
+        self.inv_denom, self.k2 = f32(1.0 / (1 + 1.0 ** 2 + 1.414 * 1.0)), f32(1.0 ** 2 - 1.414 * 1.0 + 1)
+        self.integ = np.full(n, f32(p.mass * abs(p.g) / p.pid_ki), f32)
+        assert self.ticks >= 2        # the held error makes both previous filter inputs equal at a sub-step boundary
+        self.e1, self.f1, self.f2, self.f3 = (np.zeros(n, f32) for _ in range(4))
+
+    def thrust(self, idx, error):
+        e = np.asarray(error, f32)
+        I, e1, f1, f2, f3 = self.integ[idx], self.e1[idx], self.f1[idx], self.f2[idx], self.f3[idx]
+        e2 = e1
+        T = np.zeros_like(e)
+        for _ in range(self.ticks):
+            I = np.clip(I + e * self.dt, -self.windup, self.windup).astype(np.float32)
+            f = (self.inv_denom * (((e2 + f32(2.0) * e1) + e) - self.k2 * f3)).astype(np.float32)
+            e2, e1 = e1, e
+            f3, f2, f1 = f2, f1, f
+            T = np.clip(self.kp * f + self.ki * I, self.lo, self.hi).astype(np.float32)
+        self.integ[idx], self.e1[idx], self.f1[idx], self.f2[idx], self.f3[idx] = I, e + np.zeros_like(I), f1, f2, f3
+        return T
+
+
 class KalmanAccel:
     """The acceleration estimator of the reference's observation node, vectorised over envs, fp32 with one rounding per
     operation (the CUDA kernels' kf_sample is the same arithmetic): KalmanFilter1D (PKG/filters.py:4-37; x = 0, P = 1, Q = process
@@ -234,6 +301,15 @@ class StandInDet:
         self.theta = np.zeros(n, f32)
         self.phase = np.zeros(n, np.uint32)
         self.a_d = np.zeros(n, f32)
+        self.so = params.dynamics_model == "second_order"
+        if self.so:       # pitch rate, altitude, vertical velocity are state; the PID node has memory
+            self.omega = np.zeros(n, f32)
+            self.z = np.full(n, self.d.z_init, f32)
+            self.v_z = np.zeros(n, f32)
+            self.pid = VerticalPid(n, params, float(self.d.h))
+            self.att_kr, self.att_kw = f32(params.k_R / params.inertia), f32(params.k_omega / params.inertia)
+            self.inv_m, self.inv_mg, self.g_abs = f32(1.0 / params.mass), f32(1.0 / (params.mass * abs(params.g))), f32(abs(params.g))
+            self.vz_sp = f32(params.v_z)
         self.kf = None
         if params.accel_mode != "exact":
             self.kf = KalmanAccel(n, params.accel_mode, self.d.h, params.kf_process_variance, params.kf_measurement_sd ** 2)
@@ -262,17 +338,36 @@ class StandInDet:
         self.v_d[idx] = 0
         self.theta[idx] = 0
         self.phase[idx] = phase
+        if self.so:       # teleport with zero twist (PKG/landing_simulation_env.py:203-216); the PID memory stays
+            self.omega[idx] = 0
+            self.z[idx] = self.d.z_init
+            self.v_z[idx] = 0
 
-    def advance(self, theta_sp, idx=None):
-        """One agent period (n_sub sub-steps) toward set-point theta_sp (fp32 array)."""
+    def advance(self, theta_sp, idx=None, hover: bool = False):
+        """One agent period (n_sub sub-steps) toward set-point theta_sp (fp32 array).  hover = True: the period after a reset,
+        every set-point zero (scripts/manager_node.py:328) -- only the second-order model has a vertical set-point."""
         d = self.d
         sl = slice(None) if idx is None else idx
         x, v, th, ph = self.x_d[sl], self.v_d[sl], self.theta[sl], self.phase[sl]
         sp = np.asarray(theta_sp, dtype=np.float32)
         a = self.a_d[sl]
         for _ in range(d.n_sub):
-            th = th + (sp - th) * d.k_theta
-            a = d.g * det_tan(th) - d.c_d * v
+            if self.so:
+                ii = np.arange(self.n) if idx is None else np.asarray(idx)
+                om, z, vz = self.omega[ii], self.z[ii], self.v_z[ii]
+                T = self.pid.thrust(ii, (f32(0.0) if hover else self.vz_sp) - vz)
+                # PKG/attitude_controller.py:124-156 on one axis: torque -k_R sin(theta - theta_sp) - k_w omega on inertia J
+                alpha = -(self.att_kr * det_sin_small(th - sp)) - self.att_kw * om
+                om = (om + alpha * d.h).astype(np.float32)
+                th = (th + om * d.h).astype(np.float32)
+                a = (d.g * (T * self.inv_mg)) * det_sin_small(th) - d.c_d * v
+                a_z = (T * det_cos_small(th)) * self.inv_m - self.g_abs
+                z = ((z + vz * d.h) + a_z * d.half_h2).astype(np.float32)
+                vz = (vz + a_z * d.h).astype(np.float32)
+                self.omega[ii], self.z[ii], self.v_z[ii] = om, z, vz
+            else:
+                th = th + (sp - th) * d.k_theta
+                a = d.g * det_tan(th) - d.c_d * v
             x = (x + v * d.h) + a * d.half_h2
             v = v + a * d.h
             ph = ph + np.uint32(d.dphase)
@@ -292,6 +387,8 @@ class StandInDet:
         if self.kf is not None:
             rel_a = self.kf.x[sl].copy()
         z = d.z_init + np.asarray(step_count).astype(np.float32) * d.dz
+        if self.so:
+            z = self.z[sl].copy()
         contact = (z <= d.z_touch) & (np.abs(rel_p) <= d.half_platform)
         return (rel_p.astype(np.float32), rel_v.astype(np.float32), rel_a.astype(np.float32),
                 self.theta[sl].copy(), z.astype(np.float32), contact)

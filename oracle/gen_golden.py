@@ -14,6 +14,8 @@ Fixtures:
   sim_trace.npz    SimulationMdp greedy episodes with the committed assets policy
   sim2d_trace.npz  two-axis SimulationMdp episodes (x and y states, FLYZONE_Y, contact on both axes), three platform cases
   kalman_accel.npz the reference KalmanFilter3D (PKG/filters.py) driven the way ObservationUtils drives it, on stand-in velocities
+  second_order.npz the reference PID node (PKG/pid.py, Butterworth filter included) on the v_z errors of a second-order stand-in
+                   run, and the reference AttitudeController moment (PKG/attitude_controller.py:124-156) for pure pitch states
 """
 from __future__ import annotations
 
@@ -443,6 +445,137 @@ def gen_kalman(n_steps=700, seed=11):
     print("kalman_accel:", len(v), "samples")
 
 
+def gen_second_order(n_steps=400, seed=13):
+    """SURVEY 8f-4 pins.  (1) PKG/pid.py PID.output() -- unmodified; the object is created without running __init__ (which
+    spins forever in run()), its fields are set as __init__ / load_params set them (PKG/pid.py:14-23,33-48) with the gains of
+    launch/drone.launch:33-46, rospy.Time.now() is a controllable clock at the node's 1 kHz and the publisher records the
+    efforts.  Input: the held v_z errors of a second-order stand-in episode sequence (10 node iterations per 100 Hz sample).
+    (2) AttitudeController._compute_desired_moment() -- unmodified, with tf.transformations replaced by the two textbook
+    functions it uses -- for pure pitch attitudes: the y moment must be -k_R sin(theta - theta_sp) - k_w omega."""
+    import importlib
+    import sys
+    import types
+    ref_stubs.install()
+
+    class _Dur:
+        def __init__(self, s): self.s = s
+        def to_sec(self): return self.s
+
+    class _Time:
+        def __init__(self, s): self.s = s
+        def __sub__(self, o): return _Dur(self.s - o.s)
+        def to_sec(self): return self.s
+
+    clock = [0.0]
+    rospy = types.ModuleType("rospy")
+    rospy.Time = types.SimpleNamespace(now=lambda: _Time(clock[0]))
+    rospy.logerr = lambda *a, **k: None
+    sys.modules["rospy"] = rospy
+    std = types.ModuleType("std_msgs")
+    stdm = types.ModuleType("std_msgs.msg")
+
+    class Float64:
+        def __init__(self, data=0.0): self.data = data
+
+    stdm.Float64 = Float64
+    std.msg = stdm
+    sys.modules["std_msgs"], sys.modules["std_msgs.msg"] = std, stdm
+    gm, gmm = types.ModuleType("geometry_msgs"), types.ModuleType("geometry_msgs.msg")
+    gmm.Vector3Stamped = type("Vector3Stamped", (), {})
+    gm.msg = gmm
+    sys.modules.setdefault("geometry_msgs", gm)
+    sys.modules.setdefault("geometry_msgs.msg", gmm)
+    tf = types.ModuleType("tf")
+    tft = types.ModuleType("tf.transformations")
+
+    def rotation_matrix(angle, axis):
+        x, y, z = np.asarray(axis, float) / np.linalg.norm(axis)
+        c, s_ = np.cos(angle), np.sin(angle)
+        Km = np.array([[0, -z, y], [z, 0, -x], [-y, x, 0]])
+        M = np.eye(4)
+        M[:3, :3] = np.eye(3) * c + s_ * Km + (1 - c) * np.outer([x, y, z], [x, y, z])
+        return M
+
+    def quaternion_matrix(q):
+        x, y, z, w = q
+        M = np.eye(4)
+        M[:3, :3] = [[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                     [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                     [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]]
+        return M
+
+    tft.rotation_matrix, tft.quaternion_matrix = rotation_matrix, quaternion_matrix
+    tf.transformations = tft
+    sys.modules["tf"], sys.modules["tf.transformations"] = tf, tft
+    pid_mod = importlib.import_module("dql_multirotor_landing.pid")
+    att_mod = importlib.import_module("dql_multirotor_landing.attitude_controller")
+    from collections import deque
+
+    # ---- (1) the vertical PID on a second-order stand-in run ------------------------------------------------------------
+    rng = np.random.default_rng(seed)
+    sp = StandInParams(n_sub=4, dynamics_model="second_order")
+    dyn = StandInDet(sp, 1)
+    errors, thrusts = [], []
+    orig = dyn.pid.thrust
+    def rec(idx, e):
+        T = orig(idx, e)
+        errors.append(np.float32(np.asarray(e).reshape(-1)[0]))
+        thrusts.append(np.float32(T.reshape(-1)[0]))
+        return T
+    dyn.pid.thrust = rec
+    idx = np.arange(1)
+    step = 0
+    while step < n_steps:
+        w = rng.integers(0, 2 ** 32, size=3, dtype=np.uint64).astype(np.uint32)
+        dyn.reset(idx, w[0:1], w[1:2], w[2:3], normal_init=True)
+        dyn.advance(np.zeros(1, np.float32), idx, hover=True)
+        theta = 0.0
+        for _ in range(int(rng.integers(40, 160))):
+            theta = float(np.clip(theta + rng.choice([-1, 0, 1]) * np.deg2rad(7.12574), -0.3731, 0.3731))
+            dyn.advance(np.asarray([theta], np.float32), idx)
+            step += 1
+    errors = np.asarray(errors, np.float32)
+    node = object.__new__(pid_mod.PID)
+    node.rate_hz = 1000.0
+    node.error = deque([0.0, 0.0], maxlen=3)
+    node.error_deriv = deque([0.0, 0.0, 0.0], maxlen=3)
+    node.filter_error, node.filter_deriv = pid_mod.ButterworthFilter(), pid_mod.ButterworthFilter()
+    node.error_integral = sp.mass * sp.g / sp.pid_ki          # a simulator that has been hovering
+    node.current_state, node.setpoint = 0.0, 0.0
+    node.Kp, node.Ki, node.Kd = 5.0, 10.0, 0.0               # launch/drone.launch:35-37
+    node.upper_limit, node.lower_limit, node.windup_limit = 10.0, 0.0, 10.0
+    efforts = []
+    node.effort_pub = types.SimpleNamespace(publish=lambda m: efforts.append(float(m.data)))
+    node.prev_time = _Time(0.0)
+    dt = float(dyn.pid.dt)
+    ref_T, tick = [], 0
+    for e in errors:
+        node.setpoint, node.current_state = float(e), 0.0      # error = setpoint - state
+        for _ in range(sp.pid_ticks):
+            tick += 1
+            clock[0] = tick * dt
+            node.output()
+        ref_T.append(efforts[-1])
+    out = dict(pid_error=errors, pid_thrust_ref=np.asarray(ref_T, np.float64), pid_thrust_oracle=np.asarray(thrusts, np.float32),
+               pid_dt=np.float32(dt), pid_i0=np.float64(sp.mass * sp.g / sp.pid_ki))
+
+    # ---- (2) the attitude moment for pure pitch states -------------------------------------------------------------------
+    ctrl = att_mod.AttitudeController()
+    n = 400
+    th, th_sp, om = rng.uniform(-0.45, 0.45, n), rng.uniform(-0.3731, 0.3731, n), rng.uniform(-3, 3, n)
+    M = np.zeros((n, 3))
+    for i in range(n):
+        ctrl.state = att_mod.StateMsg(roll=0.0, pitch=float(th_sp[i]), yaw_rate=0.0)
+        ctrl.odometry = types.SimpleNamespace(orientation=np.array([0.0, np.sin(th[i] / 2), 0.0, np.cos(th[i] / 2)]),
+                                              angular_velocity=np.array([0.0, om[i], 0.0]))
+        M[i] = ctrl._compute_desired_moment()
+    out.update(att_theta=th, att_theta_sp=th_sp, att_omega=om, att_moment_ref=M,
+               att_inertia=np.diag(ctrl.drone.inertia).copy(), att_mass=np.float64(ctrl.drone.mass))
+    np.savez_compressed(GOLDEN / "second_order.npz", **out)
+    print("second_order:", len(errors), "pid samples; max |T_ref - T_oracle| =",
+          float(np.abs(out["pid_thrust_ref"] - out["pid_thrust_oracle"]).max()))
+
+
 def _state_tuple(sid: int):
     th = sid % 7; sid //= 7
     a = sid % 3; sid //= 3
@@ -473,6 +606,7 @@ def main():
     gen_sim_trace(ns)
     gen_sim2d_trace(ns)
     gen_kalman()
+    gen_second_order()
     total = sum(f.stat().st_size for f in GOLDEN.glob("*.npz"))
     print("golden bytes:", total)
 

@@ -87,7 +87,7 @@ class PopulationOracle:
             return
         w0, w1, w2, _ = philox.draws(self.seed, self.pop, idx, birth, philox.PURPOSE_RESET)
         self.dyn.reset(idx, w0, w1, w2, normal_init=(self.w == 0))
-        self.dyn.advance(np.zeros(idx.size, np.float32), idx)
+        self.dyn.advance(np.zeros(idx.size, np.float32), idx, hover=True)
         rel_p, rel_v, rel_a, pitch, z, contact = self.dyn.observe(np.zeros(idx.size), idx)
         if self.sp.noise_pos_sd or self.sp.noise_vel_sd:
             n0, n1, _, _ = philox.draws(self.seed, self.pop, idx, birth, philox.PURPOSE_RESET_NOISE)
@@ -254,7 +254,7 @@ def eval_episode(policy, seed: int, population: int, episode_id: int, sp: StandI
     idx = np.asarray([0])
     w0, w1, w2, _ = philox.draws(seed, population, np.asarray([episode_id]), 0, philox.PURPOSE_RESET)
     dyn.reset(idx, w0, w1, w2, normal_init=False, simulation=True)
-    dyn.advance(np.zeros(1, np.float32))
+    dyn.advance(np.zeros(1, np.float32), hover=True)
     rp, rv, ra, pit, z, c = (x[0] for x in dyn.observe(np.zeros(1)))
     sx, _ = mdp.observe(rp, rv, ra, pit, z, c)
     rows = [dict(obs=(rp, rv, ra, pit, z), contact=c, action=255, state=state_id(sx), code=0, done=0)]

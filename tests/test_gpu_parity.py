@@ -211,6 +211,65 @@ def test_kalman_acceleration_option_vs_oracle(accel_mode):
     assert torch.equal(eng2.filter_state, eng.filter_state)
 
 
+def test_second_order_dynamics_option_vs_oracle():
+    """second-order attitude (geometric controller torque on the inertia, PKG/attitude_controller.py:124-156) +
+    the vertical PID node (PKG/pid.py:62-104, 10 node iterations per 100 Hz sub-step, Butterworth filter with the reference's
+    tap shift) + thrust-coupled horizontal acceleration; altitude is state.  Combined with the Kalman acceleration estimate
+    and observation noise, through resets and promotions (the PID memory is never reset).  Bit-exact against the oracle,
+    whose controllers tests/test_oracle_golden.py pins to the unmodified reference classes."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    dyn = dict(dynamics_model="second_order", n_sub=4, accel_mode="kalman", noise_pos_sd=0.1, noise_vel_sd=0.05)
+    n_envs, steps = 70, 260
+    eng = _engine(1, n_envs, threads_per_block=64, seeds=[9], tp=kw, dp=dyn)
+    eng.reset(0)
+    tr = eng.train(steps, trace=True)
+    eng.check_errors()
+    pop = PopulationOracle(n_envs, seed=9, population=0, w0=0, dtype=np.float32, tp=TrainerParams(**kw), sp=StandInParams(**dyn))
+    for t in range(steps):
+        o = pop.step()
+        assert np.array_equal(tr["obs"][t].view(np.uint32), o["obs"].view(np.uint32)), t
+        for key in ("action", "code", "done"):
+            assert np.array_equal(tr[key][t], o[key]), (t, key)
+        assert np.array_equal(tr["next_state"][t].astype(np.uint16), o["next_state"]), t
+        assert np.array_equal(tr["reward"][t], o["reward"]), t
+    qa, _, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(cnt, pop.agent.count) and np.array_equal(qa.view(np.uint32), pop.agent.qa.view(np.uint32))
+    assert int(eng.population_state()[0]["working_step"]) == pop.w >= 1
+    ds = eng.dynamics_state.cpu().numpy()          # [2][n][4]: {omega, z, v_z, integral}, {e1, f1, f2, f3}
+    d = pop.dyn
+    for k, ref in enumerate((d.omega, d.z, d.v_z, d.pid.integ)):
+        assert np.array_equal(ds[0, :, k].view(np.uint32), ref.view(np.uint32)), k
+    for k, ref in enumerate((d.pid.e1, d.pid.f1, d.pid.f2, d.pid.f3)):
+        assert np.array_equal(ds[1, :, k].view(np.uint32), ref.view(np.uint32)), k
+    assert np.median(np.abs(ds[0, :, 2] + 0.1)) < 0.03     # the PID holds the commanded descent rate while the drone pitches
+    # the production (non-trace) generic instance
+    eng2 = _engine(1, n_envs, threads_per_block=64, seeds=[9], tp=kw, dp=dyn)
+    eng2.reset(0)
+    eng2.train(steps)
+    assert torch.equal(eng2.tables, eng.tables) and torch.equal(eng2.env_state, eng.env_state)
+    assert torch.equal(eng2.dynamics_state, eng.dynamics_state) and torch.equal(eng2.filter_state, eng.filter_state)
+
+
+def test_second_order_greedy_evaluation_vs_oracle():
+    """The greedy SimulationMdp path (R15) on the second-order model: v_z set-point -0.4, altitude from the PID loop."""
+    from oracle.agent_oracle import state_id
+    rng = np.random.default_rng(4)
+    lut = rng.integers(0, 3, size=945).astype(np.uint8)
+    dyn = dict(dynamics_model="second_order", n_sub=4)
+    eng = _engine(1, 32, threads_per_block=32, seeds=[21], dp=dyn)
+    n_ep, trace_steps = 6, 470
+    tr = eng.eval_greedy(lut, n_ep, trace_steps=trace_steps)["trace"]
+    sp = StandInParams(v_z=-0.4, **dyn)
+    for ep in range(n_ep):
+        rows = eval_episode(lambda s: int(lut[state_id(s)]), 21, 0, ep, sp)
+        n = len(rows) - 1
+        obs = np.asarray([r["obs"] for r in rows[1:]], np.float32)
+        assert np.array_equal(tr["obs"][:n, ep].view(np.uint32), obs.view(np.uint32)), ep
+        assert list(tr["action"][:n, ep]) == [r["action"] for r in rows[1:]]
+        assert list(tr["code"][:n, ep]) == [r["code"] for r in rows[1:]]
+        assert tr["done"][n - 1, ep] == 1
+
+
 def test_kalman_acceleration_needs_its_state_buffer():
     """accel_mode != 0 without the estimator buffer is refused (no silent fall-back to the analytic acceleration), and the
     host-buffer call, which does not carry that buffer, says so."""

@@ -169,3 +169,48 @@ def test_kalman_acceleration_estimator_matches_reference_filter(golden_dir, mode
     assert err < 2e-5, err
     if key == "anchor":       # quirk Q13: against the growing time base the estimate decays toward the mean acceleration since start
         assert np.abs(ref[-200:, 0]).max() < 0.25 * np.abs(g["consecutive_sd0.1"][-200:, 0]).max()
+
+
+def test_second_order_model_pins_against_reference_controllers(golden_dir):
+    """the two controllers the second-order model restates, against the UNMODIFIED reference classes
+    (tests/golden/second_order.npz, made by oracle/gen_golden.py: gen_second_order).
+    (1) vertical PID: fp32 VerticalPid (== pid_thrust of the kernels) vs PKG/pid.py PID.output() (float64, Butterworth filter
+        of PKG/filters.py:83-108 with its shifted output taps) on the same held errors at the node's 1 kHz: 5e-5 of the thrust
+        (measured 1.4e-5 over 16 480 node iterations; the fp32 integral accumulates increments of 1e-4 on 0.67).
+    (2) attitude: M_y of AttitudeController._compute_desired_moment() for pure pitch attitudes is -k_R sin(theta - theta_sp)
+        - k_w omega, the torque the model applies to the inertia J (1e-12), and the other two moments vanish."""
+    from oracle.dynamics import StandInParams, VerticalPid, det_sin_small
+    g = np.load(golden_dir / "second_order.npz")
+    sp = StandInParams(n_sub=4, dynamics_model="second_order")
+    pid = VerticalPid(1, sp, float(g["pid_dt"]) * sp.pid_ticks)
+    assert pid.dt == g["pid_dt"] and abs(float(pid.integ[0]) - float(g["pid_i0"])) < 1e-6
+    out = np.asarray([pid.thrust(np.arange(1), np.asarray([e], np.float32))[0] for e in g["pid_error"]], np.float32)
+    assert np.array_equal(out, g["pid_thrust_oracle"])                  # the fixture's own oracle column is reproducible
+    ref = g["pid_thrust_ref"]
+    assert ref.min() > 0.0 and ref.max() < 10.0 and np.ptp(ref) > 0.5   # inside the effort limits, and really moving
+    assert np.abs(out - ref).max() < 5e-5 * np.abs(ref).max()
+    th, th_sp, om, M = g["att_theta"], g["att_theta_sp"], g["att_omega"], g["att_moment_ref"]
+    assert np.abs(M[:, 1] - (-sp.k_R * np.sin(th - th_sp) - sp.k_omega * om)).max() < 1e-12
+    assert np.abs(M[:, [0, 2]]).max() == 0.0
+    assert g["att_inertia"][1] == sp.inertia and float(g["att_mass"]) == sp.mass
+    # the kernels' polynomial sine over the range of attitude errors
+    x = np.linspace(-0.85, 0.85, 20001).astype(np.float32)
+    assert np.abs(det_sin_small(x).astype(np.float64) - np.sin(x.astype(np.float64))).max() < 2e-7
+
+
+def test_second_order_model_reduces_to_first_order_behaviour():
+    """The second-order stand-in settles on the set-point like the first-order lag (tau = k_w / k_R) and holds the commanded
+    descent rate: after 3 s at a constant set-point pitch, horizontal acceleration (g tan(theta)) and v_z agree within 2 %."""
+    from oracle.dynamics import StandInDet
+    a = StandInDet(StandInParams(n_sub=4), 1)
+    b = StandInDet(StandInParams(n_sub=4, dynamics_model="second_order"), 1)
+    for d in (a, b):
+        d.reset(np.arange(1), [123456789], [987654321], [0], normal_init=True)
+        d.advance(np.zeros(1, np.float32), hover=True) if d.so else d.advance(np.zeros(1, np.float32))
+        for _ in range(69):
+            d.advance(np.asarray([0.2], np.float32))
+    assert abs(float(b.theta[0]) - 0.2) < 2e-3 and abs(float(a.theta[0]) - 0.2) < 2e-3
+    assert abs(float(b.v_z[0]) - (-0.1)) < 2e-3
+    acc_a = 9.81 * np.tan(0.2) - 0.2 * float(a.v_d[0])
+    assert abs(float(b.a_d[0]) - (9.81 * np.tan(0.2) - 0.2 * float(b.v_d[0]))) < 0.02 * abs(acc_a)
+    assert abs(float(b.v_d[0]) - float(a.v_d[0])) < 0.05 * abs(float(a.v_d[0]))
