@@ -317,6 +317,8 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   a.k_steps = k_steps;
   a.pop_offset = pop_offset;
   a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
+  a.env_stride = (size_t)a.n_total * 16;
+  a.env_stride2 = (size_t)a.n_total * 32;
   const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
   const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
@@ -478,6 +480,8 @@ int dqlb200_eval_greedy_2d(dqlb200_handle* h, const dqlb200_eval2d_params* p, co
   if (!h || !p || !policy_x || !policy_y || !stats_out) return fail(DQLB200_ERR_ARG, "null argument");
   if (p->trajectory < 0 || p->trajectory > 2) return fail(DQLB200_ERR_ARG, "trajectory must be 0 (rectilinear x), 1 (rectilinear x and y) or 2 (eight)");
   if (p->working_step < 0 || p->working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  if (h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0)      // refuse rather than silently evaluate on the default model
+    return fail(DQLB200_ERR_ARG, "the two-axis evaluator runs the first-order model with the analytic acceleration only (accel_mode = dynamics_model = 0)");
   if (n_episodes <= 0) return DQLB200_OK;
   CUDA_TRY(cudaSetDevice(h->device));
   dqlb200_trace2d tr;

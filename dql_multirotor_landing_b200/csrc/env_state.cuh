@@ -74,6 +74,14 @@ __device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, u
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 32u * nt), "l"(p.c + i) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
+// Pointer form for the slot loop: pa = address of the env's A vector; its B and C vectors lie `stride` (= 16 n) and 2 * stride
+// bytes behind it.  One running pointer per thread instead of three index computations per slot.
+__device__ __forceinline__ void env_prefetch_async_p(const char* pa, size_t stride, size_t stride2, unsigned stage_addr, int nt) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr), "l"(pa) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 16u * nt), "l"(pa + stride) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(pa + stride2) : "memory");
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
 __device__ __forceinline__ EnvRaw env_prefetch_take(const uint4* stage, int nt, int tid) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   EnvRaw r;
@@ -111,6 +119,16 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
                           (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
   p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
                       (uint32_t)__double2hiint(e.cum_reward));
+}
+
+__device__ __forceinline__ void env_store_p(char* pa, size_t stride, size_t stride2, const Env& e) {
+  *reinterpret_cast<float4*>(pa) = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
+  *reinterpret_cast<uint4*>(pa + stride) = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
+                                                      __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
+                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
+  *reinterpret_cast<uint4*>(pa + stride2) = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
+                                                          (uint32_t)__double2hiint(e.cum_reward));
 }
 
 // R1 + R8: new episode.  `fresh_mdp` additionally clears what only a NEW TrainingMdp clears

@@ -40,6 +40,7 @@ struct TrainArgs {
   int k_steps;
   int pop_offset;                          // first population of this launch (chunked host-buffer calls)
   long long n_total;
+  size_t env_stride, env_stride2;          // 16 n_total, 32 n_total: byte offsets of the B and C vectors behind an env's A vector
 };
 
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
@@ -259,12 +260,15 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       n_queued = 0;
     };
 
+    char* p_env = reinterpret_cast<char*>(args.env.a + env_base + tid);      // running pointer to the A vector of this thread's env
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
-      if (env_i + NT < n_p) env_prefetch_async(args.env, gi + NT, stage_addr, NT);      // in flight during this slot
+      char* const p_cur = p_env;
+      p_env += NT * 16;
+      if (env_i + NT < n_p) env_prefetch_async_p(p_env, args.env_stride, args.env_stride2, stage_addr, NT);      // in flight during this slot
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -474,7 +478,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       }
       // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
       // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
-      if (valid) env_store(args.env, gi, e);
+      if (valid) env_store_p(p_cur, args.env_stride, args.env_stride2, e);
       if (filt && valid) kf_store(args.env, gi, kf);
       if (so && valid) ext_store(args.env, gi, ex);
       // queue the finished envs of this warp for the batched reset (outside the baton)

@@ -280,6 +280,15 @@ def test_kalman_acceleration_needs_its_state_buffer():
         eng.reset(0)
     with pytest.raises(RuntimeError, match="dqlb200_bind_filter_state"):
         eng.train(1)
+    eng2 = _engine(1, 32, threads_per_block=32, seeds=[1], dp=dict(dynamics_model="second_order", n_sub=4))
+    _ffi.check(eng2.lib.dqlb200_bind_dynamics_state(eng2.handle, None))
+    with pytest.raises(RuntimeError, match="dqlb200_bind_dynamics_state"):
+        eng2.reset(0)
+    lut = np.zeros(945, np.uint8)
+    with pytest.raises(RuntimeError, match="two-axis evaluator"):          # not silently evaluated on the default model
+        eng2.eval_greedy_2d(lut, lut, 4)
+    with pytest.raises(RuntimeError, match="pid_ticks"):
+        _engine(1, 32, threads_per_block=32, dp=dict(dynamics_model="second_order", n_sub=4, pid_ticks=1))
 
 
 @pytest.mark.parametrize("mode", ["reference", "paper"])
