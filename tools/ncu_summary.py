@@ -40,6 +40,9 @@ def main():
             rd, wr = r[head.index("dram__bytes_read.sum")], r[head.index("dram__bytes_write.sum")]
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
             per.append(num(rd) * scale[units[head.index("dram__bytes_read.sum")]] + num(wr) * scale[units[head.index("dram__bytes_write.sum")]])
+        # only launches of the headline shape (one global step): a capture window may also hold a fused warm-up launch
+        dur = [num(r[head.index("gpu__time_duration.sum")]) for r in data]
+        per = [p for p, d in zip(per, dur) if d <= 2.0 * min(dur)]
         json.dump({"kernel": res[0]["kernel"], "dram_bytes_per_launch": sum(per) / len(per), "launches_averaged": len(per),
                    "source": f"ncu --set full, {rep.split('/')[-1]} -> {out}"}, open(sys.argv[3], "w"))
     print(json.dumps(res[0], indent=1))
