@@ -382,6 +382,21 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
             s3 = timed(lambda: e3.train_merged(steps, M))
             res3[f"env_steps_per_s_merge_every_{M}"] = R * n_r * steps / s3
         res3["env_steps_per_s"] = res3["env_steps_per_s_merge_every_16"]
+        # per curriculum step: the same agent started at working step w from the committed tables
+        # (more live levels to stage, snapshot and discretise; no exploration draws for w > 0), merged every 16 steps
+        try:
+            cnt = np.load(ROOT / "assets" / "state_action_count.npy")
+            per_w = {}
+            for w in range(5):
+                e3.set_group_tables(0, qa, qb, cnt)
+                e3.reset(w)
+                e3.train_merged(32, 16); torch.cuda.synchronize(dev)
+                per_w[str(w)] = R * n_r * steps / timed(lambda: e3.train_merged(steps, 16))
+            res3["env_steps_per_s_by_working_step_merge_every_16"] = per_w
+            res3["promotion"] = ("the reference algorithm plateaus at a success rate of 0.80-0.87 on the analytic stand-in at step 0, below "
+                                 "the 0.96 threshold (DESIGN.md section 3); tools/train_demo.py walks the curriculum with the threshold at 0.8")
+        except Exception as exc:
+            res3["env_steps_per_s_by_working_step_merge_every_16"] = {"error": str(exc)}
         out["config3_one_agent_65536_envs"] = res3
         e3.close()
     except Exception as exc:      # never let a context measurement break the headline line

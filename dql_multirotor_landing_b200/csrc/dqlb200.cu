@@ -199,7 +199,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
     const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
     if (n_slots > 2047) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots per thread)");
     h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t) +
-                    (size_t)3 * tpb_ * 16;          // + the cp.async staging slots of the env prefetch
+                    (size_t)((cfg->accel_mode != 0 || cfg->dynamics_model != 0) ? 6 : 3) * tpb_ * 16;   // + the cp.async staging slots of the env (and extension-state) prefetch
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \

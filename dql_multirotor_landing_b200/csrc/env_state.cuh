@@ -50,6 +50,25 @@ __device__ __forceinline__ Kf kf_load(const EnvPtrs& p, size_t i) {
 __device__ __forceinline__ void kf_store(const EnvPtrs& p, size_t i, const Kf& f) {
   p.d[i] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.P), __float_as_uint(f.v_ref), f.n);
 }
+// The extension state of an env through the staging slots 3..5 of its thread (extended kernel variant): issued next to the env
+// prefetch, picked up one slot later -- a plain load at the head of a slot would expose an L2 round trip per slot.
+__device__ __forceinline__ void ext_prefetch_async(const EnvPtrs& p, size_t i, unsigned stage_addr, int nt, bool filt, bool so) {
+  if (filt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 48u * nt), "l"(p.d + i) : "memory");
+  if (so) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 64u * nt), "l"(p.e + i) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 80u * nt), "l"(p.e + p.n + i) : "memory");
+  }
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ Kf kf_take(const uint4* stage, int nt, int tid) {
+  const uint4 v = stage[3 * nt + tid];
+  return Kf{__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), v.w};
+}
+__device__ __forceinline__ Ext ext_take(const uint4* stage, int nt, int tid) {
+  const uint4 u = stage[4 * nt + tid], v = stage[5 * nt + tid];
+  return Ext{__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w),
+             __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+}
 __device__ __forceinline__ Kf kf_initial() { return Kf{0.0f, 1.0f, 0.0f, 0u}; }      // PKG/filters.py:15-16
 
 struct EnvRaw {

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15))) + (size_t)warp * RESET_QUEUE;
-  uint4* stage = reinterpret_cast<uint4*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT]
+  uint4* stage = reinterpret_cast<uint4*>(smem_raw + ((sizeof(Shared) + 15) & ~size_t(15)) + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT] (+ [3][NT] extension-state slots in the extended variant)
   const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage + tid);
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
@@ -114,6 +114,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
   const dqlb200_population_params pp = args.pop_params[pop];
   env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+  if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, kc.accel_mode != 0, kc.dynamics_model != 0);
   {
     const int w_start = args.pop_state[pop].working_step;
     const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
@@ -212,6 +213,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     advance_curriculum(sh.ps.working_step, sh.ps.t);
     (void)env_prefetch_take(stage, NT, tid);
     env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);     // every env was just restarted
+    if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
   }
 
   for (int k = 0; k < args.k_steps; ++k) {
@@ -268,7 +270,14 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
       char* const p_cur = p_env;
       p_env += NT * 16;
-      if (env_i + NT < n_p) env_prefetch_async_p(p_env, args.env_stride, args.env_stride2, stage_addr, NT);      // in flight during this slot
+      Kf kf;
+      Ext ex;
+      if (filt) kf = kf_take(stage, NT, tid);
+      if (so) ex = ext_take(stage, NT, tid);
+      if (env_i + NT < n_p) {      // in flight during this slot
+        env_prefetch_async_p(p_env, args.env_stride, args.env_stride2, stage_addr, NT);
+        if (EXT) ext_prefetch_async(args.env, gi + NT, stage_addr, NT, filt, so);
+      }
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -277,14 +286,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       uint32_t ep_steps = 0;
       double ep_return = 0.0;
       Env e;
-      Kf kf;
-      Ext ex;
       uint32_t c_hint = 0;
       float a_hint = 0.0f;
       if (valid) {
         env_unpack(cur_raw, e);
-        if (filt) kf = kf_load(args.env, gi);
-        if (so) ex = ext_load(args.env, gi);
         const uint32_t sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
@@ -490,7 +495,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     }
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
-    if (k + 1 < args.k_steps) env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+    if (k + 1 < args.k_steps) {
+      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+      if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
+    }
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
@@ -506,6 +514,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       advance_curriculum(w, t + 1u);
       (void)env_prefetch_take(stage, NT, tid);
       env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+      if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
     }
   }
 

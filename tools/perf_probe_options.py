@@ -1,5 +1,6 @@
 """Cost of the observation-realism / model-fidelity options in the generic instance of train_kernel:
-env-steps/s of 32 fused global steps for 888 x 1280 envs, default configuration (production instance) next to each option."""
+env-steps/s of 32 fused global steps for one wave of populations x 1280 envs (888 populations = 6 CTAs/SM, 740 = 5 CTAs/SM for
+the extended variant), default configuration (production instance) next to each option."""
 import sys, pathlib, json
 sys.path.insert(0, str(pathlib.Path(__file__).resolve().parent.parent))
 import torch
@@ -15,9 +16,11 @@ CASES = {
     "n_sub = 4 + second_order": dict(n_sub=4, dynamics_model="second_order"),
     "n_sub = 4 + second_order + kalman + noise": dict(n_sub=4, dynamics_model="second_order", accel_mode="kalman", noise_pos_sd=0.25, noise_vel_sd=0.1),
 }
-P, n_p, k = 888, 1280, 32
+n_p, k = 1280, 32
 out = {}
 for name, dp in CASES.items():
+    # one wave of CTAs: 6 per SM for the production / generic variants, 5 per SM for the extended variant (102 registers, 41 KB)
+    P = 148 * (5 if ("accel_mode" in dp or "dynamics_model" in dp) else 6)
     eng = Engine(P, n_p, threads_per_block=128, seeds=list(range(P)), dp=K.DynamicsParameters(**dp),
                  tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
     eng.reset(0)
@@ -28,7 +31,7 @@ for name, dp in CASES.items():
         e0.record(); eng.train(k); e1.record(); torch.cuda.synchronize()
         best = min(best, e0.elapsed_time(e1))
     eng.check_errors()
-    out[name] = dict(us_per_global_step=round(best * 1e3 / k, 1), env_steps_per_s=float(f"{P * n_p * k / (best * 1e-3):.3e}"),
+    out[name] = dict(populations=P, us_per_global_step=round(best * 1e3 / k, 1), env_steps_per_s=float(f"{P * n_p * k / (best * 1e-3):.3e}"),
                      default_instance=bool(eng.lib.dqlb200_uses_default_instance(eng.handle)))
     eng.close()
 print(json.dumps(out, indent=1))
