@@ -205,7 +205,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
-#define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, true, 2)
+#define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, false, 3) DQL_SET_SMEM1(W, true, 2)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
 #undef DQL_SET_SMEM
 #undef DQL_SET_SMEM1
@@ -323,10 +323,12 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
   const bool extended = h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0;      // options with extra per-env state
+  const bool full_slots = h->cfg.envs_per_population % h->cfg.threads_per_block == 0;
 #define DQL_LAUNCH(W)                                                                        \
   if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
   else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);            \
   else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32, smem, stream>>>(h->kc, a);      \
+  else if (full_slots) dql::train_kernel<W, false, 3><<<grid, W * 32, smem, stream>>>(h->kc, a);          \
   else dql::train_kernel<W, false, 0><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;

@@ -88,7 +88,9 @@ template <> struct ConstsOf<false> {
 // estimator, second-order model) -- a separate instance so that the generic one does not pay for their branches and registers.
 template <int WARPS, bool TRACE, int VARIANT>
 __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_GENERIC : DQL_WARPS_PER_SM) / WARPS) > 0 ? ((VARIANT == 2 ? DQL_WARPS_PER_SM_GENERIC : DQL_WARPS_PER_SM) / WARPS) : 1) train_kernel(const __grid_constant__ KC kc, const TrainArgs args) {
-  constexpr bool GENERIC = VARIANT >= 1, EXT = VARIANT == 2;
+  // VARIANT 3 = production for populations that fill every slot (envs_per_population a multiple of the block size): `valid`
+  // is a compile-time constant, which removes the predicate, the defaults of the invalid lanes and their reconvergence points
+  constexpr bool GENERIC = VARIANT == 1 || VARIANT == 2, EXT = VARIANT == 2, FULL_SLOTS = VARIANT == 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
   const auto& kk = ConstsOf<GENERIC>::get(kc);       // run-time KC (generic) or the compile-time defaults KDef (production)
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     char* p_env = reinterpret_cast<char*>(args.env.a + env_base + tid);      // running pointer to the A vector of this thread's env
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
-      const bool valid = env_i < n_p;
+      const bool valid = FULL_SLOTS || env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
       char* const p_cur = p_env;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       Ext ex;
       if (filt) kf = kf_take(stage, NT, tid);
       if (so) ex = ext_take(stage, NT, tid);
-      if (env_i + NT < n_p) {      // in flight during this slot
+      if (FULL_SLOTS ? (slot + 1 < n_slots) : (env_i + NT < n_p)) {      // in flight during this slot
         env_prefetch_async_p(p_env, args.env_stride, args.env_stride2, stage_addr, NT);
         if (EXT) ext_prefetch_async(args.env, gi + NT, stage_addr, NT, filt, so);
       }

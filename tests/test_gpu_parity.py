@@ -672,6 +672,17 @@ def test_default_and_generic_instances_agree():
     torch.cuda.synchronize()
     assert torch.equal(a.tables, c.tables) and torch.equal(a.env_state, c.env_state) and torch.equal(a.pop_state, c.pop_state)
     assert int(a.population_state()["working_step"].max()) >= 1
+    # populations that fill every slot of the block (192 = 3 x 64) run the full-slot production instance (no `valid` predicate)
+    for tpb, n_p in ((64, 192), (128, 256), (32, 32)):
+        f = _engine(2, n_p, threads_per_block=tpb, seeds=[1, 2], tp=kw)
+        g = _engine(2, n_p, threads_per_block=tpb, seeds=[1, 2], tp=kw)
+        assert f.lib.dqlb200_uses_default_instance(f.handle) == 1
+        for e, trace in ((f, False), (g, True)):
+            e.reset(0)
+            e.train(300, trace=trace)
+        torch.cuda.synchronize()
+        assert torch.equal(f.tables, g.tables) and torch.equal(f.env_state, g.env_state) and torch.equal(f.pop_state, g.pop_state), (tpb, n_p)
+        assert int(f.population_state()["working_step"].max()) >= 1
     # per-population constants (platform amplitude / speed, axis) are run-time values: the production instance stays
     d = _engine(1, 8, threads_per_block=32, dp=dict(r_mp=3.0, v_mp=0.8))
     assert d.lib.dqlb200_uses_default_instance(d.handle) == 1
