@@ -225,19 +225,22 @@ def test_training_env_gym_surface_against_reference_fixture(golden_dir, name):
     env.close()
 
 
-def test_batched_env_steps_equal_fused_training_trace():
+@pytest.mark.parametrize("options", [{}, dict(n_sub=4, accel_mode="kalman_reference", dynamics_model="second_order", noise_pos_sd=0.1)])
+def test_batched_env_steps_equal_fused_training_trace(options):
     """The un-fused entry points (dqlb200_env_reset / dqlb200_env_step, auto-reset on) walk exactly the trajectory the fused
-    train_kernel walks when it is forced to take the same actions: observations, states, rewards, codes, episode ends."""
+    train_kernel walks when it is forced to take the same actions: observations, states, rewards, codes, episode ends --
+    with the default model and with the realism options of SURVEY 8f-3 / 8f-4 (estimator + second-order model + noise)."""
     from dql_multirotor_landing_b200 import constants as K
     from dql_multirotor_landing_b200.engine import Engine
     from dql_multirotor_landing_b200.landing_simulation_env import TrainingLandingEnv
     n, steps = 300, 150
     rng = np.random.default_rng(3)
     acts = rng.integers(0, 3, size=(steps, n)).astype(np.int8)
-    eng = Engine(1, n, threads_per_block=128, seeds=[11], tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+    dp = K.DynamicsParameters(**options)
+    eng = Engine(1, n, threads_per_block=128, seeds=[11], dp=dp, tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
     eng.reset(0)
     tr = eng.train(steps, trace=True, action_override=acts)
-    env = TrainingLandingEnv(0, num_envs=n, seed=11, auto_reset=True)
+    env = TrainingLandingEnv(0, num_envs=n, seed=11, auto_reset=True, dynamics=dp)
     env.reset()
     for t in range(steps):
         s, r, done, info = env.step(acts[t])
@@ -252,7 +255,24 @@ def test_batched_env_steps_equal_fused_training_trace():
     assert tr["done"].sum() > 50
     torch.cuda.synchronize()
     assert torch.equal(env._engine.env_state, eng.env_state)
+    if options:
+        assert torch.equal(env._engine.filter_state, eng.filter_state) and torch.equal(env._engine.dynamics_state, eng.dynamics_state)
     env.close()
+
+
+def test_trainer_with_realism_options(tmp_path):
+    """The reference-facing Trainer on the extended kernel variant: estimator + second-order model + noise."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.trainer import Trainer
+    dp = K.DynamicsParameters(n_sub=4, accel_mode="kalman", dynamics_model="second_order", noise_pos_sd=0.25, noise_vel_sd=0.1)
+    tr = Trainer(save_path=tmp_path / "run", successive_successful_episodes=5, success_rate=0.2, max_num_episodes=60, num_envs=64,
+                 chunk_steps=32, threads_per_block=64, verbose=False, max_global_steps=2000, dynamics=dp)
+    info = tr.curriculum_training()
+    assert "Termination condition" in info
+    ps = tr._engine.population_state()[0]
+    agent = tr._double_q_learning_agent
+    assert agent.state_action_counter.sum() == ps["total_steps"] > 0 and np.isfinite(agent.Q_table_a).all()
+    assert ps["total_episodes"] > 0 and tr._engine.dynamics_state is not None and tr._engine.filter_state is not None
 
 
 def test_simulation_env_gym_surface(golden_dir):
