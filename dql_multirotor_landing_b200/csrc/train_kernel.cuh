@@ -28,6 +28,24 @@ __device__ __forceinline__ void baton_pass(int next_warp) {
 }
 #undef DQL_BAR_CASE
 
+// The same baton on mbarrier objects (one per warp, expected count 1): the address is a register, so no switch over immediate
+// barrier ids; arrive has release and try_wait acquire semantics at CTA scope, so no separate fence.  parity = completed phases & 1.
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n"
+      "DQL_MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DQL_MBAR_DONE_%=;\n\t"
+      "bra DQL_MBAR_WAIT_%=;\n"
+      "DQL_MBAR_DONE_%=:\n\t}" ::"r"(addr), "r"(parity), "r"(20000u) : "memory");      // suspend-time hint [ns]: park instead of polling
+}
+__device__ __forceinline__ void mbar_arrive(unsigned addr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
+}
+
 struct TrainArgs {
   EnvPtrs env;
   uint32_t* tables;                        // [P][3][CELLS]
@@ -62,6 +80,7 @@ struct Shared {
   unsigned long long n_episodes, n_success, ep_steps, hist[9];     // totals of this launch
   uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
   int promote, advance, do_advance;
+  unsigned long long mbar[8];      // baton: one mbarrier per warp
   // followed by: uint16_t reset_queue[WARPS][RESET_QUEUE]   (dynamic)
 };
 
@@ -129,6 +148,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       sh.cuts = kc.cuts[w_start];
     }
     if (tid < 5) sh.reward[tid] = kc.reward[tid];
+#ifdef DQL_BATON_MBARRIER
+    if (tid < WARPS) mbar_init((unsigned)__cvta_generic_to_shared(&sh.mbar[tid]), 1u);
+#endif
     const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
     for (int i = tid; i < live; i += NT) {
       sh.qa[i] = __uint_as_float(gt[i]);
@@ -143,6 +165,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   const bool filt = EXT && kc.accel_mode != 0;      // acceleration estimator: 16 more bytes per env, extended instance only
   const bool so = EXT && kc.dynamics_model != 0;    // second-order attitude + vertical PID: 32 more bytes per env
   uint64_t steps_done = 0;
+#ifdef DQL_BATON_MBARRIER
+  const unsigned mbar_base = (unsigned)__cvta_generic_to_shared(&sh.mbar[0]);
+  uint32_t n_wait = 0;
+#endif
 
   // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
   // fresh env + TrainingMdp for every env (PKG/trainer.py:176-189, 232-245).  All threads call it (uniform).
@@ -414,7 +440,11 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         last_code = __shfl_sync(FULL, code, last);
         last_cum = __shfl_sync(FULL, ep_return, last);
       }
+#ifdef DQL_BATON_MBARRIER
+      if (WARPS > 1 && !(slot == 0 && warp == 0)) { mbar_wait(mbar_base + 8u * warp, n_wait & 1u); ++n_wait; }
+#else
       if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
+#endif
       {
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
@@ -469,8 +499,13 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
       }
       if (WARPS > 1 && !(slot == n_slots - 1 && warp == WARPS - 1)) {
+#ifdef DQL_BATON_MBARRIER
+        __syncwarp();
+        if (lane == 0) mbar_arrive(mbar_base + 8u * ((warp + 1) % WARPS));
+#else
         __threadfence_block();
         baton_pass<WARPS>((warp + 1) % WARPS);
+#endif
       }
       // order-independent episode counters: after the baton
       if (dmask) {
