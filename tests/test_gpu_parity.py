@@ -690,3 +690,40 @@ def test_default_and_generic_instances_agree():
     for dp in (dict(c_d=0.25), dict(z_init=3.0), dict(noise_pos_sd=0.1), dict(n_sub=2)):
         e = _engine(1, 8, threads_per_block=32, dp=dp)
         assert e.lib.dqlb200_uses_default_instance(e.handle) == 0, dp
+
+
+@pytest.mark.parametrize("dp", [{}, dict(n_sub=2, accel_mode="kalman", dynamics_model="second_order")])
+def test_no_access_outside_the_bound_buffers(dp):
+    """Every borrowed buffer sits between two canary regions: ragged populations (70 envs on 64-thread blocks), several
+    populations, resets and promotions, the production / extended kernel variants and the un-fused operators leave the
+    canaries untouched (compute-sanitizer is not available on the pool)."""
+    import ctypes as C
+    from dql_multirotor_landing_b200 import _ffi, constants as K
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    eng = _engine(3, 70, threads_per_block=64, seeds=[1, 2, 3], tp=kw, dp=dp)
+    n, pad, dev = eng.n_total, 4096, eng.device
+    sizes = dict(env=3 * n * 16, tables=3 * 3 * K.MAX_CELLS * 4, pop=3 * C.sizeof(K.PopulationState), filt=n * 16, dyn=2 * n * 16)
+    big = {k: torch.full((pad + ((v + 255) // 256) * 256 + pad,), 0xAB, dtype=torch.uint8, device=dev) for k, v in sizes.items()}
+    view = {k: big[k][pad:pad + sizes[k]] for k in sizes}
+    for k in ("env", "tables", "pop", "filt", "dyn"):
+        view[k].zero_()
+    view["filt"].view(torch.int32).view(n, 4)[:, 1] = 0x3F800000
+    _ffi.check(eng.lib.dqlb200_bind(eng.handle, view["env"].data_ptr(), view["tables"].data_ptr(), view["pop"].data_ptr()))
+    if dp:
+        _ffi.check(eng.lib.dqlb200_bind_filter_state(eng.handle, view["filt"].data_ptr()))
+        _ffi.check(eng.lib.dqlb200_bind_dynamics_state(eng.handle, view["dyn"].data_ptr()))
+    eng.env_state, eng.pop_state = view["env"].view(torch.int32), view["pop"]
+    eng.tables = view["tables"].view(torch.int32).view(3, 3, K.MAX_CELLS)
+    eng.reset(0)
+    eng.train(1)
+    eng.train(260)
+    eng.train(40, trace=True)
+    w = int(eng.population_state()["working_step"].max())
+    act, _ = eng.agent_select(w, 7)                       # the un-fused operators on the same buffers
+    eng.env_step(w, 7, act, auto_reset=True)
+    eng.check_errors()
+    torch.cuda.synchronize()
+    assert int(eng.population_state()["working_step"].max()) >= 1
+    for k, b in big.items():
+        assert bool((b[:pad] == 0xAB).all()) and bool((b[pad + sizes[k]:] == 0xAB).all()), k
+    assert int(view["env"].view(torch.int32).abs().sum()) != 0
