@@ -453,6 +453,14 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
                                  "what": "2 unordered shared-memory atomics (red.shared.add.f32 + .u32) per recorded visit, 888 CTAs x 128 "
                                          "threads, tables in shared memory; an upper bound for the table update alone, NOT deterministic"}
         et.close()
+        # the shared-table configurations against the measured RMW roof (one visit = count + Q_a update = 2 RMW):
+        # frac = env-steps/s of the WHOLE step (dynamics, reward, select, ordered update) / visits/s of the unordered atomics alone
+        roof = rmw["visits_per_s"]
+        fr = {"fused_independent_populations": out["fused_64_steps_per_launch_env_steps_per_s"] / roof}
+        for key in ("config3_one_agent_65536_envs", "config4_x_and_y_agents_262144_envs_each"):
+            if isinstance(out.get(key), dict) and "env_steps_per_s" in out[key]:
+                fr[key] = out[key]["env_steps_per_s"] / roof
+        out["table_rmw_roof"]["frac_of_rmw_roof"] = fr
     except Exception as exc:
         out["table_rmw_roof"] = {"error": str(exc)}
     out["config2_greedy_eval"] = {"episodes": res["episodes"], "env_steps": res["steps"], "env_steps_per_s": res["steps"] / s,
