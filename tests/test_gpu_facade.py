@@ -345,3 +345,22 @@ def test_trainer_log_writes_the_reference_tensorboard_tags(tmp_path, capsys):
     assert {"Episode/Success Rate", "Episode/Cumulative Reward", "Episode/Exploration Rate", "Episode/Learning Rate",
             "Episode/Mean reward"} <= tags
     assert any("Episode/Termination Condition" in t for t in acc.Tags()["tensors"])
+
+
+def test_reference_shaped_scripts(tmp_path):
+    """scripts/training.py and scripts/simulation.py (the counterparts of the reference's scripts of the same names) run."""
+    import pathlib
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    run = lambda *a: subprocess.run([sys.executable, *a], capture_output=True, text=True, timeout=600, cwd=root)
+    r = run("scripts/simulation.py", "--episodes", "2")
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert r.stdout.count("Termination condition") == 2 and "current_episode: 2" in r.stdout
+    r = run("scripts/simulation.py", "--episodes", "4096", "--two-axis")
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert "episodes: 4096" in r.stdout and "Touched platform" in r.stdout
+    r = run("scripts/training.py", "--num-envs", "64", "--max-global-steps", "300", "--success-rate", "0.2", "--save-path",
+            str(tmp_path / "run"), "--kalman", "--second-order", "--noise")
+    assert r.returncode == 0, r.stderr[-1500:]
+    assert (tmp_path / "run" / "Q_table_a.npy").exists() and "Termination condition" in r.stdout
