@@ -94,7 +94,8 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* 
 constexpr int MERGE_CHUNK = 128;
 __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
                                                             int R, int pooled_promote, long long max_episodes) {
-  __shared__ uint32_t s_q[MERGE_CHUNK][32], s_dc[MERGE_CHUNK][32];
+  __shared__ float s_term[MERGE_CHUNK][32];
+  __shared__ uint32_t s_ptot[8][32], s_pvis[8][32], s_pq[8][32];
   __shared__ uint32_t s_qnew[32], s_cnew[32], s_vis[32];
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -106,9 +107,13 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
     const bool in = c < live;
     const float q_snap = in ? __uint_as_float(sg[c]) : 0.0f;
     const uint32_t cnt_snap = in ? sg[2 * CELLS + c] : 0u;
-    float num = 0.0f, q_single = q_snap;
-    uint32_t tot = 0;
-    int visitors = 0;
+    // The only order-dependent quantity is the float32 sum of the visitors' terms (replica order): warp 0 carries that chain,
+    // ONE dependent fadd per replica.  A replica that did not visit the cell contributes (q - q_snap) * 0 = +-0, which never
+    // changes the sum (it starts at +0 and +0 + -0 = +0), so the chain needs no test.  The visit counts, the number of
+    // visitors and the single visitor's value do not depend on the order: every warp accumulates them for the replicas it
+    // loads and they are combined once at the end.
+    float num = 0.0f, my_q = q_snap;
+    uint32_t my_tot = 0, my_vis = 0;
     for (int r0 = 0; r0 < R; r0 += MERGE_CHUNK) {
       const int n = min(MERGE_CHUNK, R - r0);
       {   // MERGE_CHUNK / 8 replicas per warp: all their loads are issued before the first one is consumed
@@ -124,27 +129,36 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
         for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
           const int j = warp + 8 * i;
           if (j < n) {
-            s_dc[j][lane] = cv[i] - cnt_snap;
-            s_q[j][lane] = qv[i];
+            const uint32_t dc = cv[i] - cnt_snap;
+            const float q_r = __uint_as_float(qv[i]);
+            s_term[j][lane] = fmul(fsub(q_r, q_snap), __uint2float_rn(dc));
+            my_tot += dc;
+            my_vis += dc ? 1u : 0u;
+            my_q = dc ? q_r : my_q;
           }
         }
       }
       __syncthreads();
       if (warp == 0) {
-#pragma unroll 8
-        for (int j = 0; j < n; ++j) {
-          const uint32_t dc = s_dc[j][lane];
-          const float q_r = __uint_as_float(s_q[j][lane]);
-          const float term = fmul(fsub(q_r, q_snap), __uint2float_rn(dc));      // off the dependent chain
-          if (dc) {
-            visitors += 1;
-            q_single = q_r;
-            num = fadd(num, term);
-            tot += dc;
-          }
-        }
+#pragma unroll 16
+        for (int j = 0; j < n; ++j) num = fadd(num, s_term[j][lane]);
       }
       __syncthreads();
+    }
+    s_ptot[warp][lane] = my_tot;
+    s_pvis[warp][lane] = my_vis;
+    s_pq[warp][lane] = __float_as_uint(my_q);
+    __syncthreads();
+    uint32_t tot = 0;
+    int visitors = 0;
+    float q_single = q_snap;
+    if (warp == 0) {
+#pragma unroll
+      for (int w8 = 0; w8 < 8; ++w8) {
+        tot += s_ptot[w8][lane];
+        visitors += (int)s_pvis[w8][lane];
+        if (s_pvis[w8][lane]) q_single = __uint_as_float(s_pq[w8][lane]);      // used only when there is exactly one visitor
+      }
     }
     if (warp == 0) {
       float q_new = q_snap;
