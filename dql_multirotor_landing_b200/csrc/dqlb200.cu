@@ -65,7 +65,7 @@ struct dqlb200_handle {
   // dqlb200_train_merged replays ONE captured CUDA graph (train launch of `merged_k` steps + replica merge) on its own stream
   cudaStream_t merged_stream;
   cudaEvent_t merged_in, merged_out;
-  cudaGraphExec_t merged_exec;
+  cudaGraphExec_t merged_exec, merged_exec_multi;      // one (train, merge) pair / MERGED_GRAPH_PAIRS pairs
   int merged_k, merged_promote;
   bool merged_ready;
 };
@@ -181,7 +181,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   h->env_state = h->tables = h->pop_state = h->merge_snapshot = h->filter_state = h->dynamics_state = nullptr;
   h->chunk_ready = false;
   h->merged_ready = false;
-  h->merged_exec = nullptr;
+  h->merged_exec = h->merged_exec_multi = nullptr;
   h->merged_k = 0;
   h->merged_promote = 0;
   CUDA_TRY(cudaMalloc(&h->d_cfg, sizeof(dqlb200_config)));
@@ -207,6 +207,7 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
 #define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, false, 3) DQL_SET_SMEM1(W, true, 2)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
+  CUDA_TRY(cudaFuncSetAttribute(dql::replica_merge_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::merge_smem_bytes(32)));
 #undef DQL_SET_SMEM
 #undef DQL_SET_SMEM1
   guard.h = nullptr;
@@ -238,6 +239,7 @@ int dqlb200_destroy(dqlb200_handle* h) {
     cudaEventDestroy(h->host_start);
   }
   if (h->merged_exec) cudaGraphExecDestroy(h->merged_exec);
+  if (h->merged_exec_multi) cudaGraphExecDestroy(h->merged_exec_multi);
   if (h->merged_ready) {
     cudaStreamDestroy(h->merged_stream);
     cudaEventDestroy(h->merged_in);
@@ -580,9 +582,16 @@ int dqlb200_bind_merge_snapshot(dqlb200_handle* h, void* snapshot) {
 
 static int launch_merge(dqlb200_handle* h, void* snapshot, int pooled_promote_successes, cudaStream_t stream) {
   const int R = h->cfg.replicas_per_population;
-  const dim3 grid((DQLB200_MAX_CELLS + 31) / 32, h->cfg.n_populations / R);     // one CTA per tile of 32 cells
-  dql::replica_merge_kernel<<<grid, 256, 0, stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot, (dqlb200_population_state*)h->pop_state, R,
-                                                     pooled_promote_successes, h->cfg.max_num_episodes);
+  const dim3 grid((DQLB200_MAX_CELLS + 31) / 32 + 1, h->cfg.n_populations / R);     // one CTA per tile of 32 cells + one for the pooled counters
+  if (R > 128) {      // 32 warps: 512 replicas per round trip
+    const size_t smem = dql::merge_smem_bytes(32);      // > 48 KB: the attribute is set in dqlb200_create
+    dql::replica_merge_kernel<32><<<grid, 1024, smem, stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot, (dqlb200_population_state*)h->pop_state,
+                                                              R, pooled_promote_successes, h->cfg.max_num_episodes);
+  } else {
+    dql::replica_merge_kernel<8><<<grid, 256, dql::merge_smem_bytes(8), stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
+                                                                                 (dqlb200_population_state*)h->pop_state, R,
+                                                                                 pooled_promote_successes, h->cfg.max_num_episodes);
+  }
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
@@ -612,25 +621,35 @@ int dqlb200_train_merged(dqlb200_handle* h, int total_steps, int merge_every, in
   }
   cudaStream_t ms = h->merged_stream, cs = (cudaStream_t)stream;
   const int n_full = total_steps / merge_every, rem = total_steps % merge_every;
+  constexpr int MERGED_GRAPH_PAIRS = 16;
   if (n_full > 0 && (h->merged_k != merge_every || h->merged_promote != pooled_promote_successes || !h->merged_exec)) {
-    // (train launch of merge_every steps, replica merge) captured once and replayed: the pair is launch-bound for
-    // populations of a few thousand CTAs (two ~5 us launches around ~10 us of work), a graph launch is one submission
+    // (train launch of merge_every steps, replica merge) pairs captured once and replayed: a pair is launch-bound for
+    // populations of a few hundred CTAs (two ~5 us launches around ~20 us of work).  Two graphs: one pair, and
+    // MERGED_GRAPH_PAIRS pairs back to back (one submission per 16 pairs; the kernels of a graph follow each other without
+    // a host round trip).
     if (h->merged_exec) { cudaGraphExecDestroy(h->merged_exec); h->merged_exec = nullptr; }
-    cudaGraph_t graph = nullptr;
-    CUDA_TRY(cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal));
-    int rc = launch_train(h, merge_every, nullptr, h->env_state, h->tables, h->pop_state, ms);
-    if (!rc) rc = launch_merge(h, h->merge_snapshot, pooled_promote_successes, ms);
-    const cudaError_t ce = cudaStreamEndCapture(ms, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    CUDA_TRY(ce);
-    CUDA_TRY(cudaGraphInstantiate(&h->merged_exec, graph, 0));
-    CUDA_TRY(cudaGraphDestroy(graph));
+    if (h->merged_exec_multi) { cudaGraphExecDestroy(h->merged_exec_multi); h->merged_exec_multi = nullptr; }
+    for (int pairs : {1, MERGED_GRAPH_PAIRS}) {
+      cudaGraph_t graph = nullptr;
+      CUDA_TRY(cudaStreamBeginCapture(ms, cudaStreamCaptureModeThreadLocal));
+      int rc = 0;
+      for (int p = 0; p < pairs && !rc; ++p) {
+        rc = launch_train(h, merge_every, nullptr, h->env_state, h->tables, h->pop_state, ms);
+        if (!rc) rc = launch_merge(h, h->merge_snapshot, pooled_promote_successes, ms);
+      }
+      const cudaError_t ce = cudaStreamEndCapture(ms, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      CUDA_TRY(ce);
+      CUDA_TRY(cudaGraphInstantiate(pairs == 1 ? &h->merged_exec : &h->merged_exec_multi, graph, 0));
+      CUDA_TRY(cudaGraphDestroy(graph));
+    }
     h->merged_k = merge_every;
     h->merged_promote = pooled_promote_successes;
   }
   CUDA_TRY(cudaEventRecord(h->merged_in, cs));
   CUDA_TRY(cudaStreamWaitEvent(ms, h->merged_in, 0));
-  for (int i = 0; i < n_full; ++i) CUDA_TRY(cudaGraphLaunch(h->merged_exec, ms));
+  for (int i = 0; i < n_full / MERGED_GRAPH_PAIRS; ++i) CUDA_TRY(cudaGraphLaunch(h->merged_exec_multi, ms));
+  for (int i = 0; i < n_full % MERGED_GRAPH_PAIRS; ++i) CUDA_TRY(cudaGraphLaunch(h->merged_exec, ms));
   if (rem) {
     int rc = launch_train(h, rem, nullptr, h->env_state, h->tables, h->pop_state, ms);
     if (!rc) rc = launch_merge(h, h->merge_snapshot, pooled_promote_successes, ms);

@@ -83,51 +83,56 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* 
   }
 }
 
-// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One CTA (8 warps) per tile of 32 live cells:
-//   load   : all warps stream the replicas' (count, Q_a) of the tile, lane <-> cell (128-byte coalesced rows), into shared memory,
-//            MERGE_CHUNK replicas at a time -- every load is independent of every other;
-//   reduce : warp 0 (lane <-> cell) accumulates the visitors of the chunk STRICTLY in replica order (the summation order
-//            is part of the semantics: bit-exact vs oracle/loop.py) -- the only serial part, one dependent fadd per visitor;
+// Replica-merge mode: R consecutive populations are replicas of ONE agent.  One CTA (NW warps) per tile of 32 live cells:
+//   load   : all warps stream the replicas' (count, Q_a) of the tile, lane <-> cell (128-byte coalesced rows), 16 replicas per
+//            warp and round -- every load is independent of every other; NW = 32 takes 512 replicas in ONE round trip;
+//   reduce : the only order-dependent quantity is the float32 sum of the visitors' terms in replica order (part of the
+//            semantics: bit-exact vs oracle/loop.py): warp 0 carries that chain, ONE dependent fadd per replica.  A replica that
+//            did not visit the cell contributes (q - q_snap) * 0 = +-0, which never changes the sum (it starts at +0 and
+//            +0 + -0 = +0), so the chain needs no test.  Visit counts, the number of visitors and the single visitor's value
+//            do not depend on the order: every warp accumulates them for the replicas it loads, combined once at the end;
 //   write  : the merged value goes to every replica (all warps, coalesced) and to the snapshot.
-// Only the live rows (levels 0..working step) can differ from the snapshot.  Thread 0 of block (0, g) pools the success
-// windows and arms the promotion.
-constexpr int MERGE_CHUNK = 128;
-__global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
-                                                            int R, int pooled_promote, long long max_episodes) {
-  __shared__ float s_term[MERGE_CHUNK][32];
-  __shared__ uint32_t s_ptot[8][32], s_pvis[8][32], s_pq[8][32];
+// Only the live rows (levels 0..working step) can differ from the snapshot.  One extra CTA per group (blockIdx.x == number
+// of tiles) pools the success windows and arms the promotion, beside the tiles instead of behind one of them.
+constexpr int MERGE_PER_WARP = 16;
+template <int NW>
+__global__ void __launch_bounds__(NW * 32) replica_merge_kernel(uint32_t* tables, uint32_t* snap, dqlb200_population_state* ps,
+                                                               int R, int pooled_promote, long long max_episodes) {
+  constexpr int CHUNK = NW * MERGE_PER_WARP;
+  extern __shared__ __align__(16) unsigned char merge_smem[];
+  float (*s_term)[32] = reinterpret_cast<float (*)[32]>(merge_smem);                                   // [CHUNK][32]
+  uint32_t (*s_ptot)[32] = reinterpret_cast<uint32_t (*)[32]>(merge_smem + (size_t)CHUNK * 32 * 4);      // [NW][32]
+  uint32_t (*s_pvis)[32] = s_ptot + NW;
+  uint32_t (*s_pq)[32] = s_pvis + NW;
   __shared__ uint32_t s_qnew[32], s_cnew[32], s_vis[32];
   const int g = blockIdx.y;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int c = blockIdx.x * 32 + lane;
-  uint32_t* sg = snap + (size_t)g * 3 * CELLS;
-  const uint32_t* tg = tables + (size_t)g * R * 3 * CELLS;
-  const int live = (ps[g * R].working_step + 1) * DQLB200_CELLS_PER_LEVEL;
-  if (blockIdx.x * 32 < live) {                       // block-uniform
+  const int n_tiles = (int)gridDim.x - 1;
+  if ((int)blockIdx.x < n_tiles) {
+    const int c = blockIdx.x * 32 + lane;
+    uint32_t* sg = snap + (size_t)g * 3 * CELLS;
+    const uint32_t* tg = tables + (size_t)g * R * 3 * CELLS;
+    const int live = (ps[g * R].working_step + 1) * DQLB200_CELLS_PER_LEVEL;
+    if ((int)blockIdx.x * 32 >= live) return;           // block-uniform
     const bool in = c < live;
     const float q_snap = in ? __uint_as_float(sg[c]) : 0.0f;
     const uint32_t cnt_snap = in ? sg[2 * CELLS + c] : 0u;
-    // The only order-dependent quantity is the float32 sum of the visitors' terms (replica order): warp 0 carries that chain,
-    // ONE dependent fadd per replica.  A replica that did not visit the cell contributes (q - q_snap) * 0 = +-0, which never
-    // changes the sum (it starts at +0 and +0 + -0 = +0), so the chain needs no test.  The visit counts, the number of
-    // visitors and the single visitor's value do not depend on the order: every warp accumulates them for the replicas it
-    // loads and they are combined once at the end.
     float num = 0.0f, my_q = q_snap;
     uint32_t my_tot = 0, my_vis = 0;
-    for (int r0 = 0; r0 < R; r0 += MERGE_CHUNK) {
-      const int n = min(MERGE_CHUNK, R - r0);
-      {   // MERGE_CHUNK / 8 replicas per warp: all their loads are issued before the first one is consumed
-        uint32_t cv[MERGE_CHUNK / 8], qv[MERGE_CHUNK / 8];
+    for (int r0 = 0; r0 < R; r0 += CHUNK) {
+      const int n = min(CHUNK, R - r0);
+      {   // MERGE_PER_WARP replicas per warp: all their loads are issued before the first one is consumed
+        uint32_t cv[MERGE_PER_WARP], qv[MERGE_PER_WARP];
 #pragma unroll
-        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
-          const int j = warp + 8 * i;
+        for (int i = 0; i < MERGE_PER_WARP; ++i) {
+          const int j = warp + NW * i;
           const uint32_t* tr = tg + (size_t)(r0 + min(j, n - 1)) * 3 * CELLS;
           cv[i] = in ? __ldcg(tr + 2 * CELLS + c) : cnt_snap;
           qv[i] = in ? __ldcg(tr + c) : 0u;
         }
 #pragma unroll
-        for (int i = 0; i < MERGE_CHUNK / 8; ++i) {
-          const int j = warp + 8 * i;
+        for (int i = 0; i < MERGE_PER_WARP; ++i) {
+          const int j = warp + NW * i;
           if (j < n) {
             const uint32_t dc = cv[i] - cnt_snap;
             const float q_r = __uint_as_float(qv[i]);
@@ -143,24 +148,22 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
 #pragma unroll 16
         for (int j = 0; j < n; ++j) num = fadd(num, s_term[j][lane]);
       }
-      __syncthreads();
+      if (r0 + CHUNK < R) __syncthreads();      // the next round overwrites the terms
     }
     s_ptot[warp][lane] = my_tot;
     s_pvis[warp][lane] = my_vis;
     s_pq[warp][lane] = __float_as_uint(my_q);
     __syncthreads();
-    uint32_t tot = 0;
-    int visitors = 0;
-    float q_single = q_snap;
     if (warp == 0) {
+      uint32_t tot = 0;
+      int visitors = 0;
+      float q_single = q_snap;
 #pragma unroll
-      for (int w8 = 0; w8 < 8; ++w8) {
+      for (int w8 = 0; w8 < NW; ++w8) {
         tot += s_ptot[w8][lane];
         visitors += (int)s_pvis[w8][lane];
         if (s_pvis[w8][lane]) q_single = __uint_as_float(s_pq[w8][lane]);      // used only when there is exactly one visitor
       }
-    }
-    if (warp == 0) {
       float q_new = q_snap;
       if (visitors == 1) q_new = q_single;
       else if (visitors > 1) q_new = fadd(q_snap, __fdiv_rn(num, __uint2float_rn(tot)));
@@ -175,14 +178,13 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
     __syncthreads();
     if (in && s_vis[lane]) {
       const uint32_t qn = s_qnew[lane], cn = s_cnew[lane];
-      for (int r = warp; r < R; r += 8) {
+      for (int r = warp; r < R; r += NW) {
         uint32_t* tr = tables + (size_t)(g * R + r) * 3 * CELLS;
         tr[c] = qn;
         tr[2 * CELLS + c] = cn;
       }
     }
-  }
-  if (blockIdx.x == 0) {          // pooled trainer counters of the group: block-wide reduction over the R replicas
+  } else {          // pooled trainer counters of the group: block-wide reduction over the R replicas
     __shared__ unsigned long long s_succ, s_eps;
     __shared__ int s_dead, s_pending;
     if (threadIdx.x == 0) { s_succ = s_eps = 0ull; s_dead = 0; s_pending = 0; }
@@ -207,6 +209,7 @@ __global__ void __launch_bounds__(256) replica_merge_kernel(uint32_t* tables, ui
       for (int r = threadIdx.x; r < R; r += blockDim.x) ps[g * R + r].pending_advance = pending;
   }
 }
+inline size_t merge_smem_bytes(int nw) { return (size_t)nw * MERGE_PER_WARP * 32 * 4 + (size_t)3 * nw * 32 * 4; }
 
 // -------------------------------------------------------------------------------------------------
 // Un-fused agent entry points on the float32 device tables (the batched DoubleQLearningAgent.guess / update,
