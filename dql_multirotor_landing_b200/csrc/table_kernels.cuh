@@ -197,9 +197,19 @@ __global__ void __launch_bounds__(NW * 32) replica_merge_kernel(uint32_t* tables
       episodes += (unsigned long long)p.episodes_in_step;
       dead |= (p.finished || p.pending_advance) ? 1 : 0;
     }
-    if (successes) atomicAdd(&s_succ, successes);
-    if (episodes) atomicAdd(&s_eps, episodes);
-    if (dead) atomicOr(&s_dead, 1);
+    // warp totals first: a 64-bit shared-memory atomicAdd is a compare-and-swap loop, and R threads adding to ONE address
+    // serialise (measured: 47 ns per replica, 24 of the 31 us of a merge of 512 replicas)
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      successes += __shfl_xor_sync(FULL, successes, off);
+      episodes += __shfl_xor_sync(FULL, episodes, off);
+      dead |= __shfl_xor_sync(FULL, dead, off);
+    }
+    if (lane == 0) {
+      if (successes) atomicAdd(&s_succ, successes);
+      if (episodes) atomicAdd(&s_eps, episodes);
+      if (dead) atomicOr(&s_dead, 1);
+    }
     __syncthreads();
     if (threadIdx.x == 0)
       s_pending = (s_dead || pooled_promote <= 0) ? 0 : ((long long)s_succ >= pooled_promote ? 1 : ((long long)s_eps >= max_episodes ? 2 : 0));
