@@ -42,10 +42,10 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
   const auto& kk = ConstsOf<GENERIC>::get(kc);
   __shared__ uint8_t s_policy[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
   __shared__ dqlb200_cuts cuts;
-  __shared__ unsigned long long s_hist[9], s_steps, s_eps;
+  __shared__ unsigned int s_hist[9], s_steps, s_eps;      // per-block totals fit 32 bits (256 episodes x 459 steps): native shared atomics, not 64-bit CAS loops
   for (int i = threadIdx.x; i < DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL; i += blockDim.x) s_policy[i] = policy[i];
-  if (threadIdx.x == 0) { cuts = kc.cuts[w]; s_steps = s_eps = 0ull; }
-  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) { cuts = kc.cuts[w]; s_steps = s_eps = 0u; }
+  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0u;
   __syncthreads();
   const dqlb200_population_params pp = pop_params[population];
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -89,15 +89,15 @@ __global__ void __launch_bounds__(256) eval_kernel(const __grid_constant__ KC kc
       }
       sid = sid2;
     }
-    atomicAdd(&s_hist[code], 1ull);
-    atomicAdd(&s_steps, (unsigned long long)step);
-    atomicAdd(&s_eps, 1ull);
+    atomicAdd(&s_hist[code], 1u);
+    atomicAdd(&s_steps, (unsigned int)step);
+    atomicAdd(&s_eps, 1u);
   }
   __syncthreads();
-  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
   if (threadIdx.x == 0) {
-    atomicAdd((unsigned long long*)&stats->steps, s_steps);
-    atomicAdd((unsigned long long*)&stats->episodes, s_eps);
+    atomicAdd((unsigned long long*)&stats->steps, (unsigned long long)s_steps);
+    atomicAdd((unsigned long long*)&stats->episodes, (unsigned long long)s_eps);
   }
 }
 
@@ -270,13 +270,13 @@ __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC 
   const auto& kk = ConstsOf<GENERIC>::get(kc);
   __shared__ uint8_t s_pol_x[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL], s_pol_y[DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL];
   __shared__ dqlb200_cuts cuts;
-  __shared__ unsigned long long s_hist[9], s_steps, s_eps;
+  __shared__ unsigned int s_hist[9], s_steps, s_eps;      // per-block totals fit 32 bits (256 episodes x 459 steps): native shared atomics, not 64-bit CAS loops
   for (int i = threadIdx.x; i < DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL; i += blockDim.x) {
     s_pol_x[i] = policy_x[i];
     s_pol_y[i] = policy_y[i];
   }
-  if (threadIdx.x == 0) { cuts = kc.cuts[p.working_step]; s_steps = s_eps = 0ull; }
-  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0ull;
+  if (threadIdx.x == 0) { cuts = kc.cuts[p.working_step]; s_steps = s_eps = 0u; }
+  if (threadIdx.x < 9) s_hist[threadIdx.x] = 0u;
   __syncthreads();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n_episodes) {
@@ -340,15 +340,15 @@ __global__ void __launch_bounds__(256) eval2d_kernel(const __grid_constant__ KC 
         if (trace.state_y) trace.state_y[ti] = (uint16_t)sid_y;
       }
     }
-    atomicAdd(&s_hist[code], 1ull);
-    atomicAdd(&s_steps, (unsigned long long)step);
-    atomicAdd(&s_eps, 1ull);
+    atomicAdd(&s_hist[code], 1u);
+    atomicAdd(&s_steps, (unsigned int)step);
+    atomicAdd(&s_eps, 1u);
   }
   __syncthreads();
-  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], s_hist[threadIdx.x]);
+  if (threadIdx.x < 9 && s_hist[threadIdx.x]) atomicAdd((unsigned long long*)&stats->termination_hist[threadIdx.x], (unsigned long long)s_hist[threadIdx.x]);
   if (threadIdx.x == 0) {
-    atomicAdd((unsigned long long*)&stats->steps, s_steps);
-    atomicAdd((unsigned long long*)&stats->episodes, s_eps);
+    atomicAdd((unsigned long long*)&stats->steps, (unsigned long long)s_steps);
+    atomicAdd((unsigned long long*)&stats->episodes, (unsigned long long)s_eps);
   }
 }
 
