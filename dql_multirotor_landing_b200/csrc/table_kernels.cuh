@@ -26,29 +26,57 @@ __global__ void transfer_kernel(uint32_t* tables, int n_pop, int cs, int step, f
 // [3] sum of the visiting ranks' Q (exact when one rank visited: the value that rank keeps), then the agent's pooled trainer
 // counters: successes in the windows, finished episodes of the curriculum step, number of ranks, ranks that are alive.
 constexpr int DELTA_WORDS = DQLB200_SHARED_DELTA_WORDS;
-__global__ void shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, const dqlb200_population_state* ps,
-                                   int n_agents, int R) {
+__global__ void __launch_bounds__(256) shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, const dqlb200_population_state* ps,
+                                                          int n_agents, int R) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)n_agents * CELLS) return;
-  const long long g = i / CELLS, c = i % CELLS;
-  const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
-  float* d = delta + (size_t)g * DELTA_WORDS;
-  const uint32_t dcu = tables[tb + 2 * CELLS + c] - snap[sb + 2 * CELLS + c];
-  const float dc = (float)dcu, q = __uint_as_float(tables[tb + c]);
-  d[c] = fmul(fsub(q, __uint_as_float(snap[sb + c])), dc);
-  d[CELLS + c] = dc;
-  d[2 * CELLS + c] = dcu ? 1.0f : 0.0f;
-  d[3 * CELLS + c] = dcu ? q : 0.0f;
-  if (c < 4) {
-    long long successes = 0, episodes = 0;
-    bool alive = true;
-    for (int r = 0; r < R; ++r) {
-      const dqlb200_population_state& p = ps[g * R + r];
-      successes += p.window_sum;
-      episodes += p.episodes_in_step;
-      alive = alive && !p.finished && !p.pending_advance;
+  if (i < (long long)n_agents * CELLS) {
+    const long long g = i / CELLS, c = i % CELLS;
+    const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
+    float* d = delta + (size_t)g * DELTA_WORDS;
+    const uint32_t dcu = tables[tb + 2 * CELLS + c] - snap[sb + 2 * CELLS + c];
+    const float dc = (float)dcu, q = __uint_as_float(tables[tb + c]);
+    d[c] = fmul(fsub(q, __uint_as_float(snap[sb + c])), dc);
+    d[CELLS + c] = dc;
+    d[2 * CELLS + c] = dcu ? 1.0f : 0.0f;
+    d[3 * CELLS + c] = dcu ? q : 0.0f;
+  }
+  // The agent's pooled trainer counters: the block that holds cell 0 of an agent (at most one agent starts inside a block,
+  // CELLS > blockDim) reduces over the agent's R replicas with all its threads -- one thread walking R population states took
+  // longer than everything else in a sync (R = 888 per GPU in shared-table mode).
+  const long long first = (long long)blockIdx.x * blockDim.x;
+  const long long g0 = (first + CELLS - 1) / CELLS;
+  if (g0 < n_agents && g0 * CELLS < first + blockDim.x) {      // block-uniform
+    __shared__ unsigned long long s_succ, s_eps;
+    __shared__ int s_dead;
+    if (threadIdx.x == 0) { s_succ = s_eps = 0ull; s_dead = 0; }
+    __syncthreads();
+    unsigned long long successes = 0, episodes = 0;
+    int dead = 0;
+    for (int r = threadIdx.x; r < R; r += blockDim.x) {
+      const dqlb200_population_state& p = ps[g0 * R + r];
+      successes += (unsigned long long)p.window_sum;
+      episodes += (unsigned long long)p.episodes_in_step;
+      dead |= (p.finished || p.pending_advance) ? 1 : 0;
     }
-    d[4 * CELLS + c] = c == 0 ? (float)successes : c == 1 ? (float)episodes : c == 2 ? 1.0f : (alive ? 1.0f : 0.0f);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      successes += __shfl_xor_sync(FULL, successes, off);
+      episodes += __shfl_xor_sync(FULL, episodes, off);
+      dead |= __shfl_xor_sync(FULL, dead, off);
+    }
+    if ((threadIdx.x & 31) == 0) {
+      if (successes) atomicAdd(&s_succ, successes);
+      if (episodes) atomicAdd(&s_eps, episodes);
+      if (dead) atomicOr(&s_dead, 1);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float* d = delta + (size_t)g0 * DELTA_WORDS + 4 * CELLS;
+      d[0] = (float)(long long)s_succ;
+      d[1] = (float)(long long)s_eps;
+      d[2] = 1.0f;
+      d[3] = s_dead ? 0.0f : 1.0f;
+    }
   }
 }
 __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* merge_snap, const float* delta,
