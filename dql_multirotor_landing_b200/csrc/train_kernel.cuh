@@ -503,7 +503,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         __syncwarp();
         if (lane == 0) mbar_arrive(mbar_base + 8u * ((warp + 1) % WARPS));
 #else
-        __threadfence_block();
+        // no fence: barrier.arrive / barrier.sync on the same barrier order the producer's shared-memory stores before the
+        // consumer's loads (the producer / consumer pattern of the PTX ISA, "bar.arrive"); the asm memory clobber keeps the
+        // compiler from moving the stores below the arrive
         baton_pass<WARPS>((warp + 1) % WARPS);
 #endif
       }
