@@ -1,0 +1,132 @@
+"""The plain-C restatement of the numeric core (oracle/c/standin.c) against the NumPy oracle, bit for bit: Philox4x32-10,
+the fp32 building blocks, the stand-in dynamics, the acceleration estimator and the second-order model.  Two independent
+statements of the same arithmetic (NumPy float32, C with -ffp-contract=off) agreeing on every bit is the basis of the
+claim that the CUDA kernels (explicit __fmul_rn / __fadd_rn, --fmad=false) can be bit-exact against the oracle at all."""
+import ctypes as C
+import pathlib
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import philox
+from oracle.dynamics import (StandInDet, StandInParams, derive, det_log, det_normal_pair, det_sincos_turns, det_tan)
+
+CDIR = pathlib.Path(__file__).resolve().parent.parent / "oracle" / "c"
+
+
+class Params(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("h", "half_h2", "k_theta", "g", "c_d", "r", "rw", "rw2")] + [
+        ("dphase", C.c_uint32), ("n_sub", C.c_int32), ("accel_mode", C.c_int32), ("kf_q", C.c_float), ("kf_r", C.c_float),
+        ("second_order", C.c_int32), ("pid_ticks", C.c_int32)] + [(n, C.c_float) for n in (
+            "att_kr", "att_kw", "inv_m", "inv_mg", "g_abs", "pid_kp", "pid_ki", "pid_lo", "pid_hi", "pid_windup", "pid_dt",
+            "bw_inv_denom", "bw_k2", "z_init")]
+
+
+class State(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("x_d", "v_d", "theta", "a_d")] + [("phase", C.c_uint32)] + [
+        (n, C.c_float) for n in ("kf_x", "kf_P", "kf_vref")] + [("kf_n", C.c_uint32)] + [
+        (n, C.c_float) for n in ("omega", "z", "v_z", "integ", "e1", "f1", "f2", "f3")]
+
+
+@pytest.fixture(scope="module")
+def lib():
+    so = CDIR / "libstandin_oracle.so"
+    if not so.exists() or so.stat().st_mtime < (CDIR / "standin.c").stat().st_mtime:
+        subprocess.run(["make", "-C", str(CDIR)], check=True, capture_output=True)
+    l = C.CDLL(str(so))
+    l.oracle_tan.restype = l.oracle_log.restype = C.c_float
+    l.oracle_tan.argtypes = l.oracle_log.argtypes = [C.c_float]
+    return l
+
+
+def bits(x):
+    return np.asarray(x, np.float32).view(np.uint32)
+
+
+def test_philox_c_equals_numpy(lib):
+    rng = np.random.default_rng(1)
+    ctr = rng.integers(0, 2 ** 32, size=(500, 4), dtype=np.uint64).astype(np.uint32)
+    keys = rng.integers(0, 2 ** 32, size=(500, 2), dtype=np.uint64).astype(np.uint32)
+    out = (C.c_uint32 * 4)()
+    for c, k in zip(ctr, keys):
+        lib.oracle_philox4x32_10((C.c_uint32 * 4)(*[int(v) for v in c]), C.c_uint32(int(k[0])), C.c_uint32(int(k[1])), out)
+        ref = philox.philox4x32_10(c[0:1], c[1:2], c[2:3], c[3:4], int(k[0]), int(k[1]))
+        assert list(out) == [int(r[0]) for r in ref]
+    # Random123 known answer: counter = key = 0
+    lib.oracle_philox4x32_10((C.c_uint32 * 4)(0, 0, 0, 0), C.c_uint32(0), C.c_uint32(0), out)
+    assert list(out) == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+
+
+def test_fp32_building_blocks_c_equal_numpy(lib):
+    rng = np.random.default_rng(2)
+    phases = np.concatenate([rng.integers(0, 2 ** 32, size=4000, dtype=np.uint64).astype(np.uint32),
+                             np.asarray([0, 1, 0x1FFFFFFF, 0x20000000, 0x3FFFFFFF, 0x40000000, 0x7FFFFFFF, 0x80000000, 0xFFFFFFFF], np.uint32)])
+    s_np, c_np = det_sincos_turns(phases)
+    s, c = C.c_float(), C.c_float()
+    for i, ph in enumerate(phases):
+        lib.oracle_sincos_turns(C.c_uint32(int(ph)), C.byref(s), C.byref(c))
+        assert bits(s.value) == bits(s_np[i]) and bits(c.value) == bits(c_np[i]), hex(int(ph))
+    x = rng.uniform(-0.45, 0.45, 3000).astype(np.float32)
+    assert np.array_equal(bits([lib.oracle_tan(float(v)) for v in x]), bits(det_tan(x)))
+    u = ((rng.integers(0, 2 ** 24, size=3000).astype(np.float32) + np.float32(1)) * np.float32(2.0 ** -24)).astype(np.float32)
+    assert np.array_equal(bits([lib.oracle_log(float(v)) for v in u]), bits(det_log(u)))
+    w = rng.integers(0, 2 ** 32, size=(2000, 2), dtype=np.uint64).astype(np.uint32)
+    n0_np, n1_np = det_normal_pair(w[:, 0], w[:, 1])
+    n0, n1 = C.c_float(), C.c_float()
+    for i in range(len(w)):
+        lib.oracle_normal_pair(C.c_uint32(int(w[i, 0])), C.c_uint32(int(w[i, 1])), C.byref(n0), C.byref(n1))
+        assert bits(n0.value) == bits(n0_np[i]) and bits(n1.value) == bits(n1_np[i])
+
+
+def _params(sp: StandInParams, dyn: StandInDet) -> Params:
+    d = derive(sp)
+    p = Params(h=d.h, half_h2=d.half_h2, k_theta=d.k_theta, g=d.g, c_d=d.c_d, r=d.r, rw=d.rw, rw2=d.rw2, dphase=d.dphase, n_sub=d.n_sub,
+               accel_mode={"exact": 0, "kalman_reference": 1, "kalman": 2}[sp.accel_mode], kf_q=np.float32(sp.kf_process_variance),
+               kf_r=np.float32(sp.kf_measurement_sd ** 2), second_order=int(dyn.so), pid_ticks=sp.pid_ticks, z_init=d.z_init)
+    if dyn.so:
+        pid = dyn.pid
+        p.att_kr, p.att_kw, p.inv_m, p.inv_mg, p.g_abs = dyn.att_kr, dyn.att_kw, dyn.inv_m, dyn.inv_mg, dyn.g_abs
+        p.pid_kp, p.pid_ki, p.pid_lo, p.pid_hi, p.pid_windup, p.pid_dt = pid.kp, pid.ki, pid.lo, pid.hi, pid.windup, pid.dt
+        p.bw_inv_denom, p.bw_k2 = pid.inv_denom, pid.k2
+    return p
+
+
+@pytest.mark.parametrize("opts", [dict(), dict(n_sub=4), dict(n_sub=4, accel_mode="kalman_reference"), dict(n_sub=2, accel_mode="kalman"),
+                                  dict(n_sub=4, dynamics_model="second_order"),
+                                  dict(n_sub=4, dynamics_model="second_order", accel_mode="kalman", g=-9.81)])
+def test_standin_rollouts_c_equal_numpy(lib, opts):
+    """Several episodes per env with random set-points and teleport resets in between: observations and the complete state
+    (body, estimator, PID memory) agree bit for bit after every agent period."""
+    sp = StandInParams(**opts)
+    n_env, rng = 6, np.random.default_rng(3)
+    dyn = StandInDet(sp, n_env)
+    p = _params(sp, dyn)
+    vz_sp = np.float32(sp.v_z)
+    states = [State(kf_P=1.0, z=float(dyn.d.z_init), integ=float(dyn.pid.integ[0]) if dyn.so else 0.0) for _ in range(n_env)]
+    idx = np.arange(n_env)
+    obs = (C.c_float * 4)()
+    for episode in range(3):
+        w = rng.integers(0, 2 ** 32, size=(3, n_env), dtype=np.uint64).astype(np.uint32)
+        dyn.reset(idx, w[0], w[1], w[2], normal_init=(episode % 2 == 0))
+        for i, s in enumerate(states):          # the teleport: body state from the oracle's reset law, memories untouched
+            s.x_d, s.v_d, s.theta, s.phase = float(dyn.x_d[i]), 0.0, 0.0, int(dyn.phase[i])
+            if dyn.so:
+                s.omega, s.z, s.v_z = 0.0, float(dyn.d.z_init), 0.0
+        dyn.advance(np.zeros(n_env, np.float32), idx, hover=True)
+        for s in states:
+            lib.oracle_advance(C.byref(p), C.byref(s), C.c_float(0.0), C.c_float(0.0))
+        for t in range(60):
+            sps = rng.choice(np.asarray([-0.3731, -0.1244, 0.0, 0.1244, 0.2487, 0.3731], np.float32), n_env)
+            dyn.advance(sps, idx)
+            rel_p, rel_v, rel_a, pitch, z, _ = dyn.observe(np.full(n_env, t + 1), idx)
+            for i, s in enumerate(states):
+                lib.oracle_advance(C.byref(p), C.byref(s), C.c_float(float(sps[i])), C.c_float(float(vz_sp)))
+                lib.oracle_observe(C.byref(p), C.byref(s), obs)
+                assert list(bits(list(obs))) == list(bits([rel_p[i], rel_v[i], rel_a[i], pitch[i]])), (episode, t, i)
+                assert bits(s.x_d) == bits(dyn.x_d[i]) and bits(s.v_d) == bits(dyn.v_d[i]) and s.phase == int(dyn.phase[i])
+                if dyn.kf is not None:
+                    assert bits(s.kf_x) == bits(dyn.kf.x[i]) and bits(s.kf_P) == bits(dyn.kf.P[i]) and s.kf_n == int(dyn.kf.n[i])
+                if dyn.so:
+                    assert bits(s.z) == bits(dyn.z[i]) == bits(z[i]) and bits(s.v_z) == bits(dyn.v_z[i]) and bits(s.omega) == bits(dyn.omega[i])
+                    assert bits(s.integ) == bits(dyn.pid.integ[i]) and bits(s.f3) == bits(dyn.pid.f3[i]) and bits(s.e1) == bits(dyn.pid.e1[i])
