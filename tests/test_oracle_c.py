@@ -130,3 +130,37 @@ def test_standin_rollouts_c_equal_numpy(lib, opts):
                 if dyn.so:
                     assert bits(s.z) == bits(dyn.z[i]) == bits(z[i]) and bits(s.v_z) == bits(dyn.v_z[i]) and bits(s.omega) == bits(dyn.omega[i])
                     assert bits(s.integ) == bits(dyn.pid.integ[i]) and bits(s.f3) == bits(dyn.pid.f3[i]) and bits(s.e1) == bits(dyn.pid.e1[i])
+
+
+@pytest.mark.parametrize("name", ["w0", "w1", "w2", "w3", "w4", "lowz", "highz"])
+def test_mdp_c_restatement_replays_the_reference_fixtures(lib, name):
+    """oracle/c/mdp.c (discrete_state, check, reward, continuous_action, reset of PKG/mdp.py) on the forced-action traces the
+    UNMODIFIED reference TrainingMdp produced (tests/golden/mdp_trace_*.npz): set-points, state ids, result codes, done flags,
+    float64 rewards and cumulative rewards identical (==)."""
+    golden = pathlib.Path(__file__).resolve().parent / "golden"
+    g = np.load(golden / f"mdp_trace_{name}.npz")
+    lib.mdp_sizeof.restype = C.c_size_t
+    lib.mdp_act.restype = lib.mdp_reward.restype = lib.mdp_cumulative.restype = C.c_double
+    lib.mdp_act.argtypes = [C.c_void_p, C.c_int]
+    lib.mdp_observe.argtypes = [C.c_void_p] + [C.c_double] * 5 + [C.c_int]
+    lib.mdp_init.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_double]
+    for f in (lib.mdp_reset, lib.mdp_check, lib.mdp_reward, lib.mdp_cumulative, lib.mdp_done):
+        f.argtypes = [C.c_void_p]
+    buf = C.create_string_buffer(lib.mdp_sizeof())
+    m = C.cast(buf, C.c_void_p)
+    lib.mdp_init(m, int(g["w"]), 22.92, 20.0, 4.5)
+    n_done = 0
+    for i in range(len(g["action"])):
+        o = [float(x) for x in g["obs"][i].astype(np.float64)]
+        if g["action"][i] == 255:
+            lib.mdp_reset(m)
+            assert lib.mdp_observe(m, *o, int(g["contact"][i])) == g["state"][i]
+            continue
+        assert lib.mdp_act(m, int(g["action"][i])) == g["theta_sp"][i]
+        sid = lib.mdp_observe(m, *o, int(g["contact"][i]))
+        code = lib.mdp_check(m)
+        r = lib.mdp_reward(m)
+        assert (sid, code, lib.mdp_done(m)) == (g["state"][i], g["code"][i], g["done"][i]), i
+        assert r == g["reward"][i] and lib.mdp_cumulative(m) == g["cum"][i], i
+        n_done += int(g["done"][i])
+    assert n_done >= 1
