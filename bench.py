@@ -118,7 +118,16 @@ def cpu_baseline(seconds: float = 12.0) -> dict:
         n, _, s = run_single_env(50000, seed=42 + steps)
         steps += n
         t += s
-    return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port",
+    c_port = None
+    try:          # the same loop restated in plain C (oracle/c/loop.c): what an optimised CPU implementation would reach per core
+        from oracle.c_loop import run_single_env_c
+        n_c, _, s_c = run_single_env_c(4_000_000)
+        c_port = {"value": n_c / s_c, "unit": UNIT, "cores": 1, "sample": f"{n_c} env-steps in {s_c:.2f} s",
+                  "what": "oracle/c/loop.c: the single-env trainer loop in plain C (float32 tables, Philox contract, fp32 stand-in), "
+                          "bit-identical to the reference fixtures (tests/test_oracle_c.py)"}
+    except Exception as exc:
+        c_port = {"error": str(exc)}
+    return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port", "c_port": c_port,
             "sample": f"{steps} env-steps of the single-env reference loop (oracle port, float64 tables, analytic stand-in), "
                       f"{t:.1f} s on 1 of {os.cpu_count()} host cores",
             "context": "the unmodified reference loop measures 6.9-7.5e3 env-steps/s per core on the same stand-in (BASELINE.md section 2); "

@@ -10,17 +10,10 @@ import numpy as np
 import pytest
 
 from oracle import philox
+from oracle.c_loop import LoopParams, Params
 from oracle.dynamics import (StandInDet, StandInParams, derive, det_log, det_normal_pair, det_sincos_turns, det_tan)
 
 CDIR = pathlib.Path(__file__).resolve().parent.parent / "oracle" / "c"
-
-
-class Params(C.Structure):
-    _fields_ = [(n, C.c_float) for n in ("h", "half_h2", "k_theta", "g", "c_d", "r", "rw", "rw2")] + [
-        ("dphase", C.c_uint32), ("n_sub", C.c_int32), ("accel_mode", C.c_int32), ("kf_q", C.c_float), ("kf_r", C.c_float),
-        ("second_order", C.c_int32), ("pid_ticks", C.c_int32)] + [(n, C.c_float) for n in (
-            "att_kr", "att_kw", "inv_m", "inv_mg", "g_abs", "pid_kp", "pid_ki", "pid_lo", "pid_hi", "pid_windup", "pid_dt",
-            "bw_inv_denom", "bw_k2", "z_init")]
 
 
 class State(C.Structure):
@@ -164,3 +157,39 @@ def test_mdp_c_restatement_replays_the_reference_fixtures(lib, name):
         assert r == g["reward"][i] and lib.mdp_cumulative(m) == g["cum"][i], i
         n_done += int(g["done"][i])
     assert n_done >= 1
+
+
+@pytest.mark.parametrize("name", ["replay_w0_float32", "replay_w0_float32_ep1950", "replay_w2_float32", "replay_w4_float32"])
+def test_single_env_loop_c_replays_the_reference_trainer_fixtures(lib, name):
+    """oracle/c/loop.c (guess / exploration_rate / alpha / update on float32 tables + MDP + stand-in + Philox contract, one env)
+    against the replay fixtures produced by the UNMODIFIED reference trainer loop (tests/golden/replay_*_float32.npz):
+    observations (bits), actions, states, codes, done flags, float64 rewards, episode indices, and the final float32 Q table and
+    counts are identical."""
+    golden = pathlib.Path(__file__).resolve().parent / "golden"
+    g = np.load(golden / f"{name}.npz")
+    sp = StandInParams()
+    dyn = StandInDet(sp, 1)
+    p, d = _params(sp, dyn), derive(sp)
+    lp = LoopParams(dz=d.dz, z_touch=d.z_touch, half_platform=d.half_platform, p_max_f=d.p_max, two_p_max_f=d.two_p_max, sigma_x=d.sigma_x,
+                    f_ag=22.92, t_max=20.0, p_max=4.5, alpha_min=0.02949, omega=0.51, gamma=0.99)
+    n = len(g["action"])
+    qa = np.ascontiguousarray(g["qa0"], np.float32).reshape(-1).copy()
+    qb = np.ascontiguousarray(g["qb0"], np.float32).reshape(-1).copy()
+    count = np.zeros(2835, np.float64)
+    obs = np.zeros((n, 5), np.float32)
+    i32 = lambda: np.zeros(n, np.int32)
+    action, state, nstate, code, done, episode = i32(), i32(), i32(), i32(), i32(), i32()
+    reward = np.zeros(n, np.float64)
+    lib.mdp_sizeof.restype = C.c_size_t
+    buf = C.create_string_buffer(lib.mdp_sizeof())
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.oracle_single_env_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 11
+    episodes = lib.oracle_single_env_loop(C.byref(p), C.byref(lp), C.cast(buf, C.c_void_p), int(g["seed"]), 0, int(g["w"]), int(g["ep0"]), n,
+                                          ptr(qa), ptr(qb), ptr(count), ptr(obs), ptr(action), ptr(state), ptr(nstate), ptr(code),
+                                          ptr(done), ptr(reward), ptr(episode))
+    assert np.array_equal(obs.view(np.uint32), g["obs"].view(np.uint32))
+    for mine, key in ((action, "action"), (state, "state"), (nstate, "next_state"), (code, "code"), (done, "done"), (episode, "episode")):
+        assert np.array_equal(mine, g[key].astype(np.int32)), key
+    assert np.array_equal(reward, g["reward"])
+    assert np.array_equal(qa.view(np.uint32), g["qa"].reshape(-1).view(np.uint32))
+    assert np.array_equal(count, g["count"].reshape(-1)) and episodes == int(g["done"].sum()) >= 1
