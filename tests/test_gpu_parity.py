@@ -727,3 +727,31 @@ def test_no_access_outside_the_bound_buffers(dp):
     for k, b in big.items():
         assert bool((b[:pad] == 0xAB).all()) and bool((b[pad + sizes[k]:] == 0xAB).all()), k
     assert int(view["env"].view(torch.int32).abs().sum()) != 0
+
+
+def test_production_instance_vs_c_oracle_at_size():
+    """The NON-trace production instances (full-slot and ragged) against the C statement of the batched semantics
+    (oracle/c/population.c, itself held equal to oracle/loop.py on the CPU): populations of 1 280 / 1 200 envs, 128-thread blocks,
+    ten slots per thread, promotions and transfers on the way -- sizes the Python oracle needs minutes for.  Float32 tables,
+    counts and trainer counters identical."""
+    from oracle.c_loop import run_population_c
+    kw = dict(success_rate=0.3, successive_successful_episodes=50, max_num_episodes=2500)
+    for n_envs in (1280, 1200):
+        seeds = [11, 12]
+        eng = _engine(2, n_envs, threads_per_block=128, seeds=seeds, tp=kw)
+        assert eng.lib.dqlb200_uses_default_instance(eng.handle) == 1
+        eng.reset(0)
+        steps = 400
+        eng.train(150)
+        eng.train(1)
+        eng.train(steps - 151)
+        eng.check_errors()
+        ps = eng.population_state()
+        for p in range(2):
+            out = run_population_c(n_envs, steps, seed=seeds[p], population=p, w0=0, tp=TrainerParams(**kw))
+            qa, qb, cnt = eng.get_tables(p, np.float32)
+            r = out["result"]
+            assert np.array_equal(cnt, out["count"]), (n_envs, p)
+            assert np.array_equal(qa.view(np.uint32), out["qa"].view(np.uint32)) and np.array_equal(qb.view(np.uint32), out["qb"].view(np.uint32))
+            assert (int(ps[p]["working_step"]), int(ps[p]["total_episodes"]), int(ps[p]["total_successes"])) == (r.w, r.total_episodes, r.total_successes)
+            assert list(ps[p]["termination_hist"]) == list(r.term_hist) and r.w >= 1

@@ -193,3 +193,28 @@ def test_single_env_loop_c_replays_the_reference_trainer_fixtures(lib, name):
     assert np.array_equal(reward, g["reward"])
     assert np.array_equal(qa.view(np.uint32), g["qa"].reshape(-1).view(np.uint32))
     assert np.array_equal(count, g["count"].reshape(-1)) and episodes == int(g["done"].sum()) >= 1
+
+
+@pytest.mark.parametrize("mode,opts", [("reference", {}), ("paper", {}), ("reference", dict(n_sub=2, accel_mode="kalman"))])
+def test_population_c_equals_python_population_oracle(lib, mode, opts):
+    """oracle/c/population.c (batched semantics S1 incl. success window, promotion, transfer, fresh-MDP restart) against
+    oracle/loop.py: PopulationOracle on 40 envs through several curriculum steps: traces, float32 tables, counts, counters."""
+    from oracle.c_loop import run_population_c
+    from oracle.loop import PopulationOracle, TrainerParams
+    tp = TrainerParams(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90, transfer_mode=mode)
+    sp = StandInParams(**opts)
+    n_envs, steps = 40, 420
+    out = run_population_c(n_envs, steps, seed=3, population=2, w0=0, tp=tp, sp=sp, trace=True)
+    pop = PopulationOracle(n_envs, seed=3, population=2, w0=0, dtype=np.float32, tp=tp, sp=sp)
+    for t in range(steps):
+        if pop.finished:
+            break
+        o = pop.step()
+        assert np.array_equal(out["action"][t], o["action"]) and np.array_equal(out["next_state"][t], o["next_state"]), t
+        assert np.array_equal(out["code"][t], o["code"]) and np.array_equal(out["reward"][t], o["reward"]), t
+    r = out["result"]
+    assert np.array_equal(out["qa"].view(np.uint32), pop.agent.qa.view(np.uint32)) and np.array_equal(out["qb"].view(np.uint32), pop.agent.qb.view(np.uint32))
+    assert np.array_equal(out["count"], pop.agent.count)
+    assert (r.w, bool(r.finished), r.total_episodes, r.total_successes, r.total_steps) == (pop.w, pop.finished, pop.total_episodes, pop.total_successes, pop.total_steps)
+    assert list(r.term_hist) == list(pop.term_hist) and r.window_sum == sum(pop.window) and r.window_count == len(pop.window)
+    assert r.n_promotions == len(pop.promotions) >= 2
