@@ -268,7 +268,8 @@ int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream);
 int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* stream);
 
 /* Same with HOST buffers: copies env_state/tables/pop_state in, runs k_steps, copies them back and
- * synchronises.  This is the end-to-end call bench.py times as `e2e`. */
+ * synchronises.  This is the end-to-end call bench.py times as `e2e`.  It does not carry the per-env extension state:
+ * configurations with accel_mode != 0 or dynamics_model != 0 are refused (DQLB200_ERR_ARG), use dqlb200_train. */
 int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host,
                        void* pop_state_host, void* stream);
 
