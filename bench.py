@@ -295,7 +295,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         shared = {"env_steps_per_s": world * envs_per_gpu_shared(P, n_p) * SHARED_SYNC_EVERY * rounds / (float(t_sh[0]) * 1e-3),
                   "sync_every_global_steps": SHARED_SYNC_EVERY, "envs_sharing_one_table_pair": world * P * n_p,
-                  "allreduce_bytes_per_sync": int(sync.delta.numel() * 4), "replicas_per_gpu": P,
+                  "allgather_bytes_per_rank_and_sync": int(sync.packed.numel() * 4), "replicas_per_gpu": P,
                   "tables_identical_on_all_ranks": bool(torch.equal(lo, hi)), "timing": "CUDA events, max over ranks"}
         es.close()
 

@@ -33,16 +33,19 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> pathlib.Path:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("DQL_NVCC_EXTRA", "").split(), "-o", str(LIB), str(SRC)]
+    out = pathlib.Path(os.environ.get("DQL_BUILD_OUT") or LIB)          # DQL_BUILD_OUT: kernel A/B variants (build_variants/)
+    tmp = out.with_suffix(".so.tmp")
+    cmd = [nvcc_path(), *NVCC_FLAGS, *os.environ.get("DQL_NVCC_EXTRA", "").split(), "-o", str(tmp), str(SRC)]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, out)                # atomic: a concurrent reader (gpurun snapshot) never sees a half-written library
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

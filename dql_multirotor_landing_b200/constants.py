@@ -34,7 +34,7 @@ ALPHA_LUT = 1003
 EPS_LUT = 2002
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 LIMITS_POSITION = [1.0, 0.64, 0.4096, 0.262144, 0.16777216]   # PKG/mdp.py:45-47
 LIMITS_VELOCITY = [1.0, 0.8, 0.64, 0.512, 0.4096]              # PKG/mdp.py:48-50
@@ -156,7 +156,7 @@ class Trace2D(C.Structure):
 
 
 TRAJ_RECTILINEAR_X, TRAJ_RECTILINEAR_XY, TRAJ_EIGHT = 0, 1, 2
-SHARED_DELTA_WORDS = 4 * MAX_CELLS + 4        # DQLB200_SHARED_DELTA_WORDS
+SHARED_WORDS = 2 * MAX_CELLS + 4              # DQLB200_SHARED_WORDS: 32-bit words per agent and rank in the shared-table exchange
 
 
 # ------------------------------------------------------------------------------------------------

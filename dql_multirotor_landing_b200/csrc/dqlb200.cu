@@ -192,19 +192,18 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   const size_t pp_bytes = (size_t)cfg->n_populations * sizeof(dqlb200_population_params);
   CUDA_TRY(cudaMalloc(&h->d_pop_params, pp_bytes));
   CUDA_TRY(cudaMemcpy(h->d_pop_params, pop_params, pp_bytes, cudaMemcpyHostToDevice));
-  CUDA_TRY(cudaMalloc(&h->d_error, sizeof(uint32_t)));
-  CUDA_TRY(cudaMemset(h->d_error, 0, sizeof(uint32_t)));
+  CUDA_TRY(cudaMalloc(&h->d_error, 4 * sizeof(uint32_t)));
+  CUDA_TRY(cudaMemset(h->d_error, 0, 4 * sizeof(uint32_t)));
   {
     const int tpb_ = cfg->threads_per_block;
     const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
     if (n_slots > 2047) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots per thread)");
-    h->smem_bytes = ((sizeof(dql::Shared) + 15) & ~size_t(15)) + (size_t)(tpb_ / 32) * dql::RESET_QUEUE * sizeof(uint16_t) +
-                    (size_t)((cfg->accel_mode != 0 || cfg->dynamics_model != 0) ? 6 : 3) * tpb_ * 16;   // + the cp.async staging slots of the env (and extension-state) prefetch
+    h->smem_bytes = dql::train_smem_bytes(tpb_, true);      // the largest instance (extended / trace): tables + snapshot + reset queues + env tiles + record ring
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem_bytes));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::train_smem_bytes(W * 32, T || D == 2)));
 #define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, false, 3) DQL_SET_SMEM1(W, true, 2)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
   CUDA_TRY(cudaFuncSetAttribute(dql::replica_merge_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::merge_smem_bytes(32)));
@@ -322,16 +321,16 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   a.env_stride = (size_t)a.n_total * 16;
   a.env_stride2 = (size_t)a.n_total * 32;
   const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
-  const size_t smem = h->smem_bytes;
   const bool tracing = trace != nullptr;
   const bool extended = h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0;      // options with extra per-env state
+  const size_t smem = dql::train_smem_bytes(h->cfg.threads_per_block, tracing || extended);      // the trace instances are extended ones
   const bool full_slots = h->cfg.envs_per_population % h->cfg.threads_per_block == 0;
 #define DQL_LAUNCH(W)                                                                        \
-  if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
-  else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);            \
-  else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32, smem, stream>>>(h->kc, a);      \
-  else if (full_slots) dql::train_kernel<W, false, 3><<<grid, W * 32, smem, stream>>>(h->kc, a);          \
-  else dql::train_kernel<W, false, 0><<<grid, W * 32, smem, stream>>>(h->kc, a);
+  if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);                     \
+  else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);            \
+  else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);      \
+  else if (full_slots) dql::train_kernel<W, false, 3><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);          \
+  else dql::train_kernel<W, false, 0><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;
     case 64: DQL_LAUNCH(2) break;
@@ -514,43 +513,68 @@ int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream) {
 int dqlb200_check_errors(dqlb200_handle* h, void* stream) {
   if (!h) return fail(DQLB200_ERR_ARG, "null handle");
   CUDA_TRY(cudaSetDevice(h->device));
-  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  uint32_t facade = 0;
-  CUDA_TRY(cudaMemcpy(&facade, h->d_error, sizeof(facade), cudaMemcpyDeviceToHost));
-  if (facade) {
-    CUDA_TRY(cudaMemset(h->d_error, 0, sizeof(uint32_t)));
-    return fail(DQLB200_ERR_DEVICE_FLAG, facade & 1u ? "Unexpected discretization case: NaN observation"
-                                                     : (facade & 2u ? "Cannot check an empty state" : "Previous state missing"));
+  cudaStream_t s = (cudaStream_t)stream;
+  // d_error: [0] facade kernels' flag, [1] OR of the populations' flags, [2] first offending population -- ONE reduction
+  // launch and ONE 12-byte copy, whatever the number of populations
+  if (h->pop_state) {
+    const uint32_t init[2] = {0u, 0xFFFFFFFFu};
+    CUDA_TRY(cudaMemcpyAsync(h->d_error + 1, init, sizeof(init), cudaMemcpyHostToDevice, s));
+    dql::error_reduce_kernel<<<(h->cfg.n_populations + 255) / 256, 256, 0, s>>>((const dqlb200_population_state*)h->pop_state, h->cfg.n_populations,
+                                                                                 h->d_error + 1);
+    CUDA_TRY(cudaGetLastError());
   }
-  for (int p = 0; h->pop_state && p < h->cfg.n_populations; ++p) {
-    dqlb200_population_state ps;
-    CUDA_TRY(cudaMemcpy(&ps, (dqlb200_population_state*)h->pop_state + p, sizeof(ps), cudaMemcpyDeviceToHost));
-    if (ps.error_flags) return fail(DQLB200_ERR_DEVICE_FLAG, "population " + std::to_string(p) + ": NaN observation (error_flags=" + std::to_string(ps.error_flags) + ")");
+  uint32_t e[3] = {0u, 0u, 0u};
+  CUDA_TRY(cudaMemcpyAsync(e, h->d_error, h->pop_state ? sizeof(e) : sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  if (e[0]) {
+    CUDA_TRY(cudaMemsetAsync(h->d_error, 0, sizeof(uint32_t), s));
+    return fail(DQLB200_ERR_DEVICE_FLAG, e[0] & 1u ? "Unexpected discretization case: NaN observation"
+                                                   : (e[0] & 2u ? "Cannot check an empty state" : "Previous state missing"));
   }
+  if (e[1]) return fail(DQLB200_ERR_DEVICE_FLAG, "population " + std::to_string(e[2]) + ": NaN observation (error_flags=" + std::to_string(e[1]) + ")");
   return DQLB200_OK;
 }
 
-int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream) {
-  if (!h || !h->tables || !h->pop_state || !snapshot || !delta) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+int dqlb200_selftest_discretise(dqlb200_handle* h, int working_step, int variant, int64_t n, const float* obs, uint16_t* out_state, void* stream) {
+  if (!h || !obs || !out_state) return fail(DQLB200_ERR_ARG, "null argument");
+  if (working_step < 0 || working_step >= DQLB200_MAX_CURRICULUM) return fail(DQLB200_ERR_ARG, "working_step out of range");
+  if (variant < 0 || variant > 3) return fail(DQLB200_ERR_ARG, "variant must be 0..3");
+  if ((variant & 1) && !h->kc_default) return fail(DQLB200_ERR_STATE, "the compile-time-constant variants need the reference-default configuration");
+  if (n <= 0) return DQLB200_OK;
   CUDA_TRY(cudaSetDevice(h->device));
-  const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
-  const long long n = (long long)n_agents * DQLB200_MAX_CELLS;
-  dql::shared_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)h->tables, (const uint32_t*)snapshot,
-                                                                                       (float*)delta, (const dqlb200_population_state*)h->pop_state,
-                                                                                       n_agents, R);
+  const unsigned blocks = (unsigned)((n + 127) / 128);
+  cudaStream_t s = (cudaStream_t)stream;
+  switch (variant) {
+    case 0: dql::selftest_discretise_kernel<false, true><<<blocks, 128, 0, s>>>(h->kc, working_step, n, obs, out_state); break;
+    case 1: dql::selftest_discretise_kernel<true, true><<<blocks, 128, 0, s>>>(h->kc, working_step, n, obs, out_state); break;
+    case 2: dql::selftest_discretise_kernel<false, false><<<blocks, 128, 0, s>>>(h->kc, working_step, n, obs, out_state); break;
+    default: dql::selftest_discretise_kernel<true, false><<<blocks, 128, 0, s>>>(h->kc, working_step, n, obs, out_state); break;
+  }
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
 }
 
-int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, int pooled_promote_successes, void* stream) {
-  if (!h || !h->tables || !h->pop_state || !snapshot || !delta_reduced) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+int dqlb200_shared_pack(dqlb200_handle* h, void* packed, void* stream) {
+  if (!h || !h->tables || !h->pop_state || !packed) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
+  const long long n = (long long)n_agents * DQLB200_MAX_CELLS;
+  dql::shared_pack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const uint32_t*)h->tables, (uint32_t*)packed,
+                                                                                       (const dqlb200_population_state*)h->pop_state, n_agents, R);
+  CUDA_TRY(cudaGetLastError());
+  return DQLB200_OK;
+}
+
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* gathered, int n_ranks, int pooled_promote_successes, void* stream) {
+  if (!h || !h->tables || !h->pop_state || !snapshot || !gathered) return fail(DQLB200_ERR_ARG, "null argument / not bound");
+  if (n_ranks < 1) return fail(DQLB200_ERR_ARG, "n_ranks < 1");
   CUDA_TRY(cudaSetDevice(h->device));
   const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
   if (R > 1 && !h->merge_snapshot) return fail(DQLB200_ERR_STATE, "replicated layout: bind the merge snapshot first (dqlb200_bind_merge_snapshot)");
   const long long n = (long long)n_agents * DQLB200_MAX_CELLS;
   dql::shared_apply_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>((uint32_t*)h->tables, (uint32_t*)snapshot,
                                                                                         R > 1 ? (uint32_t*)h->merge_snapshot : nullptr,
-                                                                                        (const float*)delta_reduced, (dqlb200_population_state*)h->pop_state,
+                                                                                        (const uint32_t*)gathered, n_ranks, (dqlb200_population_state*)h->pop_state,
                                                                                         n_agents, R, pooled_promote_successes, h->cfg.max_num_episodes);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;

@@ -45,6 +45,44 @@ __global__ void selftest_division_kernel(const __grid_constant__ KC kc, unsigned
 }
 
 
+// Device self-test of the fp32 cut-table discretisation (R5) on caller-supplied observations: obs [n][4] = rel_p, rel_v, rel_a,
+// pitch -> state id.  The three ways the production kernels call discretise_cuts:
+//   KDEF = false, WITH_W = true   train_kernel generic instances / env_step_kernel: run-time angle cuts, level loop bounded by w
+//   KDEF = true,  WITH_W = true   train_kernel production instances: compile-time angle cuts (KDef), cut table staged in shared memory
+//   *,            WITH_W = false  eval kernels, env_reset: every level index probed (cuts above the working step are NaN)
+// One population-state error word: any observation with a NaN component sets bit 0 (the reference raises, PKG/mdp.py:170).
+template <bool KDEF, bool WITH_W>
+__global__ void __launch_bounds__(128) selftest_discretise_kernel(const __grid_constant__ KC kc, int w, long long n, const float* __restrict__ obs,
+                                                                  uint16_t* __restrict__ out_state) {
+  __shared__ dqlb200_cuts cuts;
+  if (threadIdx.x == 0) cuts = kc.cuts[w];
+  __syncthreads();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  Obs o;
+  o.rel_p = obs[4 * i + 0]; o.rel_v = obs[4 * i + 1]; o.rel_a = obs[4 * i + 2]; o.pitch = obs[4 * i + 3];
+  o.z = 0.0f; o.contact = false;
+  DState d;
+  if (KDEF) {
+    const KDef kk{};
+    d = WITH_W ? discretise_cuts(cuts, kk.angle_cut, o, w) : discretise_cuts(cuts, kk.angle_cut, o);
+  } else {
+    d = WITH_W ? discretise_cuts(kc.cuts[w], kc.angle_cut, o, w) : discretise_cuts(kc.cuts[w], kc.angle_cut, o);
+  }
+  out_state[i] = (uint16_t)d.id();
+}
+
+// OR of the populations' error flags + the smallest offending population (dqlb200_check_errors): out[0] = flags, out[1] = index
+__global__ void error_reduce_kernel(const dqlb200_population_state* __restrict__ ps, int n_pop, uint32_t* out) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t f = p < n_pop ? ps[p].error_flags : 0u;
+  const uint32_t any = __ballot_sync(FULL, f != 0u);
+  if (f != 0u) {
+    atomicOr(out, f);
+    if ((threadIdx.x & 31) == __ffs(any) - 1) atomicMin(out + 1, (uint32_t)p);
+  }
+}
+
 // -------------------------------------------------------------------------------------------------
 // Facade kernel: float64 observations, the reference's comparisons in float64 (PKG/mdp.py:149-170,
 // 257-333, 335-439, 441-541, 784-845).  One thread per MDP object.
@@ -184,7 +222,8 @@ __global__ void agent_facade_kernel(int op, long long n, double* t, int cs, cons
     }
   } else if (op == DQLB200_AGENT_TRANSFER) {
     const int step = state[0];
-    const int src = (step - 1 + cs) % cs;
+    // the source slot (step - 1) mod the AGENT's curriculum_steps comes from the caller (next_state[0]); cs is the handle's
+    const int src = next_state ? next_state[0] : (step - 1 + cs) % cs;
     const double ratio = alpha[0];
     for (int i = 0; i < DQLB200_CELLS_PER_LEVEL; ++i) {
       qa[step * DQLB200_CELLS_PER_LEVEL + i] = __dmul_rn(qa[src * DQLB200_CELLS_PER_LEVEL + i], ratio);

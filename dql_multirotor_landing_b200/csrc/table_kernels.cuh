@@ -17,28 +17,27 @@ __global__ void transfer_kernel(uint32_t* tables, int n_pop, int cs, int step, f
   }
 }
 
-// Shared-table mode (one agent replicated on G devices).  Each replica trains on its own envs for a few
-// steps; the replicas are then merged with a visit-weighted mean of their Q deltas and the sum of
-// their visit counts:  Q <- Q_snap + sum_g(dcount_g * dQ_g) / sum_g(dcount_g),  count <- count_snap + sum_g dcount_g.
-// One "agent" below = a group of R = replicas_per_population consecutive populations whose tables are identical (after
-// replica_merge_kernel; R = 1: a plain population).  snap holds ONE [3][CELLS] entry per agent, delta ONE entry of
-// DQLB200_SHARED_DELTA_WORDS floats per agent: [0] sum dQ*dcount, [1] sum dcount, [2] number of ranks that visited the cell,
-// [3] sum of the visiting ranks' Q (exact when one rank visited: the value that rank keeps), then the agent's pooled trainer
-// counters: successes in the windows, finished episodes of the curriculum step, number of ranks, ranks that are alive.
-constexpr int DELTA_WORDS = DQLB200_SHARED_DELTA_WORDS;
-__global__ void __launch_bounds__(256) shared_pack_kernel(const uint32_t* tables, const uint32_t* snap, float* delta, const dqlb200_population_state* ps,
+// Shared-table mode (one agent replicated on G devices).  Each rank trains on its own envs for a few steps; the ranks' tables
+// are then merged exactly like the replicas of replica-merge mode, the ranks being the replicas:
+//   dcount_g = count_g - count_snap,  Q <- Q_snap + sum_g (Q_g - Q_snap) * dcount_g / sum_g dcount_g  (RANK ORDER, float32),
+//   count <- count_snap + sum_g dcount_g;  a cell ONE rank visited takes that rank's value bit for bit.
+// The exchange is an all-reduce realised as all-gather + a reduction in rank order inside shared_apply_kernel: every rank
+// contributes its raw table words (Q_a bits, 32-bit counts) and integer trainer counters, so counts and counters are exact
+// for any number of visits, and the float32 sum has ONE defined order -- identical on every rank, from run to run and for
+// every NCCL algorithm (an fp32 SUM all-reduce is none of these).
+// One "agent" = a group of R = replicas_per_population consecutive populations whose tables are identical (after
+// replica_merge_kernel; R = 1: a plain population).  packed: ONE entry of DQLB200_SHARED_WORDS 32-bit words per agent:
+// [Q_a bits | count | successes in the windows, finished episodes of the curriculum step (lo, hi), alive].
+constexpr int SHARED_WORDS = DQLB200_SHARED_WORDS;
+__global__ void __launch_bounds__(256) shared_pack_kernel(const uint32_t* tables, uint32_t* packed, const dqlb200_population_state* ps,
                                                           int n_agents, int R) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < (long long)n_agents * CELLS) {
     const long long g = i / CELLS, c = i % CELLS;
-    const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
-    float* d = delta + (size_t)g * DELTA_WORDS;
-    const uint32_t dcu = tables[tb + 2 * CELLS + c] - snap[sb + 2 * CELLS + c];
-    const float dc = (float)dcu, q = __uint_as_float(tables[tb + c]);
-    d[c] = fmul(fsub(q, __uint_as_float(snap[sb + c])), dc);
-    d[CELLS + c] = dc;
-    d[2 * CELLS + c] = dcu ? 1.0f : 0.0f;
-    d[3 * CELLS + c] = dcu ? q : 0.0f;
+    const size_t tb = (size_t)g * R * 3 * CELLS;
+    uint32_t* d = packed + (size_t)g * SHARED_WORDS;
+    d[c] = tables[tb + c];
+    d[CELLS + c] = tables[tb + 2 * CELLS + c];
   }
   // The agent's pooled trainer counters: the block that holds cell 0 of an agent (at most one agent starts inside a block,
   // CELLS > blockDim) reduces over the agent's R replicas with all its threads -- one thread walking R population states took
@@ -71,27 +70,45 @@ __global__ void __launch_bounds__(256) shared_pack_kernel(const uint32_t* tables
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      float* d = delta + (size_t)g0 * DELTA_WORDS + 4 * CELLS;
-      d[0] = (float)(long long)s_succ;
-      d[1] = (float)(long long)s_eps;
-      d[2] = 1.0f;
-      d[3] = s_dead ? 0.0f : 1.0f;
+      uint32_t* d = packed + (size_t)g0 * SHARED_WORDS + 2 * CELLS;
+      d[0] = (uint32_t)s_succ;
+      d[1] = (uint32_t)s_eps;
+      d[2] = (uint32_t)(s_eps >> 32);
+      d[3] = s_dead ? 0u : 1u;
     }
   }
 }
-__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* merge_snap, const float* delta,
+// gathered: [n_ranks][n_agents][SHARED_WORDS], rank-major (the layout all-gather produces)
+__global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* merge_snap, const uint32_t* __restrict__ gathered, int n_ranks,
                                     dqlb200_population_state* ps, int n_agents, int R, int pooled_promote, long long max_episodes) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)n_agents * CELLS) return;
   const long long g = i / CELLS, c = i % CELLS;
   const size_t tb = (size_t)g * R * 3 * CELLS, sb = (size_t)g * 3 * CELLS;
-  const float* d = delta + (size_t)g * DELTA_WORDS;
-  const float visitors = d[2 * CELLS + c];
-  uint32_t q_bits = snap[sb + c], cnt = snap[sb + 2 * CELLS + c];
-  if (visitors == 1.0f) q_bits = __float_as_uint(d[3 * CELLS + c]);       // one rank visited: its value, bit for bit, on every rank
-  else if (visitors > 1.0f) q_bits = __float_as_uint(fadd(__uint_as_float(q_bits), __fdiv_rn(d[c], d[CELLS + c])));
-  if (visitors > 0.0f) {
-    cnt += (uint32_t)__float2uint_rn(d[CELLS + c]);
+  const size_t rank_stride = (size_t)n_agents * SHARED_WORDS;
+  const uint32_t* d = gathered + (size_t)g * SHARED_WORDS;
+  const uint32_t c_snap = snap[sb + 2 * CELLS + c];
+  const float q_snap = __uint_as_float(snap[sb + c]);
+  float sum = 0.0f;
+  unsigned long long total = 0ull;
+  int visitors = 0;
+  uint32_t single = 0u;
+  for (int r = 0; r < n_ranks; ++r) {           // rank order: the one defined order of the float32 sum
+    const uint32_t dc = d[r * rank_stride + CELLS + c] - c_snap;
+    if (dc) {
+      const uint32_t qb = d[r * rank_stride + c];
+      sum = fadd(sum, fmul(fsub(__uint_as_float(qb), q_snap), __uint2float_rn(dc)));
+      total += dc;
+      single = qb;
+      visitors += 1;
+    }
+  }
+  uint32_t q_bits = snap[sb + c], cnt = c_snap;
+  if (visitors == 1) q_bits = single;       // one rank visited: its value, bit for bit, on every rank
+  else if (visitors > 1) q_bits = __float_as_uint(fadd(q_snap, __fdiv_rn(sum, __ull2float_rn(total))));
+  if (visitors > 0) {
+    const unsigned long long c_new = (unsigned long long)c_snap + total;
+    cnt = c_new > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)c_new;        // the 32-bit count saturates (alpha is constant from 1002 on)
     for (int r = 0; r < R; ++r) {
       tables[tb + (size_t)r * 3 * CELLS + c] = q_bits;
       tables[tb + (size_t)r * 3 * CELLS + 2 * CELLS + c] = cnt;
@@ -102,10 +119,16 @@ __global__ void shared_apply_kernel(uint32_t* tables, uint32_t* snap, uint32_t* 
   const uint32_t qb_bits = tables[tb + CELLS + c];
   snap[sb + c] = q_bits; snap[sb + CELLS + c] = qb_bits; snap[sb + 2 * CELLS + c] = cnt;
   if (merge_snap) { merge_snap[sb + c] = q_bits; merge_snap[sb + CELLS + c] = qb_bits; merge_snap[sb + 2 * CELLS + c] = cnt; }
-  if (c == 0 && pooled_promote > 0) {      // promotion pooled over every rank's windows (same decision on every rank)
-    const float successes = d[4 * CELLS + 0], episodes = d[4 * CELLS + 1];
-    const bool alive = d[4 * CELLS + 3] == d[4 * CELLS + 2];
-    const int pending = !alive ? 0 : (successes >= (float)pooled_promote ? 1 : (episodes >= (float)max_episodes ? 2 : 0));
+  if (c == 0 && pooled_promote > 0) {      // promotion pooled over every rank's windows (same decision on every rank), exact integers
+    unsigned long long successes = 0ull, episodes = 0ull;
+    bool alive = true;
+    for (int r = 0; r < n_ranks; ++r) {
+      const uint32_t* t = d + r * rank_stride + 2 * CELLS;
+      successes += t[0];
+      episodes += (unsigned long long)t[1] | ((unsigned long long)t[2] << 32);
+      alive = alive && t[3] != 0u;
+    }
+    const int pending = !alive ? 0 : (successes >= (unsigned long long)pooled_promote ? 1 : ((long long)episodes >= max_episodes ? 2 : 0));
     if (pending)
       for (int r = 0; r < R; ++r) ps[g * R + r].pending_advance = pending;
   }

@@ -118,7 +118,8 @@ class DoubleQLearningAgent:
 
     def transfer_learning(self, current_curriculum_step: int, transfer_learning_ratio: float):
         """PKG/double_q_learning.py:77-89 (slot k from slot k-1; k = 0 reads the last slot, quirk Q7)."""
-        self._call(_ffi.AGENT_TRANSFER, int(current_curriculum_step) % self.curriculum_steps, alpha=float(transfer_learning_ratio))
+        step = int(current_curriculum_step) % self.curriculum_steps
+        self._call(_ffi.AGENT_TRANSFER, step, next_state=(step - 1) % self.curriculum_steps, alpha=float(transfer_learning_ratio))
 
     def update(self, current_state_action: StateAction, next_state: State, alpha: float, gamma: float, reward):
         """PKG/double_q_learning.py:91-108: the table-pick draw is consumed, table A is updated either way (quirk Q1)."""

@@ -251,6 +251,15 @@ class Engine:
         raw = self.pop_state.cpu().numpy()
         return raw.view(K.POPULATION_STATE_DTYPE).copy()
 
+    def selftest_discretise(self, obs: np.ndarray, working_step: int, variant: int = 0) -> np.ndarray:
+        """Device discretisation (csrc/dqlb200_device.cuh: discretise_cuts) of fp32 observations [n][4] = rel_p, rel_v, rel_a, pitch
+        -> state ids; variant: see dqlb200_selftest_discretise (include/dqlb200.h)."""
+        o = torch.as_tensor(np.ascontiguousarray(obs, np.float32).reshape(-1, 4), device=self.device)
+        out = torch.zeros(o.shape[0], dtype=torch.int16, device=self.device)
+        _ffi.check(self.lib.dqlb200_selftest_discretise(self.handle, int(working_step), int(variant), o.shape[0], o.data_ptr(), out.data_ptr(),
+                                                        self._stream()))
+        return out.cpu().numpy().astype(np.uint16)
+
     def set_episode_index(self, episode: int):
         """Test hook: set every env's per-curriculum-step episode index (word C.y of the state)."""
         n = self.n_total

@@ -2,9 +2,12 @@
 
 The path shards by POPULATION: every rank owns a disjoint set of agents (Q-table pairs) with their envs, so the
 data path needs no collective (bench.py, `"scaling": "weak"`).  The only exchange step is the optional
-shared-table mode: one agent replicated on G ranks, merged every `sync_every` global steps by ONE all-reduce
-(SUM) of a fused [sum(dQ_a * dcount) | dcount | visitors | sum(Q_a of visitors) | counters] buffer (45 KB per agent, NCCL over NVLink on
-GPUs, gloo in the CPU tests) -- see csrc/table_kernels.cuh: shared_pack_kernel / shared_apply_kernel.
+shared-table mode: one agent replicated on G ranks, merged every `sync_every` global steps by ONE collective: an all-reduce
+of the ranks' Q-deltas and counts realised as all-gather of the raw [Q_a bits | count | trainer counters] words (22.7 KB per
+agent and rank, NCCL over NVLink on GPUs, gloo in the CPU tests) + a reduction in RANK ORDER inside the apply kernel.  Counts
+and counters are integers end to end (exact for any number of visits per sync); the float32 sum has one defined order, so the
+merged tables are bit-identical on every rank, from run to run and for any NCCL algorithm -- which an fp32 SUM all-reduce is
+not.  See csrc/table_kernels.cuh: shared_pack_kernel / shared_apply_kernel.
 """
 from __future__ import annotations
 
@@ -75,17 +78,20 @@ def max_over_ranks(values: Sequence[float], device: Optional[torch.device] = Non
     return [float(x) for x in t]
 
 
-def merge_deltas(delta: torch.Tensor) -> torch.Tensor:
-    """All-reduce (SUM) of the packed delta buffer [agents, SHARED_DELTA_WORDS] in place; returns it."""
+def gather_packed(packed: torch.Tensor, gathered: torch.Tensor) -> torch.Tensor:
+    """All-gather of every rank's packed int32 buffer [agents, SHARED_WORDS] into gathered [world, agents, SHARED_WORDS]
+    (rank-major, the layout shared_apply_kernel reduces in rank order); returns gathered."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(delta, op=dist.ReduceOp.SUM)
-    return delta
+        dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+    else:
+        gathered[0].copy_(packed)
+    return gathered
 
 
 class SharedTableSync:
     """Shared-table mode: the agents of `engine` (groups of engine.R consecutive populations) are replicated on every rank.
-    `sync()` = local replica merge (R > 1) + ONE all-reduce of the packed [dQ*dcount | dcount | trainer counters] buffer
-    (34 KB per agent) + apply.  With `pooled_promotion` the curriculum promotion is decided from the windows of ALL ranks."""
+    `sync()` = local replica merge (R > 1) + pack + ONE all-gather (22.7 KB per agent and rank) + apply (the rank-ordered
+    reduction).  With `pooled_promotion` the curriculum promotion is decided from the windows of ALL ranks."""
 
     def __init__(self, engine, pooled_promotion: bool = False):
         import ctypes as C
@@ -94,19 +100,28 @@ class SharedTableSync:
         self._C, self._ffi, self.engine = C, _ffi, engine
         self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
         self.snapshot = engine.tables[:: engine.R].clone().contiguous()
-        self.delta = torch.zeros((self.snapshot.shape[0], K.SHARED_DELTA_WORDS), dtype=torch.float32, device=engine.device)
+        n_agents = self.snapshot.shape[0]
+        self.packed = torch.zeros((n_agents, K.SHARED_WORDS), dtype=torch.int32, device=engine.device)
+        self.gathered = torch.zeros((self.world, n_agents, K.SHARED_WORDS), dtype=torch.int32, device=engine.device)
         self.pooled_promote = 0
         if pooled_promotion:
             self.pooled_promote = K.promote_threshold(engine.tp.successive_successful_episodes * engine.R * self.world, engine.tp.success_rate)
         if engine.R > 1:
             engine._ensure_merge_snapshot()
 
-    def sync(self):
-        """tables <- snapshot + visit-weighted mean of every rank's dQ_a; counts <- snapshot + sum of dcounts."""
+    def pack(self):
+        e = self.engine
+        self._ffi.check(e.lib.dqlb200_shared_pack(e.handle, self._C.c_void_p(self.packed.data_ptr()), e._stream()))
+
+    def apply(self, gathered: torch.Tensor):
         e, C = self.engine, self._C
+        self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(gathered.data_ptr()), int(gathered.shape[0]),
+                                                   self.pooled_promote, e._stream()))
+
+    def sync(self):
+        """tables <- snapshot + visit-weighted mean of every rank's dQ_a (rank order); counts <- snapshot + sum of dcounts."""
+        e = self.engine
         if e.R > 1:      # local copies first; with pooled promotion no rank decides alone
             self._ffi.check(e.lib.dqlb200_replica_merge(e.handle, e.merge_snapshot.data_ptr(), 0 if self.pooled_promote else e.pooled_promote, e._stream()))
-        self._ffi.check(e.lib.dqlb200_shared_pack(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()), e._stream()))
-        merge_deltas(self.delta)
-        self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.delta.data_ptr()),
-                                                   self.pooled_promote, e._stream()))
+        self.pack()
+        self.apply(gather_packed(self.packed, self.gathered))

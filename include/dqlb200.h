@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 5
+#define DQLB200_ABI_VERSION 6
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -34,7 +34,7 @@ extern "C" {
 #define DQLB200_ALPHA_LUT 1003                /* count 0..1002; alpha(count >= 1002) == alpha_min */
 #define DQLB200_EPS_LUT 2002                  /* episode 0..2000, [2001] = every later episode */
 #define DQLB200_MAX_WINDOW 128                /* success window (Trainer successive_successful_episodes) */
-#define DQLB200_SHARED_DELTA_WORDS (4 * DQLB200_MAX_CELLS + 4)   /* floats per agent in the shared-table all-reduce buffer */
+#define DQLB200_SHARED_WORDS (2 * DQLB200_MAX_CELLS + 4)   /* 32-bit words per agent and rank in the shared-table exchange buffer */
 #define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, SoA: [3][n_envs_total][16 B] */
 
 typedef enum dqlb200_status {
@@ -329,23 +329,29 @@ int dqlb200_eval_greedy_2d(dqlb200_handle* h, const dqlb200_eval2d_params* p, co
  * tables of every population. */
 int dqlb200_transfer(dqlb200_handle* h, int step, float ratio, void* stream);
 
-/* Checks the populations' error flags (synchronises the stream). */
+/* Checks the error flags the kernels raise where the reference raises ValueError (NaN observation PKG/mdp.py:170, empty state
+ * :353, missing previous state :442-452): ONE reduction launch over the populations' flags and ONE 12-byte copy, then a stream
+ * synchronisation.  DQLB200_ERR_DEVICE_FLAG names the first offending population. */
 int dqlb200_check_errors(dqlb200_handle* h, void* stream);
 
-/* Shared-table mode (one agent replicated on G devices; NCCL all-reduce between them).  An "agent" is a group of
+/* Shared-table mode (one agent replicated on G devices; one NCCL collective between them).  An "agent" is a group of
  * R = cfg.replicas_per_population consecutive populations (R = 1: one population; R > 1: call dqlb200_replica_merge first, so
- * that the R local copies agree).  snapshot holds ONE [3][DQLB200_MAX_CELLS] entry per agent, delta ONE entry of
- * DQLB200_SHARED_DELTA_WORDS floats per agent.
- *   pack : delta <- [ (Q_a - Q_snap) * dcount | dcount | visited ? 1 : 0 | visited ? Q_a : 0 | successes, episodes, 1, alive ]
- *   ...   the caller all-reduces delta with SUM (torch.distributed / ncclAllReduce) ...
- *   apply: Q_a <- Q_snap + sum(dQ * dcount) / sum(dcount), count <- count_snap + sum(dcount) in every local replica, the
- *          shared snapshot and the bound merge snapshot; a cell ONE rank visited takes that rank's value bit for bit on
- *          every rank (so G = 1 never alters a table).  With
- *          pooled_promote_successes > 0 the promotion / max_num_episodes decision (PKG/trainer.py:219-245) is taken from the
- *          counters summed over all ranks and armed in every local replica (it takes effect at the next dqlb200_train);
- *          pass the threshold for G * R * window_len episodes, and 0 to dqlb200_replica_merge so that no rank decides alone. */
-int dqlb200_shared_pack(dqlb200_handle* h, const void* snapshot, void* delta, void* stream);
-int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* delta_reduced, int pooled_promote_successes, void* stream);
+ * that the R local copies agree).  snapshot holds ONE [3][DQLB200_MAX_CELLS] entry per agent (the tables of the last sync),
+ * packed ONE entry of DQLB200_SHARED_WORDS 32-bit words per agent.
+ *   pack  : packed <- [ Q_a bits | count | successes in the windows, finished episodes (lo, hi), alive ]   (raw words, integers)
+ *   ...   the caller ALL-GATHERS packed over the ranks (torch.distributed.all_gather_into_tensor / ncclAllGather) into
+ *         gathered[n_ranks][n_agents][DQLB200_SHARED_WORDS] ...
+ *   apply : the all-reduce proper, in RANK ORDER: dcount_g = count_g - count_snap; Q_a <- Q_snap + sum_g (Q_g - Q_snap) * dcount_g
+ *           / sum_g dcount_g (float32, one defined order), count <- count_snap + sum_g dcount_g (exact 64-bit sum, saturating
+ *           at 2^32 - 1) in every local replica, the shared snapshot and the bound merge snapshot; a cell ONE rank visited takes
+ *           that rank's value bit for bit on every rank (so G = 1 never alters a table).  The result is identical on every
+ *           rank and from run to run, for any number of visits per sync.  With pooled_promote_successes > 0 the promotion /
+ *           max_num_episodes decision (PKG/trainer.py:219-245) is taken from the integer counters summed over all ranks and
+ *           armed in every local replica (it takes effect at the next dqlb200_train); pass the threshold for G * R * window_len
+ *           episodes, and 0 to dqlb200_replica_merge so that no rank decides alone.
+ * Replaces nothing in the reference (it has one process); the merge rule is the replica-merge rule below with ranks as replicas. */
+int dqlb200_shared_pack(dqlb200_handle* h, void* packed, void* stream);
+int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* gathered, int n_ranks, int pooled_promote_successes, void* stream);
 
 /* Replica-merge mode (one agent with more envs than one CTA can hold: BASELINE configs 2-3, "N envs sharing one
  * Q-table pair").  The agent's envs are split over R = cfg.replicas_per_population consecutive populations (replicas),
@@ -406,12 +412,22 @@ int dqlb200_bench_launch_floor(dqlb200_handle* h, int blocks, int threads, int s
  * routine used for x / theta_max on 2^32 pseudo-random numerators (must be 0).  Synchronises. */
 int dqlb200_selftest_division(dqlb200_handle* h, uint64_t* mismatches_out, void* stream);
 
+/* Device self-test of the fp32 cut-table discretisation (R5: PKG/mdp.py:149-170, 257-333) on caller-supplied observations.
+ * obs: device float [n][4] = rel_p, rel_v, rel_a, pitch; out_state: device uint16 [n] state ids for working step `working_step`.
+ * variant selects the instantiation the production kernels use: 0 = run-time constants, level loop bounded by the working step
+ * (generic train_kernel, env_step_kernel); 1 = compile-time constants + cut table in shared memory (production train_kernel;
+ * needs the reference-default configuration); 2 / 3 = the same two with every level index probed (eval kernels, env reset).
+ * tests/test_gpu_parity.py feeds it every probe of tests/golden/discretise.npz (+-3 ulp around every threshold). */
+int dqlb200_selftest_discretise(dqlb200_handle* h, int working_step, int variant, int64_t n, const float* obs, uint16_t* out_state,
+                                void* stream);
+
 /* Facade kernel behind single-object DoubleQLearningAgent calls, float64 like the reference's tables
  * (PKG/double_q_learning.py:38-40).  tables_f64: device [3][DQLB200_MAX_CELLS] doubles (Q_a, Q_b, count).
  *   DQLB200_AGENT_PREDICT : out_action[i] = argmax((Q_a[s_i] + Q_b[s_i]) / 2)          (PKG/double_q_learning.py:119-124)
  *   DQLB200_AGENT_UPDATE  : for i in order: count[sa_i] += 1; Q_a[sa_i] += alpha_i * (reward_i + (gamma * max Q_a[s'_i])
  *                           * [p-bin changed] - Q_a[sa_i])                               (PKG/double_q_learning.py:91-108,126-146)
- *   DQLB200_AGENT_TRANSFER: Q_{a,b}[step] = Q_{a,b}[step-1] * ratio  (step = state[0], ratio = alpha[0]; :77-89)
+ *   DQLB200_AGENT_TRANSFER: Q_{a,b}[step] = Q_{a,b}[src] * ratio  (step = state[0], ratio = alpha[0], src = next_state[0] = (step - 1)
+ *                           modulo the AGENT's curriculum_steps, so that step 0 reads its last slot like Q[-1]; :77-89)
  * state / next_state are state ids (< 945), action in 0..2; all pointers are device pointers. */
 #define DQLB200_AGENT_PREDICT 1
 #define DQLB200_AGENT_UPDATE 2

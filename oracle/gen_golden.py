@@ -14,6 +14,9 @@ Fixtures:
   sim_trace.npz    SimulationMdp greedy episodes with the committed assets policy
   sim2d_trace.npz  two-axis SimulationMdp episodes (x and y states, FLYZONE_Y, contact on both axes), three platform cases
   kalman_accel.npz the reference KalmanFilter3D (PKG/filters.py) driven the way ObservationUtils drives it, on stand-in velocities
+  curriculum_ref.npz the UNMODIFIED Trainer.curriculum_training() (PKG/trainer.py:169-245) driven through a gym.make stub whose env wraps
+                   the reference TrainingMdp in the order of PKG/landing_simulation_env.py:167-282 on the stand-in: success window,
+                   promotions, a max-episodes advance (window kept), transfer after every step incl. the last (quirk Q7), final tables
   second_order.npz the reference PID node (PKG/pid.py, Butterworth filter included) on the v_z errors of a second-order stand-in
                    run, and the reference AttitudeController moment (PKG/attitude_controller.py:124-156) for pure pitch states
 """
@@ -576,6 +579,125 @@ def gen_second_order(n_steps=400, seed=13):
           float(np.abs(out["pid_thrust_ref"] - out["pid_thrust_oracle"]).max()))
 
 
+class _StepFeeder:
+    """np.random for the UNMODIFIED trainer loop: per agent step the reference draws uniform (explore), randint (random
+    action) inside guess() and uniform (table pick, ignored: quirk Q1) inside update() -- words x, y, z of the step draw."""
+
+    def __init__(self, seed):
+        self.seed, self.calls = seed, 0
+
+    def _word(self, kind):
+        t, j = divmod(self.calls, 3)
+        assert kind == ("u", "i", "u")[j], (kind, j)
+        self.calls += 1
+        return philox.draws(self.seed, 0, np.asarray([0]), t, philox.PURPOSE_STEP)[j][0]
+
+    def uniform(self, lo=0.0, hi=1.0, size=None):
+        return float(philox.uniform01(self._word("u"))) * (hi - lo) + lo
+
+    def randint(self, n):
+        return int(philox.random_action(self._word("i")))
+
+
+def gen_curriculum(ns, seed=4, dtype=np.float32, tag="", **trainer_kw):
+    """R14 (+ the transfer order of R13) pinned to the reference itself: Trainer.curriculum_training() runs UNMODIFIED; only
+    gym.make (no Gazebo: a stand-in-driven env around the reference TrainingMdp), Trainer.save and Trainer.log (file and
+    TensorBoard writers) are replaced."""
+    kw = dict(successive_successful_episodes=5, success_rate=0.2, max_num_episodes=40)
+    kw.update(trainer_kw)
+    import gym
+    ctx = dict(t=0, makes=[], rec={k: [] for k in ("obs", "action", "state", "next_state", "code", "done", "reward", "episode", "w")})
+    sp = StandInParams()
+    idx = np.asarray([0])
+
+    class StandInTrainingEnv:
+        """PKG/landing_simulation_env.py:143-282 with the simulator replaced by the analytic stand-in (one env)."""
+
+        def __init__(self, initial_curriculum_step, t_max, f_ag, p_max, z_init):
+            assert z_init == sp.z_init and f_ag == F_AG
+            self.w = initial_curriculum_step
+            self.mdp = ns.mdp.TrainingMdp(initial_curriculum_step, f_ag, t_max, p_max)      # :159-164
+            self.dyn = StandInDet(sp, 1)
+            self.k, self.state = 0, None
+
+        def reset(self):                                                                      # :167-243
+            self.mdp.reset()
+            words = philox.draws(seed, 0, idx, ctx["t"], philox.PURPOSE_RESET)
+            self.dyn.reset(idx, words[0], words[1], words[2], normal_init=(self.w == 0))
+            self.dyn.advance(np.zeros(1, np.float32), idx, hover=True)
+            rp, rv, ra, pit, z, c = (x[0] for x in self.dyn.observe(np.zeros(1)))
+            self.k = 0
+            self.state = self.mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+            return self.state
+
+        def step(self, action_x, action_y=2):                                                 # :245-282
+            act = self.mdp.continuous_action(action_x, action_y)
+            self.dyn.advance(np.asarray([act.pitch], np.float32))
+            self.k += 1
+            rp, rv, ra, pit, z, c = (x[0] for x in self.dyn.observe(np.asarray([self.k])))
+            s2 = self.mdp.discrete_state(_obs(ns, rp, rv, ra, pit, z, c))
+            info = self.mdp.check()
+            reward = self.mdp.reward()
+            done = "Termination condition" in info.keys()
+            info["Current reward"] = reward
+            r = ctx["rec"]
+            r["obs"].append((rp, rv, ra, pit, z)); r["action"].append(action_x); r["state"].append(state_id(self.state))
+            r["next_state"].append(state_id(s2)); r["code"].append(_ref_code(self.mdp, ns)); r["done"].append(int(done))
+            r["reward"].append(reward); r["episode"].append(ctx["trainer"]._current_episode); r["w"].append(self.w)
+            ctx["t"] += 1
+            self.state = s2
+            return s2, reward, done, info
+
+        def close(self):
+            pass
+
+    def make(name, **k):
+        assert name == "Landing-Training-v0"
+        ctx["makes"].append((ctx["t"], k["initial_curriculum_step"]))
+        return StandInTrainingEnv(**k)
+
+    feeder = _StepFeeder(seed)
+    T = ns.trainer.Trainer
+    saved = (np.random.uniform, np.random.randint, gym.make, T.save, T.log)
+    np.random.uniform, np.random.randint, gym.make = feeder.uniform, feeder.randint, make
+    T.save = lambda self: None
+    T.log = lambda self, info, clean=False: None
+    try:
+        trainer = T(save_path=pathlib.Path(tempfile.mkdtemp()), seed=seed, **kw)
+        ctx["trainer"] = trainer
+        agent = trainer._double_q_learning_agent
+        agent.Q_table_a = agent.Q_table_a.astype(dtype)
+        agent.Q_table_b = agent.Q_table_b.astype(dtype)
+        trainer.curriculum_training()
+    finally:
+        np.random.uniform, np.random.randint, gym.make, T.save, T.log = saved
+    r = ctx["rec"]
+    ws = np.asarray(r["w"], np.int32)
+    ep = np.asarray(r["episode"], np.int32)
+    done = np.asarray(r["done"], np.uint8)
+    # how every curriculum step ended: promoted (window cleared) or max_num_episodes reached (window kept)
+    ends = []
+    for (t_make, w) in ctx["makes"]:
+        sel = np.flatnonzero(ws == w)
+        n_ep = int(done[sel].sum())
+        ends.append((w, int(sel[-1]) + 1, n_ep, int(n_ep < kw["max_num_episodes"]) if w < len(ctx["makes"]) else 0))
+    last_sel = np.flatnonzero(ws == ctx["makes"][-1][1])
+    codes = np.asarray(r["code"], np.uint8)
+    out = dict(
+        obs=np.asarray(r["obs"], np.float32), action=np.asarray(r["action"], np.uint8), state=np.asarray(r["state"], np.uint16),
+        next_state=np.asarray(r["next_state"], np.uint16), code=codes, done=done, reward=np.asarray(r["reward"], np.float64),
+        episode=ep, w=ws, step_end_t=np.asarray([e[1] for e in ends], np.int64), step_episodes=np.asarray([e[2] for e in ends], np.int64),
+        qa=agent.Q_table_a, qb=agent.Q_table_b, count=agent.state_action_counter, seed=np.int64(seed),
+        successive_successful_episodes=np.int32(kw["successive_successful_episodes"]), success_rate=np.float64(kw["success_rate"]),
+        max_num_episodes=np.int64(kw["max_num_episodes"]), window_at_end=np.asarray(list(trainer._successes), np.int8),
+    )
+    name = f"curriculum_ref{tag}.npz"
+    np.savez_compressed(GOLDEN / name, **out)
+    print(f"{name}: {len(ws)} steps; per curriculum step (w, t_end, episodes): {[(e[0], e[1], e[2]) for e in ends]}; "
+          f"window at end {list(trainer._successes)}")
+    return out
+
+
 def _state_tuple(sid: int):
     th = sid % 7; sid //= 7
     a = sid % 3; sid //= 3
@@ -603,6 +725,7 @@ def main():
     q0 = (agent.Q_table_a, agent.Q_table_b)
     gen_replay(ns, 2, 3000, np.float32, q_init=q0)
     gen_replay(ns, 4, 3000, np.float32, q_init=q0)
+    gen_curriculum(ns)
     gen_sim_trace(ns)
     gen_sim2d_trace(ns)
     gen_kalman()

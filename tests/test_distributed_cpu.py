@@ -1,5 +1,5 @@
 """N > 1 host logic on CPU: world_size 2, gloo backend (no GPU needed).  Covers the population partitioning that
-bench.py and the multi-GPU trainer use, the max-over-ranks timing reduction and the shared-table all-reduce."""
+bench.py and the multi-GPU trainer use, the max-over-ranks timing reduction and the shared-table exchange (all-gather)."""
 import os
 import socket
 
@@ -45,16 +45,14 @@ def _worker(rank, world, port, out):
     try:
         # 1. timing reduction: every rank ends up with the maximum
         mx = parallel.max_over_ranks([1.0 + rank, 10.0 - rank])
-        # 2. shared-table merge: rank r visited cell c dcount[r][c] times and moved it by dq[r][c]
+        # 2. shared-table exchange: every rank contributes its packed int32 words [agents, SHARED_WORDS]; all ranks end up
+        #    with the same rank-major stack (the reduction in rank order happens in shared_apply_kernel on the GPU)
+        from dql_multirotor_landing_b200 import constants as K
         rng = np.random.default_rng(100 + rank)
-        cells = 2835
-        dcount = rng.integers(0, 4, size=cells).astype(np.float32)
-        dq = rng.standard_normal(cells).astype(np.float32) * (dcount > 0)
-        delta = torch.zeros((1, 3, cells), dtype=torch.float32)
-        delta[0, 0] = torch.from_numpy(dq * dcount)
-        delta[0, 1] = torch.from_numpy(dcount)
-        parallel.merge_deltas(delta)
-        out[rank] = dict(mx=mx, delta=delta.numpy().copy(), dq=dq, dcount=dcount)
+        packed = torch.from_numpy(rng.integers(-2 ** 31, 2 ** 31 - 1, size=(3, K.SHARED_WORDS), dtype=np.int64).astype(np.int32))
+        gathered = torch.zeros((world, 3, K.SHARED_WORDS), dtype=torch.int32)
+        parallel.gather_packed(packed, gathered)
+        out[rank] = dict(mx=mx, packed=packed.numpy().copy(), gathered=gathered.numpy().copy())
     finally:
         dist.destroy_process_group()
 
@@ -66,11 +64,12 @@ def test_world_size_two_gloo():
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     r0, r1 = out[0], out[1]
     assert r0["mx"] == r1["mx"] == [2.0, 10.0]
-    assert np.array_equal(r0["delta"], r1["delta"])
-    assert np.array_equal(r0["delta"][0, 1], r0["dcount"] + r1["dcount"])
-    np.testing.assert_allclose(r0["delta"][0, 0], r0["dq"] * r0["dcount"] + r1["dq"] * r1["dcount"], rtol=1e-6, atol=1e-6)
-    # the merged table value: visit-weighted mean of the replicas' deltas where anybody visited
-    tot = r0["delta"][0, 1]
-    merged = np.where(tot > 0, r0["delta"][0, 0] / np.maximum(tot, 1), 0.0)
-    only0 = (r0["dcount"] > 0) & (r1["dcount"] == 0)
-    np.testing.assert_allclose(merged[only0], r0["dq"][only0], rtol=1e-6)
+    assert np.array_equal(r0["gathered"], r1["gathered"])                    # identical on every rank
+    assert np.array_equal(r0["gathered"][0], r0["packed"]) and np.array_equal(r0["gathered"][1], r1["packed"])   # rank-major, bit for bit
+
+
+def test_gather_packed_without_process_group():
+    from dql_multirotor_landing_b200 import constants as K
+    packed = torch.arange(2 * K.SHARED_WORDS, dtype=torch.int32).reshape(2, K.SHARED_WORDS)
+    gathered = torch.zeros((1, 2, K.SHARED_WORDS), dtype=torch.int32)
+    assert torch.equal(parallel.gather_packed(packed, gathered)[0], packed)

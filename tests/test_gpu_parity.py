@@ -291,6 +291,43 @@ def test_kalman_acceleration_needs_its_state_buffer():
         _engine(1, 32, threads_per_block=32, dp=dict(dynamics_model="second_order", n_sub=4, pid_ticks=1))
 
 
+def test_curriculum_bookkeeping_vs_reference_trainer(golden_dir):
+    """R14 + the order of R13 against the reference ITSELF: tests/golden/curriculum_ref.npz is the unmodified
+    Trainer.curriculum_training() (PKG/trainer.py:169-245) run through all five curriculum steps -- a promotion, a max-episodes
+    advance (window kept), a promotion on the carried-over window, two more max-episodes advances, the transfer after every step
+    incl. the last (PKG/double_q_learning.py:77-89, quirk Q7).  One env on the device, chunked launches: every observation,
+    action, state, check code and float64 reward, the steps at which the curriculum advanced, and the final tables."""
+    g = np.load(golden_dir / "curriculum_ref.npz")
+    kw = dict(successive_successful_episodes=int(g["successive_successful_episodes"]), success_rate=float(g["success_rate"]),
+              max_num_episodes=int(g["max_num_episodes"]))
+    eng = _engine(1, 1, threads_per_block=32, seeds=[int(g["seed"])], tp=kw)
+    eng.reset(0)
+    n = len(g["action"])
+    t0 = 0
+    for chunk in (1, 460, 1, 2938, 1761, 5391, 5096, 1, 64):      # launch boundaries right at and around the curriculum advances
+        tr = eng.train(chunk, trace=True)
+        m = min(chunk, n - t0)
+        sl = slice(t0, t0 + m)
+        assert np.array_equal(tr["obs"][:m, 0].view(np.uint32), g["obs"][sl].view(np.uint32)), t0
+        assert np.array_equal(tr["action"][:m, 0], g["action"][sl]), t0
+        assert np.array_equal(tr["state"][:m, 0].astype(np.uint16), g["state"][sl]), t0
+        assert np.array_equal(tr["next_state"][:m, 0].astype(np.uint16), g["next_state"][sl]), t0
+        assert np.array_equal(tr["code"][:m, 0], g["code"][sl]) and np.array_equal(tr["done"][:m, 0], g["done"][sl]), t0
+        assert np.array_equal(tr["reward"][:m, 0], g["reward"][sl]), t0          # float64, bit for bit
+        assert np.array_equal(tr["episode"][:m, 0], g["episode"][sl]), t0
+        t0 += m
+    assert t0 == n
+    eng.check_errors()
+    ps = eng.population_state()[0]
+    assert ps["finished"] == 1 and ps["t"] == n and ps["working_step"] == 4
+    assert [int(x) for x in ps["promoted_at"]] == [int(x) for x in g["step_end_t"]]
+    assert ps["total_steps"] == n and ps["total_episodes"] == int(g["done"].sum())
+    assert ps["window_count"] == len(g["window_at_end"]) and ps["window_sum"] == int(g["window_at_end"].sum())
+    qa, qb, cnt = eng.get_tables(0, np.float32)
+    assert np.array_equal(qa.view(np.uint32), g["qa"].view(np.uint32)) and np.array_equal(qb.view(np.uint32), g["qb"].view(np.uint32))
+    assert np.array_equal(cnt, g["count"])
+
+
 @pytest.mark.parametrize("mode", ["reference", "paper"])
 def test_curriculum_promotion_and_transfer(mode):
     """R13/R14: success window, promotion latch, max_num_episodes advance, transfer (quirk Q7 and the
@@ -406,10 +443,34 @@ def test_eval_greedy_fixture_and_oracle(golden_dir):
     assert big["termination_hist"][3] / big["episodes"] > 0.85
 
 
+def _rank_ordered_merge(snap, tabs):
+    """What shared_apply_kernel must produce (the replica-merge rule with ranks as replicas, float32, RANK ORDER):
+    snap, tabs[r]: uint32 [3][CELLS] (Q_a bits, Q_b bits, count).  Returns (Q_a bits, count)."""
+    q_s, c_s = snap[0].view(np.float32), snap[2]
+    s = np.zeros(q_s.shape, np.float32)
+    total = np.zeros(q_s.shape, np.uint64)
+    visitors = np.zeros(q_s.shape, np.int32)
+    single = np.zeros(q_s.shape, np.uint32)
+    for t in tabs:
+        dc = (t[2] - c_s).astype(np.uint32)
+        vis = dc != 0
+        term = ((t[0].view(np.float32) - q_s).astype(np.float32) * dc.astype(np.float32)).astype(np.float32)
+        s = np.where(vis, (s + term).astype(np.float32), s)
+        total += dc
+        visitors += vis
+        single = np.where(vis, t[0], single)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        mean = (q_s + (s / total.astype(np.float32)).astype(np.float32)).astype(np.float32)
+    q = np.where(visitors == 1, single, np.where(visitors > 1, mean.view(np.uint32), snap[0]))
+    cnt = np.minimum(c_s.astype(np.uint64) + total, np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    return q, cnt
+
+
 def test_shared_table_mode_merge():
-    """Shared-table mode kernels: with one replica the sync leaves the tables bit-identical (== no-collective mode);
-    with two replicas (the all-reduce is emulated by adding the two delta buffers: the gloo test covers the
-    collective itself) Q is the visit-weighted mean of the replicas' deltas and the counts add up."""
+    """Shared-table mode kernels: with one rank the sync leaves the tables bit-identical (== no-collective mode); with two
+    ranks (the all-gather is emulated by stacking the two packed buffers: the gloo test covers the collective itself) the
+    merged Q is the visit-weighted mean of the ranks' deltas summed in RANK ORDER (bit-exact against the NumPy statement of
+    the rule), the counts add up exactly, and repeating the sync from the same inputs gives the same bits."""
     from dql_multirotor_landing_b200.parallel import SharedTableSync
     engs, syncs = [], []
     for r in range(2):
@@ -421,43 +482,118 @@ def test_shared_table_mode_merge():
         e.train(40)
     torch.cuda.synchronize()
     before = [e.tables.cpu().numpy().copy() for e in engs]
-    # G = 1: pack + apply without any other replica
+    # G = 1: pack + apply without any other rank
     syncs[0].sync()
     torch.cuda.synchronize()
     assert np.array_equal(engs[0].tables.cpu().numpy(), before[0])
     assert np.array_equal(syncs[0].snapshot.cpu().numpy(), before[0])
-    # G = 2 (fresh engines so that both start from the same snapshot)
+
+    def two_rank_sync():
+        engs, syncs = [], []
+        for r in range(2):      # fresh engines so that both start from the same snapshot
+            e = _engine(1, 256, threads_per_block=64, seeds=[10 + r], population_ids=[r], tp=NO_PROMOTION)
+            e.reset(0)
+            engs.append(e)
+            syncs.append(SharedTableSync(e))
+            e.train(40)
+        torch.cuda.synchronize()
+        snap = syncs[0].snapshot.cpu().numpy().view(np.uint32)[0].copy()
+        tabs = [e.tables.cpu().numpy().view(np.uint32)[0].copy() for e in engs]
+        for s in syncs:
+            s.pack()
+        gathered = torch.stack([syncs[0].packed, syncs[1].packed]).contiguous()
+        for s in syncs:
+            s.apply(gathered)
+        torch.cuda.synchronize()
+        return snap, tabs, [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
+
+    snap, tabs, out = two_rank_sync()
+    assert np.array_equal(out[0], out[1])                         # ranks agree after the merge
+    q, cnt = _rank_ordered_merge(snap, tabs)
+    assert np.array_equal(out[0][0, 2], cnt) and np.array_equal(out[0][0, 0], q)
+    assert ((tabs[0][2] > 0) & (tabs[1][2] > 0)).sum() > 50       # the test does merge cells both ranks visited
+    _, _, again = two_rank_sync()
+    assert np.array_equal(again[0], out[0])                       # run-to-run identical
+
+
+def test_shared_table_counts_are_exact_beyond_2_pow_24():
+    """The exchange carries raw 32-bit counts and integer trainer counters: a cell with more than 2^24 visits per sync on each
+    rank (where an fp32 transport loses the low bits), a saturating 32-bit count, and pooled episode counters above 2^24."""
+    from dql_multirotor_landing_b200 import constants as K
+    from dql_multirotor_landing_b200.parallel import SharedTableSync
+    kw = dict(success_rate=0.5, successive_successful_episodes=100, max_num_episodes=40_000_001)
     engs, syncs = [], []
-    for r in range(2):
-        e = _engine(1, 256, threads_per_block=64, seeds=[10 + r], population_ids=[r], tp=NO_PROMOTION)
+    for r in range(3):
+        e = _engine(1, 32, threads_per_block=32, seeds=[1], population_ids=[r], tp=kw)
         e.reset(0)
         engs.append(e)
-        syncs.append(SharedTableSync(e))
-        e.train(40)
+        syncs.append(SharedTableSync(e, pooled_promotion=False))
+        syncs[-1].pooled_promote = 10 ** 6                     # never reached: only the episode counter can arm the advance
+    visits = [20_000_001, 20_000_003, 16_777_217]
+    for r, e in enumerate(engs):
+        t = e.tables.cpu().numpy().view(np.uint32).copy()
+        t[0, 2, 7] = visits[r]
+        t[0, 0, 7] = np.float32(1.0 + r).view(np.uint32)
+        t[0, 2, 9] = 0xFFFFFFF0 if r == 0 else 0x20             # saturates
+        t[0, 0, 9] = np.float32(-2.0 - r).view(np.uint32)
+        t[0, 2, 11] = 5 if r == 1 else 0                        # one visitor: its bits survive
+        t[0, 0, 11] = np.float32(0.1).view(np.uint32) if r == 1 else 0
+        e.tables.copy_(torch.from_numpy(t.view(np.int32)).to(e.device))
+        ps = e.population_state()
+        ps["episodes_in_step"] = 13_333_334 + r                 # 40,000,005 pooled: exact only as integers
+        e.pop_state.copy_(torch.from_numpy(ps.view(np.uint8).reshape(-1)).to(e.device))
+    snap = syncs[0].snapshot.cpu().numpy().view(np.uint32)[0].copy()
+    tabs = [e.tables.cpu().numpy().view(np.uint32)[0].copy() for e in engs]
+    for s in syncs:
+        s.pack()
+    gathered = torch.stack([s.packed for s in syncs]).contiguous()
+    for s in syncs:
+        s.apply(gathered)
     torch.cuda.synchronize()
-    tabs = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
-    lib = engs[0].lib
-    import ctypes as C
-    for e, s in zip(engs, syncs):
-        lib.dqlb200_shared_pack(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
-    total = syncs[0].delta + syncs[1].delta
-    for e, s in zip(engs, syncs):
-        s.delta.copy_(total)
-        lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), 0, e._stream())
+    out = [e.tables.cpu().numpy().view(np.uint32)[0] for e in engs]
+    assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
+    assert int(out[0][2, 7]) == sum(visits) == 56_777_221 and np.float32(sum(visits)) != sum(visits)
+    assert int(out[0][2, 9]) == 0xFFFFFFFF
+    assert out[0][0, 11] == np.float32(0.1).view(np.uint32) and int(out[0][2, 11]) == 5
+    q, cnt = _rank_ordered_merge(snap, tabs)
+    assert np.array_equal(out[0][0], q) and np.array_equal(out[0][2], cnt)
+    # 13,333,334 + 13,333,335 + 13,333,336 = 40,000,005 >= 40,000,001: the advance is armed; one episode less per rank would not
+    assert [int(e.population_state()[0]["pending_advance"]) for e in engs] == [2, 2, 2]
+    for r, e in enumerate(engs):
+        ps = e.population_state()
+        ps["pending_advance"] = 0
+        ps["episodes_in_step"] = 13_333_332 + r                 # 39,999,999 pooled (fp32 would round it to 40,000,000)
+        e.pop_state.copy_(torch.from_numpy(ps.view(np.uint8).reshape(-1)).to(e.device))
+    for s in syncs:
+        s.pack()
+    gathered = torch.stack([s.packed for s in syncs]).contiguous()
+    for s in syncs:
+        s.apply(gathered)
     torch.cuda.synchronize()
-    out = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]
-    assert np.array_equal(out[0], out[1])                         # replicas agree after the merge
-    cnt = [t[0, 2].astype(np.float64) for t in tabs]
-    q = [t[0, 0].view(np.float32).astype(np.float64) for t in tabs]
-    assert np.array_equal(out[0][0, 2], (cnt[0] + cnt[1]).astype(np.uint32))
-    both = (cnt[0] + cnt[1]) > 0
-    want = np.where(both, (q[0] * cnt[0] + q[1] * cnt[1]) / np.maximum(cnt[0] + cnt[1], 1), 0.0)
-    np.testing.assert_allclose(out[0][0, 0].view(np.float32), want, rtol=2e-6, atol=1e-5)
+    assert [int(e.population_state()[0]["pending_advance"]) for e in engs] == [0, 0, 0]
+
+
+def test_discretisation_edge_probes_on_device(golden_dir):
+    """R5 on the DEVICE against the reference: all 17 261 probes of tests/golden/discretise.npz (random values and +-3 ulp
+    around every threshold of PKG/mdp.py:149-170, 285-323), working steps 0..4, through every instantiation of
+    discretise_cuts the production kernels use (run-time / compile-time constants, bounded / unbounded level loop)."""
+    from oracle.agent_oracle import state_id
+    g = np.load(golden_dir / "discretise.npz")
+    eng = _engine(1, 1, threads_per_block=32)
+    obs = np.ascontiguousarray(g["obs"][:, :4], np.float32)
+    for w in range(5):
+        want_train = np.asarray([state_id(tuple(int(x) for x in row)) for row in g["train"][w]], np.uint16)
+        want_sim = np.asarray([state_id(tuple(int(x) for x in row)) for row in g["sim"][w]], np.uint16)
+        for variant in range(4):
+            got = eng.selftest_discretise(obs, w, variant)
+            want = want_train if variant < 2 else want_sim
+            bad = np.nonzero(got != want)[0]
+            assert bad.size == 0, (w, variant, obs[bad[:4]], got[bad[:4]], want[bad[:4]])
 
 
 def test_shared_table_mode_with_replicas_and_pooled_promotion():
     """BASELINE config 5 shared-table mode on top of replica-merge mode: two ranks (emulated by two engines on one device, the
-    all-reduce by adding their delta buffers; the collective itself is covered by the gloo test), each with R = 3 local
+    all-gather by stacking their packed buffers; the collective itself is covered by the gloo test), each with R = 3 local
     replicas of ONE agent.  After a sync every copy on both ranks is identical, counts add up, and the promotion is decided
     from the windows of all ranks."""
     import ctypes as C
@@ -477,11 +613,10 @@ def test_shared_table_mode_with_replicas_and_pooled_promotion():
     def sync_all():
         for e, s in zip(engs, syncs):
             lib.dqlb200_replica_merge(e.handle, e.merge_snapshot.data_ptr(), 0, e._stream())
-            lib.dqlb200_shared_pack(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), e._stream())
-        total = syncs[0].delta + syncs[1].delta
+            s.pack()
+        gathered = torch.stack([syncs[0].packed, syncs[1].packed]).contiguous()
         for e, s in zip(engs, syncs):
-            s.delta.copy_(total)
-            lib.dqlb200_shared_apply(e.handle, C.c_void_p(s.snapshot.data_ptr()), C.c_void_p(s.delta.data_ptr()), s.pooled_promote, e._stream())
+            s.apply(gathered)
         torch.cuda.synchronize()
 
     base = [e.tables.cpu().numpy().view(np.uint32).copy() for e in engs]

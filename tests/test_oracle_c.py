@@ -218,3 +218,28 @@ def test_population_c_equals_python_population_oracle(lib, mode, opts):
     assert (r.w, bool(r.finished), r.total_episodes, r.total_successes, r.total_steps) == (pop.w, pop.finished, pop.total_episodes, pop.total_successes, pop.total_steps)
     assert list(r.term_hist) == list(pop.term_hist) and r.window_sum == sum(pop.window) and r.window_count == len(pop.window)
     assert r.n_promotions == len(pop.promotions) >= 2
+
+
+def test_population_c_replays_the_reference_curriculum_run(lib, golden_dir):
+    """oracle/c/population.c with one env against tests/golden/curriculum_ref.npz = the UNMODIFIED Trainer.curriculum_training()
+    (PKG/trainer.py:169-245): every action, state, check code and float64 reward of all five curriculum steps, the step at which
+    each curriculum step ended (promotion or max-episodes advance) and the final tables after the last transfer (quirk Q7)."""
+    from oracle.c_loop import run_population_c
+    from oracle.loop import TrainerParams
+    g = np.load(golden_dir / "curriculum_ref.npz")
+    tp = TrainerParams(successive_successful_episodes=int(g["successive_successful_episodes"]), success_rate=float(g["success_rate"]),
+                       max_num_episodes=int(g["max_num_episodes"]))
+    n = len(g["action"])
+    out = run_population_c(1, n, seed=int(g["seed"]), population=0, w0=0, tp=tp, trace=True)
+    assert np.array_equal(out["action"][:, 0], g["action"])
+    assert np.array_equal(out["next_state"][:, 0], g["next_state"])
+    assert np.array_equal(out["code"][:, 0], g["code"])
+    assert np.array_equal(out["reward"][:, 0], g["reward"])
+    res = out["result"]
+    assert res.finished == 1 and res.t == n and res.n_promotions == 5
+    assert res.total_episodes == int(g["done"].sum()) and res.total_steps == n
+    assert np.array_equal(out["qa"].view(np.uint32), g["qa"].view(np.uint32)) and np.array_equal(out["qb"].view(np.uint32), g["qb"].view(np.uint32))
+    assert np.array_equal(out["count"], g["count"])
+    # one step fewer: the run is not finished and the last transfer has not happened
+    out2 = run_population_c(1, n - 1, seed=int(g["seed"]), population=0, w0=0, tp=tp)
+    assert out2["result"].finished == 0 and out2["result"].w == 4 and out2["result"].n_promotions == 4

@@ -102,6 +102,43 @@ def test_replay_single_env(golden_dir, name, dtype):
     assert np.array_equal(ag.count, g["count"])
 
 
+def test_curriculum_bookkeeping_matches_reference_trainer(golden_dir):
+    """R14 + the transfer order of R13, pinned to the reference itself: curriculum_ref.npz is the UNMODIFIED
+    Trainer.curriculum_training() (PKG/trainer.py:169-245, PKG/double_q_learning.py:77-89) run to the end of the last
+    curriculum step: a promotion (window cleared), a max-episodes advance (window NOT cleared), a promotion on the window
+    carried over, two more max-episodes advances, the transfer applied after every step including the last (quirk Q7),
+    epsilon restarting with every step.  PopulationOracle(n_envs=1) must reproduce every step; to keep the CPU suite short the
+    Python statement replays the first three curriculum steps (promotion, max-episodes advance, promotion on the carried
+    window: 5 200 of 15 649 steps) -- the C statement replays the whole run incl. the final tables (tests/test_oracle_c.py),
+    and DQL_FULL_CURRICULUM=1 makes this test do so too."""
+    import os
+    g = np.load(golden_dir / "curriculum_ref.npz")
+    tp = TrainerParams(successive_successful_episodes=int(g["successive_successful_episodes"]), success_rate=float(g["success_rate"]),
+                       max_num_episodes=int(g["max_num_episodes"]))
+    pop = PopulationOracle(1, seed=int(g["seed"]), population=0, w0=0, dtype=g["qa"].dtype.type, tp=tp)
+    full = bool(os.environ.get("DQL_FULL_CURRICULUM"))
+    n = len(g["action"]) if full else 5200
+    for t in range(n):
+        assert not pop.finished and pop.w == g["w"][t], t
+        tr = pop.step()
+        assert np.array_equal(tr["obs"][0].view(np.uint32), g["obs"][t].view(np.uint32)), t
+        assert (tr["action"][0], tr["state"][0], tr["next_state"][0], tr["code"][0], tr["done"][0]) == \
+               (g["action"][t], g["state"][t], g["next_state"][t], g["code"][t], g["done"][t]), t
+        assert tr["reward"][0] == g["reward"][t], t
+        assert tr["episode"][0] == g["episode"][t], t
+    k = len(pop.promotions)
+    assert k == (5 if full else 3) and pop.finished == full
+    assert [t + 1 for (t, _w, _p) in pop.promotions] == list(g["step_end_t"][:k])
+    # promoted <=> the step ended before max_num_episodes episodes
+    assert [bool(p) for (_t, _w, p) in pop.promotions] == [int(e) < int(g["max_num_episodes"]) for e in g["step_episodes"][:k]]
+    if not full:
+        return
+    assert list(pop.window) == list(g["window_at_end"])
+    assert pop.agent.qa.dtype == g["qa"].dtype
+    assert np.array_equal(pop.agent.qa, g["qa"]) and np.array_equal(pop.agent.qb, g["qb"])
+    assert np.array_equal(pop.agent.count, g["count"])
+
+
 def test_sim_trace(golden_dir):
     g = np.load(golden_dir / "sim_trace.npz")
     qa, qb = np.load(golden_dir.parent.parent / "assets" / "Q_table_a.npy"), np.load(golden_dir.parent.parent / "assets" / "Q_table_b.npy")
