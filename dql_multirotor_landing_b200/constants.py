@@ -32,6 +32,7 @@ CELLS_PER_LEVEL = 567
 MAX_CELLS = MAX_CURRICULUM * CELLS_PER_LEVEL
 ALPHA_LUT = 1003
 EPS_LUT = 2002
+MAX_SETPOINTS = 64              # DQLB200_MAX_SETPOINTS
 MAX_WINDOW = 128
 ENV_STATE_BYTES = 48
 ABI_VERSION = 6
@@ -64,6 +65,10 @@ class RewardLevel(C.Structure):
                 ("r_dur", C.c_double), ("r_term_succ", C.c_double), ("r_term_fail", C.c_double)]
 
 
+class SetpointNext(C.Structure):
+    _fields_ = [("next", C.c_uint32), ("value_f32", C.c_float)]
+
+
 class Config(C.Structure):
     _fields_ = [
         ("struct_bytes", C.c_uint32), ("abi_version", C.c_uint32),
@@ -94,6 +99,10 @@ class Config(C.Structure):
         ("pid_dt", C.c_float), ("pid_i0", C.c_float), ("bw_inv_denom", C.c_float), ("bw_k2", C.c_float),
         ("vz_train", C.c_float), ("vz_sim", C.c_float),
         ("eps_threshold", C.c_uint32 * EPS_LUT),
+        ("n_setpoints", C.c_int32), ("setpoint_zero", C.c_int32),
+        ("setpoint_value", C.c_double * MAX_SETPOINTS),
+        ("setpoint_next", (SetpointNext * 3) * MAX_SETPOINTS),
+        ("setpoint_rtheta", ((C.c_double * 3) * MAX_SETPOINTS) * 2),
     ]
 
 
@@ -415,6 +424,31 @@ def build_reward_levels(mp: MdpParameters) -> List[RewardLevel]:
     return out
 
 
+def build_setpoints(mp: MdpParameters):
+    """Closure of the pitch set-point under TrainingMdp.continuous_action (PKG/mdp.py:543-560) starting from 0.0, with the
+    reference's own float64 operations (min / max of Python floats after one add).  Returns (values sorted, index of 0.0,
+    next[i][a], rtheta[fresh][prev][a]) -- rtheta is the set-point part of the reward in the reference's operation order:
+    w_theta * (|phi(next)| - |phi(prev)|) / theta_max with phi(i) = w_theta * |value[i] / theta_max| (PKG/mdp.py:463-474, 506-514)."""
+    tm, d = float(mp.theta_max), float(mp.delta_theta)
+    seen, frontier = {0.0}, [0.0]
+    while frontier:
+        v = frontier.pop()
+        for nv in (min((v + d, tm)), max((v - d, -tm))):
+            if nv not in seen:
+                if len(seen) >= MAX_SETPOINTS:
+                    raise ValueError(f"more than {MAX_SETPOINTS} reachable pitch set-points for theta_max={tm}, delta_theta={d}")
+                seen.add(nv)
+                frontier.append(nv)
+    values = sorted(seen)
+    index = {v: i for i, v in enumerate(values)}
+    zero = index[0.0]
+    nxt = [[index[min((v + d, tm))], index[max((v - d, -tm))], i] for i, v in enumerate(values)]
+    phi = [mp.w_theta * np.abs(v / mp.theta_max) for v in values]
+    rtheta = [[[float(mp.w_theta * (np.abs(phi[nxt[zero if fresh else p][a]]) - np.abs(phi[p])) / mp.theta_max) for a in range(3)]
+               for p in range(len(values))] for fresh in (0, 1)]
+    return values, zero, nxt, rtheta
+
+
 def first_int_at_least(x: float) -> int:
     n = max(int(x) - 1, 0)
     while not (n >= x):
@@ -509,4 +543,13 @@ def build_config(n_populations: int, envs_per_population: int, threads_per_block
     cfg.replicas_per_population = replicas_per_population
     for e in range(EPS_LUT):
         cfg.eps_threshold[e] = explore_threshold(exploration_rate(e, 0))
+    values, zero, nxt, rtheta = build_setpoints(mp)
+    cfg.n_setpoints, cfg.setpoint_zero = len(values), zero
+    for i, v in enumerate(values):
+        cfg.setpoint_value[i] = v
+        for a in range(3):
+            cfg.setpoint_next[i][a].next = nxt[i][a]
+            cfg.setpoint_next[i][a].value_f32 = np.float32(values[nxt[i][a]])
+            for fresh in (0, 1):
+                cfg.setpoint_rtheta[fresh][i][a] = rtheta[fresh][i][a]
     return cfg

@@ -154,6 +154,8 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
   if (tpb != 32 && tpb != 64 && tpb != 128 && tpb != 256) return fail(DQLB200_ERR_ARG, "threads_per_block must be 32, 64, 128 or 256");
   if (cfg->window_len < 1 || cfg->window_len > DQLB200_MAX_WINDOW) return fail(DQLB200_ERR_ARG, "window_len out of range");
   if (cfg->n_alpha_luts < 1 || cfg->n_sub < 1) return fail(DQLB200_ERR_ARG, "n_alpha_luts / n_sub must be >= 1");
+  if (cfg->n_setpoints < 1 || cfg->n_setpoints > DQLB200_MAX_SETPOINTS || cfg->setpoint_zero < 0 || cfg->setpoint_zero >= cfg->n_setpoints)
+    return fail(DQLB200_ERR_ARG, "set-point tables missing or too large (constants.py: build_setpoints)");
   if (cfg->accel_mode < 0 || cfg->accel_mode > 2) return fail(DQLB200_ERR_ARG, "accel_mode must be 0 (exact), 1 (reference filter) or 2 (consecutive-sample filter)");
   if (cfg->dynamics_model < 0 || cfg->dynamics_model > 1) return fail(DQLB200_ERR_ARG, "dynamics_model must be 0 (first order) or 1 (second order)");
   if (cfg->dynamics_model != 0 && (cfg->pid_ticks < 2 || cfg->pid_ticks > 64 || !(cfg->inv_m > 0.0f) || !(cfg->pid_hi >= cfg->pid_lo)))
@@ -198,12 +200,12 @@ int dqlb200_create(const dqlb200_config* cfg, const float* alpha_luts, const dql
     const int tpb_ = cfg->threads_per_block;
     const int n_slots = (cfg->envs_per_population + tpb_ - 1) / tpb_;
     if (n_slots > 2047) return fail(DQLB200_ERR_ARG, "envs_per_population too large for threads_per_block (max 2047 slots per thread)");
-    h->smem_bytes = dql::train_smem_bytes(tpb_, true);      // the largest instance (extended / trace): tables + snapshot + reset queues + env tiles + record ring
+    h->smem_bytes = dql::train_smem_bytes(tpb_, true, cfg->n_setpoints);      // the largest instance (extended / trace): tables + snapshot + set-point table + reset queues + staging slots
     if (h->smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "population does not fit in shared memory: lower envs_per_population");
   }
 #define DQL_SET_SMEM1(W, T, D)                                                                                            \
   CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
-  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::train_smem_bytes(W * 32, T || D == 2)));
+  CUDA_TRY(cudaFuncSetAttribute(dql::train_kernel<W, T, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::train_smem_bytes(W * 32, T || D == 2, cfg->n_setpoints)));
 #define DQL_SET_SMEM(W) DQL_SET_SMEM1(W, false, 0) DQL_SET_SMEM1(W, false, 1) DQL_SET_SMEM1(W, false, 2) DQL_SET_SMEM1(W, false, 3) DQL_SET_SMEM1(W, true, 2)
   DQL_SET_SMEM(1) DQL_SET_SMEM(2) DQL_SET_SMEM(4) DQL_SET_SMEM(8)
   CUDA_TRY(cudaFuncSetAttribute(dql::replica_merge_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dql::merge_smem_bytes(32)));
@@ -289,6 +291,11 @@ static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
   p.d = h->cfg.accel_mode != 0 ? reinterpret_cast<uint4*>(h->filter_state) : nullptr;
   p.e = h->cfg.dynamics_model != 0 ? reinterpret_cast<uint4*>(h->dynamics_state) : nullptr;
   p.n = n;
+  p.sp_value = h->d_cfg->setpoint_value;            // device addresses inside the device copy of the configuration
+  p.sp_next = reinterpret_cast<const uint2*>(&h->d_cfg->setpoint_next[0][0]);
+  p.sp_rtheta = &h->d_cfg->setpoint_rtheta[0][0][0];
+  p.sp_zero = h->cfg.setpoint_zero;
+  p.n_sp = h->cfg.n_setpoints;
   return p;
 }
 
@@ -323,14 +330,14 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
   const bool tracing = trace != nullptr;
   const bool extended = h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0;      // options with extra per-env state
-  const size_t smem = dql::train_smem_bytes(h->cfg.threads_per_block, tracing || extended);      // the trace instances are extended ones
+  const size_t smem = dql::train_smem_bytes(h->cfg.threads_per_block, tracing || extended, h->cfg.n_setpoints);      // the trace instances are extended ones
   const bool full_slots = h->cfg.envs_per_population % h->cfg.threads_per_block == 0;
 #define DQL_LAUNCH(W)                                                                        \
-  if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);                     \
-  else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);            \
-  else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);      \
-  else if (full_slots) dql::train_kernel<W, false, 3><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);          \
-  else dql::train_kernel<W, false, 0><<<grid, W * 32 + 32, smem, stream>>>(h->kc, a);
+  if (tracing) dql::train_kernel<W, true, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);                     \
+  else if (extended) dql::train_kernel<W, false, 2><<<grid, W * 32, smem, stream>>>(h->kc, a);            \
+  else if (!h->kc_default) dql::train_kernel<W, false, 1><<<grid, W * 32, smem, stream>>>(h->kc, a);      \
+  else if (full_slots) dql::train_kernel<W, false, 3><<<grid, W * 32, smem, stream>>>(h->kc, a);          \
+  else dql::train_kernel<W, false, 0><<<grid, W * 32, smem, stream>>>(h->kc, a);
   switch (h->cfg.threads_per_block) {
     case 32: DQL_LAUNCH(1) break;
     case 64: DQL_LAUNCH(2) break;

@@ -463,4 +463,15 @@ __device__ __forceinline__ double reward_f64(const KT& kc, const dqlb200_reward_
   return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
 }
 
+// R7 with the set-point term taken from the configuration's table (dqlb200_config.setpoint_rtheta: w_theta * (|phi'| - |phi|) /
+// theta_max evaluated on the host in the reference's operation order); same sum order as reward_f64.
+__device__ __forceinline__ double reward_sp(const dqlb200_reward_level& rl, double phi_p, double phi_v, double prev_p, double prev_v,
+                                            double r_theta0, bool success) {
+  const double r_p = clipd_finite(__dsub_rn(phi_p, prev_p), -rl.r_p_max, rl.r_p_max);
+  const double r_v = clipd_finite(__dsub_rn(phi_v, prev_v), -rl.r_v_max, rl.r_v_max);
+  const double r_t = __dmul_rn(r_theta0, rl.lim_v);
+  const double r_term = success ? rl.r_term_succ : rl.r_term_fail;
+  return __dadd_rn(__dadd_rn(__dadd_rn(__dadd_rn(r_p, r_v), r_t), rl.r_dur), r_term);
+}
+
 }  // namespace dql

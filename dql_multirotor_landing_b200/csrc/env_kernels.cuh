@@ -18,7 +18,7 @@ __global__ void reset_kernel(const __grid_constant__ KC kc, EnvPtrs env, dqlb200
     Env e;
     Kf kf = kf_initial();       // a new simulator: the only place the estimator and the PID memory are ever cleared
     Ext ex = ext_initial(kc);
-    env_reset(kc, pp, cuts, kc.angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true, env.d ? &kf : nullptr, env.e ? &ex : nullptr);
+    env_reset(kc, pp, cuts, kc.angle_cut, e, (uint32_t)env_i, 0u, initial_step, /*fresh_mdp=*/true, (uint32_t)env.sp_zero, env.d ? &kf : nullptr, env.e ? &ex : nullptr);
     env_store(env, (size_t)pop * kc.envs_per_population + env_i, e);
     if (kc.accel_mode != 0 && env.d) kf_store(env, (size_t)pop * kc.envs_per_population + env_i, kf);
     if (kc.dynamics_model != 0 && env.e) ext_store(env, (size_t)pop * kc.envs_per_population + env_i, ex);
@@ -131,10 +131,10 @@ __global__ void __launch_bounds__(128) env_reset_kernel(const __grid_constant__ 
       const DState ds = discretise_cuts(kc.cuts[w], kc.angle_cut, o);
       e.sid = (uint32_t)ds.id(); e.bp = (uint32_t)ds.bp;
       e.step_count = 0; e.curriculum_check = 0; e.sticky_success = false; e.fresh = true; e.cum_reward = 0.0;
-      e.theta_sp = 0.0; e.prev_rel_p = 0.0f; e.prev_rel_v = 0.0f;
+      e.sp_idx = (uint32_t)env.sp_zero; e.prev_rel_p = 0.0f; e.prev_rel_v = 0.0f;
       if (fresh_mdp) e.episode = 0;
     } else {
-      env_reset(kc, pp, kc.cuts[w], kc.angle_cut, e, env_i, birth, w, fresh_mdp != 0, filt ? &kf : nullptr, so ? &ex : nullptr);
+      env_reset(kc, pp, kc.cuts[w], kc.angle_cut, e, env_i, birth, w, fresh_mdp != 0, (uint32_t)env.sp_zero, filt ? &kf : nullptr, so ? &ex : nullptr);
     }
     env_store(env, (size_t)i, e);
     if (filt) kf_store(env, (size_t)i, kf);
@@ -165,8 +165,10 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   if (so) ex = ext_load(env, (size_t)i);
   const int a = actions[i];
   // R3 .. R8 in the order of TrainingLandingEnv.step (PKG/landing_simulation_env.py:245-282)
-  const double prev_sp = e.theta_sp;
-  const double sp = apply_action(kc, e.fresh ? 0.0 : e.theta_sp, a);
+  // R3 through the set-point tables (the memoised float64 arithmetic of continuous_action, see dqlb200_config)
+  const double prev_sp = env.sp_value[e.sp_idx];
+  const uint32_t sp_new = env.sp_next[(e.fresh ? (uint32_t)env.sp_zero : e.sp_idx) * 3u + (uint32_t)a].x;
+  const double sp = env.sp_value[sp_new];
   dyn_advance(kc, pp, e.b, (float)sp, filt ? &kf : nullptr, so ? &ex : nullptr, simulation ? kc.vz_sim : kc.vz_train);
   const uint32_t step_count = e.step_count + 1u;
   Obs o = dyn_observe(kc, pp, e.b, (int)step_count, simulation ? kc.dz_sim : kc.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   if (out_obs) { float* po = out_obs + i * 5; po[0] = o.rel_p; po[1] = o.rel_v; po[2] = o.rel_a; po[3] = o.pitch; po[4] = o.z; }
   if (out_steps) out_steps[i] = step_count;
   if (out_cumulative) out_cumulative[i] = e.cum_reward;          // quirk Q12: without this step's reward
-  e.theta_sp = sp;
+  e.sp_idx = sp_new;
   e.prev_rel_p = o.rel_p;
   e.prev_rel_v = o.rel_v;
   e.episode += done ? 1u : 0u;
@@ -221,7 +223,7 @@ __global__ void __launch_bounds__(128) env_step_kernel(const __grid_constant__ K
   e.sticky_success = (code == DQLB200_NON_TERMINAL_SUCCESS);
   e.fresh = false;
   e.cum_reward = __dadd_rn(e.cum_reward, r);
-  if (done && auto_reset && !simulation) env_reset(kc, pp, cuts, kc.angle_cut, e, env_i, t + 1u, w, /*fresh_mdp=*/false, filt ? &kf : nullptr, so ? &ex : nullptr);
+  if (done && auto_reset && !simulation) env_reset(kc, pp, cuts, kc.angle_cut, e, env_i, t + 1u, w, /*fresh_mdp=*/false, (uint32_t)env.sp_zero, filt ? &kf : nullptr, so ? &ex : nullptr);
   if (out_state) out_state[i] = (uint16_t)e.sid;       // of a finished env with auto_reset: the first state of its next episode
   env_store(env, (size_t)i, e);
   if (filt) kf_store(env, (size_t)i, kf);

@@ -15,7 +15,8 @@ constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25, BP_SHIFT = 26;  
 
 struct Env {
   Body b;
-  double theta_sp;     // NOT cleared by an episode reset while `fresh` (keeps the shaping potential, quirk Q11)
+  uint32_t sp_idx;     // pitch set-point as an index into dqlb200_config.setpoint_value; NOT cleared by an episode reset while
+                       // `fresh` (keeps the shaping potential, quirk Q11)
   float prev_rel_p, prev_rel_v;
   uint32_t sid, bp, step_count, curriculum_check;     // bp = position bin of sid ((sid / 63) % 3, kept to avoid the division)
   bool sticky_success, fresh;
@@ -30,6 +31,11 @@ struct EnvPtrs {
   uint4* d;      // acceleration-estimator state (accel_mode != 0 only, else null): {x, P, v_ref, n}
   uint4* e;      // second-order model state (dynamics_model != 0 only, else null): [2][n] {omega, z, v_z, integral}, {e1, f1, f2, f3}
   size_t n;      // envs in the SoA (stride of `e`)
+  // the set-point tables of the configuration (device copies inside dqlb200_config, see include/dqlb200.h)
+  const double* sp_value;       // [n_setpoints]
+  const uint2* sp_next;         // [n_setpoints][3] {next index, float32 bits of its value}
+  const double* sp_rtheta;      // [2][DQLB200_MAX_SETPOINTS][3]
+  int sp_zero, n_sp;
 };
 __device__ __forceinline__ Ext ext_load(const EnvPtrs& p, size_t i) {
   const uint4 u = p.e[i], v = p.e[p.n + i];
@@ -116,7 +122,7 @@ __device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
   const uint4 B = r.B;
   const uint4 Cw = r.C;
   e.b.x_d = A.x; e.b.v_d = A.y; e.b.theta = A.z; e.b.phase = __float_as_uint(A.w); e.b.a_d = 0.0f;
-  e.theta_sp = __hiloint2double((int)B.y, (int)B.x);
+  e.sp_idx = B.x;
   e.prev_rel_p = __uint_as_float(B.z);
   e.prev_rel_v = __uint_as_float(B.w);
   e.sid = Cw.x & ((1u << SID_BITS) - 1u);
@@ -132,8 +138,7 @@ __device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { e
 
 __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) {
   p.a[i] = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
-  p.b[i] = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
-                      __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  p.b[i] = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
   const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
                           (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
   p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
@@ -142,8 +147,7 @@ __device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env&
 
 __device__ __forceinline__ void env_store_p(char* pa, size_t stride, size_t stride2, const Env& e) {
   *reinterpret_cast<float4*>(pa) = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
-  *reinterpret_cast<uint4*>(pa + stride) = make_uint4((uint32_t)__double2loint(e.theta_sp), (uint32_t)__double2hiint(e.theta_sp),
-                                                      __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  *reinterpret_cast<uint4*>(pa + stride) = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
   const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
                           (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
   *reinterpret_cast<uint4*>(pa + stride2) = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
@@ -155,7 +159,7 @@ __device__ __forceinline__ void env_store_p(char* pa, size_t stride, size_t stri
 template <class KT, class AC>
 __device__ __forceinline__ void env_reset(const KT& kc, const dqlb200_population_params& pp,
                                           const dqlb200_cuts& cuts, const AC& angle_cut, Env& e,
-                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp, Kf* kf = nullptr, Ext* ext = nullptr) {
+                                          uint32_t env_index, uint32_t birth, int w, bool fresh_mdp, uint32_t sp_zero, Kf* kf = nullptr, Ext* ext = nullptr) {
   const uint4 d = philox4x32_10(make_uint4(env_index, birth, PURPOSE_RESET, pp.population_id), pp.seed_lo, pp.seed_hi);
   Obs o = dyn_reset(kc, pp, e.b, d, /*normal_init=*/w == 0, /*simulation=*/false, kc.dz_train, kf, ext);
   if (kc.noise_enabled) {
@@ -171,7 +175,7 @@ __device__ __forceinline__ void env_reset(const KT& kc, const dqlb200_population
   e.fresh = true;
   e.cum_reward = 0.0;
   if (fresh_mdp) {
-    e.theta_sp = 0.0;
+    e.sp_idx = sp_zero;
     e.prev_rel_p = 0.0f;
     e.prev_rel_v = 0.0f;
     e.episode = 0;

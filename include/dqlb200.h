@@ -33,6 +33,7 @@ extern "C" {
 #define DQLB200_MAX_CELLS (DQLB200_MAX_CURRICULUM * DQLB200_CELLS_PER_LEVEL)   /* 2835 */
 #define DQLB200_ALPHA_LUT 1003                /* count 0..1002; alpha(count >= 1002) == alpha_min */
 #define DQLB200_EPS_LUT 2002                  /* episode 0..2000, [2001] = every later episode */
+#define DQLB200_MAX_SETPOINTS 64              /* reachable pitch set-points (33 for the reference defaults) */
 #define DQLB200_MAX_WINDOW 128                /* success window (Trainer successive_successful_episodes) */
 #define DQLB200_SHARED_WORDS (2 * DQLB200_MAX_CELLS + 4)   /* 32-bit words per agent and rank in the shared-table exchange buffer */
 #define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, SoA: [3][n_envs_total][16 B] */
@@ -141,6 +142,18 @@ typedef struct dqlb200_config {
   float bw_inv_denom, bw_k2;        /* 1 / (1 + c^2 + 1.414 c), c^2 - 1.414 c + 1 with c = 1 (PKG/filters.py:92-93,103) */
   float vz_train, vz_sim;           /* v_z set-points -0.1 / -0.4 (PKG/mdp.py:212, 580) */
   uint32_t eps_threshold[DQLB200_EPS_LUT];           /* ceil(eps(episode) * 2^24) for working step 0 */
+  /* ---- pitch set-point as an index (R3).  TrainingMdp.continuous_action (PKG/mdp.py:543-560) only ever adds / subtracts
+   * delta_theta and clamps to +-theta_max, starting from 0 at every reset: the float64 values it can reach form a small closed
+   * set (33 for the defaults -- three interleaved lattices, because 3 delta_theta < theta_max by 1.4e-6 delta_theta),
+   * enumerated on the host with the reference's own float64 operations (constants.py: build_setpoints).  The env state
+   * stores the INDEX; the kernels read, per (index, action), the next index and the float32 set-point for the dynamics, and
+   * per (fresh episode?, previous index, action) the set-point term of the reward, w_theta * (|phi(next)| - |phi(prev)|) /
+   * theta_max with phi(i) = w_theta * |value[i] / theta_max| (PKG/mdp.py:463-474, 506-514), evaluated on the host in the
+   * reference's operation order.  A memoisation of exact arithmetic: identical bits, ~35 instructions per env-step fewer. */
+  int32_t n_setpoints, setpoint_zero;                /* size of the set (<= DQLB200_MAX_SETPOINTS), index of 0.0 */
+  double setpoint_value[DQLB200_MAX_SETPOINTS];
+  struct { uint32_t next; float value_f32; } setpoint_next[DQLB200_MAX_SETPOINTS][3];      /* [index][action] */
+  double setpoint_rtheta[2][DQLB200_MAX_SETPOINTS][3];                                      /* [fresh][previous index][action] */
 } dqlb200_config;
 
 /* Per-population constants (sweep axes: seed x platform speed x learning-rate schedule). */

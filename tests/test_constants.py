@@ -112,3 +112,57 @@ def test_scalar_thresholds(cfg):
     assert abs(r0.r_term_fail / -2.6 - 5.054188) < 1e-6                # r_max level 0, SURVEY.md A.5
     with pytest.raises(ValueError):
         K.alpha_lut(alpha_min=0.001)                                   # does not saturate within the LUT
+
+
+def test_setpoint_tables_closure(cfg):
+    """The pitch set-point is stored as an index: the tables must be closed under the three actions and reproduce the float64
+    arithmetic of continuous_action (PKG/mdp.py:543-560) from every reachable value."""
+    mp = K.MdpParameters()
+    n, zero = cfg.n_setpoints, cfg.setpoint_zero
+    vals = [cfg.setpoint_value[i] for i in range(n)]
+    assert n == 33 and vals[zero] == 0.0 and vals == sorted(vals) and len(set(vals)) == n       # 3 interleaved lattices, SURVEY.md R3
+    assert max(vals) == mp.theta_max and min(vals) == -mp.theta_max
+    for i, v in enumerate(vals):
+        want = [min((v + mp.delta_theta, mp.theta_max)), max((v - mp.delta_theta, -mp.theta_max)), v]
+        for a in range(3):
+            nx = cfg.setpoint_next[i][a]
+            assert vals[nx.next] == want[a] and nx.value_f32 == np.float32(want[a])
+    # every value is reachable from 0
+    seen, todo = {zero}, [zero]
+    while todo:
+        i = todo.pop()
+        for a in range(3):
+            j = cfg.setpoint_next[i][a].next
+            if j not in seen:
+                seen.add(j); todo.append(j)
+    assert len(seen) == n
+
+
+def test_setpoint_tables_vs_reference_live(cfg, reference_ns):
+    """Against the unmodified TrainingMdp: continuous_action from every reachable set-point, and the set-point term of reward()
+    (everything else held at zero) for every (previous index, action), in a running and in a fresh episode (quirk Q11)."""
+    ns = reference_ns
+    n, zero = cfg.n_setpoints, cfg.setpoint_zero
+    vals = [cfg.setpoint_value[i] for i in range(n)]
+    lim_v = 1.0                                                  # Limits.velocity[0]
+    obs0 = ns.mdp.ContinuousObservation(ns.Observation(), 0.0, 0.0, 3.0)
+    for p in range(n):
+        for a in range(3):
+            for fresh in (0, 1):
+                mdp = ns.mdp.TrainingMdp(0, 22.92, 20, 4.5)
+                mdp.reset()
+                mdp._current_continuous_action.pitch = vals[p]
+                mdp.discrete_state(obs0); mdp.continuous_action(2); mdp.discrete_state(obs0); mdp.check(); mdp.reward()   # phi_theta(prev) in place
+                base = mdp.reward()                               # a step that changes nothing: r_p = r_v = r_theta = 0
+                if fresh:
+                    mdp.reset()                                   # keeps the shaping values (quirk Q11), zeroes the set-point
+                    mdp.discrete_state(obs0)
+                act = mdp.continuous_action(a)
+                assert act.pitch == vals[cfg.setpoint_next[zero if fresh else p][a].next]
+                mdp.discrete_state(obs0); mdp.check()
+                r = mdp.reward()
+                want = cfg.setpoint_rtheta[fresh][p][a] * lim_v
+                assert r - base == pytest.approx(want, abs=1e-12), (p, a, fresh, r - base, want)
+                # exactly: the reference's own expression (PKG/mdp.py:506-514) on the shaping values reward() just used
+                cur, prev = mdp.current_shaping_value.angle, mdp.previous_shaping_value.angle
+                assert mdp._w_theta * (np.abs(cur) - np.abs(prev)) / mdp._theta_max * lim_v == want, (p, a, fresh)

@@ -552,7 +552,7 @@ def test_shared_table_counts_are_exact_beyond_2_pow_24():
     torch.cuda.synchronize()
     out = [e.tables.cpu().numpy().view(np.uint32)[0] for e in engs]
     assert np.array_equal(out[0], out[1]) and np.array_equal(out[0], out[2])
-    assert int(out[0][2, 7]) == sum(visits) == 56_777_221 and np.float32(sum(visits)) != sum(visits)
+    assert int(out[0][2, 7]) == sum(visits) == 56_777_221 and int(np.float32(sum(visits))) != sum(visits)      # not an fp32 number
     assert int(out[0][2, 9]) == 0xFFFFFFFF
     assert out[0][0, 11] == np.float32(0.1).view(np.uint32) and int(out[0][2, 11]) == 5
     q, cnt = _rank_ordered_merge(snap, tabs)
