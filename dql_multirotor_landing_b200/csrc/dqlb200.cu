@@ -87,6 +87,10 @@ int dqlb200_abi_version(void) { return DQLB200_ABI_VERSION; }
 size_t dqlb200_config_bytes(void) { return sizeof(dqlb200_config); }
 size_t dqlb200_population_state_bytes(void) { return sizeof(dqlb200_population_state); }
 size_t dqlb200_eval2d_params_bytes(void) { return sizeof(dqlb200_eval2d_params); }
+size_t dqlb200_env_state_bytes(int n_populations, int envs_per_population) {
+  if (n_populations < 0 || envs_per_population < 0) return 0;
+  return (size_t)n_populations * (((size_t)envs_per_population + 31) / 32) * dql::ENV_TILE_BYTES;
+}
 const char* dqlb200_last_error(void) { return g_last_error.c_str(); }
 
 const char* dqlb200_termination_string(int code) {
@@ -282,12 +286,15 @@ int dqlb200_bind_dynamics_state(dqlb200_handle* h, void* dynamics_state) {
   if ((h)->cfg.accel_mode != 0 && !(h)->filter_state) return fail(DQLB200_ERR_STATE, "accel_mode != 0 needs dqlb200_bind_filter_state()"); \
   if ((h)->cfg.dynamics_model != 0 && !(h)->dynamics_state) return fail(DQLB200_ERR_STATE, "dynamics_model != 0 needs dqlb200_bind_dynamics_state()")
 
+static size_t env_tiles_per_pop(const dqlb200_config& c) { return ((size_t)c.envs_per_population + 31) / 32; }
+static size_t env_state_bytes(const dqlb200_config& c, size_t n_pop) { return n_pop * env_tiles_per_pop(c) * dql::ENV_TILE_BYTES; }
+
 static dql::EnvPtrs env_ptrs(const dqlb200_handle* h, void* base) {
   const size_t n = (size_t)h->cfg.n_populations * h->cfg.envs_per_population;
   dql::EnvPtrs p;
-  p.a = reinterpret_cast<float4*>(base);
-  p.b = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 16 * n);
-  p.c = reinterpret_cast<uint4*>(reinterpret_cast<unsigned char*>(base) + 32 * n);
+  p.base = reinterpret_cast<unsigned char*>(base);
+  p.n_p = h->cfg.envs_per_population;
+  p.tiles_per_pop = (int)env_tiles_per_pop(h->cfg);
   p.d = h->cfg.accel_mode != 0 ? reinterpret_cast<uint4*>(h->filter_state) : nullptr;
   p.e = h->cfg.dynamics_model != 0 ? reinterpret_cast<uint4*>(h->dynamics_state) : nullptr;
   p.n = n;
@@ -325,8 +332,6 @@ static int launch_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* tra
   a.k_steps = k_steps;
   a.pop_offset = pop_offset;
   a.n_total = (long long)h->cfg.n_populations * h->cfg.envs_per_population;
-  a.env_stride = (size_t)a.n_total * 16;
-  a.env_stride2 = (size_t)a.n_total * 32;
   const int grid = pop_count < 0 ? h->cfg.n_populations : pop_count;
   const bool tracing = trace != nullptr;
   const bool extended = h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0;      // options with extra per-env state
@@ -387,17 +392,15 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
     if (p1 == p0) continue;
     cudaStream_t cs = h->chunk_stream[c];
     CUDA_TRY(cudaStreamWaitEvent(cs, h->host_start, 0));
-    const size_t e0 = (size_t)p0 * n_p * 16, eb = (size_t)(p1 - p0) * n_p * 16;
-    for (int a = 0; a < 3; ++a)       // the three 16-byte vectors of the env-state SoA
-      CUDA_TRY(cudaMemcpyAsync((char*)h->env_state + a * 16 * n + e0, (const char*)env_state_host + a * 16 * n + e0, eb, cudaMemcpyHostToDevice, cs));
+    const size_t e0 = env_state_bytes(h->cfg, (size_t)p0), eb = env_state_bytes(h->cfg, (size_t)(p1 - p0));      // a range of populations is one block
+    CUDA_TRY(cudaMemcpyAsync((char*)h->env_state + e0, (const char*)env_state_host + e0, eb, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)h->tables + p0 * tab_stride, (const char*)tables_host + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)h->pop_state + p0 * ps_stride, (const char*)pop_state_host + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyHostToDevice, cs));
     if (k_steps > 0) {
       const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, cs, p0, p1 - p0);
       if (rc) return rc;
     }
-    for (int a = 0; a < 3; ++a)
-      CUDA_TRY(cudaMemcpyAsync((char*)env_state_host + a * 16 * n + e0, (const char*)h->env_state + a * 16 * n + e0, eb, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpyAsync((char*)env_state_host + e0, (const char*)h->env_state + e0, eb, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)tables_host + p0 * tab_stride, (const char*)h->tables + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)pop_state_host + p0 * ps_stride, (const char*)h->pop_state + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaEventRecord(h->chunk_done[c], cs));

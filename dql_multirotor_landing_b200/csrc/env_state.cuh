@@ -1,4 +1,4 @@
-// env_state.cuh -- the 48-byte environment state (SoA of three 16-byte vectors): pack/unpack, reset law, asynchronous prefetch
+// env_state.cuh -- the 48-byte environment state (tiles of 32 envs x three 16-byte vectors): pack/unpack, reset law, asynchronous prefetch
 // Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
 #pragma once
 #include "dqlb200_device.cuh"
@@ -24,10 +24,15 @@ struct Env {
   double cum_reward;
 };
 
+// Layout of the env state in HBM: [population][tile][3][32 envs][16 B] -- a tile is the 48 bytes of 32 consecutive envs of ONE
+// population as three 512-byte runs (vectors A, B, C), 1536 contiguous bytes: exactly what one warp reads and writes per slot,
+// with the vectors of an env at constant offsets (+512, +1024) from its A vector.  A population occupies tiles_per_pop =
+// ceil(envs_per_population / 32) tiles (the last one padded), so a population's state -- and any range of populations -- is one
+// contiguous block (host-buffer calls copy it with one transfer).
+constexpr size_t ENV_TILE_BYTES = 3 * 32 * 16;
 struct EnvPtrs {
-  float4* a;
-  uint4* b;
-  uint4* c;
+  unsigned char* base;
+  int n_p, tiles_per_pop;      // envs per population, tiles per population
   uint4* d;      // acceleration-estimator state (accel_mode != 0 only, else null): {x, P, v_ref, n}
   uint4* e;      // second-order model state (dynamics_model != 0 only, else null): [2][n] {omega, z, v_z, integral}, {e1, f1, f2, f3}
   size_t n;      // envs in the SoA (stride of `e`)
@@ -37,6 +42,15 @@ struct EnvPtrs {
   const double* sp_rtheta;      // [2][DQLB200_MAX_SETPOINTS][3]
   int sp_zero, n_sp;
 };
+// address of vector A of env `env` of population `pop` (B at +512, C at +1024)
+__device__ __forceinline__ unsigned char* env_addr(const EnvPtrs& p, int pop, int env) {
+  return p.base + ((size_t)pop * p.tiles_per_pop + (size_t)(env >> 5)) * ENV_TILE_BYTES + (size_t)(env & 31) * 16;
+}
+// the same from the global env index i = pop * envs_per_population + env (the index of traces, action arrays and extension state)
+__device__ __forceinline__ unsigned char* env_addr(const EnvPtrs& p, size_t i) {
+  const int pop = (int)(i / (size_t)p.n_p);
+  return env_addr(p, pop, (int)(i - (size_t)pop * p.n_p));
+}
 __device__ __forceinline__ Ext ext_load(const EnvPtrs& p, size_t i) {
   const uint4 u = p.e[i], v = p.e[p.n + i];
   return Ext{__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w),
@@ -81,30 +95,22 @@ struct EnvRaw {
   float4 A;
   uint4 B, C;
 };
-__device__ __forceinline__ EnvRaw env_fetch(const EnvPtrs& p, size_t i) {
+__device__ __forceinline__ EnvRaw env_fetch(const unsigned char* pa) {
   EnvRaw r;
-  r.A = p.a[i];
-  r.B = p.b[i];
-  r.C = p.c[i];
+  r.A = *reinterpret_cast<const float4*>(pa);
+  r.B = *reinterpret_cast<const uint4*>(pa + 512);
+  r.C = *reinterpret_cast<const uint4*>(pa + 1024);
   return r;
 }
 // Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
 // unlike a register prefetch it holds no registers while in flight and cannot be consumed early by the scheduler's copies.
 // stage_addr = shared-state-space address of the thread's first staging slot (__cvta_generic_to_shared(stage + tid), hoisted
 // out of the slot loop by the caller: the conversion reads a special register).
-__device__ __forceinline__ void env_prefetch_async(const EnvPtrs& p, size_t i, unsigned stage_addr, int nt) {
-  const unsigned s0 = stage_addr;
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0), "l"(p.a + i) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 16u * nt), "l"(p.b + i) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s0 + 32u * nt), "l"(p.c + i) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
-}
-// Pointer form for the slot loop: pa = address of the env's A vector; its B and C vectors lie `stride` (= 16 n) and 2 * stride
-// bytes behind it.  One running pointer per thread instead of three index computations per slot.
-__device__ __forceinline__ void env_prefetch_async_p(const char* pa, size_t stride, size_t stride2, unsigned stage_addr, int nt) {
+// pa = address of the env's A vector; its B and C vectors lie 512 and 1024 bytes behind it (immediate offsets)
+__device__ __forceinline__ void env_prefetch_async(const unsigned char* pa, unsigned stage_addr, int nt) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr), "l"(pa) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 16u * nt), "l"(pa + stride) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(pa + stride2) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 16u * nt), "l"(pa + 512) : "memory");
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(pa + 1024) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ EnvRaw env_prefetch_take(const uint4* stage, int nt, int tid) {
@@ -134,25 +140,17 @@ __device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
   e.episode = Cw.y;
   e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
 }
-__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { env_unpack(env_fetch(p, i), e); }
-
-__device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) {
-  p.a[i] = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
-  p.b[i] = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
-  const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
-                          (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
-  p.c[i] = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
-                      (uint32_t)__double2hiint(e.cum_reward));
-}
-
-__device__ __forceinline__ void env_store_p(char* pa, size_t stride, size_t stride2, const Env& e) {
+__device__ __forceinline__ void env_store(unsigned char* pa, const Env& e) {
   *reinterpret_cast<float4*>(pa) = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
-  *reinterpret_cast<uint4*>(pa + stride) = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  *reinterpret_cast<uint4*>(pa + 512) = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
   const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
                           (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
-  *reinterpret_cast<uint4*>(pa + stride2) = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
-                                                          (uint32_t)__double2hiint(e.cum_reward));
+  *reinterpret_cast<uint4*>(pa + 1024) = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
+                                                    (uint32_t)__double2hiint(e.cum_reward));
 }
+// by global env index (kernels off the hot path)
+__device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { env_unpack(env_fetch(env_addr(p, i)), e); }
+__device__ __forceinline__ void env_store(const EnvPtrs& p, size_t i, const Env& e) { env_store(env_addr(p, i), e); }
 
 // R1 + R8: new episode.  `fresh_mdp` additionally clears what only a NEW TrainingMdp clears
 // (shaping potentials, PKG/trainer.py:176 + quirk Q11) and the per-step episode index.

@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(128) agent_select_kernel(const __grid_constant
   const int pop = (int)(i / kc.envs_per_population);
   const uint32_t env_i = (uint32_t)(i % kc.envs_per_population);
   const dqlb200_population_params pp = pop_params[pop];
-  const uint4 Cw = env.c[i];
+  const uint4 Cw = *reinterpret_cast<const uint4*>(env_addr(env, (size_t)i) + 1024);
   const uint32_t sid = Cw.x & ((1u << SID_BITS) - 1u), episode = Cw.y;
   const float* qa = reinterpret_cast<const float*>(tables + (size_t)pop * 3 * CELLS);
   const float* qb = qa + CELLS;

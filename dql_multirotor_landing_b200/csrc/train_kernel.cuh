@@ -40,7 +40,6 @@ struct TrainArgs {
   int k_steps;
   int pop_offset;                          // first population of this launch (chunked host-buffer calls)
   long long n_total;
-  size_t env_stride, env_stride2;          // 16 n_total, 32 n_total: byte offsets of the B and C vectors behind an env's A vector
 };
 
 constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it runs the batched reset pass
@@ -127,7 +126,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
   constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
   const dqlb200_population_params pp = args.pop_params[pop];
-  env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+  // this thread's env of slot 0 (a lane beyond the population reads the padding of the last tile)
+  unsigned char* const p_env0 = env_addr(args.env, pop, min(tid, n_p - 1) & ~31) + (size_t)lane * 16;
+  env_prefetch_async(p_env0, stage_addr, NT);
   if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, kc.accel_mode != 0, kc.dynamics_model != 0);
   {
     const int w_start = args.pop_state[pop].working_step;
@@ -230,14 +231,14 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
           if (filt) kf = kf_load(args.env, env_base + env_i);       // the estimator outlives the curriculum step
           if (so) ex = ext_load(args.env, env_base + env_i);
           env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_i, birth, w + 1, /*fresh_mdp=*/true, sp_zero, filt ? &kf : nullptr, so ? &ex : nullptr);
-          env_store(args.env, env_base + env_i, e);
+          env_store(env_addr(args.env, pop, env_i), e);
           if (filt) kf_store(args.env, env_base + env_i, kf);
           if (so) ext_store(args.env, env_base + env_i, ex);
         }
       }
       // every env was just restarted: the slot-0 prefetch in flight is stale
       (void)env_prefetch_take(stage, NT, tid);
-      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+      env_prefetch_async(p_env0, stage_addr, NT);
       if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
       build_snapshot(w + 1);
     }
@@ -268,14 +269,15 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
           const int qv = reset_queue[base + lane];
           const int env_r = (qv >> 5) * NT + warp * 32 + (qv & 31);
           const size_t gr = env_base + (size_t)env_r;
+          unsigned char* const pr = env_addr(args.env, pop, env_r);
           Env e;
-          env_load(args.env, gr, e);
+          env_unpack(env_fetch(pr), e);
           Kf kf;
           Ext ex;
           if (filt) kf = kf_load(args.env, gr);
           if (so) ex = ext_load(args.env, gr);
           env_reset(kk, pp, sh.cuts, kk.angle_cut, e, (uint32_t)env_r, t + 1u, w, /*fresh_mdp=*/false, sp_zero, filt ? &kf : nullptr, so ? &ex : nullptr);
-          env_store(args.env, gr, e);
+          env_store(pr, e);
           if (filt) kf_store(args.env, gr, kf);
           if (so) ext_store(args.env, gr, ex);
         }
@@ -284,20 +286,20 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       n_queued = 0;
     };
 
-    char* p_env = reinterpret_cast<char*>(args.env.a + env_base + tid);      // running pointer to the A vector of this thread's env
+    unsigned char* p_env = env_addr(args.env, pop, tid);      // running pointer to the A vector of this thread's env: tile = slot * WARPS + warp
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = FULL_SLOTS || env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
       const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
-      char* const p_cur = p_env;
-      p_env += NT * 16;
+      unsigned char* const p_cur = p_env;
+      p_env += WARPS * ENV_TILE_BYTES;
       Kf kf;
       Ext ex;
       if (filt) kf = kf_take(stage, NT, tid);
       if (so) ex = ext_take(stage, NT, tid);
       if (FULL_SLOTS ? (slot + 1 < n_slots) : (env_i + NT < n_p)) {      // in flight during this slot
-        env_prefetch_async_p(p_env, args.env_stride, args.env_stride2, stage_addr, NT);
+        env_prefetch_async(p_env, stage_addr, NT);
         if (EXT) ext_prefetch_async(args.env, gi + NT, stage_addr, NT, filt, so);
       }
       // ---------------- phase A: everything that only reads the snapshot ----------------------
@@ -422,6 +424,24 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
       const uint32_t peers = __match_any_sync(FULL, key);
       const int rank = __popc(peers & ((1u << lane) - 1u));
+      const int n_group = valid ? __popc(peers) : 0;
+      // The targets of the lane's group, in lane order, gathered BEFORE the baton (every member gathers the same list and
+      // evaluates the same chain; the first one stores): the serialised section then holds no shuffle and no vote, only the
+      // dependent float32 chain itself.  Groups of more than GROUP_FAST members finish in the general loop below.
+      constexpr int GROUP_FAST = 8;
+      float tj[GROUP_FAST];
+      uint32_t rem = valid ? peers : 0u;
+      int n_rounds = 0;            // warp-uniform: size of the largest group, capped
+#pragma unroll
+      for (int j = 0; j < GROUP_FAST; ++j) {
+        tj[j] = 0.0f;
+        if (j == n_rounds && __any_sync(FULL, rem != 0u)) {
+          tj[j] = __shfl_sync(FULL, target, rem ? (__ffs(rem) - 1) : lane);
+          rem &= rem - 1u;
+          n_rounds = j + 1;
+        }
+      }
+      const bool big_group = __any_sync(FULL, rem != 0u);
       uint32_t smask = 0u;
       double ret = 0.0;
       if (dmask) {
@@ -435,23 +455,36 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       {
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
-        const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
-        float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
-        if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
-        // the group's updates in lane order, two members per round (their four shuffles are issued together)
-        uint32_t rem = valid ? peers : 0u;
-        while (__any_sync(FULL, rem != 0u)) {
-          const uint32_t rem1 = rem & (rem - 1u);
-          const int src0 = rem ? (__ffs(rem) - 1) : lane, src1 = rem1 ? (__ffs(rem1) - 1) : lane;
-          const float a_0 = __shfl_sync(FULL, alpha, src0), t_0 = __shfl_sync(FULL, target, src0);
-          const float a_1 = __shfl_sync(FULL, alpha, src1), t_1 = __shfl_sync(FULL, target, src1);
-          if (rem) q = fadd(q, fmul(a_0, fsub(t_0, q)));       // q += alpha * (target - q)
-          if (rem1) q = fadd(q, fmul(a_1, fsub(t_1, q)));
-          rem = rem1 & (rem1 - 1u);
+        const bool saturated = c0 >= (uint32_t)(DQLB200_ALPHA_LUT - 1);      // alpha_min for every member, whatever its rank
+        // fast path: every group either sits on a saturated cell or is a single update whose hinted learning rate is still valid
+        const bool lane_fast = !valid || saturated || (n_group == 1 && c0 == c_hint);
+        if (!big_group && __all_sync(FULL, lane_fast)) {
+          const float alpha = saturated ? alpha_min : a_hint;                // R11: alpha of the pre-increment count
+#pragma unroll
+          for (int j = 0; j < GROUP_FAST; ++j) {
+            if (j < n_rounds) {                                              // uniform
+              if (j < n_group) q = fadd(q, fmul(alpha, fsub(tj[j], q)));     // q += alpha * (target - q), members in lane order
+            }
+          }
+        } else {
+          const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
+          float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
+          if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
+          // the group's updates in lane order, two members per round (their four shuffles are issued together)
+          uint32_t rm = valid ? peers : 0u;
+          while (__any_sync(FULL, rm != 0u)) {
+            const uint32_t rm1 = rm & (rm - 1u);
+            const int src0 = rm ? (__ffs(rm) - 1) : lane, src1 = rm1 ? (__ffs(rm1) - 1) : lane;
+            const float a_0 = __shfl_sync(FULL, alpha, src0), t_0 = __shfl_sync(FULL, target, src0);
+            const float a_1 = __shfl_sync(FULL, alpha, src1), t_1 = __shfl_sync(FULL, target, src1);
+            if (rm) q = fadd(q, fmul(a_0, fsub(t_0, q)));       // q += alpha * (target - q)
+            if (rm1) q = fadd(q, fmul(a_1, fsub(t_1, q)));
+            rm = rm1 & (rm1 - 1u);
+          }
         }
         if (valid && rank == 0) {
           sh.qa[cell] = q;
-          sh.cnt[cell] = c0 + (uint32_t)__popc(peers);
+          sh.cnt[cell] = c0 + (uint32_t)n_group;
         }
         // finished episodes, in env order: success window + promotion test after every append (R14), PKG/trainer.py:219-236
         if (dmask) {
@@ -537,7 +570,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       }
       // The env state is written AFTER the baton: a barrier waits for the thread's outstanding global stores, which
       // would put an L2 round trip into the serialised section (ncu: stall_lg on the named barrier).
-      if (valid) env_store_p(p_cur, args.env_stride, args.env_stride2, e);
+      if (valid) env_store(p_cur, e);
       if (filt && valid) kf_store(args.env, gi, kf);
       if (so && valid) ext_store(args.env, gi, ex);
       // queue the finished envs of this warp for the batched reset (outside the baton)
@@ -550,7 +583,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
     if (k + 1 < args.k_steps) {
-      env_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT);
+      env_prefetch_async(p_env0, stage_addr, NT);
       if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
     }
     __syncthreads();

@@ -59,7 +59,9 @@ class Engine:
         n = n_populations * envs_per_population
         self.n_total = n
         with torch.cuda.device(self.device):
-            self.env_state = torch.zeros(3 * n * 4, dtype=torch.int32, device=self.device)        # [3][n][16 B]
+            # [population][tile][3][32 envs][16 B]: tiles of 32 envs, 1536 contiguous bytes each (csrc/env_state.cuh)
+            self.tiles_per_population = (envs_per_population + 31) // 32
+            self.env_state = torch.zeros(self.lib.dqlb200_env_state_bytes(n_populations, envs_per_population) // 4, dtype=torch.int32, device=self.device)
             self.tables = torch.zeros((n_populations, 3, K.MAX_CELLS), dtype=torch.int32, device=self.device)
             self.pop_state = torch.zeros(n_populations * C.sizeof(K.PopulationState), dtype=torch.uint8, device=self.device)
         _ffi.check(self.lib.dqlb200_bind(self.handle, self.env_state.data_ptr(), self.tables.data_ptr(), self.pop_state.data_ptr()))
@@ -262,9 +264,8 @@ class Engine:
 
     def set_episode_index(self, episode: int):
         """Test hook: set every env's per-curriculum-step episode index (word C.y of the state)."""
-        n = self.n_total
-        v = self.env_state.view(3, n, 4)
-        v[2, :, 1] = int(episode)
+        v = self.env_state.view(self.P, self.tiles_per_population, 3, 32, 4)
+        v[:, :, 2, :, 1] = int(episode)
 
     # ------------------------------------------------------------------------------------------
     def eval_greedy(self, policy: np.ndarray, n_episodes: int, *, population: int = 0, first_episode: int = 0,

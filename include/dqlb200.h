@@ -36,7 +36,8 @@ extern "C" {
 #define DQLB200_MAX_SETPOINTS 64              /* reachable pitch set-points (33 for the reference defaults) */
 #define DQLB200_MAX_WINDOW 128                /* success window (Trainer successive_successful_episodes) */
 #define DQLB200_SHARED_WORDS (2 * DQLB200_MAX_CELLS + 4)   /* 32-bit words per agent and rank in the shared-table exchange buffer */
-#define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, SoA: [3][n_envs_total][16 B] */
+#define DQLB200_ENV_STATE_BYTES 48            /* 3 x 16 B per environment, in tiles of 32 envs: [population][tile][3][32][16 B] */
+#define DQLB200_ENV_TILE_BYTES 1536           /* one tile = 32 envs of one population = three contiguous 512-byte runs */
 
 typedef enum dqlb200_status {
   DQLB200_OK = 0,
@@ -235,6 +236,8 @@ int dqlb200_abi_version(void);
 size_t dqlb200_config_bytes(void);
 size_t dqlb200_population_state_bytes(void);
 size_t dqlb200_eval2d_params_bytes(void);
+/* Bytes of the env-state buffer for a layout: n_populations * ceil(envs_per_population / 32) * DQLB200_ENV_TILE_BYTES. */
+size_t dqlb200_env_state_bytes(int n_populations, int envs_per_population);
 const char* dqlb200_last_error(void);
 /* CheckResult.value strings (PKG/mdp.py:69-75); NULL for non-terminal codes. */
 const char* dqlb200_termination_string(int code);
@@ -252,7 +255,9 @@ int dqlb200_uses_default_instance(dqlb200_handle* h);
 int dqlb200_config_is_default(const dqlb200_config* cfg);
 
 /* Borrow device buffers.
- *   env_state : DQLB200_ENV_STATE_BYTES * n_populations * envs_per_population bytes, 16-B aligned
+ *   env_state : dqlb200_env_state_bytes() bytes, 16-B aligned: [population][tile][3][32][16 B] -- a tile holds 32 consecutive
+ *               envs of one population as three 512-byte runs (vectors A, B, C); the last tile of a population is padded, so
+ *               a population (and any range of populations) is one contiguous block
  *   tables    : [n_populations][3][DQLB200_MAX_CELLS] 32-bit words: Q_a (f32), Q_b (f32), count (u32)
  *               == DoubleQLearningAgent.Q_table_a / Q_table_b / state_action_counter, row-major
  *               (curriculum, p, v, a, theta, action) like the .npy files (PKG/double_q_learning.py:38-53)

@@ -837,7 +837,7 @@ def test_no_access_outside_the_bound_buffers(dp):
     kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
     eng = _engine(3, 70, threads_per_block=64, seeds=[1, 2, 3], tp=kw, dp=dp)
     n, pad, dev = eng.n_total, 4096, eng.device
-    sizes = dict(env=3 * n * 16, tables=3 * 3 * K.MAX_CELLS * 4, pop=3 * C.sizeof(K.PopulationState), filt=n * 16, dyn=2 * n * 16)
+    sizes = dict(env=int(eng.lib.dqlb200_env_state_bytes(3, 70)), tables=3 * 3 * K.MAX_CELLS * 4, pop=3 * C.sizeof(K.PopulationState), filt=n * 16, dyn=2 * n * 16)
     big = {k: torch.full((pad + ((v + 255) // 256) * 256 + pad,), 0xAB, dtype=torch.uint8, device=dev) for k, v in sizes.items()}
     view = {k: big[k][pad:pad + sizes[k]] for k in sizes}
     for k in ("env", "tables", "pop", "filt", "dyn"):
