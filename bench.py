@@ -63,42 +63,86 @@ def workload_config(n_gpus: int) -> dict:
 
 # ----------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons DURING the timed region (B200_PROFILING.md): NVML polled every 10 ms from a thread
+    (the timed region of the headline is a few milliseconds; nvidia-smi -lms cannot sample that fast), nvidia-smi as the
+    fallback.  stop() raises when not a single sample was taken: a bench line without clocks is not a measurement."""
+    REASONS = (("hw_slowdown", "HwSlowdown"), ("hw_thermal_slowdown", "HwThermalSlowdown"), ("sw_thermal_slowdown", "SwThermalSlowdown"),
+               ("sw_power_cap", "SwPowerCap"), ("hw_power_brake", "HwPowerBrakeSlowdown"))
 
     def __init__(self, gpu_index: int):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.idx, self.samples, self.max_mhz, self.reasons, self.power = gpu_index, [], None, set(), []
+        self._stop = threading.Event()
+        self._thread, self._nvml, self._h, self.source = None, None, None, None
+
+    def _visible_index(self) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[self.idx])
+            except (ValueError, IndexError):
+                pass
+        return self.idx
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml, self._h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(self._visible_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+            self.source = "nvml, 10 ms period"
+            self._thread = threading.Thread(target=self._poll_nvml, daemon=True)
+        except Exception:
+            self._nvml, self.source = None, "nvidia-smi -lms 50"
+            self._thread = threading.Thread(target=self._poll_smi, daemon=True)
+        self._thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for r in self.rows:
+    def _poll_nvml(self):
+        n = self._nvml
+        get_reasons = getattr(n, "nvmlDeviceGetCurrentClocksEventReasons", None) or n.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
             try:
-                sm.append(float(r[0])); mx.append(float(r[1]))
+                self.samples.append(float(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+                mask = int(get_reasons(self._h))
+                for name, suffix in self.REASONS:
+                    bit = getattr(n, "nvmlClocksEventReason" + suffix, None) or getattr(n, "nvmlClocksThrottleReason" + suffix, 0)
+                    if mask & bit:
+                        self.reasons.add(name)
+                self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+            except Exception:
+                pass
+            self._stop.wait(0.010)
+
+    def _poll_smi(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            proc = subprocess.Popen(["nvidia-smi", f"--id={self._visible_index()}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "50"],
+                                    stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            return
+        for line in proc.stdout:
+            r = [c.strip() for c in line.split(",")]
+            try:
+                self.samples.append(float(r[0])); self.max_mhz = float(r[1]); self.power.append(float(r[2]))
             except (ValueError, IndexError):
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    self.reasons.add(name)
+            if self._stop.is_set():
+                break
+        proc.terminate()
+
+    def stop(self) -> dict:
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join(timeout=2.0)
+        if not self.samples:
+            raise RuntimeError("clock sampler took no sample (NVML and nvidia-smi both unavailable?): the bench line would carry no clocks")
+        sm = sorted(self.samples)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_mhz_min": sm[0], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(sm), "power_w_max": max(self.power) if self.power else None, "source": self.source,
+                "window": "from before the warm-up launches to the end of the e2e calls"}
 
 
 def measured_peak_hbm():
@@ -127,7 +171,10 @@ def cpu_baseline(seconds: float = 12.0) -> dict:
                           "bit-identical to the reference fixtures (tests/test_oracle_c.py)"}
     except Exception as exc:
         c_port = {"error": str(exc)}
-    return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port", "c_port": c_port,
+    flat = {}
+    if c_port and "value" in c_port:      # scalar copies at the top level of cpu_baseline (a parser that keeps only scalars keeps them)
+        flat = {"c_port_value": c_port["value"], "c_port_cores": c_port["cores"], "c_port_sample": c_port["sample"]}
+    return {"value": steps / t, "unit": UNIT, "cores": 1, "kind": "port", **flat, "c_port": c_port,
             "sample": f"{steps} env-steps of the single-env reference loop (oracle port, float64 tables, analytic stand-in), "
                       f"{t:.1f} s on 1 of {os.cpu_count()} host cores",
             "context": "the unmodified reference loop measures 6.9-7.5e3 env-steps/s per core on the same stand-in (BASELINE.md section 2); "
@@ -219,12 +266,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     while time.perf_counter() < t_end:
         eng.train(32)
         torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(args.warmup):
         flush.zero_()
         eng.train(1)
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches = 0
     for k in range(args.steps):
@@ -304,11 +351,12 @@ def run_ours(args, rank: int, local_rank: int, world: int):
         peak, peak_src = measured_peak_hbm()
         launch_s = ms_max * 1e-3 / args.steps
         achieved = ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu / launch_s / 1e9
-        traffic = None
+        traffic, traffic_src = None, None
         prof = ROOT / "profiles" / "train_kernel_traffic.json"
-        if prof.exists():
+        if prof.exists():      # DRAM bytes per launch cannot be measured outside a profiler: the committed ncu figure of the same launch shape
             try:
-                traffic = json.loads(prof.read_text()).get("dram_bytes_per_launch")
+                tj = json.loads(prof.read_text())
+                traffic, traffic_src = tj.get("dram_bytes_per_launch"), "static: " + str(tj.get("source", "profiles/train_kernel_traffic.json")) + " (ncu --set full of this launch shape, not measured in this run)"
             except Exception:
                 traffic = None
         extra = {}
@@ -321,7 +369,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src, "kernel": "dql::train_kernel<4>",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                         "kernel": "dql::train_kernel<4, false, 3>  (4 warps per CTA, no trace, production instance for full slots)",
                          "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu,
                          "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 6 and profiles/"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
@@ -332,6 +381,14 @@ def run_ours(args, rank: int, local_rank: int, world: int):
             "cpu_baseline": cpu_baseline() if not args.no_cpu else None,
             "extra": extra,
         }
+        # "two candidate roofs; report both, the lower one binds": the measured unordered-atomic RMW roof next to HBM
+        rmw = extra.get("table_rmw_roof") if isinstance(extra, dict) else None
+        if isinstance(rmw, dict) and "visits_per_s" in rmw:
+            per_gpu = value / world
+            line["roofline_rmw"] = {"bound": "smem-atomics", "achieved": per_gpu, "peak": rmw["visits_per_s"], "unit": "table visits/s (1 visit = count + Q_a read-modify-write)",
+                                    "frac": per_gpu / rmw["visits_per_s"], "peak_source": "measured in this run: dqlb200_bench_table_rmw on the recorded cell sequence of a traced run",
+                                    "binding_roof": "hbm" if line["roofline"]["frac"] >= per_gpu / rmw["visits_per_s"] else "smem-atomics",
+                                    "note": "headline launch shape (one global step per launch); the HBM roof is the lower (binding) one for independent populations"}
     eng.close()
     if world > 1:
         dist.barrier()

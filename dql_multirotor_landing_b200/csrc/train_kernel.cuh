@@ -61,6 +61,7 @@ struct Shared {
   unsigned long long n_episodes, n_success, ep_steps, hist[9];     // totals of this launch
   uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
   int promote, advance, do_advance;
+  uint4 philox_keys[5];   // round keys of the population's Philox key (philox_round_keys)
   // followed by (dynamic): uint2 sp_next[n_setpoints][3]; uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]
 };
 
@@ -142,6 +143,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       sh.cuts = kc.cuts[w_start];
     }
     if (tid < 5) sh.reward[tid] = kc.reward[tid];
+    if (tid == 31) philox_round_keys(pp.seed_lo, pp.seed_hi, sh.philox_keys);
     for (int i = tid; i < args.env.n_sp * 3; i += NT) sp_next[i] = args.env.sp_next[i];
     const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
     for (int i = tid; i < live; i += NT) {
@@ -320,7 +322,11 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         int a = sh.greedy[sid];
         uint32_t noise_w0 = 0u, noise_w1 = 0u;      // words z, w of the step draw feed the observation noise (off by default)
         if (w == 0 || (GENERIC && kk.noise_enabled)) {
+#ifdef DQL_PHILOX_INLINE_KEYS
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
+#else
+          const uint4 d = philox4x32_10_keyed(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), sh.philox_keys);
+#endif
           if (w == 0) {
             const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
             if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
@@ -425,9 +431,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const uint32_t peers = __match_any_sync(FULL, key);
       const int rank = __popc(peers & ((1u << lane) - 1u));
       const int n_group = valid ? __popc(peers) : 0;
-      // The targets of the lane's group, in lane order, gathered BEFORE the baton (every member gathers the same list and
-      // evaluates the same chain; the first one stores): the serialised section then holds no shuffle and no vote, only the
-      // dependent float32 chain itself.  Groups of more than GROUP_FAST members finish in the general loop below.
+#ifdef DQL_GATHER
+      // Variant (measured: the serialised section gets shorter, ncu stall_barrier 2.2 -> 1.3 per issue, but 48 more instructions
+      // per warp-slot make the step 6 % slower): the targets of the lane's group, in lane order, gathered BEFORE the baton.
       constexpr int GROUP_FAST = 8;
       float tj[GROUP_FAST];
       uint32_t rem = valid ? peers : 0u;
@@ -442,6 +448,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
       }
       const bool big_group = __any_sync(FULL, rem != 0u);
+#endif
       uint32_t smask = 0u;
       double ret = 0.0;
       if (dmask) {
@@ -455,6 +462,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       {
         float q = valid ? sh.qa[cell] : 0.0f;
         const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
+#ifdef DQL_GATHER
         const bool saturated = c0 >= (uint32_t)(DQLB200_ALPHA_LUT - 1);      // alpha_min for every member, whatever its rank
         // fast path: every group either sits on a saturated cell or is a single update whose hinted learning rate is still valid
         const bool lane_fast = !valid || saturated || (n_group == 1 && c0 == c_hint);
@@ -466,7 +474,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
               if (j < n_group) q = fadd(q, fmul(alpha, fsub(tj[j], q)));     // q += alpha * (target - q), members in lane order
             }
           }
-        } else {
+        } else
+#endif
+        {
           const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
           float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
           if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
