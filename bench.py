@@ -37,6 +37,7 @@ POPULATIONS_PER_GPU = 888          # 6 CTAs per SM x 148 SMs (shared-memory limi
 ENVS_PER_POPULATION = 1280         # 10 full slots of 128 threads; 888 * 1280 = 1,136,640 envs per GPU  (BASELINE config 5: "1M envs per GPU")
 THREADS_PER_BLOCK = 128
 E2E_CHUNK = 64                     # global steps per host-buffer call (about one episode, the reference's save interval)
+E2E_TABLE_LEVELS = 2               # curriculum step 0 with promotions off: levels 0 (live) and 1 (next) of the tables travel, checked by the library
 ALGORITHMIC_BYTES_PER_ENV_STEP = 96   # 48 B env state read + 48 B written, one step per launch
 
 
@@ -292,16 +293,20 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     torch.cuda.synchronize(dev)
     e2e_calls = max(3, min(args.steps, 20))
     for _ in range(2):
-        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h)
+        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h, table_levels=E2E_TABLE_LEVELS)
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_calls):
-        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h)          # synchronises inside
-        launches += min(8, P)                                   # one train_kernel launch per pipelined chunk of populations
+        eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h, table_levels=E2E_TABLE_LEVELS)          # synchronises inside
+        launches += min(16, P)                                  # one train_kernel launch per pipelined chunk of populations
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()
-    h2d = env_h.numel() * 4 + tab_h.numel() * 4 + ps_h.numel()
+    # bytes that cross PCIe per call and direction: env state + E2E_TABLE_LEVELS of 5 table levels (+ the last level on the way in,
+    # which quirk Q7 reads at the end of step 0) + trainer state
+    tab_level = tab_h.numel() * 4 // K.MAX_CURRICULUM
+    d2h = env_h.numel() * 4 + E2E_TABLE_LEVELS * tab_level + ps_h.numel()
+    h2d = d2h + tab_level
     steps_done = int(np.frombuffer(ps_h.numpy().tobytes(), dtype=K.POPULATION_STATE_DTYPE)["total_steps"].sum())
 
     t_ms = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
@@ -373,7 +378,8 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                          "kernel": "dql::train_kernel<4, false, 3>  (4 warps per CTA, no trace, production instance for full slots)",
                          "algorithmic_bytes_per_launch": ALGORITHMIC_BYTES_PER_ENV_STEP * envs_gpu,
                          "note": "instruction-issue bound, not HBM bound: see DESIGN.md section 6 and profiles/"},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": h2d,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "h2d_gb_per_s_per_rank": h2d * e2e_calls / e2e_s / 1e9, "d2h_gb_per_s_per_rank": d2h * e2e_calls / e2e_s / 1e9,
                     "global_steps_per_call": E2E_CHUNK, "calls": e2e_calls, "api": "dqlb200_train_host (pinned host buffers)",
                     "host_numa_node_rank0": numa_node,
                     "step": "one e2e step = one dqlb200_train_host call: env state + tables + trainer state copied in, 64 global steps, all copied back"},

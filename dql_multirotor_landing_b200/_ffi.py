@@ -58,7 +58,7 @@ def load() -> C.CDLL:
     lib.dqlb200_bind.argtypes = [vp, vp, vp, vp]
     lib.dqlb200_reset.argtypes = [vp, i32, vp]
     lib.dqlb200_train.argtypes = [vp, i32, C.POINTER(K.Trace), vp]
-    lib.dqlb200_train_host.argtypes = [vp, i32, vp, vp, vp, vp]
+    lib.dqlb200_train_host.argtypes = [vp, i32, vp, vp, vp, i32, vp]
     lib.dqlb200_eval_greedy.argtypes = [vp, i32, vp, i64, i64, i32, vp, C.POINTER(K.Trace), i32, vp]
     lib.dqlb200_eval_greedy_2d.argtypes = [vp, C.POINTER(K.Eval2DParams), vp, vp, i64, i64, vp, C.POINTER(K.Trace2D), i32, vp]
     lib.dqlb200_bench_table_rmw.argtypes = [vp, vp, i64, i32, i32, i32, vp, vp]

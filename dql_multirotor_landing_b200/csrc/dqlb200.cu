@@ -57,7 +57,7 @@ struct dqlb200_handle {
   bool kc_default;              // the configuration equals the compile-time defaults: the production instance may run
   size_t smem_bytes;
   // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
-  static constexpr int MAX_HOST_CHUNKS = 8;
+  static constexpr int MAX_HOST_CHUNKS = 16;
   cudaStream_t chunk_stream[MAX_HOST_CHUNKS];
   cudaEvent_t chunk_done[MAX_HOST_CHUNKS];
   cudaEvent_t host_start;
@@ -364,12 +364,13 @@ int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, vo
 }
 
 int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host, void* pop_state_host,
-                       void* stream) {
+                       int table_levels, void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
   if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
   if (h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0)
     return fail(DQLB200_ERR_ARG, "dqlb200_train_host does not carry the estimator / second-order state (accel_mode, dynamics_model != 0): use dqlb200_train on bound device buffers");
   if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
+  if (table_levels < 0 || table_levels > h->cfg.curriculum_steps) return fail(DQLB200_ERR_ARG, "table_levels must be 0 (all) .. curriculum_steps");
   CUDA_TRY(cudaSetDevice(h->device));
   cudaStream_t s = (cudaStream_t)stream;
   if (!h->chunk_ready) {
@@ -382,31 +383,52 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
   }
   // Populations are independent within a launch, so the call is pipelined over chunks of populations: while chunk c
   // trains, chunk c+1 is copied in and chunk c-1 is copied out (PCIe is full duplex, the copy engines run beside the SMs).
-  const int P = h->cfg.n_populations, n_p = h->cfg.envs_per_population;
+  // Tables: `table_levels` = L > 0 transfers only levels 0 .. L-1 of every table row (one strided copy per chunk and
+  // direction) -- the caller's promise that no population reaches working step L - 1 + 1 inside the call (a launch touches
+  // the levels 0 .. w of its working step w, and w + 1 when it is promoted); checked after the call.  L = 0: all levels.
+  const int P = h->cfg.n_populations, cs_levels = h->cfg.curriculum_steps;
   const int n_chunks = P < dqlb200_handle::MAX_HOST_CHUNKS ? P : dqlb200_handle::MAX_HOST_CHUNKS;
-  const size_t n = (size_t)P * n_p;
-  const size_t tab_stride = (size_t)3 * DQLB200_MAX_CELLS * 4, ps_stride = sizeof(dqlb200_population_state);
+  const size_t row_bytes = (size_t)DQLB200_MAX_CELLS * 4, tab_stride = 3 * row_bytes, ps_stride = sizeof(dqlb200_population_state);
+  const size_t level_bytes = (size_t)DQLB200_CELLS_PER_LEVEL * 4;
+  const dqlb200_population_state* ps_h = reinterpret_cast<const dqlb200_population_state*>(pop_state_host);
   CUDA_TRY(cudaEventRecord(h->host_start, s));
   for (int c = 0; c < n_chunks; ++c) {
     const int p0 = (int)((long long)P * c / n_chunks), p1 = (int)((long long)P * (c + 1) / n_chunks);
     if (p1 == p0) continue;
+    int w_max = 0, w_min = cs_levels;
+    for (int p = p0; p < p1; ++p) {
+      w_max = ps_h[p].working_step > w_max ? ps_h[p].working_step : w_max;
+      w_min = ps_h[p].working_step < w_min ? ps_h[p].working_step : w_min;
+    }
+    const int levels = table_levels > 0 ? table_levels : cs_levels;
+    if (w_max + 1 > levels) return fail(DQLB200_ERR_ARG, "table_levels is smaller than the live levels of a population's working step");
     cudaStream_t cs = h->chunk_stream[c];
     CUDA_TRY(cudaStreamWaitEvent(cs, h->host_start, 0));
     const size_t e0 = env_state_bytes(h->cfg, (size_t)p0), eb = env_state_bytes(h->cfg, (size_t)(p1 - p0));      // a range of populations is one block
     CUDA_TRY(cudaMemcpyAsync((char*)h->env_state + e0, (const char*)env_state_host + e0, eb, cudaMemcpyHostToDevice, cs));
-    CUDA_TRY(cudaMemcpyAsync((char*)h->tables + p0 * tab_stride, (const char*)tables_host + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyHostToDevice, cs));
+    CUDA_TRY(cudaMemcpy2DAsync((char*)h->tables + p0 * tab_stride, row_bytes, (const char*)tables_host + p0 * tab_stride, row_bytes,
+                               levels * level_bytes, (size_t)3 * (p1 - p0), cudaMemcpyHostToDevice, cs));
+    if (h->cfg.transfer_mode == 0 && w_min == 0 && levels < cs_levels)      // quirk Q7: ending step 0 reads the LAST level (slot -1)
+      CUDA_TRY(cudaMemcpy2DAsync((char*)h->tables + p0 * tab_stride + (cs_levels - 1) * level_bytes, row_bytes,
+                                 (const char*)tables_host + p0 * tab_stride + (cs_levels - 1) * level_bytes, row_bytes, level_bytes,
+                                 (size_t)3 * (p1 - p0), cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)h->pop_state + p0 * ps_stride, (const char*)pop_state_host + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyHostToDevice, cs));
     if (k_steps > 0) {
       const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, cs, p0, p1 - p0);
       if (rc) return rc;
     }
     CUDA_TRY(cudaMemcpyAsync((char*)env_state_host + e0, (const char*)h->env_state + e0, eb, cudaMemcpyDeviceToHost, cs));
-    CUDA_TRY(cudaMemcpyAsync((char*)tables_host + p0 * tab_stride, (const char*)h->tables + p0 * tab_stride, (p1 - p0) * tab_stride, cudaMemcpyDeviceToHost, cs));
+    CUDA_TRY(cudaMemcpy2DAsync((char*)tables_host + p0 * tab_stride, row_bytes, (const char*)h->tables + p0 * tab_stride, row_bytes,
+                               levels * level_bytes, (size_t)3 * (p1 - p0), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)pop_state_host + p0 * ps_stride, (const char*)h->pop_state + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaEventRecord(h->chunk_done[c], cs));
     CUDA_TRY(cudaStreamWaitEvent(s, h->chunk_done[c], 0));
   }
   CUDA_TRY(cudaStreamSynchronize(s));
+  // the promise behind table_levels: nobody went beyond the transferred levels
+  for (int p = 0; p < P && table_levels > 0 && table_levels < cs_levels; ++p)
+    if (ps_h[p].working_step + 1 > table_levels && !ps_h[p].finished)
+      return fail(DQLB200_ERR_STATE, "population " + std::to_string(p) + " was promoted beyond the transferred table levels: repeat the call with table_levels = 0");
   return DQLB200_OK;
 }
 

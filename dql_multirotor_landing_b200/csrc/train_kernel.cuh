@@ -46,6 +46,15 @@ constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it ru
 
 constexpr int STATES = DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL;   // 945
 
+// One warp-slot with finished episodes: which lanes finished / succeeded, the fixed-tree sum of their returns, and the last
+// finished env's episode (what the trainer logs).
+struct EpisodeEntry {
+  uint32_t dmask, smask;
+  double ret, last_cum;
+  int last_steps, last_code;
+};
+constexpr int EP_LOG = 32;
+
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
 // loop, L1-resident): that keeps the footprint at ~37 KB so that six CTAs fit on one SM.
 struct Shared {
@@ -62,6 +71,11 @@ struct Shared {
   uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
   int promote, advance, do_advance;
   uint4 philox_keys[5];   // round keys of the population's Philox key (philox_round_keys)
+  // Finished episodes of the warp-slots committed so far, in commit (= env) order: the serialised section only appends an
+  // entry; success window, promotion test and logged sums are brought up to date from the log at the end of the global step
+  // (or when the log is full), off the critical path of the baton.
+  EpisodeEntry ep_log[EP_LOG];
+  int n_ep_log;
   // followed by (dynamic): uint2 sp_next[n_setpoints][3]; uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]
 };
 
@@ -140,6 +154,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
       for (int i = 0; i < 9; ++i) { sh.hist[i] = 0ull; sh.step_hist[i] = 0u; }
       sh.promote = sh.advance = sh.do_advance = 0;
+      sh.n_ep_log = 0;
       sh.cuts = kc.cuts[w_start];
     }
     if (tid < 5) sh.reward[tid] = kc.reward[tid];
@@ -175,6 +190,80 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       sh.greedy[st] = (uint8_t)a;
       sh.qmax[st] = fmaxf(fmaxf(q0, q1), q2);
     }
+  };
+
+  // R14 from the episode log: the finished episodes enter the success window in env order, the promotion test runs after every
+  // append (PKG/trainer.py:219-236).  Called by ONE converged warp that has exclusive access to the trainer state: the baton
+  // holder when the log is full, warp 0 between the two barriers at the end of a global step.
+  auto drain_episode_log = [&]() {
+    dqlb200_population_state& ps = sh.ps;
+    const int ne = sh.n_ep_log;
+    const int L = kc.window_len;
+    bool promote = false;
+    for (int i = 0; i < ne; ++i) {
+      const uint32_t dmask = sh.ep_log[i].dmask, smask = sh.ep_log[i].smask;
+      const int n = __popc(dmask);
+      const int head = ps.window_head, count = ps.window_count, sum = ps.window_sum;      // broadcast reads
+      if (n <= L) {
+        // all appends of the warp-slot at once: the j-th finished env (lane order) writes ring position head + j, evicts what
+        // was there once the window is full, and sees the running sum of the appends up to and including its own
+        const bool mine = (dmask >> lane) & 1u;
+        const int j = __popc(dmask & ((1u << lane) - 1u));
+        int pos = head + j;
+        pos -= (pos >= L) ? L : 0;
+        const int ok = (int)((smask >> lane) & 1u);
+        const bool evicts = mine && (count + j >= L);
+        const int old = evicts ? (int)ps.window[pos] : 0;
+        const uint32_t emask = __ballot_sync(FULL, evicts && old != 0);
+        const uint32_t upto = (2u << lane) - 1u;      // lanes 0..lane
+        const int s_here = sum + __popc(smask & upto) - __popc(emask & upto);
+        promote = promote || __any_sync(FULL, mine && s_here >= kc.promote_successes);
+        __syncwarp();                                  // every eviction read precedes every write
+        if (mine) ps.window[pos] = (uint8_t)ok;
+        if (lane == 0) {
+          int h2 = head + n;
+          h2 -= (h2 >= L) ? L : 0;
+          ps.window_head = h2;
+          ps.window_count = min(count + n, L);
+          ps.window_sum = sum + __popc(smask) - __popc(emask);
+        }
+      } else {      // a window shorter than the number of episodes that ended in this warp-slot: one by one
+        bool pr = false;
+        if (lane == 0) {
+          int h2 = head, c2 = count, s2 = sum;
+          uint32_t m = dmask;
+          while (m) {
+            const int b = __ffs(m) - 1;
+            m &= m - 1u;
+            const int ok = (smask >> b) & 1u;
+            if (c2 == L) s2 -= ps.window[h2];
+            else c2 += 1;
+            ps.window[h2] = (uint8_t)ok;
+            s2 += ok;
+            h2 = (h2 + 1 == L) ? 0 : h2 + 1;
+            pr = pr || (s2 >= kc.promote_successes);
+          }
+          ps.window_head = h2; ps.window_count = c2; ps.window_sum = s2;
+        }
+        promote = promote || (__shfl_sync(FULL, (int)pr, 0) != 0);
+      }
+      if (lane == 0) {
+        ps.episodes_in_step += n;
+        ps.return_sum = __dadd_rn(ps.return_sum, sh.ep_log[i].ret);
+      }
+      __syncwarp();
+    }
+    if (lane == 0 && ne > 0) {
+      ps.last_code = sh.ep_log[ne - 1].last_code;
+      ps.last_steps = sh.ep_log[ne - 1].last_steps;
+      ps.last_cumulative = sh.ep_log[ne - 1].last_cum;
+      if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
+        if (promote) sh.promote = 1;
+        if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
+      }
+      sh.n_ep_log = 0;
+    }
+    __syncwarp();
   };
 
   // R13/R14 end of a curriculum step: transfer (PKG/double_q_learning.py:77-89), window handling, next working step,
@@ -312,15 +401,15 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       uint32_t ep_steps = 0;
       double ep_return = 0.0;
       Env e;
-      uint32_t c_hint = 0;
-      float a_hint = 0.0f;
+      int a = 0;
+      uint32_t sid = 0u, noise_w0 = 0u, noise_w1 = 0u;      // words z, w of the step draw feed the observation noise (off by default)
+      size_t trace_i = 0;
       if (valid) {
         env_unpack(cur_raw, e);
-        const uint32_t sid = e.sid;
+        sid = e.sid;
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
-        int a = sh.greedy[sid];
-        uint32_t noise_w0 = 0u, noise_w1 = 0u;      // words z, w of the step draw feed the observation noise (off by default)
+        a = sh.greedy[sid];
         if (w == 0 || (GENERIC && kk.noise_enabled)) {
 #ifdef DQL_PHILOX_INLINE_KEYS
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
@@ -333,7 +422,6 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
           }
           if (GENERIC) { noise_w0 = d.z; noise_w1 = d.w; }
         }
-        size_t trace_i = 0;
         if (TRACE) {
           trace_i = (size_t)k * (size_t)args.n_total + gi;
           if (args.trace.action_override) {
@@ -341,12 +429,23 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
             if (o >= 0) a = o;
           }
         }
-        // learning-rate hint for phase B: the LUT entry of the cell's count as it is NOW (an unsynchronised peek at the
-        // live table; phase B uses it only if the count is still the same, so the result does not depend on it).  Issued
-        // here, a whole phase A before the baton: a barrier waits for the thread's outstanding global loads too.
         cell = sid * 3u + (uint32_t)a;
-        c_hint = min(sh.cnt[cell], (uint32_t)(DQLB200_ALPHA_LUT - 1));
-        a_hint = __ldg(alpha_lut + c_hint);
+      }
+      // Same-cell groups of the warp-slot (lanes that update the same cell), formed as soon as the actions are known: the
+      // ordered commit applies a group's updates in lane order by handing the running value from member to member.
+      const uint32_t peers = __match_any_sync(FULL, valid ? cell : (0x80000000u | (uint32_t)lane));
+      const uint32_t lower = peers & ((1u << lane) - 1u);
+      const int rank = __popc(lower);                                   // position in the group
+      const int n_group = valid ? __popc(peers) : 0;
+      const int pred = lower ? (31 - __clz(lower)) : lane;              // the member before this lane
+      const bool is_last = valid && (peers >> lane) == 1u;              // no member above: stores the group's result
+      const int n_max = __reduce_max_sync(FULL, n_group);               // rounds of the commit (warp-uniform)
+      // learning-rate hint: the LUT entry for the count this update will PROBABLY see (the cell's count now + the lane's rank;
+      // an unsynchronised peek at the live table -- the commit uses it only if the count is still that, so the result does not
+      // depend on it).  Issued a whole phase A before the baton: the load is an L2 round trip.
+      const uint32_t c_hint = min(sh.cnt[cell] + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1));
+      const float a_hint = __ldg(alpha_lut + c_hint);
+      if (valid) {
         // R3: the set-point through the tables of the configuration (memoised float64 arithmetic of continuous_action, see
         // dqlb200_config.setpoint_*).  A fresh episode starts from 0 but keeps the old value for shaping (quirk Q11).
         const uint32_t sp_prev = e.sp_idx;
@@ -423,32 +522,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         e.cum_reward = __dadd_rn(e.cum_reward, r);
       }
       // ---------------- phase B: ordered commit (baton between warps) --------------------------
-      // The serialised section is the critical path of a global step (n_p / 32 links per population), so everything that
-      // does not read the live table happens BEFORE the baton arrives: same-cell groups, ranks, and the reductions over
-      // the finished episodes of this warp-slot.
+      // The serialised section is the critical path of a global step (n_p / 32 links per population, and every warp waits for
+      // its turn), so it holds nothing that can be done outside: groups, ranks and learning rates are known before the baton
+      // arrives, the finished episodes are only logged (the window is updated from the log at the end of the step).
       const uint32_t dmask = __ballot_sync(FULL, valid && done);
-      const uint32_t key = valid ? cell : (0x80000000u | (uint32_t)lane);
-      const uint32_t peers = __match_any_sync(FULL, key);
-      const int rank = __popc(peers & ((1u << lane) - 1u));
-      const int n_group = valid ? __popc(peers) : 0;
-#ifdef DQL_GATHER
-      // Variant (measured: the serialised section gets shorter, ncu stall_barrier 2.2 -> 1.3 per issue, but 48 more instructions
-      // per warp-slot make the step 6 % slower): the targets of the lane's group, in lane order, gathered BEFORE the baton.
-      constexpr int GROUP_FAST = 8;
-      float tj[GROUP_FAST];
-      uint32_t rem = valid ? peers : 0u;
-      int n_rounds = 0;            // warp-uniform: size of the largest group, capped
-#pragma unroll
-      for (int j = 0; j < GROUP_FAST; ++j) {
-        tj[j] = 0.0f;
-        if (j == n_rounds && __any_sync(FULL, rem != 0u)) {
-          tj[j] = __shfl_sync(FULL, target, rem ? (__ffs(rem) - 1) : lane);
-          rem &= rem - 1u;
-          n_rounds = j + 1;
-        }
-      }
-      const bool big_group = __any_sync(FULL, rem != 0u);
-#endif
       uint32_t smask = 0u;
       double ret = 0.0;
       if (dmask) {
@@ -460,104 +537,37 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       }
       if (WARPS > 1 && !(slot == 0 && warp == 0)) baton_wait<WARPS>(warp);
       {
-        float q = valid ? sh.qa[cell] : 0.0f;
-        const uint32_t c0 = valid ? sh.cnt[cell] : 0u;
-#ifdef DQL_GATHER
-        const bool saturated = c0 >= (uint32_t)(DQLB200_ALPHA_LUT - 1);      // alpha_min for every member, whatever its rank
-        // fast path: every group either sits on a saturated cell or is a single update whose hinted learning rate is still valid
-        const bool lane_fast = !valid || saturated || (n_group == 1 && c0 == c_hint);
-        if (!big_group && __all_sync(FULL, lane_fast)) {
-          const float alpha = saturated ? alpha_min : a_hint;                // R11: alpha of the pre-increment count
-#pragma unroll
-          for (int j = 0; j < GROUP_FAST; ++j) {
-            if (j < n_rounds) {                                              // uniform
-              if (j < n_group) q = fadd(q, fmul(alpha, fsub(tj[j], q)));     // q += alpha * (target - q), members in lane order
-            }
-          }
-        } else
-#endif
-        {
-          const uint32_t c_pre = c0 + (uint32_t)rank;                                  // R11: pre-increment count
-          float alpha = (c_pre == c_hint) ? a_hint : alpha_min;
-          if (c_pre != c_hint && c_pre < (uint32_t)(DQLB200_ALPHA_LUT - 1)) alpha = __ldg(alpha_lut + c_pre);
-          // the group's updates in lane order, two members per round (their four shuffles are issued together)
-          uint32_t rm = valid ? peers : 0u;
-          while (__any_sync(FULL, rm != 0u)) {
-            const uint32_t rm1 = rm & (rm - 1u);
-            const int src0 = rm ? (__ffs(rm) - 1) : lane, src1 = rm1 ? (__ffs(rm1) - 1) : lane;
-            const float a_0 = __shfl_sync(FULL, alpha, src0), t_0 = __shfl_sync(FULL, target, src0);
-            const float a_1 = __shfl_sync(FULL, alpha, src1), t_1 = __shfl_sync(FULL, target, src1);
-            if (rm) q = fadd(q, fmul(a_0, fsub(t_0, q)));       // q += alpha * (target - q)
-            if (rm1) q = fadd(q, fmul(a_1, fsub(t_1, q)));
-            rm = rm1 & (rm1 - 1u);
-          }
+        float q = sh.qa[cell];
+        const uint32_t c0 = sh.cnt[cell];
+        const uint32_t c_pre = min(c0 + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1));      // R11: pre-increment count
+        float alpha = a_hint;
+        if (c_pre != c_hint) alpha = __ldg(alpha_lut + c_pre);      // the cell was visited between the peek and the baton (rare below the LUT end)
+        // q += alpha * (target - q), members of a group in lane order: round r is member r's, which takes the running value from
+        // member r - 1 (one shuffle per round; singleton groups -- most lanes -- are done after round 0)
+        if (rank == 0) q = fadd(q, fmul(alpha, fsub(target, q)));
+        for (int r = 1; r < n_max; ++r) {
+          const float qp = __shfl_sync(FULL, q, pred);
+          if (rank == r) q = fadd(qp, fmul(alpha, fsub(target, qp)));
         }
-        if (valid && rank == 0) {
+        if (is_last) {
           sh.qa[cell] = q;
           sh.cnt[cell] = c0 + (uint32_t)n_group;
         }
-        // finished episodes, in env order: success window + promotion test after every append (R14), PKG/trainer.py:219-236
-        if (dmask) {
-          dqlb200_population_state& ps = sh.ps;
-          const int L = kc.window_len, n = __popc(dmask);
-          const int head = ps.window_head, count = ps.window_count, sum = ps.window_sum;      // broadcast reads
-          const long long eps = ps.episodes_in_step + n;
-          bool promote = false;
-          if (n <= L) {
-            // all appends of the warp-slot at once: the j-th finished env (lane order) writes ring position head + j, evicts what
-            // was there once the window is full, and sees the running sum of the appends up to and including its own
-            const bool mine = (dmask >> lane) & 1u;
-            const int j = __popc(dmask & ((1u << lane) - 1u));
-            int pos = head + j;
-            pos -= (pos >= L) ? L : 0;
-            const int ok = (int)((smask >> lane) & 1u);
-            const bool evicts = mine && (count + j >= L);
-            const int old = evicts ? (int)ps.window[pos] : 0;
-            const uint32_t emask = __ballot_sync(FULL, evicts && old != 0);
-            const uint32_t upto = (2u << lane) - 1u;      // lanes 0..lane
-            const int s_here = sum + __popc(smask & upto) - __popc(emask & upto);
-            promote = __any_sync(FULL, mine && s_here >= kc.promote_successes);
-            __syncwarp();                                  // every eviction read precedes every write
-            if (mine) ps.window[pos] = (uint8_t)ok;
-            if (lane == 0) {
-              int h2 = head + n;
-              h2 -= (h2 >= L) ? L : 0;
-              ps.window_head = h2;
-              ps.window_count = min(count + n, L);
-              ps.window_sum = sum + __popc(smask) - __popc(emask);
-            }
-          } else {      // a window shorter than the number of episodes that ended in this warp-slot: one by one
-            if (lane == 0) {
-              int h2 = head, c2 = count, s2 = sum;
-              uint32_t m = dmask;
-              while (m) {
-                const int b = __ffs(m) - 1;
-                m &= m - 1u;
-                const int ok = (smask >> b) & 1u;
-                if (c2 == L) s2 -= ps.window[h2];
-                else c2 += 1;
-                ps.window[h2] = (uint8_t)ok;
-                s2 += ok;
-                h2 = (h2 + 1 == L) ? 0 : h2 + 1;
-                promote = promote || (s2 >= kc.promote_successes);
-              }
-              ps.window_head = h2; ps.window_count = c2; ps.window_sum = s2;
-            }
-            promote = __shfl_sync(FULL, (int)promote, 0) != 0;
-          }
+        if (dmask) {      // finished episodes: append to the log, in commit order
+          if (sh.n_ep_log == EP_LOG) drain_episode_log();      // warp-uniform (every lane reads the same word)
+          const int idx = sh.n_ep_log;
           const int last = 31 - __clz(dmask);
-          if (lane == last) {          // the last finished episode in env order is what the trainer logs
-            ps.last_code = code;
-            ps.last_steps = (int)ep_steps;
-            ps.last_cumulative = ep_return;
-          }
+          __syncwarp();
           if (lane == 0) {
-            ps.episodes_in_step = eps;
-            if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
-              if (promote) sh.promote = 1;
-              if (eps >= kc.max_num_episodes) sh.advance = 1;
-            }
-            ps.return_sum = __dadd_rn(ps.return_sum, ret);
+            sh.ep_log[idx].dmask = dmask;
+            sh.ep_log[idx].smask = smask;
+            sh.ep_log[idx].ret = ret;
+            sh.n_ep_log = idx + 1;
+          }
+          if (lane == last) {          // the last finished episode in env order is what the trainer logs
+            sh.ep_log[idx].last_cum = ep_return;
+            sh.ep_log[idx].last_steps = (int)ep_steps;
+            sh.ep_log[idx].last_code = code;
           }
         }
       }
@@ -599,6 +609,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
     steps_done += (uint64_t)n_p;
+    if (warp == 0) drain_episode_log();      // the other warps build the next snapshot meanwhile
     if (tid == 0) {
       sh.ps.t = t + 1u;
       sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;

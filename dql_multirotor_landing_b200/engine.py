@@ -130,10 +130,13 @@ class Engine:
             return {k: v.cpu().numpy() for k, v in out.items()}
         return None
 
-    def train_host(self, k_steps: int, env_state_host: torch.Tensor, tables_host: torch.Tensor, pop_state_host: torch.Tensor):
-        """End-to-end call with pinned HOST buffers (copies in, k_steps, copies out, synchronises)."""
+    def train_host(self, k_steps: int, env_state_host: torch.Tensor, tables_host: torch.Tensor, pop_state_host: torch.Tensor,
+                   table_levels: int = 0):
+        """End-to-end call with pinned HOST buffers (copies in, k_steps, copies out, synchronises).  table_levels = L > 0: only
+        the table levels 0 .. L-1 travel (the caller's promise that no population is promoted beyond them inside the call; the
+        library checks it afterwards); 0 = every level."""
         _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
-                                               pop_state_host.data_ptr(), self._stream()))
+                                               pop_state_host.data_ptr(), int(table_levels), self._stream()))
 
     # ------------------------------------------------------------------------------------------
     # replica-merge mode: R consecutive populations are replicas of one agent (more envs than one CTA holds)

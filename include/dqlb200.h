@@ -285,11 +285,17 @@ int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream);
  * trace may be NULL. */
 int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* stream);
 
-/* Same with HOST buffers: copies env_state/tables/pop_state in, runs k_steps, copies them back and
- * synchronises.  This is the end-to-end call bench.py times as `e2e`.  It does not carry the per-env extension state:
- * configurations with accel_mode != 0 or dynamics_model != 0 are refused (DQLB200_ERR_ARG), use dqlb200_train. */
+/* Same with HOST buffers (pinned): copies env_state / tables / pop_state in, runs k_steps, copies them back and synchronises.
+ * This is the end-to-end call bench.py times as `e2e`.  The call is pipelined over up to 16 chunks of populations on internal
+ * streams (copy-in of chunk c+1 and copy-out of chunk c-1 overlap the training of chunk c).
+ * table_levels: 0 = transfer every table level; L > 0 = only levels 0 .. L-1 of every table row travel (both directions, plus
+ * -- in reference transfer mode -- the last level on the way in for populations at step 0, which quirk Q7 reads): the caller's
+ * promise that no population needs more (working step w touches levels 0 .. w, a promotion inside the call w + 1).  Refused
+ * up front when a working step already exceeds it, reported (DQLB200_ERR_STATE) when a promotion inside the call broke it.
+ * Does not carry the per-env extension state: configurations with accel_mode != 0 or dynamics_model != 0 are refused
+ * (DQLB200_ERR_ARG), use dqlb200_train on bound device buffers. */
 int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host,
-                       void* pop_state_host, void* stream);
+                       void* pop_state_host, int table_levels, void* stream);
 
 /* Replaces: scripts/simulation.py:48-63 (+ SimulationLandingEnv.reset/step, SimulationMdp):
  * n_episodes greedy episodes of population `population`'s policy, episode i uses reset draws

@@ -739,6 +739,42 @@ def test_train_host_equals_device_resident_training(P):
     assert int(a.population_state()["working_step"].max()) >= 1
 
 
+def test_train_host_with_partial_table_levels():
+    """table_levels = L: only levels 0 .. L-1 of the tables travel.  Without promotions the result equals the full transfer
+    bit for bit (the rows that stay behind on the host are untouched); a working step beyond L is refused up front, a promotion
+    beyond L inside the call is reported."""
+    from dql_multirotor_landing_b200 import _ffi
+    P = 5
+    a = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=NO_PROMOTION)
+    b = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=NO_PROMOTION)
+    rng = np.random.default_rng(0)
+    t0 = rng.standard_normal((P, 3, 2835)).astype(np.float32).view(np.int32)      # non-zero rows at every level
+    t0[:, 2] = rng.integers(0, 2000, size=(P, 2835))
+    for e in (a, b):
+        e.tables.copy_(torch.from_numpy(t0).to(e.device))
+        e.reset(0)
+    env_h, tab_h, ps_h = b.env_state.cpu().pin_memory(), b.tables.cpu().pin_memory(), b.pop_state.cpu().pin_memory()
+    b.env_state.zero_(); b.tables.zero_(); b.pop_state.zero_()
+    for k in (30, 1, 50):
+        a.train(k)
+        b.train_host(k, env_h, tab_h, ps_h, table_levels=2)
+    torch.cuda.synchronize()
+    assert torch.equal(a.env_state.cpu(), env_h) and torch.equal(a.tables.cpu(), tab_h) and torch.equal(a.pop_state.cpu(), ps_h)
+    assert not np.array_equal(tab_h.numpy()[:, 0, :567], t0[:, 0, :567])                # level 0 was trained ...
+    assert np.array_equal(tab_h.numpy()[:, :, 2 * 567:], t0[:, :, 2 * 567:])             # ... the levels above L never moved
+    # promotions inside the call beyond the transferred levels are reported, a working step beyond them is refused
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=60)
+    c = _engine(2, 70, threads_per_block=64, seeds=[1, 2], tp=kw)
+    c.reset(0)
+    env_h, tab_h, ps_h = c.env_state.cpu().pin_memory(), c.tables.cpu().pin_memory(), c.pop_state.cpu().pin_memory()
+    with pytest.raises(_ffi.Dqlb200Error, match="promoted beyond the transferred table levels"):
+        for _ in range(20):
+            c.train_host(64, env_h, tab_h, ps_h, table_levels=1)
+    assert int(np.frombuffer(ps_h.numpy().tobytes(), dtype=c.population_state().dtype)["working_step"].max()) >= 1
+    with pytest.raises(_ffi.Dqlb200Error, match="smaller than the live levels"):
+        c.train_host(1, env_h, tab_h, ps_h, table_levels=1)
+
+
 @pytest.mark.parametrize("case", ["reference", "xy", "eight", "ywrong"])
 def test_two_axis_greedy_evaluation(golden_dir, case):
     """eval2d_kernel against (a) the fixture the unmodified reference SimulationMdp produced on the two-axis
