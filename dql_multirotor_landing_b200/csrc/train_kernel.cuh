@@ -46,14 +46,11 @@ constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it ru
 
 constexpr int STATES = DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL;   // 945
 
-// One warp-slot with finished episodes: which lanes finished / succeeded, the fixed-tree sum of their returns, and the last
-// finished env's episode (what the trainer logs).
-struct EpisodeEntry {
-  uint32_t dmask, smask;
-  double ret, last_cum;
-  int last_steps, last_code;
-};
-constexpr int EP_LOG = 32;
+// Finished episodes of a global step, logged by the ordered commit and folded into the trainer state at the end of the step:
+// the success flags of the finished episodes in commit (= env) order, one byte each, and per warp-slot the fixed-tree float64 sum
+// of its finished episodes' returns (added to the running sum one after the other, in commit order).
+constexpr int EP_OK_CAP = 256;     // success flags buffered before a drain (a warp-slot appends at most 32)
+constexpr int EP_RET_CAP = 64;     // warp-slots with finished episodes buffered before a drain
 
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
 // loop, L1-resident): that keeps the footprint at ~37 KB so that six CTAs fit on one SM.
@@ -71,11 +68,12 @@ struct Shared {
   uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
   int promote, advance, do_advance;
   uint4 philox_keys[5];   // round keys of the population's Philox key (philox_round_keys)
-  // Finished episodes of the warp-slots committed so far, in commit (= env) order: the serialised section only appends an
-  // entry; success window, promotion test and logged sums are brought up to date from the log at the end of the global step
-  // (or when the log is full), off the critical path of the baton.
-  EpisodeEntry ep_log[EP_LOG];
-  int n_ep_log;
+  // Finished episodes of the warp-slots committed so far (see EP_OK_CAP): the serialised section only appends; success window,
+  // promotion test and logged sums are brought up to date at the end of the global step (or when a buffer is full), off the
+  // critical path of the baton.
+  double ep_ret[EP_RET_CAP];
+  uint8_t ep_ok[EP_OK_CAP];
+  int n_ep_ok, n_ep_ret;
   // followed by (dynamic): uint2 sp_next[n_setpoints][3]; uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]
 };
 
@@ -154,7 +152,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
       for (int i = 0; i < 9; ++i) { sh.hist[i] = 0ull; sh.step_hist[i] = 0u; }
       sh.promote = sh.advance = sh.do_advance = 0;
-      sh.n_ep_log = 0;
+      sh.n_ep_ok = sh.n_ep_ret = 0;
       sh.cuts = kc.cuts[w_start];
     }
     if (tid < 5) sh.reward[tid] = kc.reward[tid];
@@ -197,22 +195,27 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   // holder when the log is full, warp 0 between the two barriers at the end of a global step.
   auto drain_episode_log = [&]() {
     dqlb200_population_state& ps = sh.ps;
-    const int ne = sh.n_ep_log;
+    const int n_fin = sh.n_ep_ok, n_ret = sh.n_ep_ret;
+    if (n_fin == 0) return;      // warp-uniform
     const int L = kc.window_len;
     bool promote = false;
-    for (int i = 0; i < ne; ++i) {
-      const uint32_t dmask = sh.ep_log[i].dmask, smask = sh.ep_log[i].smask;
-      const int n = __popc(dmask);
+    if (lane == 31) {      // the float64 sum of the returns, one warp-slot after the other (a lane the window code below does not single out)
+      double s = ps.return_sum;
+      for (int i = 0; i < n_ret; ++i) s = __dadd_rn(s, sh.ep_ret[i]);
+      ps.return_sum = s;
+    }
+    for (int base = 0; base < n_fin; base += 32) {
+      const int n = min(32, n_fin - base);
+      const bool mine = lane < n;
+      const int ok = mine ? (int)sh.ep_ok[base + lane] : 0;
+      const uint32_t smask = __ballot_sync(FULL, ok != 0);
       const int head = ps.window_head, count = ps.window_count, sum = ps.window_sum;      // broadcast reads
       if (n <= L) {
-        // all appends of the warp-slot at once: the j-th finished env (lane order) writes ring position head + j, evicts what
-        // was there once the window is full, and sees the running sum of the appends up to and including its own
-        const bool mine = (dmask >> lane) & 1u;
-        const int j = __popc(dmask & ((1u << lane) - 1u));
-        int pos = head + j;
+        // 32 appends at once: the j-th finished episode writes ring position head + j, evicts what was there once the window is
+        // full, and sees the running sum of the appends up to and including its own
+        int pos = head + lane;
         pos -= (pos >= L) ? L : 0;
-        const int ok = (int)((smask >> lane) & 1u);
-        const bool evicts = mine && (count + j >= L);
+        const bool evicts = mine && (count + lane >= L);
         const int old = evicts ? (int)ps.window[pos] : 0;
         const uint32_t emask = __ballot_sync(FULL, evicts && old != 0);
         const uint32_t upto = (2u << lane) - 1u;      // lanes 0..lane
@@ -227,19 +230,16 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
           ps.window_count = min(count + n, L);
           ps.window_sum = sum + __popc(smask) - __popc(emask);
         }
-      } else {      // a window shorter than the number of episodes that ended in this warp-slot: one by one
+      } else {      // a window shorter than the chunk: one by one
         bool pr = false;
         if (lane == 0) {
           int h2 = head, c2 = count, s2 = sum;
-          uint32_t m = dmask;
-          while (m) {
-            const int b = __ffs(m) - 1;
-            m &= m - 1u;
-            const int ok = (smask >> b) & 1u;
+          for (int b = 0; b < n; ++b) {
+            const int okb = (smask >> b) & 1u;
             if (c2 == L) s2 -= ps.window[h2];
             else c2 += 1;
-            ps.window[h2] = (uint8_t)ok;
-            s2 += ok;
+            ps.window[h2] = (uint8_t)okb;
+            s2 += okb;
             h2 = (h2 + 1 == L) ? 0 : h2 + 1;
             pr = pr || (s2 >= kc.promote_successes);
           }
@@ -247,21 +247,15 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
         promote = promote || (__shfl_sync(FULL, (int)pr, 0) != 0);
       }
-      if (lane == 0) {
-        ps.episodes_in_step += n;
-        ps.return_sum = __dadd_rn(ps.return_sum, sh.ep_log[i].ret);
-      }
       __syncwarp();
     }
-    if (lane == 0 && ne > 0) {
-      ps.last_code = sh.ep_log[ne - 1].last_code;
-      ps.last_steps = sh.ep_log[ne - 1].last_steps;
-      ps.last_cumulative = sh.ep_log[ne - 1].last_cum;
+    if (lane == 0) {
+      ps.episodes_in_step += n_fin;
       if (kc.replicas == 1) {      // replicas are promoted together by replica_merge_kernel
         if (promote) sh.promote = 1;
         if (ps.episodes_in_step >= kc.max_num_episodes) sh.advance = 1;
       }
-      sh.n_ep_log = 0;
+      sh.n_ep_ok = sh.n_ep_ret = 0;
     }
     __syncwarp();
   };
@@ -434,33 +428,27 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       // Same-cell groups of the warp-slot (lanes that update the same cell), formed as soon as the actions are known: the
       // ordered commit applies a group's updates in lane order by handing the running value from member to member.
       const uint32_t peers = __match_any_sync(FULL, valid ? cell : (0x80000000u | (uint32_t)lane));
-      const uint32_t lower = peers & ((1u << lane) - 1u);
-      const int rank = __popc(lower);                                   // position in the group
-      const int n_group = valid ? __popc(peers) : 0;
-      const int pred = lower ? (31 - __clz(lower)) : lane;              // the member before this lane
-      const bool is_last = valid && (peers >> lane) == 1u;              // no member above: stores the group's result
-      const int n_max = __reduce_max_sync(FULL, n_group);               // rounds of the commit (warp-uniform)
-      // learning-rate hint: the LUT entry for the count this update will PROBABLY see (the cell's count now + the lane's rank;
-      // an unsynchronised peek at the live table -- the commit uses it only if the count is still that, so the result does not
-      // depend on it).  Issued a whole phase A before the baton: the load is an L2 round trip.
-      const uint32_t c_hint = min(sh.cnt[cell] + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1));
-      const float a_hint = __ldg(alpha_lut + c_hint);
+      uint2 spn = make_uint2(0u, 0u);
+      double r_theta0 = 0.0;
+      Obs o = {};
+      DState ds = {};
+      uint32_t sid2 = 0u, step_count = 0u, cc = 0u;
       if (valid) {
         // R3: the set-point through the tables of the configuration (memoised float64 arithmetic of continuous_action, see
         // dqlb200_config.setpoint_*).  A fresh episode starts from 0 but keeps the old value for shaping (quirk Q11).
         const uint32_t sp_prev = e.sp_idx;
-        const uint2 spn = sp_next[(e.fresh ? sp_zero : sp_prev) * 3u + (uint32_t)a];
+        spn = sp_next[(e.fresh ? sp_zero : sp_prev) * 3u + (uint32_t)a];
         const float sp = __uint_as_float(spn.y);
         // set-point part of the reward (without the level factor): a global read far ahead of its use
-        const double r_theta0 = __ldg(args.env.sp_rtheta + ((e.fresh ? (uint32_t)DQLB200_MAX_SETPOINTS : 0u) + sp_prev) * 3u + (uint32_t)a);
+        r_theta0 = __ldg(args.env.sp_rtheta + ((e.fresh ? (uint32_t)DQLB200_MAX_SETPOINTS : 0u) + sp_prev) * 3u + (uint32_t)a);
         // R4
         dyn_advance(kk, pp, e.b, sp, filt ? &kf : nullptr, so ? &ex : nullptr, kk.vz_train);
-        const uint32_t step_count = e.step_count + 1u;
-        Obs o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
+        step_count = e.step_count + 1u;
+        o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
         if (GENERIC && kk.noise_enabled) add_observation_noise(kk, o, noise_w0, noise_w1);
         // R5
-        const DState ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
-        const uint32_t sid2 = (uint32_t)ds.id();
+        ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
+        sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
         // The priority chain of PKG/mdp.py:359-425 as selects (the ladder of branches diverges inside a warp).
         const bool t_fx = !(o.rel_p >= kk.fz_lo) || (o.rel_p >= kk.fz_hi);
@@ -468,7 +456,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         const bool t_time = (int)step_count >= kk.timeout_steps;
         const bool goal_bins = !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
         const bool at_level = sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;   // previous level == w (it never exceeds w)
-        const uint32_t cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
+        cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
         if (goal_bins && at_level) code = ((int)cc >= kk.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
         code = t_time ? DQLB200_TERMINAL_TIMEOUT : code;
@@ -480,6 +468,20 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         success = code == DQLB200_TERMINAL_SUCCESS;
         if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
           atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
+      }
+      const uint32_t lower = peers & ((1u << lane) - 1u);
+      const int rank = __popc(lower);                                   // position in the group
+      const int n_group = valid ? __popc(peers) : 0;
+      const int pred = lower ? (31 - __clz(lower)) : lane;              // the member before this lane
+      const bool is_last = valid && (peers >> lane) == 1u;              // no member above: stores the group's result
+      const int n_max = __reduce_max_sync(FULL, n_group);               // rounds of the commit (warp-uniform)
+      // (the match result is consumed here, a dynamics step after it was issued: its latency is a few hundred cycles)
+      // learning-rate hint: the LUT entry for the count this update will PROBABLY see (the cell's count now + the lane's rank;
+      // an unsynchronised peek at the live table -- the commit uses it only if the count is still that, so the result does not
+      // depend on it).  Issued a reward evaluation before the baton: the load is an L1/L2 round trip.
+      const uint32_t c_hint = min(sh.cnt[cell] + (uint32_t)rank, (uint32_t)(DQLB200_ALPHA_LUT - 1));
+      const float a_hint = __ldg(alpha_lut + c_hint);
+      if (valid) {
         // R7 (float64, reference operation order; level-dependent constants from the host)
         const double phi_p = shaping(kk.w_p, o.rel_p, kk.p_max, kk.rcp_p_max, kk.clip_p_f, GENERIC);
         const double phi_v = shaping(kk.w_v, o.rel_v, kk.v_max, kk.rcp_v_max, kk.clip_v_f, GENERIC);
@@ -554,20 +556,20 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
           sh.cnt[cell] = c0 + (uint32_t)n_group;
         }
         if (dmask) {      // finished episodes: append to the log, in commit order
-          if (sh.n_ep_log == EP_LOG) drain_episode_log();      // warp-uniform (every lane reads the same word)
-          const int idx = sh.n_ep_log;
+          if (sh.n_ep_ret == EP_RET_CAP || sh.n_ep_ok > EP_OK_CAP - 32) drain_episode_log();      // warp-uniform (every lane reads the same words)
+          const int idx = sh.n_ep_ret, base = sh.n_ep_ok;
           const int last = 31 - __clz(dmask);
           __syncwarp();
+          if (valid && done) sh.ep_ok[base + __popc(dmask & ((1u << lane) - 1u))] = (uint8_t)success;
           if (lane == 0) {
-            sh.ep_log[idx].dmask = dmask;
-            sh.ep_log[idx].smask = smask;
-            sh.ep_log[idx].ret = ret;
-            sh.n_ep_log = idx + 1;
+            sh.ep_ret[idx] = ret;
+            sh.n_ep_ret = idx + 1;
+            sh.n_ep_ok = base + __popc(dmask);
           }
           if (lane == last) {          // the last finished episode in env order is what the trainer logs
-            sh.ep_log[idx].last_cum = ep_return;
-            sh.ep_log[idx].last_steps = (int)ep_steps;
-            sh.ep_log[idx].last_code = code;
+            sh.ps.last_cumulative = ep_return;
+            sh.ps.last_steps = (int)ep_steps;
+            sh.ps.last_code = code;
           }
         }
       }
