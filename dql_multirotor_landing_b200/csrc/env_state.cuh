@@ -9,6 +9,13 @@ namespace dql {
 constexpr int CELLS = DQLB200_MAX_CELLS;
 constexpr uint32_t FULL = 0xFFFFFFFFu;
 
+// 16-byte read through a shared-state-space address
+__device__ __forceinline__ uint4 lds128(unsigned addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+
 // env-state word C.x layout
 constexpr uint32_t SID_BITS = 10, STEP_SHIFT = 10, STEP_BITS = 9, CC_SHIFT = 19, CC_BITS = 5;
 constexpr uint32_t STICKY_BIT = 1u << 24, FRESH_BIT = 1u << 25, BP_SHIFT = 26;   // bits 26-27: position bin of `sid`
@@ -80,12 +87,12 @@ __device__ __forceinline__ void ext_prefetch_async(const EnvPtrs& p, size_t i, u
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ Kf kf_take(const uint4* stage, int nt, int tid) {
-  const uint4 v = stage[3 * nt + tid];
+__device__ __forceinline__ Kf kf_take(unsigned stage_addr, int nt) {
+  const uint4 v = lds128(stage_addr + 48u * nt);
   return Kf{__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), v.w};
 }
-__device__ __forceinline__ Ext ext_take(const uint4* stage, int nt, int tid) {
-  const uint4 u = stage[4 * nt + tid], v = stage[5 * nt + tid];
+__device__ __forceinline__ Ext ext_take(unsigned stage_addr, int nt) {
+  const uint4 u = lds128(stage_addr + 64u * nt), v = lds128(stage_addr + 80u * nt);
   return Ext{__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w),
              __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
 }
@@ -95,11 +102,14 @@ struct EnvRaw {
   float4 A;
   uint4 B, C;
 };
+// The env state streams: it is read once and written once per global step and never re-read through L1, so every access is
+// L2-only (ld/st.global.cg).  What stays in the small L1 next to 228 KB of shared memory are the look-up tables all CTAs of an SM
+// share (epsilon thresholds, learning rates, set-point rewards): ncu showed a 31 % L1 hit rate for them with default stores.
 __device__ __forceinline__ EnvRaw env_fetch(const unsigned char* pa) {
   EnvRaw r;
-  r.A = *reinterpret_cast<const float4*>(pa);
-  r.B = *reinterpret_cast<const uint4*>(pa + 512);
-  r.C = *reinterpret_cast<const uint4*>(pa + 1024);
+  r.A = __ldcg(reinterpret_cast<const float4*>(pa));
+  r.B = __ldcg(reinterpret_cast<const uint4*>(pa + 512));
+  r.C = __ldcg(reinterpret_cast<const uint4*>(pa + 1024));
   return r;
 }
 // Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
@@ -113,13 +123,15 @@ __device__ __forceinline__ void env_prefetch_async(const unsigned char* pa, unsi
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(pa + 1024) : "memory");
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
-__device__ __forceinline__ EnvRaw env_prefetch_take(const uint4* stage, int nt, int tid) {
+// stage_addr as above: the staging slots are read through their shared-state-space address (a generic pointer into the dynamic
+// part of shared memory made the compiler rebuild the window base -- S2UR SR_CgaCtaId + address arithmetic -- in every slot)
+__device__ __forceinline__ EnvRaw env_prefetch_take(unsigned stage_addr, int nt) {
   asm volatile("cp.async.wait_group 0;" ::: "memory");
   EnvRaw r;
-  const uint4 a = stage[tid];
+  const uint4 a = lds128(stage_addr);
   r.A = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-  r.B = stage[nt + tid];
-  r.C = stage[2 * nt + tid];
+  r.B = lds128(stage_addr + 16u * nt);
+  r.C = lds128(stage_addr + 32u * nt);
   return r;
 }
 
@@ -141,12 +153,12 @@ __device__ __forceinline__ void env_unpack(const EnvRaw& r, Env& e) {
   e.cum_reward = __hiloint2double((int)Cw.w, (int)Cw.z);
 }
 __device__ __forceinline__ void env_store(unsigned char* pa, const Env& e) {
-  *reinterpret_cast<float4*>(pa) = make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase));
-  *reinterpret_cast<uint4*>(pa + 512) = make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v));
+  __stcg(reinterpret_cast<float4*>(pa), make_float4(e.b.x_d, e.b.v_d, e.b.theta, __uint_as_float(e.b.phase)));
+  __stcg(reinterpret_cast<uint4*>(pa + 512), make_uint4(e.sp_idx, 0u, __float_as_uint(e.prev_rel_p), __float_as_uint(e.prev_rel_v)));
   const uint32_t packed = e.sid | (e.step_count << STEP_SHIFT) | (e.curriculum_check << CC_SHIFT) |
                           (e.sticky_success ? STICKY_BIT : 0u) | (e.fresh ? FRESH_BIT : 0u) | (e.bp << BP_SHIFT);
-  *reinterpret_cast<uint4*>(pa + 1024) = make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
-                                                    (uint32_t)__double2hiint(e.cum_reward));
+  __stcg(reinterpret_cast<uint4*>(pa + 1024), make_uint4(packed, e.episode, (uint32_t)__double2loint(e.cum_reward),
+                                                          (uint32_t)__double2hiint(e.cum_reward)));
 }
 // by global env index (kernels off the hot path)
 __device__ __forceinline__ void env_load(const EnvPtrs& p, size_t i, Env& e) { env_unpack(env_fetch(env_addr(p, i)), e); }

@@ -1,6 +1,8 @@
 // train_kernel.cuh -- the fused training kernel (one CTA per population): phase A per env, ordered commit, auto-reset, curriculum
 // Part of libdqlb200 (see dqlb200.cu for the kernel inventory and the C-ABI).
 #pragma once
+#include <type_traits>
+
 #include "env_state.cuh"
 
 namespace dql {
@@ -42,25 +44,32 @@ struct TrainArgs {
   long long n_total;
 };
 
-constexpr int RESET_QUEUE = 128;   // finished envs a warp collects before it runs the batched reset pass
+constexpr int RESET_QUEUE = 64;    // finished envs a warp collects before it runs the batched reset pass (flushed early beyond 32)
 
 constexpr int STATES = DQLB200_MAX_CURRICULUM * DQLB200_STATES_PER_LEVEL;   // 945
 
 // Finished episodes of a global step, logged by the ordered commit and folded into the trainer state at the end of the step:
 // the success flags of the finished episodes in commit (= env) order, one byte each, and per warp-slot the fixed-tree float64 sum
 // of its finished episodes' returns (added to the running sum one after the other, in commit order).
-constexpr int EP_OK_CAP = 256;     // success flags buffered before a drain (a warp-slot appends at most 32)
-constexpr int EP_RET_CAP = 64;     // warp-slots with finished episodes buffered before a drain
+constexpr int EP_OK_CAP = 128;     // success flags buffered before a drain (a warp-slot appends at most 32)
+constexpr int EP_RET_CAP = 32;     // warp-slots with finished episodes buffered before a drain
 
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
 // loop, L1-resident): that keeps the footprint at ~37 KB so that six CTAs fit on one SM.
 struct Shared {
+#ifdef DQL_HACK_LEVELS      // occupancy experiment only (tools/perf_probe.py at working step 0): tables of DQL_HACK_LEVELS levels
+  float qa[DQL_HACK_LEVELS * DQLB200_CELLS_PER_LEVEL];
+  uint32_t cnt[DQL_HACK_LEVELS * DQLB200_CELLS_PER_LEVEL];
+  float qmax[DQL_HACK_LEVELS * DQLB200_STATES_PER_LEVEL];
+  uint8_t greedy[DQL_HACK_LEVELS * DQLB200_STATES_PER_LEVEL + 3];
+#else
   float qa[CELLS];        // live table A
   uint32_t cnt[CELLS];    // state_action_counter
   // Snapshot of the start of the global step.  Phase A reads the tables only through two per-STATE quantities, so the
   // snapshot is those two instead of a copy of Q_a: the greedy action argmax_a (Q_a+Q_b)/2 (R9) and max_a Q_a (R12).
   float qmax[STATES];
   uint8_t greedy[STATES + 3];
+#endif
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   dqlb200_population_state ps;
@@ -74,12 +83,21 @@ struct Shared {
   double ep_ret[EP_RET_CAP];
   uint8_t ep_ok[EP_OK_CAP];
   int n_ep_ok, n_ep_ret;
-  // followed by (dynamic): uint2 sp_next[n_setpoints][3]; uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]
+  // followed by (dynamic): uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]; SpEntry sp_tab[n_setpoints][3]
 };
 
 // dynamic shared memory of a launch: Shared + the set-point table + the reset queues + the cp.async staging slots of the env
 // (and, for the extended / trace instances, extension-state) prefetch
-__host__ __device__ constexpr size_t train_sp_bytes(int n_setpoints) { return ((size_t)n_setpoints * 3 * sizeof(uint2) + 15) & ~size_t(15); }
+// The set-point tables of the configuration in shared memory, one entry per (set-point index, action): the integrator's next index
+// and its float32 value (R3), and the set-point term of the reward for an ordinary step and for the first step of an episode
+// (dqlb200_config.setpoint_rtheta[0 / 1]).  In global memory the reward term was an L2 round trip per env-step: the L1 next to
+// 228 KB of shared memory does not hold the tables (ncu: 26 % hit rate).
+struct SpEntry {
+  uint32_t next;
+  float value;
+  double r_step, r_first;
+};
+__host__ __device__ constexpr size_t train_sp_bytes(int n_setpoints) { return ((size_t)n_setpoints * 3 * sizeof(SpEntry) + 15) & ~size_t(15); }
 __host__ __device__ constexpr size_t train_smem_bytes(int threads, bool extended, int n_setpoints) {
   return ((sizeof(Shared) + 15) & ~size_t(15)) + train_sp_bytes(n_setpoints) + (size_t)(threads / 32) * RESET_QUEUE * sizeof(uint16_t) +
          (size_t)(extended ? 6 : 3) * threads * 16;
@@ -119,11 +137,13 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   const int pop = blockIdx.x + args.pop_offset;
   const int n_p = kc.envs_per_population;
   const int n_slots = (n_p + NT - 1) / NT;
+  // dynamic part: everything of run-time size (the set-point table) comes LAST, so that every base is a compile-time offset
   unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~size_t(15));
-  uint2* sp_next = reinterpret_cast<uint2*>(dyn);                     // [n_setpoints][3] {next index, float32 set-point}
-  dyn += train_sp_bytes(args.env.n_sp);
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(dyn) + (size_t)warp * RESET_QUEUE;
-  uint4* stage = reinterpret_cast<uint4*>(dyn + (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t));   // [3][NT] (+ [3][NT] extension-state slots in the extended variant)
+  dyn += (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t);
+  uint4* stage = reinterpret_cast<uint4*>(dyn);      // [3][NT] (+ [3][NT] extension-state slots in the extended / trace instances)
+  dyn += (size_t)((TRACE || EXT) ? 6 : 3) * NT * 16;
+  SpEntry* sp_tab = reinterpret_cast<SpEntry*>(dyn);     // [n_setpoints][3]
   const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage + tid);
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
@@ -157,7 +177,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     }
     if (tid < 5) sh.reward[tid] = kc.reward[tid];
     if (tid == 31) philox_round_keys(pp.seed_lo, pp.seed_hi, sh.philox_keys);
-    for (int i = tid; i < args.env.n_sp * 3; i += NT) sp_next[i] = args.env.sp_next[i];
+    for (int i = tid; i < args.env.n_sp * 3; i += NT) {
+      const uint2 nx = args.env.sp_next[i];
+      sp_tab[i] = SpEntry{nx.x, __uint_as_float(nx.y), args.env.sp_rtheta[i], args.env.sp_rtheta[DQLB200_MAX_SETPOINTS * 3 + i]};
+    }
     const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
     for (int i = tid; i < live; i += NT) {
       sh.qa[i] = __uint_as_float(gt[i]);
@@ -178,9 +201,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   auto build_snapshot = [&](int w) {
     for (int st = tid; st < (w + 1) * DQLB200_STATES_PER_LEVEL; st += NT) {
       const float q0 = sh.qa[st * 3 + 0], q1 = sh.qa[st * 3 + 1], q2 = sh.qa[st * 3 + 2];
-      const float p0 = fmul(fadd(q0, gqb[st * 3 + 0]), 0.5f);
-      const float p1 = fmul(fadd(q1, gqb[st * 3 + 1]), 0.5f);
-      const float p2 = fmul(fadd(q2, gqb[st * 3 + 2]), 0.5f);
+      const float p0 = fmul(fadd(q0, __ldcg(gqb + st * 3 + 0)), 0.5f);
+      const float p1 = fmul(fadd(q1, __ldcg(gqb + st * 3 + 1)), 0.5f);
+      const float p2 = fmul(fadd(q2, __ldcg(gqb + st * 3 + 2)), 0.5f);
       int a = 0;
       float best = p0;
       if (p1 > best) { best = p1; a = 1; }
@@ -322,7 +345,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
       }
       // every env was just restarted: the slot-0 prefetch in flight is stale
-      (void)env_prefetch_take(stage, NT, tid);
+      (void)env_prefetch_take(stage_addr, NT);
       env_prefetch_async(p_env0, stage_addr, NT);
       if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
       build_snapshot(w + 1);
@@ -371,18 +394,25 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       n_queued = 0;
     };
 
+    // The slot loop, specialised at compile time for working step 0 (W0): there the only level is 0, so the level search and the
+    // level tests vanish and the bin cuts / reward constants of level 0 are read from the kernel parameters (constant bank ->
+    // uniform registers, loop-invariant) instead of shared memory; the Philox draw is unconditional.  Curriculum step 0 is
+    // where training spends most of its time (and what the benchmark measures); only the production instances pay the code size.
+    auto slot_loop = [&](auto w0_tag) {
+    constexpr bool W0 = decltype(w0_tag)::value;
+    bool bad_obs = false;
     unsigned char* p_env = env_addr(args.env, pop, tid);      // running pointer to the A vector of this thread's env: tile = slot * WARPS + warp
     for (int slot = 0; slot < n_slots; ++slot) {
       const int env_i = slot * NT + tid;
       const bool valid = FULL_SLOTS || env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
-      const EnvRaw cur_raw = env_prefetch_take(stage, NT, tid);
+      const EnvRaw cur_raw = env_prefetch_take(stage_addr, NT);
       unsigned char* const p_cur = p_env;
       p_env += WARPS * ENV_TILE_BYTES;
       Kf kf;
       Ext ex;
-      if (filt) kf = kf_take(stage, NT, tid);
-      if (so) ex = ext_take(stage, NT, tid);
+      if (filt) kf = kf_take(stage_addr, NT);
+      if (so) ex = ext_take(stage_addr, NT);
       if (FULL_SLOTS ? (slot + 1 < n_slots) : (env_i + NT < n_p)) {      // in flight during this slot
         env_prefetch_async(p_env, stage_addr, NT);
         if (EXT) ext_prefetch_async(args.env, gi + NT, stage_addr, NT, filt, so);
@@ -404,13 +434,13 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         // R9/R10: epsilon-greedy on the snapshot; both draws are always consumed (quirk Q4).  With eps = 0
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
         a = sh.greedy[sid];
-        if (w == 0 || (GENERIC && kk.noise_enabled)) {
+        if (W0 || w == 0 || (GENERIC && kk.noise_enabled)) {
 #ifdef DQL_PHILOX_INLINE_KEYS
           const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
 #else
           const uint4 d = philox4x32_10_keyed(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), sh.philox_keys);
 #endif
-          if (w == 0) {
+          if (W0 || w == 0) {
             const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
             if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
           }
@@ -427,7 +457,13 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       }
       // Same-cell groups of the warp-slot (lanes that update the same cell), formed as soon as the actions are known: the
       // ordered commit applies a group's updates in lane order by handing the running value from member to member.
-      const uint32_t peers = __match_any_sync(FULL, valid ? cell : (0x80000000u | (uint32_t)lane));
+      // (volatile asm: the compiler otherwise sinks the match down to its first consumer, where its latency -- a few hundred
+      // cycles -- is exposed; issued here it is covered by the dynamics)
+      uint32_t peers;
+      asm volatile("match.any.sync.b32 %0, %1, 0xffffffff;" : "=r"(peers) : "r"(valid ? cell : (0x80000000u | (uint32_t)lane)) : "memory");
+#ifdef DQL_MATCH_ANCHOR
+      __syncwarp();
+#endif
       uint2 spn = make_uint2(0u, 0u);
       double r_theta0 = 0.0;
       Obs o = {};
@@ -437,17 +473,20 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         // R3: the set-point through the tables of the configuration (memoised float64 arithmetic of continuous_action, see
         // dqlb200_config.setpoint_*).  A fresh episode starts from 0 but keeps the old value for shaping (quirk Q11).
         const uint32_t sp_prev = e.sp_idx;
-        spn = sp_next[(e.fresh ? sp_zero : sp_prev) * 3u + (uint32_t)a];
+        {
+          const SpEntry* en = sp_tab + (e.fresh ? sp_zero : sp_prev) * 3u + (uint32_t)a;
+          spn = make_uint2(en->next, __float_as_uint(en->value));
+        }
         const float sp = __uint_as_float(spn.y);
-        // set-point part of the reward (without the level factor): a global read far ahead of its use
-        r_theta0 = __ldg(args.env.sp_rtheta + ((e.fresh ? (uint32_t)DQLB200_MAX_SETPOINTS : 0u) + sp_prev) * 3u + (uint32_t)a);
+        // set-point part of the reward (without the level factor); the first step of an episode shapes against the old set-point
+        r_theta0 = *(&sp_tab[sp_prev * 3u + (uint32_t)a].r_step + (e.fresh ? 1 : 0));
         // R4
         dyn_advance(kk, pp, e.b, sp, filt ? &kf : nullptr, so ? &ex : nullptr, kk.vz_train);
         step_count = e.step_count + 1u;
         o = dyn_observe(kk, pp, e.b, (int)step_count, kk.dz_train, filt ? &kf : nullptr, so ? &ex : nullptr);
         if (GENERIC && kk.noise_enabled) add_observation_noise(kk, o, noise_w0, noise_w1);
         // R5
-        ds = discretise_cuts(sh.cuts, kk.angle_cut, o, w);
+        ds = W0 ? discretise_cuts(kc.cuts[0], kk.angle_cut, o, 0) : discretise_cuts(sh.cuts, kk.angle_cut, o, w);
         sid2 = (uint32_t)ds.id();
         // R6 (sticky result: only ever set, quirk Q9)
         // The priority chain of PKG/mdp.py:359-425 as selects (the ladder of branches diverges inside a warp).
@@ -455,7 +494,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         const bool t_zmin = !(o.z >= kk.z_min_cut), t_zmax = o.z >= kk.z_max_cut;
         const bool t_time = (int)step_count >= kk.timeout_steps;
         const bool goal_bins = !(o.contact || t_fx || t_zmin || t_zmax || t_time) && ds.bp == 1 && ds.bv == 1;
-        const bool at_level = sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w;   // previous level == w (it never exceeds w)
+        const bool at_level = W0 || (sid >= (uint32_t)(w * DQLB200_STATES_PER_LEVEL) && ds.level == w);   // previous level == w (it never exceeds w)
         cc = goal_bins ? (at_level ? e.curriculum_check + 1u : 0u) : e.curriculum_check;
         code = e.sticky_success ? DQLB200_NON_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL;
         if (goal_bins && at_level) code = ((int)cc >= kk.success_steps) ? DQLB200_TERMINAL_SUCCESS : DQLB200_NON_TERMINAL_SUCCESS;
@@ -466,8 +505,9 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         code = o.contact ? DQLB200_TERMINAL_CONTACT : code;
         done = code >= DQLB200_TERMINAL_SUCCESS;
         success = code == DQLB200_TERMINAL_SUCCESS;
-        if (!(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f))
-          atomicOr(&sh.ps.error_flags, 1u);      // NaN/inf observation (PKG/mdp.py:170 raises)
+        // NaN/inf observation (PKG/mdp.py:170 raises): remembered in a register and reported after the slot loop -- a branch here
+        // would end the basic block, and ptxas waits at the end of a block for the match issued above
+        bad_obs = bad_obs || !(fabsf(o.rel_p) <= 3.4028234664e38f) || !(fabsf(o.rel_v) <= 3.4028234664e38f) || !(fabsf(o.rel_a) <= 3.4028234664e38f);
       }
       const uint32_t lower = peers & ((1u << lane) - 1u);
       const int rank = __popc(lower);                                   // position in the group
@@ -488,7 +528,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         const double prev_p = shaping(kk.w_p, e.prev_rel_p, kk.p_max, kk.rcp_p_max, kk.clip_p_f, GENERIC);
         const double prev_v = shaping(kk.w_v, e.prev_rel_v, kk.v_max, kk.rcp_v_max, kk.clip_v_f, GENERIC);
         const bool succ_reward = code == DQLB200_NON_TERMINAL_SUCCESS || code == DQLB200_TERMINAL_SUCCESS;
-        const double r = reward_sp(sh.reward[ds.level], phi_p, phi_v, prev_p, prev_v, r_theta0, succ_reward);
+        const double r = reward_sp(W0 ? kc.reward[0] : sh.reward[ds.level], phi_p, phi_v, prev_p, prev_v, r_theta0, succ_reward);
         // R12 target: r + (gamma * max_a Q_a[s'][a]) * [p-bin changed]   (quirks Q2, Q3), float32 like NEP 50
         const float qn = sh.qmax[sid2];
         const float changed = (e.bp != (uint32_t)ds.bp) ? 1.0f : 0.0f;
@@ -601,6 +641,14 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         n_queued += __popc(dmask);
         if (n_queued > RESET_QUEUE - 32) flush_resets();       // never overflows, whatever fraction of envs finishes at once
       }
+    }
+    if (bad_obs) atomicOr(&sh.ps.error_flags, 1u);
+    };
+    if constexpr (!GENERIC && !TRACE) {
+      if (w == 0) slot_loop(std::true_type{});
+      else slot_loop(std::false_type{});
+    } else {
+      slot_loop(std::false_type{});
     }
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)

@@ -22,21 +22,23 @@ def line_table(kernel: str):
     cubin = next(tmp.glob("*.cubin"))
     txt = subprocess.run(["nvdisasm", "-gi", "-c", str(cubin)], capture_output=True, text=True).stdout.splitlines()
     start = next(i for i, l in enumerate(txt) if l.startswith(".text." + kernel + ":"))
-    rows, cur, outer, in_group = [], ("?", 0), ("?", 0), False
+    rows, group, in_group = [], [("?", 0)], False
     for l in txt[start + 1:]:
         if l.startswith("\t.section") or l.startswith("//-----"):
             break
         m = re.search(r'//## File "([^"]+)", line (\d+)', l)
-        if m:      # consecutive markers: the first is the innermost (inlined) location, the last the outermost caller
+        if m:      # consecutive markers: the inline chain of the next instruction, innermost location first
             loc = (pathlib.Path(m.group(1)).name, int(m.group(2)))
-            if not in_group:
-                cur = loc
-            outer, in_group = loc, True
+            group = group + [loc] if in_group else [loc]
+            in_group = True
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,})\*/\s+(.*?);", l)
         if m:
             in_group = False
-            rows.append((int(m.group(1), 16), cur, outer, m.group(2).strip()))
+            # attribute to the innermost frame inside train_kernel.cuh (helpers of other headers are charged to their call site;
+            # the body of a lambda to its own line, not to the line that calls the lambda)
+            key = next((g for g in group if g[0] == "train_kernel.cuh"), group[-1])
+            rows.append((int(m.group(1), 16), group[0], key, m.group(2).strip()))
     return rows
 
 
