@@ -77,22 +77,25 @@ __device__ __forceinline__ Kf kf_load(const EnvPtrs& p, size_t i) {
 __device__ __forceinline__ void kf_store(const EnvPtrs& p, size_t i, const Kf& f) {
   p.d[i] = make_uint4(__float_as_uint(f.x), __float_as_uint(f.P), __float_as_uint(f.v_ref), f.n);
 }
-// The extension state of an env through the staging slots 3..5 of its thread (extended kernel variant): issued next to the env
+// The extension state of an env through three staging slots of its thread ([3][threads] x 16 B behind the env tiles; extended
+// kernel variant, stage_addr = shared-space address of the thread's first slot there): issued next to the env
 // prefetch, picked up one slot later -- a plain load at the head of a slot would expose an L2 round trip per slot.
 __device__ __forceinline__ void ext_prefetch_async(const EnvPtrs& p, size_t i, unsigned stage_addr, int nt, bool filt, bool so) {
-  if (filt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 48u * nt), "l"(p.d + i) : "memory");
+  if (filt) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr), "l"(p.d + i) : "memory");
   if (so) {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 64u * nt), "l"(p.e + i) : "memory");
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 80u * nt), "l"(p.e + p.n + i) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 16u * nt), "l"(p.e + i) : "memory");
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(p.e + p.n + i) : "memory");
   }
   asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ Kf kf_take(unsigned stage_addr, int nt) {
-  const uint4 v = lds128(stage_addr + 48u * nt);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const uint4 v = lds128(stage_addr);
   return Kf{__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), v.w};
 }
 __device__ __forceinline__ Ext ext_take(unsigned stage_addr, int nt) {
-  const uint4 u = lds128(stage_addr + 64u * nt), v = lds128(stage_addr + 80u * nt);
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  const uint4 u = lds128(stage_addr + 16u * nt), v = lds128(stage_addr + 32u * nt);
   return Ext{__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w),
              __uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
 }
@@ -112,26 +115,45 @@ __device__ __forceinline__ EnvRaw env_fetch(const unsigned char* pa) {
   r.C = __ldcg(reinterpret_cast<const uint4*>(pa + 1024));
   return r;
 }
-// Asynchronous prefetch of one env's 48 bytes into the thread's private staging slots in shared memory (cp.async, L2 only):
-// unlike a register prefetch it holds no registers while in flight and cannot be consumed early by the scheduler's copies.
-// stage_addr = shared-state-space address of the thread's first staging slot (__cvta_generic_to_shared(stage + tid), hoisted
-// out of the slot loop by the caller: the conversion reads a special register).
-// pa = address of the env's A vector; its B and C vectors lie 512 and 1024 bytes behind it (immediate offsets)
-__device__ __forceinline__ void env_prefetch_async(const unsigned char* pa, unsigned stage_addr, int nt) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr), "l"(pa) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 16u * nt), "l"(pa + 512) : "memory");
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(stage_addr + 32u * nt), "l"(pa + 1024) : "memory");
-  asm volatile("cp.async.commit_group;" ::: "memory");
+// Asynchronous prefetch of a warp's next tile -- the 48-byte states of 32 consecutive envs, ENV_TILE_BYTES contiguous bytes in
+// HBM -- into the warp's staging tile in shared memory by ONE bulk copy of the copy engine (cp.async.bulk, SASS UBLKCP), issued
+// by an elected lane and completed on the warp's mbarrier (complete_tx::bytes); the lanes pick their three vectors up one slot
+// later.  It replaces three 16-byte cp.async per thread plus their address arithmetic and group bookkeeping, holds no registers
+// while in flight and cannot be consumed early by the scheduler's copies (a register prefetch was).
+//   mbar       shared-space address of the warp's mbarrier (8 bytes, initialised with count 1 by tile_mbar_init)
+//   stage_tile shared-space address of the warp's staging tile ([3][32] x 16 B, the layout of a tile in HBM)
+__device__ __forceinline__ void tile_mbar_init(unsigned mbar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // the initialised barrier is seen by the copy engine
 }
-// stage_addr as above: the staging slots are read through their shared-state-space address (a generic pointer into the dynamic
-// part of shared memory made the compiler rebuild the window base -- S2UR SR_CgaCtaId + address arithmetic -- in every slot)
-__device__ __forceinline__ EnvRaw env_prefetch_take(unsigned stage_addr, int nt) {
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
+__device__ __forceinline__ void tile_prefetch_bulk(const unsigned char* tile, unsigned stage_tile, unsigned mbar) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "n"((int)ENV_TILE_BYTES) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(stage_tile), "l"(tile),
+               "n"((int)ENV_TILE_BYTES), "r"(mbar)
+               : "memory");
+}
+// all lanes: wait for the phase `parity` of the warp's mbarrier (the bytes of the tile have landed)
+__device__ __forceinline__ void tile_wait(unsigned mbar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "TILE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra TILE_DONE;\n"
+      "bra TILE_WAIT;\n"
+      "TILE_DONE:\n"
+      "}\n" ::"r"(mbar),
+      "r"(parity)
+      : "memory");
+}
+// this lane's env of the staged tile (stage_lane = stage_tile + lane * 16)
+__device__ __forceinline__ EnvRaw tile_take(unsigned stage_lane) {
   EnvRaw r;
-  const uint4 a = lds128(stage_addr);
+  const uint4 a = lds128(stage_lane);
   r.A = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
-  r.B = lds128(stage_addr + 16u * nt);
-  r.C = lds128(stage_addr + 32u * nt);
+  r.B = lds128(stage_lane + 512u);
+  r.C = lds128(stage_lane + 1024u);
   return r;
 }
 

@@ -80,10 +80,11 @@ struct Shared {
   // Finished episodes of the warp-slots committed so far (see EP_OK_CAP): the serialised section only appends; success window,
   // promotion test and logged sums are brought up to date at the end of the global step (or when a buffer is full), off the
   // critical path of the baton.
+  unsigned long long tile_mbar[8];      // one mbarrier per warp: completion of the bulk copy of its next env tile
   double ep_ret[EP_RET_CAP];
   uint8_t ep_ok[EP_OK_CAP];
   int n_ep_ok, n_ep_ret;
-  // followed by (dynamic): uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[3 or 6][NT]; SpEntry sp_tab[n_setpoints][3]
+  // followed by (dynamic): uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[WARPS][3][32] (+ [3][NT]); SpEntry sp_tab[n_setpoints][3]
 };
 
 // dynamic shared memory of a launch: Shared + the set-point table + the reset queues + the cp.async staging slots of the env
@@ -141,10 +142,31 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   unsigned char* dyn = smem_raw + ((sizeof(Shared) + 15) & ~size_t(15));
   uint16_t* reset_queue = reinterpret_cast<uint16_t*>(dyn) + (size_t)warp * RESET_QUEUE;
   dyn += (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t);
-  uint4* stage = reinterpret_cast<uint4*>(dyn);      // [3][NT] (+ [3][NT] extension-state slots in the extended / trace instances)
+  uint4* stage = reinterpret_cast<uint4*>(dyn);      // [WARPS][3][32]: one staging tile per warp (+ [3][NT] extension-state slots in the extended / trace instances)
   dyn += (size_t)((TRACE || EXT) ? 6 : 3) * NT * 16;
   SpEntry* sp_tab = reinterpret_cast<SpEntry*>(dyn);     // [n_setpoints][3]
-  const unsigned stage_addr = (unsigned)__cvta_generic_to_shared(stage + tid);
+  const unsigned stage_tile = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)warp * (unsigned)ENV_TILE_BYTES;
+  const unsigned stage_lane = stage_tile + (unsigned)lane * 16u;                                   // this lane's A vector in the staged tile
+  const unsigned ext_stage = (unsigned)__cvta_generic_to_shared(stage + WARPS * 96 + tid);       // extension-state slots of this thread
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sh.tile_mbar[warp]);
+  const int tiles_pp = args.env.tiles_per_pop;
+  uint32_t tile_phase = 0u;       // parity of the mbarrier phase the next wait is for
+  bool tile_pending = false;      // a bulk copy is in flight (warp-uniform)
+  // issue the bulk copy of `tile` into the warp's staging tile.  The tile may have been written by this warp's lanes (env_store,
+  // resets) a moment ago: the warp converges, and the issuing lane orders those generic-proxy writes before the async-proxy read.
+  auto prefetch_tile = [&](const unsigned char* tile) {
+    __syncwarp();
+    if (lane == 0) {
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      tile_prefetch_bulk(tile, stage_tile, mbar);
+    }
+    tile_pending = true;
+  };
+  auto wait_tile = [&]() {
+    tile_wait(mbar, tile_phase);
+    tile_phase ^= 1u;
+    tile_pending = false;
+  };
   const size_t env_base = (size_t)pop * n_p;
   uint32_t* gt = args.tables + (size_t)pop * 3 * CELLS;
   float* gqb = reinterpret_cast<float*>(gt + CELLS);      // table B, written only by the transfer below
@@ -159,10 +181,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   static_assert(sizeof(dqlb200_population_state) % 4 == 0, "word copies");
   constexpr int PS_WORDS = sizeof(dqlb200_population_state) / 4;
   const dqlb200_population_params pp = args.pop_params[pop];
-  // this thread's env of slot 0 (a lane beyond the population reads the padding of the last tile)
-  unsigned char* const p_env0 = env_addr(args.env, pop, min(tid, n_p - 1) & ~31) + (size_t)lane * 16;
-  env_prefetch_async(p_env0, stage_addr, NT);
-  if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, kc.accel_mode != 0, kc.dynamics_model != 0);
+  unsigned char* const p_tile0 = env_addr(args.env, pop, warp * 32);      // tile `warp` of the population (exists if warp < tiles_pp)
+  if (lane == 0) tile_mbar_init(mbar);
+  if (warp < tiles_pp) prefetch_tile(p_tile0);
+  if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), ext_stage, NT, kc.accel_mode != 0, kc.dynamics_model != 0);
   {
     const int w_start = args.pop_state[pop].working_step;
     const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
@@ -181,11 +203,18 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const uint2 nx = args.env.sp_next[i];
       sp_tab[i] = SpEntry{nx.x, __uint_as_float(nx.y), args.env.sp_rtheta[i], args.env.sp_rtheta[DQLB200_MAX_SETPOINTS * 3 + i]};
     }
+    // level 0 is live at every working step: its rows do not wait for the working step to arrive (a second, dependent round trip
+    // to HBM when one global step is run per launch); the rows of levels 1..w follow
     const int live = (w_start + 1) * DQLB200_CELLS_PER_LEVEL;
-    for (int i = tid; i < live; i += NT) {
+    for (int i = tid; i < DQLB200_CELLS_PER_LEVEL; i += NT) {
       sh.qa[i] = __uint_as_float(gt[i]);
       sh.cnt[i] = gt[2 * CELLS + i];
       if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(gqb + i));     // table B rows for the first snapshot
+    }
+    for (int i = DQLB200_CELLS_PER_LEVEL + tid; i < live; i += NT) {
+      sh.qa[i] = __uint_as_float(gt[i]);
+      sh.cnt[i] = gt[2 * CELLS + i];
+      if ((i & 31) == 0) asm volatile("prefetch.global.L2 [%0];" ::"l"(gqb + i));
     }
   }
   __syncthreads();
@@ -345,9 +374,12 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
       }
       // every env was just restarted: the slot-0 prefetch in flight is stale
-      (void)env_prefetch_take(stage_addr, NT);
-      env_prefetch_async(p_env0, stage_addr, NT);
-      if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
+      if (tile_pending) wait_tile();
+      if (warp < tiles_pp) prefetch_tile(p_tile0);
+      if (EXT) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), ext_stage, NT, filt, so);
+      }
       build_snapshot(w + 1);
     }
     __syncthreads();
@@ -406,17 +438,17 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const int env_i = slot * NT + tid;
       const bool valid = FULL_SLOTS || env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
-      const EnvRaw cur_raw = env_prefetch_take(stage_addr, NT);
+      if (FULL_SLOTS || slot * WARPS + warp < tiles_pp) wait_tile();      // warp-uniform: this warp has a tile in this slot
+      const EnvRaw cur_raw = tile_take(stage_lane);
       unsigned char* const p_cur = p_env;
       p_env += WARPS * ENV_TILE_BYTES;
       Kf kf;
       Ext ex;
-      if (filt) kf = kf_take(stage_addr, NT);
-      if (so) ex = ext_take(stage_addr, NT);
-      if (FULL_SLOTS ? (slot + 1 < n_slots) : (env_i + NT < n_p)) {      // in flight during this slot
-        env_prefetch_async(p_env, stage_addr, NT);
-        if (EXT) ext_prefetch_async(args.env, gi + NT, stage_addr, NT, filt, so);
-      }
+      if (filt) kf = kf_take(ext_stage, NT);
+      if (so) ex = ext_take(ext_stage, NT);
+      // the next tile of this warp: in flight during this slot (every lane has read the staged tile: prefetch_tile converges first)
+      if (FULL_SLOTS ? (slot + 1 < n_slots) : ((slot + 1) * WARPS + warp < tiles_pp)) prefetch_tile(p_env - (size_t)lane * 16);
+      if (EXT && env_i + NT < n_p) ext_prefetch_async(args.env, gi + NT, ext_stage, NT, filt, so);
       // ---------------- phase A: everything that only reads the snapshot ----------------------
       uint32_t cell = 0;
       float target = 0.0f;
@@ -587,6 +619,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         // q += alpha * (target - q), members of a group in lane order: round r is member r's, which takes the running value from
         // member r - 1 (one shuffle per round; singleton groups -- most lanes -- are done after round 0)
         if (rank == 0) q = fadd(q, fmul(alpha, fsub(target, q)));
+#pragma unroll 1
         for (int r = 1; r < n_max; ++r) {
           const float qp = __shfl_sync(FULL, q, pred);
           if (rank == r) q = fadd(qp, fmul(alpha, fsub(target, qp)));
@@ -653,8 +686,8 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     flush_resets();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
     if (k + 1 < args.k_steps) {
-      env_prefetch_async(p_env0, stage_addr, NT);
-      if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), stage_addr, NT, filt, so);
+      if (warp < tiles_pp) prefetch_tile(p_tile0);
+      if (EXT) ext_prefetch_async(args.env, env_base + (size_t)min(tid, n_p - 1), ext_stage, NT, filt, so);
     }
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
@@ -673,24 +706,26 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   }
 
   // ---- write back (live rows only) ----------------------------------------------------------------
-  asm volatile("cp.async.wait_all;" ::: "memory");      // a prefetch issued for a step that did not run
-  __syncthreads();
+  if (tile_pending) wait_tile();                         // a prefetch issued for a step that did not run: the CTA must not exit under it
+  if (EXT) asm volatile("cp.async.wait_all;" ::: "memory");
+  // No barrier here: every path into this point ends with a CTA barrier that lies behind the last write of another warp to the
+  // tables and to the trainer state (the second barrier of a global step, the one that ends advance_curriculum, the prologue's).
   for (int i = tid; i < (sh.ps.working_step + 1) * DQLB200_CELLS_PER_LEVEL; i += NT) {
     gt[i] = __float_as_uint(sh.qa[i]);
     gt[2 * CELLS + i] = sh.cnt[i];
   }
-  if (tid == 0) {
-    dqlb200_population_state& ps = sh.ps;
-    ps.total_steps += steps_done;
-    ps.total_episodes += sh.n_episodes;
-    ps.total_successes += sh.n_success;
-    ps.episode_steps_sum += sh.ep_steps;
-    for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
-  }
-  __syncthreads();
-  {
+  if (warp == 0) {      // the trainer state is finished and written back by one warp (no CTA barrier between the two)
+    if (lane == 0) {
+      dqlb200_population_state& ps = sh.ps;
+      ps.total_steps += steps_done;
+      ps.total_episodes += sh.n_episodes;
+      ps.total_successes += sh.n_success;
+      ps.episode_steps_sum += sh.ep_steps;
+      for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
+    }
+    __syncwarp();
     uint32_t* gps = reinterpret_cast<uint32_t*>(args.pop_state + pop);
-    for (int i = tid; i < PS_WORDS; i += NT) gps[i] = reinterpret_cast<const uint32_t*>(&sh.ps)[i];
+    for (int i = lane; i < PS_WORDS; i += 32) gps[i] = reinterpret_cast<const uint32_t*>(&sh.ps)[i];
   }
 }
 
