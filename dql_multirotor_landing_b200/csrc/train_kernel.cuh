@@ -73,18 +73,16 @@ struct Shared {
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   dqlb200_population_state ps;
-  unsigned long long n_episodes, n_success, ep_steps, hist[9];     // totals of this launch
-  uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics)
+  uint32_t step_episodes, step_success, step_ep_steps, step_hist[9];   // counters of the current global step (native 32-bit shared atomics), folded into the 64-bit totals of `ps` once per step
   int promote, advance, do_advance;
   uint4 philox_keys[5];   // round keys of the population's Philox key (philox_round_keys)
   // Finished episodes of the warp-slots committed so far (see EP_OK_CAP): the serialised section only appends; success window,
   // promotion test and logged sums are brought up to date at the end of the global step (or when a buffer is full), off the
   // critical path of the baton.
-  unsigned long long tile_mbar[8];      // one mbarrier per warp: completion of the bulk copy of its next env tile
   double ep_ret[EP_RET_CAP];
   uint8_t ep_ok[EP_OK_CAP];
   int n_ep_ok, n_ep_ret;
-  // followed by (dynamic): uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[WARPS][3][32] (+ [3][NT]); SpEntry sp_tab[n_setpoints][3]
+  // followed by (dynamic): uint16_t reset_queue[WARPS][RESET_QUEUE]; uint4 stage[WARPS][3][32] (+ [3][NT]); uint64_t tile_mbar[WARPS] (one mbarrier per warp: completion of the bulk copy of its next env tile); SpEntry sp_tab[n_setpoints][3]
 };
 
 // dynamic shared memory of a launch: Shared + the set-point table + the reset queues + the cp.async staging slots of the env
@@ -101,9 +99,14 @@ struct SpEntry {
 __host__ __device__ constexpr size_t train_sp_bytes(int n_setpoints) { return ((size_t)n_setpoints * 3 * sizeof(SpEntry) + 15) & ~size_t(15); }
 __host__ __device__ constexpr size_t train_smem_bytes(int threads, bool extended, int n_setpoints) {
   return ((sizeof(Shared) + 15) & ~size_t(15)) + train_sp_bytes(n_setpoints) + (size_t)(threads / 32) * RESET_QUEUE * sizeof(uint16_t) +
-         (size_t)(extended ? 6 : 3) * threads * 16;
+         (size_t)(extended ? 6 : 3) * threads * 16 + (((size_t)(threads / 32) * 8 + 15) & ~size_t(15));
 }
 
+// the production launch shape (128 threads, 33 reachable set-points of the reference defaults) must keep six populations resident
+// per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA (a 96-byte overshoot once halved the occupancy unnoticed)
+#ifndef DQL_HACK_LEVELS
+static_assert((train_smem_bytes(128, false, 33) + 1024) * 6 <= 228 * 1024, "train_kernel<4>: six CTAs per SM no longer fit in shared memory");
+#endif
 #ifndef DQL_WARPS_PER_SM
 #define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
@@ -144,24 +147,27 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   dyn += (size_t)WARPS * RESET_QUEUE * sizeof(uint16_t);
   uint4* stage = reinterpret_cast<uint4*>(dyn);      // [WARPS][3][32]: one staging tile per warp (+ [3][NT] extension-state slots in the extended / trace instances)
   dyn += (size_t)((TRACE || EXT) ? 6 : 3) * NT * 16;
+  unsigned long long* tile_mbar = reinterpret_cast<unsigned long long*>(dyn);
+  dyn += ((size_t)WARPS * 8 + 15) & ~size_t(15);
   SpEntry* sp_tab = reinterpret_cast<SpEntry*>(dyn);     // [n_setpoints][3]
   const unsigned stage_tile = (unsigned)__cvta_generic_to_shared(stage) + (unsigned)warp * (unsigned)ENV_TILE_BYTES;
   const unsigned stage_lane = stage_tile + (unsigned)lane * 16u;                                   // this lane's A vector in the staged tile
   const unsigned ext_stage = (unsigned)__cvta_generic_to_shared(stage + WARPS * 96 + tid);       // extension-state slots of this thread
-  const unsigned mbar = (unsigned)__cvta_generic_to_shared(&sh.tile_mbar[warp]);
+  const unsigned mbar = (unsigned)__cvta_generic_to_shared(tile_mbar + warp);
   const int tiles_pp = args.env.tiles_per_pop;
   uint32_t tile_phase = 0u;       // parity of the mbarrier phase the next wait is for
   bool tile_pending = false;      // a bulk copy is in flight (warp-uniform)
-  // issue the bulk copy of `tile` into the warp's staging tile.  The tile may have been written by this warp's lanes (env_store,
-  // resets) a moment ago: the warp converges, and the issuing lane orders those generic-proxy writes before the async-proxy read.
+  // issue the bulk copy of `tile` into the warp's staging tile (every lane has read the staged tile: the warp converges first).
+  // The copy engine reads through the async proxy what the lanes of this warp wrote through the generic proxy (env_store, resets):
+  // every thread orders its writes of a global step with ONE proxy fence behind its last store of the step (env_writes_done),
+  // and a warp / CTA barrier lies between that fence and every later prefetch.  A fence per prefetch waits for the stores of the
+  // slot before it -- an L2 round trip in every slot (measured: -24 %).
   auto prefetch_tile = [&](const unsigned char* tile) {
     __syncwarp();
-    if (lane == 0) {
-      asm volatile("fence.proxy.async.global;" ::: "memory");
-      tile_prefetch_bulk(tile, stage_tile, mbar);
-    }
+    if (lane == 0) tile_prefetch_bulk(tile, stage_tile, mbar);
     tile_pending = true;
   };
+  auto env_writes_done = [&]() { asm volatile("fence.proxy.async.global;" ::: "memory"); };
   auto wait_tile = [&]() {
     tile_wait(mbar, tile_phase);
     tile_phase ^= 1u;
@@ -190,9 +196,8 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     const uint32_t* gps = reinterpret_cast<const uint32_t*>(args.pop_state + pop);
     for (int i = tid; i < PS_WORDS; i += NT) reinterpret_cast<uint32_t*>(&sh.ps)[i] = gps[i];
     if (tid == 0) {
-      sh.n_episodes = sh.n_success = sh.ep_steps = 0ull;
       sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
-      for (int i = 0; i < 9; ++i) { sh.hist[i] = 0ull; sh.step_hist[i] = 0u; }
+      for (int i = 0; i < 9; ++i) sh.step_hist[i] = 0u;
       sh.promote = sh.advance = sh.do_advance = 0;
       sh.n_ep_ok = sh.n_ep_ret = 0;
       sh.cuts = kc.cuts[w_start];
@@ -374,6 +379,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         }
       }
       // every env was just restarted: the slot-0 prefetch in flight is stale
+      env_writes_done();
       if (tile_pending) wait_tile();
       if (warp < tiles_pp) prefetch_tile(p_tile0);
       if (EXT) {
@@ -684,6 +690,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       slot_loop(std::false_type{});
     }
     flush_resets();
+    env_writes_done();
     // software prefetch of slot 0 of the next global step (this warp's envs are final: resets only touch the warp's own)
     if (k + 1 < args.k_steps) {
       if (warp < tiles_pp) prefetch_tile(p_tile0);
@@ -696,10 +703,10 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     if (tid == 0) {
       sh.ps.t = t + 1u;
       sh.do_advance = (sh.promote || sh.advance) ? 1 : 0;
-      sh.n_episodes += sh.step_episodes; sh.n_success += sh.step_success; sh.ep_steps += sh.step_ep_steps;
+      sh.ps.total_episodes += sh.step_episodes; sh.ps.total_successes += sh.step_success; sh.ps.episode_steps_sum += sh.step_ep_steps;
       sh.step_episodes = sh.step_success = sh.step_ep_steps = 0u;
     }
-    if (tid < 9) { sh.hist[tid] += sh.step_hist[tid]; sh.step_hist[tid] = 0u; }
+    if (tid < 9) { sh.ps.termination_hist[tid] += sh.step_hist[tid]; sh.step_hist[tid] = 0u; }
     if (k + 1 < args.k_steps) build_snapshot(w);      // for the next step, unless the curriculum advances (rebuilt there)
     __syncthreads();
     if (sh.do_advance) advance_curriculum(w, t + 1u);
@@ -718,10 +725,6 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     if (lane == 0) {
       dqlb200_population_state& ps = sh.ps;
       ps.total_steps += steps_done;
-      ps.total_episodes += sh.n_episodes;
-      ps.total_successes += sh.n_success;
-      ps.episode_steps_sum += sh.ep_steps;
-      for (int i = 0; i < 9; ++i) ps.termination_hist[i] += sh.hist[i];
     }
     __syncwarp();
     uint32_t* gps = reinterpret_cast<uint32_t*>(args.pop_state + pop);
