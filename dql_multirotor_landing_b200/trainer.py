@@ -6,6 +6,12 @@ parameters).  `curriculum_training()` replaces the Python `for episode: while no
 169-245) by `Engine.train(chunk_steps)` launches: the select -> step -> update -> auto-reset -> promotion -> transfer
 cycle runs inside one CUDA kernel for all envs (csrc/train_kernel.cuh: train_kernel); the host only reads the
 320-byte population state between launches to log, checkpoint and stop.
+
+`max_num_episodes` keeps its per-env meaning (PKG/trainer.py:190: one env runs at most that many episodes per curriculum
+step, and epsilon is a function of that env's episode index, :112-126): with N envs sharing the agent the device counts
+finished episodes pooled over all of them, so the limit handed to it is `max_num_episodes * N` -- the forced advance
+comes when the MEAN per-env episode index reaches `max_num_episodes`, and N = 1 is the reference.  The logged episode
+index, remaining episodes and exploration rate are per-env figures (pooled count // N).
 """
 from __future__ import annotations
 
@@ -93,6 +99,7 @@ class Trainer:
             self._num_envs = envs_per_replica
             self._threads_per_block = 128 if envs_per_replica >= 128 else 32
         self._merge_every = merge_every
+        self._envs_per_agent = self._num_envs * self._replicas      # envs that share one table pair (and one episode budget)
         self._tensorboard, self._verbose = tensorboard, verbose
         if direction not in ("x", "y"):
             raise ValueError("direction must be 'x' or 'y' (training.launch direction:=x|y, training_x.sh / training_y.sh)")
@@ -164,7 +171,7 @@ class Trainer:
         from .engine import Engine
         tp = K.TrainerParameters(
             curriculum_steps=self._curriculum_steps, successive_successful_episodes=self._successive_successful_episodes,
-            success_rate=self._success_rate, max_num_episodes=self._max_num_episodes, alpha_min=self._alpha_min,
+            success_rate=self._success_rate, max_num_episodes=self._max_num_episodes * self._envs_per_agent, alpha_min=self._alpha_min,
             omega=self._omega, gamma=self._gamma, scale_modification_value=self._scale_modification_value,
             transfer_mode=self._transfer_mode)
         mp = K.MdpParameters(f_ag=self._f_ag, t_max=self._t_max, p_max=self._p_max)
@@ -205,7 +212,8 @@ class Trainer:
             ps = eng.population_state()
             p0 = ps[0]
             self._working_curriculum_step = int(p0["working_step"])
-            self._current_episode = int(ps["episodes_in_step"].sum()) if self._replicas > 1 else int(p0["episodes_in_step"])
+            pooled_episodes = int(ps["episodes_in_step"].sum()) if self._replicas > 1 else int(p0["episodes_in_step"])
+            self._current_episode = pooled_episodes // self._envs_per_agent      # mean per-env episode index in this curriculum step
             self._curriculum_episode_count = int(ps["total_episodes"].sum()) if self._replicas > 1 else int(p0["total_episodes"])
             window = list(p0["window"][: int(p0["window_count"])])
             self._successes = deque(window, maxlen=self._successive_successful_episodes)
@@ -217,13 +225,16 @@ class Trainer:
                 "Mean reward": float(p0["last_cumulative"]) / max(int(p0["last_steps"]), 1),
                 "Curent episode": self._current_episode,
                 "Remaining episodes": self._max_num_episodes - self._current_episode + 1,
-                "Exploration rate": self.exploration_rate(self._current_episode // max(self._num_envs, 1), self._working_curriculum_step),
+                "Exploration rate": self.exploration_rate(self._current_episode, self._working_curriculum_step),
                 "Learning rate": self._alpha,
                 "Success rate": (int(ps["window_sum"].sum()) / (self._successive_successful_episodes * self._replicas)
                                  if self._replicas > 1 else int(p0["window_sum"]) / self._successive_successful_episodes),
                 "Global steps": int(p0["t"]), "Env steps": int(ps["total_steps"].sum()), "Episodes in chunk": d_ep,
+                "Pooled episodes": pooled_episodes,
             }
             self.history.append(dict(info, working_step=self._working_curriculum_step))
+            if len(self.history) > 2048:          # bounded: the history is pickled with every checkpoint
+                del self.history[:1024]
             advanced = any(int(ps[p]["working_step"]) != int(prev[p]["working_step"]) or int(ps[p]["finished"]) != int(prev[p]["finished"])
                            for p in range(len(ps)))
             if advanced:                       # checkpoint on promotion instead of after every episode

@@ -159,7 +159,8 @@ def test_agent_save_load_transfer(tmp_path, golden_dir):
 
 def test_trainer_schedules_and_short_curriculum(tmp_path):
     from dql_multirotor_landing_b200.trainer import Trainer
-    tr = Trainer(save_path=tmp_path / "run", successive_successful_episodes=5, success_rate=0.2, max_num_episodes=60,
+    # max_num_episodes is per env (PKG/trainer.py:190): 64 envs x 2 episodes = 128 pooled episodes force the advance of a step
+    tr = Trainer(save_path=tmp_path / "run", successive_successful_episodes=5, success_rate=0.2, max_num_episodes=2,
                  num_envs=64, chunk_steps=32, threads_per_block=64, verbose=False, max_global_steps=4000)
     assert tr.alpha((0, 1, 1, 1, 3, 2)) == 0.02949 and tr.exploration_rate(900, 0) == 0.9175
     assert tr.transfer_learning_ratio(0) == 1.0 and tr.transfer_learning_ratio(1) == 0.8172650252856599
@@ -176,6 +177,24 @@ def test_trainer_schedules_and_short_curriculum(tmp_path):
     import pickle
     again = pickle.load(open(tmp_path / "run" / "trainer.pickle", "rb"))
     assert np.array_equal(again._double_q_learning_agent.Q_table_a, agent.Q_table_a)
+
+
+def test_trainer_episode_budget_is_per_env(tmp_path):
+    """with the reference's defaults the forced advance of a curriculum step must not come before the envs have
+    walked the epsilon ramp (episodes 800-2000 of EACH env, PKG/trainer.py:112-126): 256 envs, ~1,000 episodes per env."""
+    from dql_multirotor_landing_b200.trainer import Trainer
+    tr = Trainer(save_path=tmp_path / "run", num_envs=256, chunk_steps=2048, threads_per_block=128, verbose=False,
+                 max_global_steps=65536, success_rate=2.0)
+    info = tr.curriculum_training()
+    ps = tr._engine.population_state()[0]
+    per_env = int(ps["episodes_in_step"]) // 256
+    assert per_env > 800, per_env
+    assert ps["working_step"] == 0 and ps["finished"] == 0            # 50,000 pooled episodes are long past, 50,000 per env are not
+    assert info["Curent episode"] == per_env and info["Exploration rate"] < 1.0
+    assert info["Remaining episodes"] == 50000 - per_env + 1
+    agent = tr._double_q_learning_agent
+    greedy_share = 1.0 - info["Exploration rate"]
+    assert greedy_share > 0 and agent.state_action_counter.sum() == ps["total_steps"]
 
 
 def test_trainer_large_population_uses_replica_merge(tmp_path):

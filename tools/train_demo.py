@@ -6,10 +6,10 @@ from dql_multirotor_landing_b200.trainer import Trainer
 
 def main(num_envs=65536, mode="paper", max_steps=60000, merge_every=1, success_rate=0.8):
     """success_rate: the reference default 0.96 is not reached on the analytic stand-in at curriculum step 0 (the success rate
-    of the reference algorithm plateaus at 0.80-0.87 there, for one env as for 65,536: tools/learn_probe*.py); 0.8 lets the
+    of the reference algorithm plateaus at 0.80-0.87 there, for one env as for 65,536: tools/learn_probe.py); 0.8 lets the
     demo walk through all five steps."""
     tr = Trainer(save_path=pathlib.Path(tempfile.mkdtemp()) / "run", success_rate=success_rate, num_envs=num_envs, chunk_steps=256, merge_every=merge_every,
-                 transfer_mode=mode, verbose=False, max_global_steps=max_steps, max_num_episodes=50000 * num_envs)
+                 transfer_mode=mode, verbose=False, max_global_steps=max_steps)
     t0 = time.perf_counter()
     tr.curriculum_training()
     torch.cuda.synchronize()
