@@ -39,34 +39,46 @@ def sweep_axes(population_ids: Sequence[int], seeds_per_point: int, speeds: Sequ
     return seeds, v_mp, alpha
 
 
+last_bind_note = "not called"      # why the last bind_to_gpu_numa_node call returned what it did (reported by bench.py)
+
+
 def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
     """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that pinned host buffers allocated
     afterwards are first-touched on that node and the host<->device copies of the ranks do not cross sockets.  Returns the
-    node id, or None when the topology cannot be read (nothing is changed then)."""
+    node id, or None when nothing was changed; `last_bind_note` says why (no sysfs entry, a single-node host, ...)."""
     import os
+    global last_bind_note
     try:
-        bus = torch.cuda.get_device_properties(device_index).pci_bus_id if hasattr(torch.cuda.get_device_properties(device_index), "pci_bus_id") else None
-        if bus is None:
-            import ctypes
-            rt = ctypes.CDLL("libcudart.so.12")
-            buf = ctypes.create_string_buffer(32)
-            if rt.cudaDeviceGetPCIBusId(buf, 32, device_index) != 0:
-                return None
-            bus = buf.value.decode()
-        node_file = f"/sys/bus/pci/devices/{bus.lower()}/numa_node"
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so.12")
+        buf = ctypes.create_string_buffer(32)
+        rc = rt.cudaDeviceGetPCIBusId(buf, 32, device_index)
+        if rc != 0:
+            last_bind_note = f"cudaDeviceGetPCIBusId failed ({rc})"
+            return None
+        bus = buf.value.decode().lower()
+        node_file = f"/sys/bus/pci/devices/{bus}/numa_node"
+        if not os.path.exists(node_file):
+            last_bind_note = f"{node_file} does not exist (virtualised PCI topology)"
+            return None
         node = int(open(node_file).read().strip())
         if node < 0:
+            last_bind_note = f"{node_file} = {node}: the platform reports no NUMA affinity for the GPU"
             return None
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node") and d[4:].isdigit()]
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.extend(range(int(lo), int(hi or lo) + 1))
         allowed = set(cpus) & os.sched_getaffinity(0)
         if not allowed:
+            last_bind_note = f"node {node} has no CPU this process may run on"
             return None
         os.sched_setaffinity(0, allowed)
+        last_bind_note = f"bound to node {node} ({len(allowed)} CPUs; the host has {len(nodes)} NUMA node(s))"
         return node
-    except Exception:
+    except Exception as exc:      # never fatal: the binding is an optimisation
+        last_bind_note = f"{type(exc).__name__}: {exc}"
         return None
 
 
@@ -78,11 +90,11 @@ def max_over_ranks(values: Sequence[float], device: Optional[torch.device] = Non
     return [float(x) for x in t]
 
 
-def gather_packed(packed: torch.Tensor, gathered: torch.Tensor) -> torch.Tensor:
+def gather_packed(packed: torch.Tensor, gathered: torch.Tensor, group=None) -> torch.Tensor:
     """All-gather of every rank's packed int32 buffer [agents, SHARED_WORDS] into gathered [world, agents, SHARED_WORDS]
-    (rank-major, the layout shared_apply_kernel reduces in rank order); returns gathered."""
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1))
+    (rank-major, the layout shared_apply_kernel reduces in rank order) over `group` (default: all ranks); returns gathered."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_gather_into_tensor(gathered.view(-1), packed.view(-1), group=group)
     else:
         gathered[0].copy_(packed)
     return gathered
@@ -91,14 +103,16 @@ def gather_packed(packed: torch.Tensor, gathered: torch.Tensor) -> torch.Tensor:
 class SharedTableSync:
     """Shared-table mode: the agents of `engine` (groups of engine.R consecutive populations) are replicated on every rank.
     `sync()` = local replica merge (R > 1) + pack + ONE all-gather (22.7 KB per agent and rank) + apply (the rank-ordered
-    reduction).  With `pooled_promotion` the curriculum promotion is decided from the windows of ALL ranks."""
+    reduction).  With `pooled_promotion` the curriculum promotion is decided from the windows of ALL ranks.  `group`: the ranks
+    that share the agents (default: every rank; BASELINE config 4 on 4+ GPUs uses one group per axis)."""
 
-    def __init__(self, engine, pooled_promotion: bool = False):
+    def __init__(self, engine, pooled_promotion: bool = False, group=None):
         import ctypes as C
         from . import _ffi
         from . import constants as K
         self._C, self._ffi, self.engine = C, _ffi, engine
-        self.world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
         self.snapshot = engine.tables[:: engine.R].clone().contiguous()
         n_agents = self.snapshot.shape[0]
         self.packed = torch.zeros((n_agents, K.SHARED_WORDS), dtype=torch.int32, device=engine.device)
@@ -124,4 +138,4 @@ class SharedTableSync:
         if e.R > 1:      # local copies first; with pooled promotion no rank decides alone
             self._ffi.check(e.lib.dqlb200_replica_merge(e.handle, e.merge_snapshot.data_ptr(), 0 if self.pooled_promote else e.pooled_promote, e._stream()))
         self.pack()
-        self.apply(gather_packed(self.packed, self.gathered))
+        self.apply(gather_packed(self.packed, self.gathered, self.group))
