@@ -5,6 +5,12 @@ Same constructor, attributes (`Q_table_a`, `Q_table_b`, `state_action_counter`: 
 `transfer_learning` runs on the GPU in float64 (csrc/facade_kernels.cuh: agent_facade_kernel); the NumPy arrays are
 host mirrors, kept coherent lazily.  The batched trainer (`trainer.Trainer`) uses float32 device tables
 instead and writes its result back into these attributes.
+
+Coherence rule of the mirrors: the three arrays are STABLE objects (a GPU update is copied into them in place, so a
+reference taken once -- `qa = agent.Q_table_a` -- keeps showing the current values after the next attribute access or
+`save`).  Reading an attribute marks the host side as possibly modified (the reference's arrays are mutable in place):
+it is uploaded before the next GPU call.  An in-place write through a reference taken BEFORE a later `update()` is only
+picked up if the attribute is read again first; `counter(state_action)` reads one count without forcing an upload.
 """
 from __future__ import annotations
 
@@ -43,8 +49,11 @@ class DoubleQLearningAgent:
         if self._dev_dirty:
             n = self.curriculum_steps * K.CELLS_PER_LEVEL
             h = self._dev.cpu().numpy()
-            for i in range(3):
-                self._host[i] = h[i, :n].reshape(self._host[i].shape).copy()
+            for i in range(3):      # in place: references handed out earlier stay live (like the reference's own arrays)
+                if self._host[i].dtype == np.float64 and self._host[i].flags.writeable:
+                    self._host[i][...] = h[i, :n].reshape(self._host[i].shape)
+                else:
+                    self._host[i] = h[i, :n].reshape(self._host[i].shape).copy()
             self._dev_dirty = False
 
     def _get(self, i):
@@ -56,6 +65,12 @@ class DoubleQLearningAgent:
         self._pull()
         self._host[i] = np.asarray(v)
         self._host_dirty = True
+
+    def counter(self, state_action: StateAction) -> float:
+        """state_action_counter[state_action] without marking the host mirror as modified (Trainer.alpha reads one count per step;
+        through the attribute every read would force a re-upload of all three tables before the next GPU call)."""
+        self._pull()
+        return float(self._host[2][tuple(state_action)])
 
     Q_table_a = property(lambda self: self._get(0), lambda self, v: self._set(0, v))
     Q_table_b = property(lambda self: self._get(1), lambda self, v: self._set(1, v))

@@ -27,7 +27,7 @@ class AbstractLandingEnv:
 
     _simulation = False
 
-    def __init__(self, t_max: int = 20, initial_curriculum_step: int = 0, f_ag: float = 22.92, p_max: float = 4.5, z_init: float = 4,
+    def __init__(self, t_max: int = 20, initial_curriculum_step: int = 0, f_ag: float = 22.92, p_max: float = 4.5, z_init: float = 2.0,
                  *, num_envs: int = 1, seed: int = 42, device: int = 0, platform_speed: float = 1.6, direction: str = "x",
                  dynamics: Optional[K.DynamicsParameters] = None, auto_reset: bool = False):
         from .engine import Engine
@@ -119,7 +119,9 @@ class AbstractLandingEnv:
 class TrainingLandingEnv(AbstractLandingEnv):
     """PKG/landing_simulation_env.py:143-282."""
 
-    def __init__(self, initial_curriculum_step: int = 0, *, t_max: int = 20, f_ag: float = 22.92, p_max: float = 4.5, z_init: float = 4, **extras):
+    def __init__(self, initial_curriculum_step: int = 0, *, t_max: int = 20, f_ag: float = 22.92, p_max: float = 4.5, z_init: float = 2.0, **extras):
+        # z_init = 2.0 like the reference's AbstractLandingEnv / TrainingLandingEnv (PKG/landing_simulation_env.py:37,150); the Trainer
+        # passes 4.0 explicitly (PKG/trainer.py:41,180), SimulationLandingEnv defaults to 4 (:293)
         super().__init__(t_max=t_max, initial_curriculum_step=initial_curriculum_step, f_ag=f_ag, p_max=p_max, z_init=z_init, **extras)
 
     def reset(self, mask=None):

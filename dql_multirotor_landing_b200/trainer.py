@@ -111,7 +111,7 @@ class Trainer:
     # schedules, same formulas and side effects as the reference
     def alpha(self, current_state_action: StateAction):
         """Current learning rate (PKG/trainer.py:88-110)."""
-        counter = self._double_q_learning_agent.state_action_counter[tuple(current_state_action)]
+        counter = self._double_q_learning_agent.counter(current_state_action)
         self._alpha = K.alpha_value(counter, self._alpha_min, self._omega)
         if math.isnan(self._alpha):
             raise ValueError(f"Leaning rate cannot be NaN, {counter}, {self._omega}, {self._alpha_min}")

@@ -157,6 +157,30 @@ def test_agent_save_load_transfer(tmp_path, golden_dir):
     assert raw[:6] == b"\x93NUMPY" and raw[6:8] == b"\x01\x00" and b"'<f8'" in raw[:128] and b"(5, 3, 3, 3, 7, 3)" in raw[:128]
 
 
+def test_agent_three_curriculum_steps_and_stable_mirrors():
+    """(a) an agent with curriculum_steps != 5: transfer_learning(0, r) reads slot -1 = 2 of ITS tables (quirk Q7, PKG/
+    double_q_learning.py:77-89), not slot 4 of a 5-step layout; (b) the host mirrors are stable objects: a reference taken once
+    shows GPU updates, and counter() reads a count without forcing an upload."""
+    from dql_multirotor_landing_b200.double_q_learning import DoubleQLearningAgent
+    agent = DoubleQLearningAgent(3)
+    rng = np.random.default_rng(3)
+    qa0, qb0 = rng.normal(size=(3, 3, 3, 3, 7, 3)), rng.normal(size=(3, 3, 3, 3, 7, 3))
+    agent.Q_table_a, agent.Q_table_b = qa0.copy(), qb0.copy()
+    agent.transfer_learning(0, 0.75)                           # the reference: Q[0] = Q[0 - 1] * r = Q[2] * r
+    assert np.array_equal(agent.Q_table_a[0], qa0[2] * 0.75) and np.array_equal(agent.Q_table_b[0], qb0[2] * 0.75)
+    agent.transfer_learning(2, 0.5)
+    assert np.array_equal(agent.Q_table_a[2], qa0[1] * 0.5) and np.array_equal(agent.Q_table_a[1], qa0[1])
+    held = agent.Q_table_a                                     # a reference kept by the caller
+    cnt = agent.state_action_counter
+    before = held[1, 1, 1, 1, 3, 2]
+    agent.update((1, 1, 1, 1, 3, 2), (1, 1, 0, 1, 3), 0.5, 0.99, 10.0)
+    assert agent.counter((1, 1, 1, 1, 3, 2)) == 1.0 and not agent._host_dirty          # no upload pending after a counter read
+    assert held is agent.Q_table_a and cnt is agent.state_action_counter              # same objects ...
+    assert held[1, 1, 1, 1, 3, 2] != before and cnt[1, 1, 1, 1, 3, 2] == 1.0          # ... showing the GPU update
+    held[0, 0, 0, 0, 0, 0] = 7.0                                                       # in-place write after re-reading the attribute
+    assert agent.predict((0, 0, 0, 0, 0)) == 0 and agent.Q_table_a[0, 0, 0, 0, 0, 0] == 7.0
+
+
 def test_trainer_schedules_and_short_curriculum(tmp_path):
     from dql_multirotor_landing_b200.trainer import Trainer
     # max_num_episodes is per env (PKG/trainer.py:190): 64 envs x 2 episodes = 128 pooled episodes force the advance of a step
