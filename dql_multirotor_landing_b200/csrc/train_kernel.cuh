@@ -160,8 +160,8 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   // issue the bulk copy of `tile` into the warp's staging tile (every lane has read the staged tile: the warp converges first).
   // The copy engine reads through the async proxy what the lanes of this warp wrote through the generic proxy (env_store, resets):
   // every thread orders its writes of a global step with ONE proxy fence behind its last store of the step (env_writes_done),
-  // and a warp / CTA barrier lies between that fence and every later prefetch.  A fence per prefetch waits for the stores of the
-  // slot before it -- an L2 round trip in every slot (measured: -24 %).
+  // and a warp / CTA barrier lies between that fence and every later prefetch (a fence per prefetch would wait for the stores of
+  // the slot before it: an L2 round trip in every slot).
   auto prefetch_tile = [&](const unsigned char* tile) {
     __syncwarp();
     if (lane == 0) tile_prefetch_bulk(tile, stage_tile, mbar);
