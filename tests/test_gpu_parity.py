@@ -716,6 +716,55 @@ def test_replica_merge_mode_vs_oracle(R, merge_every):
     assert all(np.array_equal(t[0, 0], t[r, 0]) and np.array_equal(t[0, 2], t[r, 2]) for r in range(R))
 
 
+@pytest.mark.parametrize("R,n_r,tpb", [(512, 128, 128), (1024, 512, 128)])
+def test_replica_merge_at_bench_shapes(R, n_r, tpb):
+    """The replica merge at the shapes bench.py runs (config 3: 512 replicas x 128 envs; config 4: 2 agents x 512 replicas x 512
+    envs; the 32-warp instance of replica_merge_kernel for R > 128): every replica trains M steps on its own copy (each replica is an
+    S1 population, checked against the C oracle at size above), then the device merge must equal the oracle's merge formula
+    (oracle/loop.py: ReplicatedPopulationOracle.merge, replica order, float32) evaluated in NumPy on the replicas' tables; twice in a
+    row (the second merge starts from the first one's snapshot)."""
+    groups = 2 if R == 1024 else 1
+    Rg = R // groups
+    eng = _engine(R, n_r, threads_per_block=tpb, seeds=[42] * R, population_ids=list(range(R)), replicas_per_population=Rg,
+                  axes=(["x"] * Rg + ["y"] * Rg) if groups == 2 else None, tp=dict(success_rate=2.0, max_num_episodes=10 ** 12))
+    eng.reset(0)
+    eng._ensure_merge_snapshot()
+    f32 = np.float32
+    for M in (3, 16):
+        snap = eng.merge_snapshot.cpu().numpy().view(np.uint32).copy()       # [groups][3][CELLS] as the device holds it
+        eng.train(M)
+        before = eng.tables.cpu().numpy().view(np.uint32).copy()              # [R][3][CELLS] uint32 words
+        eng.replica_merge()
+        eng.check_errors()
+        after = eng.tables.cpu().numpy().view(np.uint32)
+        for g in range(groups):
+            t = before[g * Rg:(g + 1) * Rg]
+            q = t[:, 0].view(f32)
+            c = t[:, 2].astype(np.int64)
+            sq, sc = snap[g, 0].view(f32), snap[g, 2].astype(np.int64)
+            d = c - sc
+            assert (d >= 0).all()
+            tot, visitors = d.sum(0), (d > 0).sum(0)
+            num = np.zeros_like(sq)
+            single = sq.copy()
+            for r in range(Rg):                                                # replica order: the float32 sum is order dependent
+                hit = d[r] > 0
+                contrib = ((q[r] - sq).astype(f32) * d[r].astype(f32)).astype(f32)
+                num = np.where(hit, (num + contrib).astype(f32), num)
+                single = np.where(hit, q[r], single)
+            with np.errstate(invalid="ignore", divide="ignore"):
+                mean = (sq + (num / tot.astype(f32)).astype(f32)).astype(f32)
+            q_new = np.where(visitors == 1, single, np.where(visitors > 1, mean, sq)).astype(f32)
+            c_new = (sc + tot).astype(np.uint32)
+            assert (visitors > 1).sum() > 100                                  # the order-dependent path is exercised
+            for r in (0, 1, Rg // 2, Rg - 1):
+                assert np.array_equal(after[g * Rg + r, 0], q_new.view(np.uint32)), (M, g, r)
+                assert np.array_equal(after[g * Rg + r, 2], c_new), (M, g, r)
+            assert (after[g * Rg:(g + 1) * Rg, 0] == after[g * Rg, 0]).all() and (after[g * Rg:(g + 1) * Rg, 2] == after[g * Rg, 2]).all()
+            assert int(c_new.astype(np.int64).sum() - sc.sum()) == Rg * n_r * M  # every env-step of every replica is in the merged counts
+    eng.close()
+
+
 @pytest.mark.parametrize("P", [3, 21])
 def test_train_host_equals_device_resident_training(P):
     """dqlb200_train_host (host buffers, chunk-pipelined copies) leaves exactly the state the device-resident entry point
