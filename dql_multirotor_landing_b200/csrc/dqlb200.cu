@@ -726,6 +726,15 @@ int dqlb200_bench_table_rmw(dqlb200_handle* h, const uint16_t* cells, int64_t n_
   return DQLB200_OK;
 }
 
+#ifdef DQL_TIMING
+// probe builds only (tools/perf_probe_timeline.py): the %globaltimer stamps of the last train_kernel launch, [4096][8]
+int dqlb200_debug_timing(unsigned long long* out, int n_words) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  CUDA_TRY(cudaMemcpyFromSymbol(out, dql::dql_timing, (size_t)n_words * sizeof(unsigned long long)));
+  return DQLB200_OK;
+}
+#endif
+
 int dqlb200_bench_launch_floor(dqlb200_handle* h, int blocks, int threads, int smem_bytes, void* stream) {
   if (!h || blocks < 1 || threads < 32 || threads > 1024 || smem_bytes < 0 || smem_bytes > 227 * 1024) return fail(DQLB200_ERR_ARG, "bad launch shape");
   CUDA_TRY(cudaSetDevice(h->device));

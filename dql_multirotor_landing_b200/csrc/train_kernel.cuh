@@ -30,6 +30,22 @@ __device__ __forceinline__ void baton_pass(int next_warp) {
 }
 #undef DQL_BAR_CASE
 
+// Probe builds only (-DDQL_TIMING, tools/perf_probe_timeline.py): %globaltimer stamps of every CTA at a few points of a launch and
+// the SM / hardware warp slot it runs in, fetched with dqlb200_debug_timing.  Compiled out of the product library.
+#ifdef DQL_TIMING
+__device__ unsigned long long dql_timing[4096 * 8];
+#define DQL_STAMP(i)                                                                                                      \
+  do {                                                                                                                    \
+    if (threadIdx.x == 0 && blockIdx.x < 2048) {                                                                          \
+      unsigned long long t_;                                                                                              \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_)::"memory");                                                    \
+      dql_timing[blockIdx.x * 8 + (i)] = t_;                                                                              \
+    }                                                                                                                     \
+  } while (0)
+#else
+#define DQL_STAMP(i) do { } while (0)
+#endif
+
 struct TrainArgs {
   EnvPtrs env;
   uint32_t* tables;                        // [P][3][CELLS]
@@ -135,6 +151,15 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   constexpr bool GENERIC = VARIANT == 1 || VARIANT == 2, EXT = VARIANT == 2, FULL_SLOTS = VARIANT == 3;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   Shared& sh = *reinterpret_cast<Shared*>(smem_raw);
+  DQL_STAMP(0);      // entry
+#ifdef DQL_TIMING
+  if (threadIdx.x == 0 && blockIdx.x < 2048) {      // where the CTA runs (written from the tail of the buffer)
+    unsigned smid_, warpid_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid_));
+    asm volatile("mov.u32 %0, %%warpid;" : "=r"(warpid_));
+    dql_timing[4096 * 8 - 1 - blockIdx.x] = ((unsigned long long)smid_ << 32) | warpid_;
+  }
+#endif
   const auto& kk = ConstsOf<GENERIC>::get(kc);       // run-time KC (generic) or the compile-time defaults KDef (production)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = WARPS * 32;
@@ -224,6 +249,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
   }
   __syncthreads();
 
+  DQL_STAMP(1);      // tables staged (first barrier passed)
   const float* __restrict__ alpha_lut = args.alpha_luts + (size_t)pp.alpha_lut * DQLB200_ALPHA_LUT;
   const float alpha_min = __ldg(alpha_lut + DQLB200_ALPHA_LUT - 1);      // alpha(count >= 1002), PKG/trainer.py:95-105
   const bool filt = EXT && kc.accel_mode != 0;      // acceleration estimator: 16 more bytes per env, extended instance only
@@ -400,6 +426,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     __syncthreads();
   }
 
+  DQL_STAMP(2);      // first snapshot built: the step loop starts
   for (int k = 0; k < args.k_steps; ++k) {
     if (sh.ps.finished) break;     // uniform: written only between barriers
     const int w = sh.ps.working_step;
@@ -445,6 +472,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       const bool valid = FULL_SLOTS || env_i < n_p;
       const size_t gi = env_base + (size_t)env_i;          // only dereferenced under `valid`
       if (FULL_SLOTS || slot * WARPS + warp < tiles_pp) wait_tile();      // warp-uniform: this warp has a tile in this slot
+      if (slot == 0) DQL_STAMP(7);      // the first tile has landed
       const EnvRaw cur_raw = tile_take(stage_lane);
       unsigned char* const p_cur = p_env;
       p_env += WARPS * ENV_TILE_BYTES;
@@ -680,6 +708,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         n_queued += __popc(dmask);
         if (n_queued > RESET_QUEUE - 32) flush_resets();       // never overflows, whatever fraction of envs finishes at once
       }
+      if (slot == 0) DQL_STAMP(6);      // slot 0 done
     }
     if (bad_obs) atomicOr(&sh.ps.error_flags, 1u);
     };
@@ -698,6 +727,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     }
     __syncthreads();
     // ---------------- end of the global step: promotion / next curriculum step (R13, R14) -----
+    DQL_STAMP(3);      // first barrier of the end of the global step passed
     steps_done += (uint64_t)n_p;
     if (warp == 0) drain_episode_log();      // the other warps build the next snapshot meanwhile
     if (tid == 0) {
@@ -712,6 +742,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     if (sh.do_advance) advance_curriculum(w, t + 1u);
   }
 
+  DQL_STAMP(4);      // step loop left
   // ---- write back (live rows only) ----------------------------------------------------------------
   if (tile_pending) wait_tile();                         // a prefetch issued for a step that did not run: the CTA must not exit under it
   if (EXT) asm volatile("cp.async.wait_all;" ::: "memory");
@@ -730,6 +761,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
     uint32_t* gps = reinterpret_cast<uint32_t*>(args.pop_state + pop);
     for (int i = lane; i < PS_WORDS; i += 32) gps[i] = reinterpret_cast<const uint32_t*>(&sh.ps)[i];
   }
+  DQL_STAMP(5);      // exit
 }
 
 
