@@ -299,7 +299,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     t0 = time.perf_counter()
     for _ in range(e2e_calls):
         eng.train_host(E2E_CHUNK, env_h, tab_h, ps_h, table_levels=E2E_TABLE_LEVELS)          # synchronises inside
-        launches += min(16, P)                                  # one train_kernel launch per pipelined chunk of populations
+        launches += min(8, P)                                   # one train_kernel launch per pipelined chunk of populations
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

@@ -57,7 +57,7 @@ struct dqlb200_handle {
   bool kc_default;              // the configuration equals the compile-time defaults: the production instance may run
   size_t smem_bytes;
   // dqlb200_train_host pipelines the populations in chunks over these streams (copy-in / train / copy-out overlap)
-  static constexpr int MAX_HOST_CHUNKS = 16;
+  static constexpr int MAX_HOST_CHUNKS = 64;
   cudaStream_t chunk_stream[MAX_HOST_CHUNKS];
   cudaEvent_t chunk_done[MAX_HOST_CHUNKS];
   cudaEvent_t host_start;
@@ -387,7 +387,13 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
   // direction) -- the caller's promise that no population reaches working step L - 1 + 1 inside the call (a launch touches
   // the levels 0 .. w of its working step w, and w + 1 when it is promoted); checked after the call.  L = 0: all levels.
   const int P = h->cfg.n_populations, cs_levels = h->cfg.curriculum_steps;
-  const int n_chunks = P < dqlb200_handle::MAX_HOST_CHUNKS ? P : dqlb200_handle::MAX_HOST_CHUNKS;
+  // Chunk count: measured on one B200 (tools/perf_probe_e2e.py, 888 x 1,280 envs, 64 steps): 1 chunk 4.25 ms, 4: 3.05, 8: 2.93, 16: 3.03,
+  // 32: 3.40, 64: 4.06 -- every chunk costs ~11 API calls of host time, and the call cannot end before the copy-in of everything
+  // plus the 64 sequential steps of the last chunk.  DQLB200_HOST_CHUNKS overrides the default (measurement aid).
+  int want_chunks = 8;
+  if (const char* e = getenv("DQLB200_HOST_CHUNKS")) want_chunks = atoi(e);
+  want_chunks = want_chunks < 1 ? 1 : (want_chunks > dqlb200_handle::MAX_HOST_CHUNKS ? dqlb200_handle::MAX_HOST_CHUNKS : want_chunks);
+  const int n_chunks = P < want_chunks ? P : want_chunks;
   const size_t row_bytes = (size_t)DQLB200_MAX_CELLS * 4, tab_stride = 3 * row_bytes, ps_stride = sizeof(dqlb200_population_state);
   const size_t level_bytes = (size_t)DQLB200_CELLS_PER_LEVEL * 4;
   const dqlb200_population_state* ps_h = reinterpret_cast<const dqlb200_population_state*>(pop_state_host);

@@ -286,7 +286,7 @@ int dqlb200_reset(dqlb200_handle* h, int initial_step, void* stream);
 int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, void* stream);
 
 /* Same with HOST buffers (pinned): copies env_state / tables / pop_state in, runs k_steps, copies them back and synchronises.
- * This is the end-to-end call bench.py times as `e2e`.  The call is pipelined over up to 16 chunks of populations on internal
+ * This is the end-to-end call bench.py times as `e2e`.  The call is pipelined over 8 chunks of populations (DQLB200_HOST_CHUNKS overrides: measurement aid) on internal
  * streams (copy-in of chunk c+1 and copy-out of chunk c-1 overlap the training of chunk c).
  * table_levels: 0 = transfer every table level; L > 0 = only levels 0 .. L-1 of every table row travel (both directions, plus
  * -- in reference transfer mode -- the last level on the way in for populations at step 0, which quirk Q7 reads): the caller's

@@ -8,11 +8,20 @@ P, n_p, k = 888, 1280, 64
 eng = Engine(P, n_p, threads_per_block=128, seeds=list(range(P)), tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10**12))
 eng.reset(0); eng.train(300); torch.cuda.synchronize()
 env_h = eng.env_state.cpu().pin_memory(); tab_h = eng.tables.cpu().pin_memory(); ps_h = eng.pop_state.cpu().pin_memory()
-for _ in range(2): eng.train_host(k, env_h, tab_h, ps_h)
-t0 = time.perf_counter(); n = 10
-for _ in range(n): eng.train_host(k, env_h, tab_h, ps_h)
-s = (time.perf_counter() - t0) / n
-print(json.dumps(dict(ms_per_call=round(s * 1e3, 3), env_steps_per_s=f"{P * n_p * k / s:.3e}")))
+import os
+def call_ms(kk, levels=2, n=10):
+    for _ in range(2): eng.train_host(kk, env_h, tab_h, ps_h, table_levels=levels)
+    t0 = time.perf_counter()
+    for _ in range(n): eng.train_host(kk, env_h, tab_h, ps_h, table_levels=levels)
+    return (time.perf_counter() - t0) / n
+for chunks in os.environ.get("CHUNKS", "8").split(","):
+    os.environ["DQLB200_HOST_CHUNKS"] = chunks
+    row = {"chunks": int(chunks)}
+    for kk in (0, 1, 16, 64):
+        s = call_ms(kk)
+        row[f"k{kk}_ms"] = round(s * 1e3, 3)
+    row["env_steps_per_s_k64"] = f"{P * n_p * 64 / (row['k64_ms'] * 1e-3):.3e}"
+    print(json.dumps(row), flush=True)
 # raw components
 def t(fn, n=10):
     fn(); torch.cuda.synchronize()

@@ -15,7 +15,7 @@ from dql_multirotor_landing_b200.engine import Engine
 
 NAMES = ["entry", "tables staged (1st barrier)", "snapshot built (loop starts)", "end-of-step barrier passed", "loop left", "exit",
          "slot 0 done (warp 0)", "first tile landed"]
-P, n_p = 888, 1280
+P, n_p = (int(sys.argv[2]) if len(sys.argv) > 2 else 888), 1280      # argv: [clean|dirty] [populations]
 eng = Engine(P, n_p, threads_per_block=128, seeds=list(range(P)), tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
 eng.reset(0); eng.train(600); torch.cuda.synchronize()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
