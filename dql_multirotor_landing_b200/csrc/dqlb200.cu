@@ -28,6 +28,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <dlfcn.h>
 
 
 #include "env_state.cuh"
@@ -616,6 +617,43 @@ int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* gathered
                                                                                         n_agents, R, pooled_promote_successes, h->cfg.max_num_episodes);
   CUDA_TRY(cudaGetLastError());
   return DQLB200_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The shared-table exchange as ONE call under the C-ABI (allreduce_tables(h, ncclComm_t, stream)).  NCCL is not a
+// link-time dependency of the library: ncclAllGather is looked up at run time, first among the symbols already loaded into the
+// process (a caller that created a communicator has NCCL loaded -- PyTorch's bundled copy, or the system's), then in libnccl.so.2.
+namespace {
+typedef int (*nccl_all_gather_fn)(const void*, void*, size_t, int /*ncclDataType_t*/, void* /*ncclComm_t*/, cudaStream_t);
+nccl_all_gather_fn find_nccl_all_gather() {
+  static nccl_all_gather_fn fn = nullptr;
+  if (fn) return fn;
+  void* sym = dlsym(RTLD_DEFAULT, "ncclAllGather");
+  if (!sym) {
+    if (void* lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL)) sym = dlsym(lib, "ncclAllGather");
+  }
+  fn = reinterpret_cast<nccl_all_gather_fn>(sym);
+  return fn;
+}
+}  // namespace
+
+int dqlb200_shared_sync_nccl(dqlb200_handle* h, void* snapshot, void* packed, void* gathered, void* nccl_comm, int n_ranks,
+                             int replica_promote_successes, int pooled_promote_successes, void* stream) {
+  if (!h || !snapshot || !packed || !gathered || !nccl_comm) return fail(DQLB200_ERR_ARG, "null argument");
+  if (n_ranks < 1) return fail(DQLB200_ERR_ARG, "n_ranks < 1");
+  nccl_all_gather_fn all_gather = find_nccl_all_gather();
+  if (!all_gather) return fail(DQLB200_ERR_STATE, "ncclAllGather not found: load NCCL (libnccl.so.2) into the process first");
+  const int R = h->cfg.replicas_per_population, n_agents = h->cfg.n_populations / R;
+  int rc;
+  if (R > 1) {      // the local copies agree first; with a pooled promotion no rank decides alone
+    if (!h->merge_snapshot) return fail(DQLB200_ERR_STATE, "replicated layout: bind the merge snapshot first (dqlb200_bind_merge_snapshot)");
+    if ((rc = dqlb200_replica_merge(h, h->merge_snapshot, pooled_promote_successes > 0 ? 0 : replica_promote_successes, stream))) return rc;
+  }
+  if ((rc = dqlb200_shared_pack(h, packed, stream))) return rc;
+  const size_t words = (size_t)n_agents * DQLB200_SHARED_WORDS;
+  const int nccl_rc = all_gather(packed, gathered, words, /*ncclInt32*/ 2, nccl_comm, (cudaStream_t)stream);
+  if (nccl_rc != 0) return fail(DQLB200_ERR_CUDA, "ncclAllGather failed with ncclResult_t " + std::to_string(nccl_rc));
+  return dqlb200_shared_apply(h, snapshot, gathered, n_ranks, pooled_promote_successes, stream);
 }
 
 int dqlb200_mdp_facade_step(dqlb200_handle* h, int working_step, int ops, int64_t n, const double* obs, const uint8_t* contact,

@@ -132,6 +132,16 @@ class SharedTableSync:
         self._ffi.check(e.lib.dqlb200_shared_apply(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(gathered.data_ptr()), int(gathered.shape[0]),
                                                    self.pooled_promote, e._stream()))
 
+    def sync_nccl(self, nccl_comm: int, n_ranks: int):
+        """The same exchange as ONE C call on a raw ncclComm_t (address as int) -- what a non-Python caller uses
+        (dqlb200_shared_sync_nccl: replica merge -> pack -> ncclAllGather -> apply); `gathered` must hold n_ranks entries."""
+        e, C = self.engine, self._C
+        if self.gathered.shape[0] != n_ranks:
+            self.gathered = torch.zeros((n_ranks,) + tuple(self.packed.shape), dtype=torch.int32, device=e.device)
+        self._ffi.check(e.lib.dqlb200_shared_sync_nccl(e.handle, C.c_void_p(self.snapshot.data_ptr()), C.c_void_p(self.packed.data_ptr()),
+                                                       C.c_void_p(self.gathered.data_ptr()), C.c_void_p(nccl_comm), int(n_ranks),
+                                                       int(e.pooled_promote), int(self.pooled_promote), e._stream()))
+
     def sync(self):
         """tables <- snapshot + visit-weighted mean of every rank's dQ_a (rank order); counts <- snapshot + sum of dcounts."""
         e = self.engine

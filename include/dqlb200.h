@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 6
+#define DQLB200_ABI_VERSION 7
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -376,6 +376,16 @@ int dqlb200_check_errors(dqlb200_handle* h, void* stream);
  * Replaces nothing in the reference (it has one process); the merge rule is the replica-merge rule below with ranks as replicas. */
 int dqlb200_shared_pack(dqlb200_handle* h, void* packed, void* stream);
 int dqlb200_shared_apply(dqlb200_handle* h, void* snapshot, const void* gathered, int n_ranks, int pooled_promote_successes, void* stream);
+/* The whole exchange as ONE call for a caller that holds an NCCL communicator (allreduce_tables(h, ncclComm_t,
+ * stream)): dqlb200_replica_merge on the bound merge snapshot (R > 1 only; with replica_promote_successes, or 0 when a pooled
+ * threshold is given: no rank decides alone) -> dqlb200_shared_pack -> ncclAllGather(packed -> gathered, n_agents *
+ * DQLB200_SHARED_WORDS int32 per rank) on `stream` -> dqlb200_shared_apply.  nccl_comm is the caller's ncclComm_t (passed as
+ * void*: this header does not include nccl.h), n_ranks its size; packed: [n_agents][DQLB200_SHARED_WORDS] words, gathered:
+ * n_ranks times that.  NCCL is resolved at run time (dlsym on the process, then libnccl.so.2): the library itself does not link
+ * against it, and the call fails with DQLB200_ERR_STATE when it cannot be found.  In Python the same sequence is
+ * parallel.SharedTableSync.sync (torch.distributed all-gather between the two C calls). */
+int dqlb200_shared_sync_nccl(dqlb200_handle* h, void* snapshot, void* packed, void* gathered, void* nccl_comm, int n_ranks,
+                             int replica_promote_successes, int pooled_promote_successes, void* stream);
 
 /* Replica-merge mode (one agent with more envs than one CTA can hold: BASELINE configs 2-3, "N envs sharing one
  * Q-table pair").  The agent's envs are split over R = cfg.replicas_per_population consecutive populations (replicas),

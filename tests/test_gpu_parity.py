@@ -975,3 +975,34 @@ def test_production_instance_vs_c_oracle_at_size():
             assert np.array_equal(qa.view(np.uint32), out["qa"].view(np.uint32)) and np.array_equal(qb.view(np.uint32), out["qb"].view(np.uint32))
             assert (int(ps[p]["working_step"]), int(ps[p]["total_episodes"]), int(ps[p]["total_successes"])) == (r.w, r.total_episodes, r.total_successes)
             assert list(ps[p]["termination_hist"]) == list(r.term_hist) and r.w >= 1
+
+
+def _run_nccl_sync_check(n_ranks):
+    import json
+    import pathlib
+    import subprocess
+    import sys
+    root = pathlib.Path(__file__).resolve().parent.parent
+    if n_ranks == 1:
+        cmd = [sys.executable, str(root / "tools" / "nccl_sync_check.py")]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n_ranks}", "--master-addr", "127.0.0.1",
+               "--master-port", "29631", str(root / "tools" / "nccl_sync_check.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root)
+    assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+    rows = [json.loads(l) for l in res.stdout.splitlines() if l.startswith("{")]
+    assert len(rows) == n_ranks and all(r["identical"] and r["cells_visited"] > 0 for r in rows), rows
+
+
+def test_shared_sync_nccl_single_rank():
+    """dqlb200_shared_sync_nccl (replica merge -> pack -> ncclAllGather on a raw ncclComm_t -> apply, all under the C-ABI) leaves the
+    same tables / trainer states as the Python sequence around a torch all-gather; one rank, so it runs in the 1-GPU suite."""
+    _run_nccl_sync_check(1)
+
+
+def test_shared_sync_nccl_two_ranks():
+    """The same with two ranks (two GPUs, real NCCL between them); skipped on a one-GPU box."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    _run_nccl_sync_check(2)
