@@ -600,7 +600,10 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
             e3.train_merged(2 * M, M); torch.cuda.synchronize(dev)
             s3 = timed(lambda: e3.train_merged(steps, M))
             res3[f"env_steps_per_s_merge_every_{M}"] = R * n_r * steps / s3
-        res3["env_steps_per_s"] = res3["env_steps_per_s_merge_every_16"]
+        # the config's own figure is the one at the Trainer default (merge after EVERY step: the setting that learns, see
+        # config3_promotion_enabled); every 16 steps is the throughput end of the trade-off
+        res3["env_steps_per_s"] = res3["env_steps_per_s_merge_every_1"]
+        res3["merge_every_of_env_steps_per_s"] = 1
         # per curriculum step: the same agent started at working step w from the committed tables
         # (more live levels to stage, snapshot and discretise; no exploration draws for w > 0), merged every 16 steps
         try:
