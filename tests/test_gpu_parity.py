@@ -878,6 +878,32 @@ def test_train_merged_graph_replay_equals_python_loop():
         assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("R,n_r,tpb,merge_every,default_cfg", [(8, 128, 128, 1, True), (8, 200, 128, 3, True), (24, 64, 32, 1, False), (5, 300, 128, 2, False)])
+def test_cooperative_replica_merge_equals_two_launch_sequence(R, n_r, tpb, merge_every, default_cfg):
+    """dqlb200_train_merged runs eligible layouts as ONE cooperative launch (train_kernel instances 4 / 5: the replicas of an agent
+    are co-resident CTAs, the merge of replica_merge_kernel runs between two barriers of the agent's CTAs inside the launch).  It
+    must leave exactly the state of the two-launch sequence train -> replica_merge (which the oracle tests pin): tables, env state,
+    trainer state and merge snapshot, through pooled promotions, a max-episodes advance, ragged last slots, several tiles of cells per
+    CTA, the production and the generic instance, and a call whose length is not a multiple of the merge interval."""
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=60)
+    from dql_multirotor_landing_b200 import constants as K
+    mp = None if default_cfg else K.MdpParameters(w_v=-12.0)      # any non-default constant selects the generic instance
+    out = []
+    for graph in (True, False):
+        e = _engine(2 * R, n_r, threads_per_block=tpb, seeds=[5] * R + [9] * R, population_ids=list(range(2 * R)), replicas_per_population=R, tp=kw,
+                    **({} if mp is None else {"mp": mp}))
+        assert e.lib.dqlb200_uses_default_instance(e.handle) == (1 if default_cfg else 0)
+        e.reset(0)
+        for steps in (101, 64, 7):
+            e.train_merged(steps, merge_every, graph=graph)
+        e.check_errors()
+        out.append((e.tables.cpu(), e.env_state.cpu(), e.pop_state.cpu(), e.merge_snapshot.cpu()))
+        ws = e.population_state()["working_step"]
+        assert int(ws.max()) >= 1, "the run should cross a pooled curriculum decision"
+    for a, b in zip(*out):
+        assert torch.equal(a, b)
+
+
 def test_default_and_generic_instances_agree():
     """The production instance of train_kernel has the reference-default MDP / dynamics constants compiled in (KDef); the generic
     instance reads them at run time.  dqlb200_create picks the production instance only for a bit-identical configuration; the
