@@ -196,8 +196,21 @@ __global__ void __launch_bounds__(NW * 32) replica_merge_kernel(uint32_t* tables
       }
       __syncthreads();
       if (warp == 0) {
-#pragma unroll 16
-        for (int j = 0; j < n; ++j) num = fadd(num, s_term[j][lane]);
+        // the chain is the critical path of the merge: the next eight terms are loaded before the eight dependent additions of
+        // the current ones are issued (otherwise every batch exposes a shared-memory latency between 4-cycle additions)
+        int j = 0;
+        if (n >= 8) {
+          float a0 = s_term[0][lane], a1 = s_term[1][lane], a2 = s_term[2][lane], a3 = s_term[3][lane], a4 = s_term[4][lane], a5 = s_term[5][lane],
+                a6 = s_term[6][lane], a7 = s_term[7][lane];
+          for (j = 8; j + 8 <= n; j += 8) {
+            const float b0 = s_term[j][lane], b1 = s_term[j + 1][lane], b2 = s_term[j + 2][lane], b3 = s_term[j + 3][lane], b4 = s_term[j + 4][lane],
+                        b5 = s_term[j + 5][lane], b6 = s_term[j + 6][lane], b7 = s_term[j + 7][lane];
+            num = fadd(fadd(fadd(fadd(fadd(fadd(fadd(fadd(num, a0), a1), a2), a3), a4), a5), a6), a7);
+            a0 = b0; a1 = b1; a2 = b2; a3 = b3; a4 = b4; a5 = b5; a6 = b6; a7 = b7;
+          }
+          num = fadd(fadd(fadd(fadd(fadd(fadd(fadd(fadd(num, a0), a1), a2), a3), a4), a5), a6), a7);
+        }
+        for (; j < n; ++j) num = fadd(num, s_term[j][lane]);
       }
       if (r0 + CHUNK < R) __syncthreads();      // the next round overwrites the terms
     }

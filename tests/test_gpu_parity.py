@@ -879,12 +879,12 @@ def test_train_merged_graph_replay_equals_python_loop():
 
 
 @pytest.mark.parametrize("R,n_r,tpb,merge_every,default_cfg", [(8, 128, 128, 1, True), (8, 200, 128, 3, True), (24, 64, 32, 1, False), (5, 300, 128, 2, False)])
-def test_cooperative_replica_merge_equals_two_launch_sequence(R, n_r, tpb, merge_every, default_cfg):
-    """dqlb200_train_merged runs eligible layouts as ONE cooperative launch (train_kernel instances 4 / 5: the replicas of an agent
-    are co-resident CTAs, the merge of replica_merge_kernel runs between two barriers of the agent's CTAs inside the launch).  It
-    must leave exactly the state of the two-launch sequence train -> replica_merge (which the oracle tests pin): tables, env state,
-    trainer state and merge snapshot, through pooled promotions, a max-episodes advance, ragged last slots, several tiles of cells per
-    CTA, the production and the generic instance, and a call whose length is not a multiple of the merge interval."""
+def test_train_merged_equals_two_launch_sequence(R, n_r, tpb, merge_every, default_cfg):
+    """dqlb200_train_merged (graphs of (train, merge) pairs replayed from C) must leave exactly the state of the two-launch sequence
+    train -> replica_merge driven from Python (which the oracle tests pin): tables, env state, trainer state and merge snapshot, for
+    TWO agents side by side, through pooled promotions and a max-episodes advance, ragged last slots, 32- and 128-thread blocks, the
+    production and the generic instance, and calls whose length is not a multiple of the merge interval.  (Any other way of running
+    the merged loop -- round 2 tried one cooperative launch, profiles/r02_coop_merge_rejected.txt -- has to pass this test.)"""
     kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=60)
     from dql_multirotor_landing_b200 import constants as K
     mp = None if default_cfg else K.MdpParameters(w_v=-12.0)      # any non-default constant selects the generic instance
