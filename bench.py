@@ -508,12 +508,16 @@ def config3_with_promotion(dev, np, torch, K, Engine, timed_events) -> dict:
         env-steps/s, wall time, and the success rate reached after a fixed budget of global steps -- speed and learning quality side
         by side (the reference algorithm plateaus below 0.96 on the analytic stand-in, DESIGN.md section 3, so this is time to plateau);
     (b) the curriculum walk with the threshold at 0.80 and transfer_mode "paper": wall time to every promotion."""
-    R, n_r = 512, 128
-    envs = R * n_r
-    out = {"replicas": R, "envs_per_replica": n_r, "envs": envs, "timing": "CUDA events around every chunk of global steps"}
+    from dql_multirotor_landing_b200.trainer import replica_shape
+    envs = 65536
+    out = {"envs": envs, "timing": "CUDA events around every chunk of global steps",
+           "replica_shape": "Trainer default per merge interval (trainer.replica_shape): 128 replicas x 512 envs in 256-thread blocks when merging after every "
+                            "step, 512 x 128 in 128-thread blocks when merging every 16 steps; the learning curve does not depend on the split"}
 
     def run(tp, merge_every, budget_steps, chunk):
-        e = Engine(R, n_r, device=dev.index or 0, threads_per_block=128, seeds=[42] * R, population_ids=list(range(R)), replicas_per_population=R, tp=tp)
+        n_r = replica_shape(envs, merge_every)
+        R = envs // n_r
+        e = Engine(R, n_r, device=dev.index or 0, threads_per_block=256 if n_r >= 256 else 128, seeds=[42] * R, population_ids=list(range(R)), replicas_per_population=R, tp=tp)
         e.reset(0)
         e.train_merged(merge_every, merge_every); torch.cuda.synchronize(dev)       # graph instantiation outside the timed region
         wall, done, rows, prev = 0.0, 0, [], e.population_state()
@@ -536,7 +540,7 @@ def config3_with_promotion(dev, np, torch, K, Engine, timed_events) -> dict:
                 break
         e.check_errors()
         e.close()
-        return {"merge_every": merge_every, "global_steps": done, "env_steps": envs * done, "wall_s": wall, "env_steps_per_s": envs * done / wall,
+        return {"merge_every": merge_every, "replicas": R, "envs_per_replica": n_r, "global_steps": done, "env_steps": envs * done, "wall_s": wall, "env_steps_per_s": envs * done / wall,
                 "success_rate_last_chunk": rows[-1]["success_rate_in_chunk"], "window_success_rate_at_end": rows[-1]["window_success_rate"],
                 "working_step_at_end": rows[-1]["working_step"], "promotions": promoted,
                 "curve": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in rows[:: max(len(rows) // 8, 1)]]}
@@ -591,15 +595,26 @@ def extra_measurements(eng, dev, np, torch, greedy_policy) -> dict:
     try:
         from dql_multirotor_landing_b200 import constants as K
         from dql_multirotor_landing_b200.engine import Engine
-        R, n_r, steps = 512, 128, 256
-        e3 = Engine(R, n_r, device=dev.index or 0, threads_per_block=128, seeds=[42] * R, population_ids=list(range(R)),
-                    replicas_per_population=R, tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
-        e3.reset(0)
-        res3 = {"replicas": R, "envs_per_replica": n_r, "timing": "CUDA events, best of 3; (train launch, replica merge) pairs replayed as one CUDA graph"}
+        from dql_multirotor_landing_b200.trainer import replica_shape
+        steps = 256
+        res3 = {"timing": "CUDA events, best of 3; (train launch, replica merge) pairs replayed as one CUDA graph"}
+
+        def agent3(M):          # the Trainer's replica split for this merge interval (trainer.replica_shape)
+            n_r = replica_shape(65536, M)
+            R = 65536 // n_r
+            e = Engine(R, n_r, device=dev.index or 0, threads_per_block=256 if n_r >= 256 else 128, seeds=[42] * R, population_ids=list(range(R)),
+                       replicas_per_population=R, tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
+            e.reset(0)
+            return e, R, n_r
+
         for M in (1, 16):          # merge after every step (closest to one shared table) / every 16 steps (throughput)
+            e3, R, n_r = agent3(M)
             e3.train_merged(2 * M, M); torch.cuda.synchronize(dev)
             s3 = timed(lambda: e3.train_merged(steps, M))
             res3[f"env_steps_per_s_merge_every_{M}"] = R * n_r * steps / s3
+            res3[f"replicas_x_envs_merge_every_{M}"] = [R, n_r]
+            if M == 1:
+                e3.close()
         # the config's own figure is the one at the Trainer default (merge after EVERY step: the setting that learns, see
         # config3_promotion_enabled); every 16 steps is the throughput end of the trade-off
         res3["env_steps_per_s"] = res3["env_steps_per_s_merge_every_1"]

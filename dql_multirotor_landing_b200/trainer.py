@@ -31,6 +31,19 @@ from .double_q_learning import DoubleQLearningAgent, StateAction
 _TIME_FORMAT = r"%d-%m-%Y %H:%M:%S"
 
 
+def replica_shape(num_envs: int, merge_every: int = 1) -> int:
+    """Envs per replica for ONE agent on `num_envs` envs (replica-merge mode).  Merging after every step the
+    merge grows with the number of replicas while a replica's step grows with its envs: about 128 replicas is the measured optimum
+    on a B200 up to 1,024 envs per replica (65,536 envs: 128 x 512 envs 15.3 us per step, 512 x 128 18.6, 64 x 1,024 18.9; 262,144
+    envs: 256 x 1,024 24.1, 128 x 2,048 28.1, 512 x 512 32.0; profiles/r02_coop_merge_rejected.txt), and the learning curve does not depend on the split (tools/learn_probe.py:
+    0.814 / 0.815 after 2,700 episodes per env for 64, 128 and 512 replicas).  With rarer merges more, smaller replicas win
+    (every 16 steps: 512 x 128 5.0 us per step, 128 x 512 7.3)."""
+    if merge_every > 1:
+        return 128
+    per = -(-num_envs // 128)
+    return min(max(-(-per // 128) * 128, 128), 1024)
+
+
 class Trainer:
     def __init__(
         self,
@@ -61,7 +74,7 @@ class Trainer:
         platform_speed: float = 1.6,
         dynamics: Optional[K.DynamicsParameters] = None,
         max_global_steps: Optional[int] = None,
-        envs_per_replica: int = 128,
+        envs_per_replica: Optional[int] = None,
         merge_every: int = 1,
         tensorboard: bool = False,
         verbose: bool = True,
@@ -95,9 +108,11 @@ class Trainer:
         # one agent with more envs than a CTA should hold -> replica-merge mode
         self._replicas = 1
         if num_populations == 1 and num_envs > 2048:
+            if envs_per_replica is None:
+                envs_per_replica = replica_shape(num_envs, merge_every)
             self._replicas = -(-num_envs // envs_per_replica)
             self._num_envs = envs_per_replica
-            self._threads_per_block = 128 if envs_per_replica >= 128 else 32
+            self._threads_per_block = 256 if envs_per_replica >= 256 else (128 if envs_per_replica >= 128 else 32)
         self._merge_every = merge_every
         self._envs_per_agent = self._num_envs * self._replicas      # envs that share one table pair (and one episode budget)
         self._tensorboard, self._verbose = tensorboard, verbose

@@ -166,3 +166,14 @@ def test_setpoint_tables_vs_reference_live(cfg, reference_ns):
                 # exactly: the reference's own expression (PKG/mdp.py:506-514) on the shaping values reward() just used
                 cur, prev = mdp.current_shaping_value.angle, mdp.previous_shaping_value.angle
                 assert mdp._w_theta * (np.abs(cur) - np.abs(prev)) / mdp._theta_max * lim_v == want, (p, a, fresh)
+
+
+def test_trainer_replica_shape():
+    """Trainer splits ONE agent's envs into replicas of trainer.replica_shape() envs: about 128 replicas when merging after every
+    step (multiples of 128 envs, at most 1,024 per replica), 128-env replicas for rarer merges; every env is covered."""
+    from dql_multirotor_landing_b200.trainer import replica_shape
+    assert [replica_shape(n) for n in (4096, 16384, 65536, 262144, 1 << 20)] == [128, 128, 512, 1024, 1024]
+    assert replica_shape(65536, merge_every=16) == 128
+    for n in (2049, 5000, 70000, 300000):
+        n_r = replica_shape(n)
+        assert n_r % 128 == 0 and 128 <= n_r <= 1024 and -(-n // n_r) * n_r >= n
