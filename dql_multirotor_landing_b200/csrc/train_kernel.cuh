@@ -73,19 +73,12 @@ constexpr int EP_RET_CAP = 32;     // warp-slots with finished episodes buffered
 // Shared memory of one population (CTA).  Q_b and the alpha LUT stay in global memory (read-only in the step
 // loop, L1-resident): that keeps the footprint at ~37 KB so that six CTAs fit on one SM.
 struct Shared {
-#ifdef DQL_HACK_LEVELS      // occupancy experiment only (tools/perf_probe.py at working step 0): tables of DQL_HACK_LEVELS levels
-  float qa[DQL_HACK_LEVELS * DQLB200_CELLS_PER_LEVEL];
-  uint32_t cnt[DQL_HACK_LEVELS * DQLB200_CELLS_PER_LEVEL];
-  float qmax[DQL_HACK_LEVELS * DQLB200_STATES_PER_LEVEL];
-  uint8_t greedy[DQL_HACK_LEVELS * DQLB200_STATES_PER_LEVEL + 3];
-#else
   float qa[CELLS];        // live table A
   uint32_t cnt[CELLS];    // state_action_counter
   // Snapshot of the start of the global step.  Phase A reads the tables only through two per-STATE quantities, so the
   // snapshot is those two instead of a copy of Q_a: the greedy action argmax_a (Q_a+Q_b)/2 (R9) and max_a Q_a (R12).
   float qmax[STATES];
   uint8_t greedy[STATES + 3];
-#endif
   dqlb200_cuts cuts;
   dqlb200_reward_level reward[DQLB200_MAX_CURRICULUM];
   dqlb200_population_state ps;
@@ -120,9 +113,7 @@ __host__ __device__ constexpr size_t train_smem_bytes(int threads, bool extended
 
 // the production launch shape (128 threads, 33 reachable set-points of the reference defaults) must keep six populations resident
 // per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA (a 96-byte overshoot once halved the occupancy unnoticed)
-#ifndef DQL_HACK_LEVELS
 static_assert((train_smem_bytes(128, false, 33) + 1024) * 6 <= 228 * 1024, "train_kernel<4>: six CTAs per SM no longer fit in shared memory");
-#endif
 #ifndef DQL_WARPS_PER_SM
 #define DQL_WARPS_PER_SM 24     // resident warps per SM the register allocation is tuned for (launch bounds)
 #endif
@@ -501,11 +492,7 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
         // (every working step > 0) no draw can change the outcome and the Philox call is skipped.
         a = sh.greedy[sid];
         if (W0 || w == 0 || (GENERIC && kk.noise_enabled)) {
-#ifdef DQL_PHILOX_INLINE_KEYS
-          const uint4 d = philox4x32_10(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), pp.seed_lo, pp.seed_hi);
-#else
           const uint4 d = philox4x32_10_keyed(make_uint4((uint32_t)env_i, t, PURPOSE_STEP, pp.population_id), sh.philox_keys);
-#endif
           if (W0 || w == 0) {
             const uint32_t thr = __ldg(args.eps_threshold + min(e.episode, (uint32_t)(DQLB200_EPS_LUT - 1)));
             if ((d.x >> 8) < thr) a = (int)__umulhi(d.y, 3u);
@@ -527,9 +514,6 @@ __global__ void __launch_bounds__(WARPS * 32, ((VARIANT == 2 ? DQL_WARPS_PER_SM_
       // cycles -- is exposed; issued here it is covered by the dynamics)
       uint32_t peers;
       asm volatile("match.any.sync.b32 %0, %1, 0xffffffff;" : "=r"(peers) : "r"(valid ? cell : (0x80000000u | (uint32_t)lane)) : "memory");
-#ifdef DQL_MATCH_ANCHOR
-      __syncwarp();
-#endif
       uint2 spn = make_uint2(0u, 0u);
       double r_theta0 = 0.0;
       Obs o = {};
