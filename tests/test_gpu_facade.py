@@ -221,14 +221,16 @@ def test_trainer_episode_budget_is_per_env(tmp_path):
     assert greedy_share > 0 and agent.state_action_counter.sum() == ps["total_steps"]
 
 
-def test_trainer_large_population_uses_replica_merge(tmp_path):
-    """Config 3 through the Trainer facade: one agent, 8,192 envs -> 64 replicas x 128 envs merged every 4 steps."""
+@pytest.mark.parametrize("num_envs,merge_every,steps,shape", [(8192, 4, 1024, (64, 128)), (65536, 1, 256, (128, 512))])
+def test_trainer_large_population_uses_replica_merge(tmp_path, num_envs, merge_every, steps, shape):
+    """Config 3 through the Trainer facade: one agent, 8,192 envs -> 64 replicas x 128 envs merged every 4 steps; 65,536 envs merged
+    after every step (the default) -> 128 replicas x 512 envs in 256-thread blocks (trainer.replica_shape)."""
     from dql_multirotor_landing_b200.trainer import Trainer
-    tr = Trainer(save_path=tmp_path / "run", success_rate=0.5, max_num_episodes=30000, num_envs=8192, chunk_steps=64,
-                 merge_every=4, verbose=False, max_global_steps=1024)
+    tr = Trainer(save_path=tmp_path / "run", success_rate=0.5, max_num_episodes=30000, num_envs=num_envs, chunk_steps=64,
+                 merge_every=merge_every, verbose=False, max_global_steps=steps)
     tr.curriculum_training()
     eng = tr._engine
-    assert eng.R == 64 and eng.n_p == 128
+    assert (eng.R, eng.n_p) == shape
     ps = eng.population_state()
     agent = tr._double_q_learning_agent
     assert agent.state_action_counter.sum() == ps["total_steps"].sum() > 0       # every env-step of every replica is in the merged counts
