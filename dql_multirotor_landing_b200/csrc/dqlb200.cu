@@ -366,10 +366,20 @@ int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, vo
 
 int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host, void* pop_state_host,
                        int table_levels, void* stream) {
+  return dqlb200_train_host_ext(h, k_steps, env_state_host, tables_host, pop_state_host, nullptr, nullptr, table_levels, stream);
+}
+
+int dqlb200_train_host_ext(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host, void* pop_state_host,
+                           void* filter_state_host, void* dynamics_state_host, int table_levels, void* stream) {
   if (!h || !h->env_state) return fail(DQLB200_ERR_STATE, "buffers not bound (device staging buffers are the bound ones)");
   if (!env_state_host || !tables_host || !pop_state_host) return fail(DQLB200_ERR_ARG, "null host buffer");
-  if (h->cfg.accel_mode != 0 || h->cfg.dynamics_model != 0)
-    return fail(DQLB200_ERR_ARG, "dqlb200_train_host does not carry the estimator / second-order state (accel_mode, dynamics_model != 0): use dqlb200_train on bound device buffers");
+  // the per-env extension state of the options travels like the env state (never computed with a default model instead)
+  if (h->cfg.accel_mode != 0 && !filter_state_host)
+    return fail(DQLB200_ERR_ARG, "accel_mode != 0: the estimator state must travel too (dqlb200_train_host_ext with filter_state_host)");
+  if (h->cfg.dynamics_model != 0 && !dynamics_state_host)
+    return fail(DQLB200_ERR_ARG, "dynamics_model != 0: the second-order state must travel too (dqlb200_train_host_ext with dynamics_state_host)");
+  DQL_NEED_FILTER(h);
+  const bool with_filter = h->cfg.accel_mode != 0, with_dyn = h->cfg.dynamics_model != 0;
   if (k_steps < 0) return fail(DQLB200_ERR_ARG, "k_steps < 0");
   if (table_levels < 0 || table_levels > h->cfg.curriculum_steps) return fail(DQLB200_ERR_ARG, "table_levels must be 0 (all) .. curriculum_steps");
   CUDA_TRY(cudaSetDevice(h->device));
@@ -420,6 +430,11 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
                                  (const char*)tables_host + p0 * tab_stride + (cs_levels - 1) * level_bytes, row_bytes, level_bytes,
                                  (size_t)3 * (p1 - p0), cudaMemcpyHostToDevice, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)h->pop_state + p0 * ps_stride, (const char*)pop_state_host + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyHostToDevice, cs));
+    // extension state of the chunk's envs: [n] x 16 B (estimator) and [2][n] x 16 B (second-order model: two planes, one 2-D copy)
+    const size_t x0 = (size_t)p0 * h->cfg.envs_per_population * 16, xb = (size_t)(p1 - p0) * h->cfg.envs_per_population * 16;
+    const size_t plane = (size_t)P * h->cfg.envs_per_population * 16;
+    if (with_filter) CUDA_TRY(cudaMemcpyAsync((char*)h->filter_state + x0, (const char*)filter_state_host + x0, xb, cudaMemcpyHostToDevice, cs));
+    if (with_dyn) CUDA_TRY(cudaMemcpy2DAsync((char*)h->dynamics_state + x0, plane, (const char*)dynamics_state_host + x0, plane, xb, 2, cudaMemcpyHostToDevice, cs));
     if (k_steps > 0) {
       const int rc = launch_train(h, k_steps, nullptr, h->env_state, h->tables, h->pop_state, cs, p0, p1 - p0);
       if (rc) return rc;
@@ -428,6 +443,8 @@ int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, voi
     CUDA_TRY(cudaMemcpy2DAsync((char*)tables_host + p0 * tab_stride, row_bytes, (const char*)h->tables + p0 * tab_stride, row_bytes,
                                levels * level_bytes, (size_t)3 * (p1 - p0), cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaMemcpyAsync((char*)pop_state_host + p0 * ps_stride, (const char*)h->pop_state + p0 * ps_stride, (p1 - p0) * ps_stride, cudaMemcpyDeviceToHost, cs));
+    if (with_filter) CUDA_TRY(cudaMemcpyAsync((char*)filter_state_host + x0, (const char*)h->filter_state + x0, xb, cudaMemcpyDeviceToHost, cs));
+    if (with_dyn) CUDA_TRY(cudaMemcpy2DAsync((char*)dynamics_state_host + x0, plane, (const char*)h->dynamics_state + x0, plane, xb, 2, cudaMemcpyDeviceToHost, cs));
     CUDA_TRY(cudaEventRecord(h->chunk_done[c], cs));
     CUDA_TRY(cudaStreamWaitEvent(s, h->chunk_done[c], 0));
   }

@@ -131,12 +131,20 @@ class Engine:
         return None
 
     def train_host(self, k_steps: int, env_state_host: torch.Tensor, tables_host: torch.Tensor, pop_state_host: torch.Tensor,
-                   table_levels: int = 0):
+                   table_levels: int = 0, filter_state_host: Optional[torch.Tensor] = None,
+                   dynamics_state_host: Optional[torch.Tensor] = None):
         """End-to-end call with pinned HOST buffers (copies in, k_steps, copies out, synchronises).  table_levels = L > 0: only
         the table levels 0 .. L-1 travel (the caller's promise that no population is promoted beyond them inside the call; the
-        library checks it afterwards); 0 = every level."""
-        _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
-                                               pop_state_host.data_ptr(), int(table_levels), self._stream()))
+        library checks it afterwards); 0 = every level.  With accel_mode / dynamics_model the per-env extension state travels too
+        (filter_state_host [n, 4], dynamics_state_host [2, n, 4] float32, the layouts of the bound device buffers)."""
+        if filter_state_host is None and dynamics_state_host is None:
+            _ffi.check(self.lib.dqlb200_train_host(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
+                                                   pop_state_host.data_ptr(), int(table_levels), self._stream()))
+            return
+        ptr = lambda t: t.data_ptr() if t is not None else None
+        _ffi.check(self.lib.dqlb200_train_host_ext(self.handle, k_steps, env_state_host.data_ptr(), tables_host.data_ptr(),
+                                                   pop_state_host.data_ptr(), ptr(filter_state_host), ptr(dynamics_state_host),
+                                                   int(table_levels), self._stream()))
 
     # ------------------------------------------------------------------------------------------
     # replica-merge mode: R consecutive populations are replicas of one agent (more envs than one CTA holds)

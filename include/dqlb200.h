@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define DQLB200_ABI_VERSION 7
+#define DQLB200_ABI_VERSION 8
 #define DQLB200_MAX_CURRICULUM 5
 #define DQLB200_STATES_PER_LEVEL 189          /* 3*3*3*7      (PKG/double_q_learning.py:38-40) */
 #define DQLB200_CELLS_PER_LEVEL 567           /* 189 * 3 actions */
@@ -292,10 +292,18 @@ int dqlb200_train(dqlb200_handle* h, int k_steps, const dqlb200_trace* trace, vo
  * -- in reference transfer mode -- the last level on the way in for populations at step 0, which quirk Q7 reads): the caller's
  * promise that no population needs more (working step w touches levels 0 .. w, a promotion inside the call w + 1).  Refused
  * up front when a working step already exceeds it, reported (DQLB200_ERR_STATE) when a promotion inside the call broke it.
- * Does not carry the per-env extension state: configurations with accel_mode != 0 or dynamics_model != 0 are refused
- * (DQLB200_ERR_ARG), use dqlb200_train on bound device buffers. */
+ * Configurations with accel_mode != 0 or dynamics_model != 0 have per-env extension state that must travel too: they are
+ * refused here (DQLB200_ERR_ARG) and served by dqlb200_train_host_ext. */
 int dqlb200_train_host(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host,
                        void* pop_state_host, int table_levels, void* stream);
+
+/* dqlb200_train_host with the per-env extension state of the options travelling beside the env state,
+ * chunk by chunk: filter_state_host = [n_envs] x 16 B (accel_mode != 0, the layout of dqlb200_bind_filter_state),
+ * dynamics_state_host = [2][n_envs] x 16 B (dynamics_model != 0, the layout of dqlb200_bind_dynamics_state); either may be NULL
+ * when its option is off (both NULL: exactly dqlb200_train_host).  The device buffers bound with dqlb200_bind_filter_state /
+ * dqlb200_bind_dynamics_state are the staging buffers. */
+int dqlb200_train_host_ext(dqlb200_handle* h, int k_steps, void* env_state_host, void* tables_host, void* pop_state_host,
+                           void* filter_state_host, void* dynamics_state_host, int table_levels, void* stream);
 
 /* Replaces: scripts/simulation.py:48-63 (+ SimulationLandingEnv.reset/step, SimulationMdp):
  * n_episodes greedy episodes of population `population`'s policy, episode i uses reset draws

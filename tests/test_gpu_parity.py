@@ -271,8 +271,8 @@ def test_second_order_greedy_evaluation_vs_oracle():
 
 
 def test_kalman_acceleration_needs_its_state_buffer():
-    """accel_mode != 0 without the estimator buffer is refused (no silent fall-back to the analytic acceleration), and the
-    host-buffer call, which does not carry that buffer, says so."""
+    """accel_mode != 0 without the estimator buffer is refused (no silent fall-back to the analytic acceleration); the host-buffer
+    call carries the buffer through dqlb200_train_host_ext (test_train_host_carries_the_extension_state)."""
     from dql_multirotor_landing_b200 import _ffi
     eng = _engine(1, 32, threads_per_block=32, seeds=[1], dp=dict(accel_mode="kalman", n_sub=4))
     _ffi.check(eng.lib.dqlb200_bind_filter_state(eng.handle, None))
@@ -786,6 +786,33 @@ def test_train_host_equals_device_resident_training(P):
     assert torch.equal(a.tables.cpu(), tab_h)
     assert torch.equal(a.pop_state.cpu(), ps_h)
     assert int(a.population_state()["working_step"].max()) >= 1
+
+
+def test_train_host_carries_the_extension_state():
+    """dqlb200_train_host_ext: with the acceleration estimator and the second-order model switched on, their per-env state
+    travels beside the env state (one block / one two-plane copy per chunk) and the call leaves exactly what the device-resident
+    entry point leaves; the plain entry point refuses such a configuration instead of stepping with a default model."""
+    from dql_multirotor_landing_b200 import _ffi
+    kw = dict(success_rate=0.15, successive_successful_episodes=6, max_num_episodes=90)
+    dp = dict(accel_mode="kalman", dynamics_model="second_order", n_sub=4, noise_pos_sd=0.02, noise_vel_sd=0.05)
+    P = 11
+    a = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=kw, dp=dp)
+    b = _engine(P, 70, threads_per_block=64, seeds=list(range(P)), tp=kw, dp=dp)
+    a.reset(0)
+    b.reset(0)
+    env_h, tab_h, ps_h = b.env_state.cpu().pin_memory(), b.tables.cpu().pin_memory(), b.pop_state.cpu().pin_memory()
+    fs_h, ds_h = b.filter_state.cpu().pin_memory(), b.dynamics_state.cpu().pin_memory()
+    with pytest.raises(_ffi.Dqlb200Error, match="must travel too"):
+        b.train_host(1, env_h, tab_h, ps_h)
+    for t in (b.env_state, b.tables, b.pop_state, b.filter_state, b.dynamics_state):
+        t.zero_()                                                      # the call must not depend on what the staging buffers hold
+    for k in (40, 1, 90):
+        a.train(k)
+        b.train_host(k, env_h, tab_h, ps_h, filter_state_host=fs_h, dynamics_state_host=ds_h)
+    torch.cuda.synchronize()
+    assert torch.equal(a.env_state.cpu(), env_h) and torch.equal(a.tables.cpu(), tab_h) and torch.equal(a.pop_state.cpu(), ps_h)
+    assert torch.equal(a.filter_state.cpu(), fs_h) and torch.equal(a.dynamics_state.cpu(), ds_h)
+    assert float(fs_h.abs().sum()) > 0 and int(a.population_state()["total_episodes"].sum()) > 0
 
 
 def test_train_host_with_partial_table_levels():
