@@ -6,9 +6,9 @@
 // R7 reward PKG/mdp.py:441-541, R9 guess/predict PKG/double_q_learning.py:110-124.
 //
 // Bit-exactness rules used throughout:
-//   * fp32 dynamics: every operation is an explicit __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn (never
-//     contracted to FMA), polynomials in Horner form -> identical to NumPy float32 and to C with
-//     -ffp-contract=off;
+//   * fp32 dynamics: every operation is an explicit __fmul_rn/__fadd_rn/__fdiv_rn/__fsqrt_rn/__fmaf_rn (the
+//     compiler never contracts on its own: --fmad=false); the Horner steps of sin/cos/tan are explicit fused
+//     multiply-adds -> identical to NumPy float32 (with an exact FMA emulation) and to C with -ffp-contract=off;
 //   * float64 reward: explicit __dmul_rn/__dadd_rn/__ddiv_rn in the reference's operation order;
 //   * comparisons on fp32 observations use host-computed cut points (constants.py).
 #pragma once
@@ -142,17 +142,19 @@ __device__ __forceinline__ void det_sincos_turns(uint32_t phase, float& s_out, f
   const int32_t rem = (int32_t)(phase - (q << 30));
   const float x = fmul(__int2float_rn(rem), (float)(6.283185307179586 / 4294967296.0));
   const float z = fmul(x, x);
+  // Horner steps as fused multiply-adds (FFMA, one rounding each): the stand-in is DEFINED that way (oracle/dynamics.py: fma32,
+  // oracle/c/standin.c: fmaf) -- a separately rounded product would cost one more instruction per step
   float ps = (float)(1.0 / 362880.0);
-  ps = fadd(fmul(ps, z), (float)(-1.0 / 5040.0));
-  ps = fadd(fmul(ps, z), (float)(1.0 / 120.0));
-  ps = fadd(fmul(ps, z), (float)(-1.0 / 6.0));
-  const float s = fadd(x, fmul(x, fmul(z, ps)));
+  ps = __fmaf_rn(ps, z, (float)(-1.0 / 5040.0));
+  ps = __fmaf_rn(ps, z, (float)(1.0 / 120.0));
+  ps = __fmaf_rn(ps, z, (float)(-1.0 / 6.0));
+  const float s = __fmaf_rn(x, fmul(z, ps), x);
   float pc = (float)(-1.0 / 3628800.0);
-  pc = fadd(fmul(pc, z), (float)(1.0 / 40320.0));
-  pc = fadd(fmul(pc, z), (float)(-1.0 / 720.0));
-  pc = fadd(fmul(pc, z), (float)(1.0 / 24.0));
-  pc = fadd(fmul(pc, z), -0.5f);
-  const float c = fadd(1.0f, fmul(z, pc));
+  pc = __fmaf_rn(pc, z, (float)(1.0 / 40320.0));
+  pc = __fmaf_rn(pc, z, (float)(-1.0 / 720.0));
+  pc = __fmaf_rn(pc, z, (float)(1.0 / 24.0));
+  pc = __fmaf_rn(pc, z, -0.5f);
+  const float c = __fmaf_rn(z, pc, 1.0f);
   // quadrant q: (sin, cos) = (s, c), (c, -s), (-s, -c), (-c, s) -- branch-free: swap on odd q, then sign bits
   const bool odd = (q & 1u) != 0u;
   const uint32_t sb = __float_as_uint(odd ? c : s), cb = __float_as_uint(odd ? s : c);
@@ -163,12 +165,12 @@ __device__ __forceinline__ void det_sincos_turns(uint32_t phase, float& s_out, f
 __device__ __forceinline__ float det_tan(float x) {
   const float z = fmul(x, x);
   float p = (float)(21844.0 / 6081075.0);
-  p = fadd(fmul(p, z), (float)(1382.0 / 155925.0));
-  p = fadd(fmul(p, z), (float)(62.0 / 2835.0));
-  p = fadd(fmul(p, z), (float)(17.0 / 315.0));
-  p = fadd(fmul(p, z), (float)(2.0 / 15.0));
-  p = fadd(fmul(p, z), (float)(1.0 / 3.0));
-  return fadd(x, fmul(x, fmul(z, p)));
+  p = __fmaf_rn(p, z, (float)(1382.0 / 155925.0));
+  p = __fmaf_rn(p, z, (float)(62.0 / 2835.0));
+  p = __fmaf_rn(p, z, (float)(17.0 / 315.0));
+  p = __fmaf_rn(p, z, (float)(2.0 / 15.0));
+  p = __fmaf_rn(p, z, (float)(1.0 / 3.0));
+  return __fmaf_rn(x, fmul(z, p), x);
 }
 
 // sin / cos of a small angle in radians (|x| <= ~0.8: attitude angles and attitude errors), Taylor polynomials in Horner form

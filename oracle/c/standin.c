@@ -3,7 +3,7 @@
  * Plain-C restatement of the deterministic numeric core of the hot path, the third statement of the same arithmetic
  * next to oracle/dynamics.py + oracle/philox.py (NumPy float32) and the CUDA kernels (csrc/dqlb200_device.cuh):
  *   - Philox4x32-10 (Salmon et al. 2011) and the draw contract counter = (env, step, purpose, population), key = seed
- *   - the fp32 building blocks: sin/cos of a uint32 "turns" phase, tan, log, Box-Muller normal (Horner, no FMA)
+ *   - the fp32 building blocks: sin/cos of a uint32 "turns" phase, tan (Horner in fused multiply-adds), log, Box-Muller normal (Horner, no FMA)
  *   - the analytic stand-in (there is no reference function for it): first-order pitch lag,
  *     a = g tan(theta) - c_d v, platform x = r sin(w t) (PKG/moving_platform.py:116-125), rel = platform - drone
  *     (PKG/observation_utils.py:225,249)
@@ -54,17 +54,19 @@ void oracle_sincos_turns(uint32_t phase, float* s_out, float* c_out) {
   const int32_t rem = (int32_t)(phase - (q << 30));
   const float x = (float)rem * (float)(6.283185307179586 / 4294967296.0);
   const float z = x * x;
+  /* Horner steps as FUSED multiply-adds (one rounding each, fmaf is exact): the statement the kernels' FFMA and the NumPy
+   * emulation (oracle/dynamics.py: fma32) agree with bit for bit */
   float ps = (float)(1.0 / 362880.0);
-  ps = ps * z + (float)(-1.0 / 5040.0);
-  ps = ps * z + (float)(1.0 / 120.0);
-  ps = ps * z + (float)(-1.0 / 6.0);
-  const float s = x + x * (z * ps);
+  ps = fmaf(ps, z, (float)(-1.0 / 5040.0));
+  ps = fmaf(ps, z, (float)(1.0 / 120.0));
+  ps = fmaf(ps, z, (float)(-1.0 / 6.0));
+  const float s = fmaf(x, z * ps, x);
   float pc = (float)(-1.0 / 3628800.0);
-  pc = pc * z + (float)(1.0 / 40320.0);
-  pc = pc * z + (float)(-1.0 / 720.0);
-  pc = pc * z + (float)(1.0 / 24.0);
-  pc = pc * z + -0.5f;
-  const float c = 1.0f + z * pc;
+  pc = fmaf(pc, z, (float)(1.0 / 40320.0));
+  pc = fmaf(pc, z, (float)(-1.0 / 720.0));
+  pc = fmaf(pc, z, (float)(1.0 / 24.0));
+  pc = fmaf(pc, z, -0.5f);
+  const float c = fmaf(z, pc, 1.0f);
   switch (q & 3u) {
     case 0: *s_out = s; *c_out = c; break;
     case 1: *s_out = c; *c_out = -s; break;
@@ -76,12 +78,12 @@ void oracle_sincos_turns(uint32_t phase, float* s_out, float* c_out) {
 float oracle_tan(float x) {
   const float z = x * x;
   float p = (float)(21844.0 / 6081075.0);
-  p = p * z + (float)(1382.0 / 155925.0);
-  p = p * z + (float)(62.0 / 2835.0);
-  p = p * z + (float)(17.0 / 315.0);
-  p = p * z + (float)(2.0 / 15.0);
-  p = p * z + (float)(1.0 / 3.0);
-  return x + x * (z * p);
+  p = fmaf(p, z, (float)(1382.0 / 155925.0));
+  p = fmaf(p, z, (float)(62.0 / 2835.0));
+  p = fmaf(p, z, (float)(17.0 / 315.0));
+  p = fmaf(p, z, (float)(2.0 / 15.0));
+  p = fmaf(p, z, (float)(1.0 / 3.0));
+  return fmaf(x, z * p, x);
 }
 
 static float sin_small(float x) {

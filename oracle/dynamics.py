@@ -119,8 +119,25 @@ _SQRT2 = f32(math.sqrt(2.0))
 ONE = f32(1.0)
 
 
+def fma32(a, b, c):
+    """Correctly rounded float32 fused multiply-add RN(a * b + c) on arrays (what FFMA / fmaf compute), in NumPy: the product of
+    two float32 is exact in float64; the float64 sum is rounded TO ODD (if it is inexact -- TwoSum gives the exact error -- the
+    neighbour with an odd last bit is taken), so that the final rounding to float32 sees no double rounding (53 >= 2 * 24 + 2)."""
+    a64, b64, c64 = (np.asarray(v, dtype=np.float32).astype(np.float64) for v in (a, b, c))
+    p = a64 * b64
+    s = p + c64
+    bb = s - p
+    err = (p - (s - bb)) + (c64 - bb)
+    s, err = np.broadcast_arrays(s, err)
+    bits = s.copy().view(np.uint64)
+    fix = (err != 0) & ((bits & np.uint64(1)) == 0)
+    grows = (err > 0) == (s > 0)                      # the exact sum is further from zero than s
+    bits = np.where(fix, np.where(grows, bits + np.uint64(1), bits - np.uint64(1)), bits)
+    return bits.view(np.float64).astype(np.float32)
+
+
 def det_sincos_turns(phase):
-    """sin, cos of 2*pi*phase/2**32 for uint32 phase (array)."""
+    """sin, cos of 2*pi*phase/2**32 for uint32 phase (array).  Horner steps are fused multiply-adds (fma32)."""
     phase = np.atleast_1d(np.asarray(phase, dtype=np.uint32))
     q = ((phase + np.uint32(0x20000000)) >> np.uint32(30)).astype(np.uint32)
     rem = (phase - (q << np.uint32(30))).astype(np.uint32).view(np.int32)
@@ -128,12 +145,12 @@ def det_sincos_turns(phase):
     z = x * x
     ps = _S[3]
     for c in (_S[2], _S[1], _S[0]):
-        ps = ps * z + c
-    s = x + x * (z * ps)
+        ps = fma32(ps, z, c)
+    s = fma32(x, z * ps, x)
     pc = _C[4]
     for c in (_C[3], _C[2], _C[1], _C[0]):
-        pc = pc * z + c
-    c_ = ONE + z * pc
+        pc = fma32(pc, z, c)
+    c_ = fma32(z, pc, ONE)
     qq = q & np.uint32(3)
     sin = np.where(qq == 0, s, np.where(qq == 1, c_, np.where(qq == 2, -s, -c_)))
     cos = np.where(qq == 0, c_, np.where(qq == 1, -s, np.where(qq == 2, -c_, s)))
@@ -141,13 +158,13 @@ def det_sincos_turns(phase):
 
 
 def det_tan(x):
-    """tan(x) for |x| <= ~0.45 rad (odd Taylor polynomial to x**13, Horner, no FMA)."""
+    """tan(x) for |x| <= ~0.45 rad (odd Taylor polynomial to x**13, Horner in fused multiply-adds)."""
     x = np.atleast_1d(np.asarray(x, dtype=np.float32))
     z = x * x
     p = _T[5]
     for c in (_T[4], _T[3], _T[2], _T[1], _T[0]):
-        p = p * z + c
-    return (x + x * (z * p)).astype(np.float32)
+        p = fma32(p, z, c)
+    return fma32(x, z * p, x)
 
 
 def det_log(u):
