@@ -317,11 +317,13 @@ __device__ __forceinline__ void dyn_advance(const KT& kc, const dqlb200_populati
       x.z = fadd(fadd(x.z, fmul(x.v_z, kc.h)), fmul(a_z, kc.half_h2));
       x.v_z = fadd(x.v_z, fmul(a_z, kc.h));
     } else {
-      b.theta = fadd(b.theta, fmul(fsub(sp, b.theta), kc.k_theta));
-      b.a_d = fsub(fmul(pp.g, det_tan(b.theta)), fmul(kc.c_d, b.v_d));
+      // first-order lag, a = g tan(theta) - c_d v, x + v h + a h^2 / 2, v + a h: fused multiply-adds by definition (the oracles
+      // say fma32 / fmaf), one FFMA where a separately rounded product would be two instructions
+      b.theta = __fmaf_rn(fsub(sp, b.theta), kc.k_theta, b.theta);
+      b.a_d = __fmaf_rn(-kc.c_d, b.v_d, fmul(pp.g, det_tan(b.theta)));
     }
-    b.x_d = fadd(fadd(b.x_d, fmul(b.v_d, kc.h)), fmul(b.a_d, kc.half_h2));
-    b.v_d = fadd(b.v_d, fmul(b.a_d, kc.h));
+    b.x_d = __fmaf_rn(b.a_d, kc.half_h2, __fmaf_rn(b.v_d, kc.h, b.x_d));
+    b.v_d = __fmaf_rn(b.a_d, kc.h, b.v_d);
     b.phase += pp.dphase;
     if (kc.accel_mode != 0 && kf) {       // one estimator sample per sub-step (the node publishes at the sub-step rate)
       float s, c;
@@ -337,9 +339,9 @@ __device__ __forceinline__ Obs dyn_observe(const KT& kc, const dqlb200_populatio
   float s, c;
   det_sincos_turns(b.phase, s, c);
   Obs o;
-  o.rel_p = fsub(fmul(pp.r, s), b.x_d);
-  o.rel_v = fsub(fmul(pp.rw, c), b.v_d);
-  o.rel_a = fsub(-fmul(pp.rw2, s), b.a_d);
+  o.rel_p = __fmaf_rn(pp.r, s, -b.x_d);
+  o.rel_v = __fmaf_rn(pp.rw, c, -b.v_d);
+  o.rel_a = __fmaf_rn(-pp.rw2, s, -b.a_d);
   if (kc.accel_mode != 0 && kf) o.rel_a = kf->x;
   o.pitch = b.theta;
   o.z = fadd(kc.z_init, fmul(__int2float_rn(step_count), dz));

@@ -171,11 +171,11 @@ void oracle_advance(const standin_params* p, standin_state* s, float sp, float v
       s->z = (s->z + s->v_z * p->h) + a_z * p->half_h2;
       s->v_z = s->v_z + a_z * p->h;
     } else {
-      s->theta = s->theta + (sp - s->theta) * p->k_theta;
-      s->a_d = p->g * oracle_tan(s->theta) - p->c_d * s->v_d;
+      s->theta = fmaf(sp - s->theta, p->k_theta, s->theta);      /* fused multiply-adds, like the kernels' FFMA */
+      s->a_d = fmaf(-p->c_d, s->v_d, p->g * oracle_tan(s->theta));
     }
-    s->x_d = (s->x_d + s->v_d * p->h) + s->a_d * p->half_h2;
-    s->v_d = s->v_d + s->a_d * p->h;
+    s->x_d = fmaf(s->a_d, p->half_h2, fmaf(s->v_d, p->h, s->x_d));
+    s->v_d = fmaf(s->a_d, p->h, s->v_d);
     s->phase += p->dphase;
     if (p->accel_mode != 0) {
       float sn, cs;
@@ -189,9 +189,9 @@ void oracle_advance(const standin_params* p, standin_state* s, float sp, float v
 void oracle_observe(const standin_params* p, const standin_state* s, float out[4]) {
   float sn, cs;
   oracle_sincos_turns(s->phase, &sn, &cs);
-  out[0] = p->r * sn - s->x_d;
-  out[1] = p->rw * cs - s->v_d;
-  out[2] = -(p->rw2 * sn) - s->a_d;
+  out[0] = fmaf(p->r, sn, -s->x_d);
+  out[1] = fmaf(p->rw, cs, -s->v_d);
+  out[2] = fmaf(-p->rw2, sn, -s->a_d);
   if (p->accel_mode != 0) out[2] = s->kf_x;
   out[3] = s->theta;
 }

@@ -382,11 +382,11 @@ class StandInDet:
                 z = ((z + vz * d.h) + a_z * d.half_h2).astype(np.float32)
                 vz = (vz + a_z * d.h).astype(np.float32)
                 self.omega[ii], self.z[ii], self.v_z[ii] = om, z, vz
-            else:
-                th = th + (sp - th) * d.k_theta
-                a = d.g * det_tan(th) - d.c_d * v
-            x = (x + v * d.h) + a * d.half_h2
-            v = v + a * d.h
+            else:       # first-order lag and a = g tan(theta) - c_d v, as fused multiply-adds (fma32)
+                th = fma32(sp - th, d.k_theta, th)
+                a = fma32(-d.c_d, v, d.g * det_tan(th))
+            x = fma32(a, d.half_h2, fma32(v, d.h, x))       # x + v h + a h^2 / 2 and v + a h, fused
+            v = fma32(a, d.h, v)
             ph = ph + np.uint32(d.dphase)
             if self.kf is not None:       # one estimator sample per sub-step
                 _, c = det_sincos_turns(ph)
@@ -398,9 +398,9 @@ class StandInDet:
         d = self.d
         sl = slice(None) if idx is None else idx
         s, c = det_sincos_turns(self.phase[sl])
-        rel_p = d.r * s - self.x_d[sl]
-        rel_v = d.rw * c - self.v_d[sl]
-        rel_a = -(d.rw2 * s) - self.a_d[sl]
+        rel_p = fma32(d.r, s, -self.x_d[sl])          # platform minus drone, one rounding each
+        rel_v = fma32(d.rw, c, -self.v_d[sl])
+        rel_a = fma32(-d.rw2, s, -self.a_d[sl])
         if self.kf is not None:
             rel_a = self.kf.x[sl].copy()
         z = d.z_init + np.asarray(step_count).astype(np.float32) * d.dz
