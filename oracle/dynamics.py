@@ -28,6 +28,7 @@ start phase is just a Philox word.
 from __future__ import annotations
 
 import math
+import struct
 from dataclasses import dataclass
 
 import numpy as np
@@ -120,20 +121,30 @@ ONE = f32(1.0)
 
 
 def fma32(a, b, c):
-    """Correctly rounded float32 fused multiply-add RN(a * b + c) on arrays (what FFMA / fmaf compute), in NumPy: the product of
-    two float32 is exact in float64; the float64 sum is rounded TO ODD (if it is inexact -- TwoSum gives the exact error -- the
-    neighbour with an odd last bit is taken), so that the final rounding to float32 sees no double rounding (53 >= 2 * 24 + 2)."""
-    a64, b64, c64 = (np.asarray(v, dtype=np.float32).astype(np.float64) for v in (a, b, c))
-    p = a64 * b64
-    s = p + c64
-    bb = s - p
-    err = (p - (s - bb)) + (c64 - bb)
-    s, err = np.broadcast_arrays(s, err)
-    bits = s.copy().view(np.uint64)
-    fix = (err != 0) & ((bits & np.uint64(1)) == 0)
-    grows = (err > 0) == (s > 0)                      # the exact sum is further from zero than s
-    bits = np.where(fix, np.where(grows, bits + np.uint64(1), bits - np.uint64(1)), bits)
-    return bits.view(np.float64).astype(np.float32)
+    """Correctly rounded float32 fused multiply-add RN(a * b + c) on arrays (what FFMA / fmaf compute), in NumPy.  The product of
+    two float32 is exact in float64.  Rounding the float64 sum s to float32 can only go wrong (double rounding) when s sits exactly
+    on a float32 tie AND the float64 addition was inexact: no other float32 tie can lie between the exact sum and s, because a tie
+    is itself a float64 number and s is the float64 nearest to the exact sum.  Those entries (one in 2**29) are redone with the
+    exact error of the addition (TwoSum): the sum is moved off the tie toward the exact value before the final rounding."""
+    a, b, c = np.asarray(a), np.asarray(b), np.asarray(c)
+    if a.size == 1 and b.size == 1 and c.size == 1:      # single env: Python floats (IEEE double) instead of NumPy call overhead
+        sf = float(a.reshape(-1)[0]) * float(b.reshape(-1)[0]) + float(c.reshape(-1)[0])
+        if (struct.unpack("<Q", struct.pack("<d", sf))[0] & 0x1FFFFFFF) != 0x10000000:
+            return np.full(np.broadcast(a, b, c).shape, sf, dtype=np.float32)
+    p = np.multiply(a, b, dtype=np.float64)
+    c64 = np.asarray(c, dtype=np.float64)
+    s = np.asarray(p + c64)
+    bits = s.view(np.uint64)
+    tie = (bits & np.uint64(0x1FFFFFFF)) == np.uint64(0x10000000)
+    if tie.any():
+        p, c64 = np.broadcast_arrays(p, c64)
+        bb = s - p
+        err = (p - (s - bb)) + (c64 - bb)
+        grows = (err > 0) == (s > 0)                      # the exact sum is further from zero than s
+        fix = tie & (err != 0)
+        bits = np.where(fix, np.where(grows, bits + np.uint64(1), bits - np.uint64(1)), bits)
+        s = bits.view(np.float64)
+    return s.astype(np.float32)
 
 
 def det_sincos_turns(phase):
