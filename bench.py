@@ -459,7 +459,7 @@ def config4_multi_gpu(rank, local_rank, world, dev, barrier, torch, dist, K) -> 
     g_rank = rank % half
     groups = [dist.new_group(ranks=list(range(0, half))), dist.new_group(ranks=list(range(half, world)))]      # created by every rank
     group = groups[0 if rank < half else 1]
-    n_r, total_per_agent, M, rounds = 512, 262144, CONFIG4_SYNC_EVERY, 8
+    n_r, total_per_agent, M, rounds = 512, 262144, CONFIG4_SYNC_EVERY, 32          # 32 exchange rounds: a timed region of a few ms is at the mercy of one late rank
     R = total_per_agent // n_r // half                     # replicas of this rank
     e4 = Engine(R, n_r, device=local_rank, threads_per_block=128, seeds=[42] * R, population_ids=[g_rank * R + p for p in range(R)],
                 replicas_per_population=R, axes=[axis] * R, tp=K.TrainerParameters(success_rate=2.0, max_num_episodes=10 ** 12))
